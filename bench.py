@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- fused fake-quant+Linear tokens/sec, BERT-base seq512 6-bit (BASELINE.json config 2).
+
+One step = one pass of the hot path over one synthetic batch [32, 512, 768]: the 72 QLinear sites of
+the BERT-base encoder stack (12 layers x {q, k, v, attn-out: 768->768, FFN-up 768->3072, FFN-down
+3072->768}), each executed as ONE fused activation-fake-quant + weight-fake-quant + Linear launch
+(LSQ+ 6-bit asymmetric activations calibrated by AvgPruneMinMax p=0.99, Fixed 6-bit symmetric
+per-channel weights, gamma folded at load).  tokens/s = 16384 / step time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU): batches are independent, every rank runs its own
+batch (weak scaling, no data-path collective); timing is the max over ranks of CUDA-event time
+bracketed by barrier + synchronize.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, S, H, FF, LAYERS = 32, 512, 768, 3072, 12
+M = B * S
+SITES = [("q", H, H, True), ("k", H, H, True), ("v", H, H, True), ("attn_out", H, H, False),
+         ("ffn_up", H, FF, True), ("ffn_down", FF, H, False)]  # name, K, N, gamma-folded (gamma_migration.py:8-42)
+A_BIT = W_BIT = 6
+METRIC = "fused fake-quant+Linear tokens/sec, BERT-base seq512 6-bit"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def site_bytes(k, n):
+    """ALGORITHMIC bytes of one fused site: A read once (fp32), Y written once (fp32),
+    weight bins in their 8-bit container, per-column scale / rowsum / bias."""
+    return 4 * M * k + 4 * M * n + n * k + 12 * n
+
+
+def synth_act(k, seed, device="cpu"):
+    g = torch.Generator(device=device).manual_seed(seed)
+    a = torch.randn(B, S, k, generator=g, dtype=torch.float32, device=device)
+    idx = torch.randperm(k, generator=g, device=device)[:6]
+    a[..., idx] *= 30.0
+    return a
+
+
+def synth_weight(n, k, seed, gamma):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(n, k, generator=g) * 0.05
+    b = torch.randn(n, generator=g) * 0.02
+    if gamma:
+        w = w * (torch.rand(k, generator=g) * 2.0 + 0.2)[None, :]
+    return w, b
+
+
+def synth_lens(seed=7):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(S // 4, S + 1, (B,), generator=g)
+    lens[0] = S
+    return lens
+
+
+class QC:
+    def __init__(self, quantizer, observer, bit, symmetric, ch_axis):
+        self.quantizer, self.observer, self.bit, self.symmetric, self.ch_axis = quantizer, observer, bit, symmetric, ch_axis
+
+
+A_QCFG = QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", A_BIT, False, -1)
+W_QCFG = QC("FixedFakeQuantize", "MinMaxObserver", W_BIT, True, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores (reference is Python and cannot travel)
+# ---------------------------------------------------------------------------------------------
+def cpu_layer_time(reps, warmup=1):
+    """seconds for ONE encoder layer's six sites (act LSQ+ fq -> weight fq -> F.linear) on all host threads."""
+    from oracle import osq_oracle as O  # CPU baseline leg only
+    torch.set_num_threads(os.cpu_count() or 1)
+    a768, a3072 = synth_act(H, 11).reshape(M, H), synth_act(FF, 12).reshape(M, FF)
+    sites = []
+    for i, (_, k, n, gam) in enumerate(SITES):
+        w, b = synth_weight(n, k, 100 + i, gam)
+        ws, wz, wqmin, wqmax = O.weight_qparams_minmax(w, W_BIT, True)
+        a = a768 if k == H else a3072
+        qmin, qmax = O.quant_range(A_BIT, False)
+        st = O.ObserverState()
+        O.observe_avg_prune_minmax(st, a.reshape(B, S, k)[:4], 0.99, "x", None, 1)
+        s, z = O.qparams_from_minmax(st.min_val, st.max_val, qmin, qmax, False)
+        sites.append((a, s.reshape(1), z.reshape(1).float(), qmin, qmax, w, ws, wz, wqmin, wqmax, b))
+    times = []
+    with torch.no_grad():
+        for r in range(warmup + reps):
+            t0 = time.perf_counter()
+            for a, s, z, qmin, qmax, w, ws, wz, wqmin, wqmax, b in sites:
+                x_fq = O.fq_lsqplus_per_tensor(a, s, z, qmin, qmax)
+                O.qlinear(x_fq, w, ws, wz, wqmin, wqmax, b)
+            if r >= warmup:
+                times.append(time.perf_counter() - t0)
+    return statistics.median(times), times
+
+
+def cpu_baseline_record(reps):
+    t_layer, _ = cpu_layer_time(reps)
+    return {"value": M / (LAYERS * t_layer), "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "1 of 12 identical encoder layers (6 QLinear sites, M=16384) x %d reps, median, scaled x12; "
+                      "oracle port of util_quant.py/quantized_module.py on torch CPU threads" % reps}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_layer, times = cpu_layer_time(max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
+    value = M / (LAYERS * t_layer)
+    rec = {"impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": LAYERS * t_layer * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BERT-base seq512 6-bit twc_fine_gamma, batch 32 (M=16384), 72 QLinear sites",
+                      "note": "each step times one encoder layer (1/12 of the stack) and is scaled x12"},
+           "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": "port",
+                            "sample": "1 of 12 identical encoder layers per step, scaled x12"},
+           "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(rec))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def build_stack(device):
+    """72 calibrated (activation quantizer, QLinear) module pairs + device-resident activations."""
+    from outlier_suppression_b200 import ops
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer
+    lens = synth_lens().to(device)
+    # inputs larger than L2 (126 MB): 4 x 50 MB for K=768, 2 x 201 MB for K=3072, rotated per launch
+    acts = {H: [synth_act(H, 11 + i, device) for i in range(4)], FF: [synth_act(FF, 21 + i, device) for i in range(2)]}
+    outs = {H: [torch.empty(M, H, device=device) for _ in range(4)], FF: [torch.empty(M, FF, device=device) for _ in range(2)]}
+    layers = []
+    for layer in range(LAYERS):
+        mods = []
+        for i, (name, k, n, gam) in enumerate(SITES):
+            w, b = synth_weight(n, k, 1000 * layer + 100 + i, gam)
+            lin = torch.nn.Linear(k, n)
+            lin.weight.data, lin.bias.data = w, b
+            ql = Quantizer(lin, W_QCFG).to(device)
+            aq = Quantizer(None, A_QCFG).to(device)
+            aq.observer.set_name("layer.%d.%s" % (layer, name))
+            aq.observer.set_percentile(0.99)
+            # calibration (ptq_glue_quant.py:234-246): weight observer once, activation observer on one batch
+            ql.weight_fake_quant.enable_observer(); ql.weight_fake_quant(ql.weight); ql.weight_fake_quant.disable_observer()
+            aq.enable_observer(); aq(acts[k][0], lens, 1); aq.disable_observer()
+            aq.enable_fake_quant(); ql.weight_fake_quant.enable_fake_quant()
+            codes, rowsum, w_scale = ql._packed_weight()
+            mods.append({"name": name, "k": k, "n": n, "aq": aq, "ql": ql, "codes": codes, "rowsum": rowsum, "w_scale": w_scale,
+                         "g": aq.grad_factor(acts[k][0])})
+        layers.append(mods)
+    torch.cuda.synchronize()
+    return layers, acts, outs, ops
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-reps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--only-value", action="store_true", help="profiling runs: timed stack only, no roofline/e2e/cpu legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    torch.set_grad_enabled(False)  # inference / calibration path (HF Trainer.evaluate runs under no_grad)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    layers, acts, outs, ops = build_stack(device)
+    counters = {H: 0, FF: 0}
+
+    def launch(site, a=None):
+        k, n = site["k"], site["n"]
+        if a is None:
+            a = acts[k][counters[k] % len(acts[k])]
+            counters[k] += 1
+        out = outs[n][counters[n] % len(outs[n])]
+        aq = site["aq"]
+        return ops.fused_fq_linear(a, aq.scale.data, aq.zero_point.data, aq.quant_min, aq.quant_max, site["codes"],
+                                   site["w_scale"], site["rowsum"], site["ql"].bias, lsq_grad_factor=site["g"], out=out)
+
+    def step():
+        for mods in layers:
+            for site in mods:
+                launch(site)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: whole stack, inputs resident in HBM ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+    ms_step = ms_total / args.steps
+    value = world * M / (ms_step * 1e-3)
+
+    if args.only_value:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "tokens/s", "ms_per_step": ms_step, "only_value": True}))
+        return
+
+    # ---- roofline of the dominant kernel, per site shape, CUDA events around each launch ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    if os.path.exists(peaks_path):
+        try:
+            pk = json.load(open(peaks_path))
+            peak, peak_src = float(pk.get("hbm_gbs", pk.get("hbm_gbps", FALLBACK_HBM_GBS))), "measured"
+        except Exception:
+            pass
+    per_site, tot_bytes, tot_ms, n_launch = {}, 0.0, 0.0, 0
+    reps = 4
+    for name, k, n, _ in SITES:
+        evs = []
+        for r in range(reps):
+            for mods in layers[:6]:
+                site = [s for s in mods if s["name"] == name][0]
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); launch(site); b_.record()
+                evs.append((a, b_))
+        torch.cuda.synchronize()
+        ms = statistics.mean(x.elapsed_time(y) for x, y in evs[6:])  # first sweep = warm-up
+        by = site_bytes(k, n)
+        per_site[name] = {"K": k, "N": n, "us": ms * 1e3, "bytes": by, "gbs": by / (ms * 1e-3) / 1e9, "frac": by / (ms * 1e-3) / 1e9 / peak}
+        mult = LAYERS
+        tot_bytes += by * mult; tot_ms += ms * mult; n_launch += mult
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "fused_fq_linear_kernel (kind::i8)", "bytes_per_launch_avg": tot_bytes / n_launch,
+                "us_per_launch_avg": tot_ms * 1e3 / n_launch, "sites": per_site}
+
+    # ---- e2e: module-level API, batch from pinned host memory, result read back to the host ----
+    host_in = synth_act(H, 99).pin_memory()
+    host_out = torch.empty(M, H).pin_memory()
+    lens = synth_lens().to(device)
+
+    def e2e_step():
+        x = host_in.to(device, non_blocking=True)                       # H2D inside the timed region
+        h = x
+        for mods in layers:
+            by_name = {s["name"]: s for s in mods}
+            hq = by_name["q"]["aq"](h, lens, 1)                          # act quantizer module (tags its output)
+            for nme in ("q", "k"):
+                by_name[nme]["ql"](hq)                                   # QLinear module -> fused kernel
+            v = by_name["v"]["ql"](hq).reshape(B, S, H)
+            ctx = by_name["attn_out"]["aq"](v, lens, 1)
+            ao = by_name["attn_out"]["ql"](ctx).reshape(B, S, H)
+            f_in = by_name["ffn_up"]["aq"](ao, lens, 1)
+            up = by_name["ffn_up"]["ql"](f_in).reshape(B, S, FF)
+            d_in = by_name["ffn_down"]["aq"](up, lens, 1)
+            h = by_name["ffn_down"]["ql"](d_in).reshape(B, S, H)
+        host_out.copy_(h.reshape(M, H), non_blocking=True)              # D2H of the step's result
+        return h
+
+    e2e = None
+    try:
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0.record()
+        n_e2e = max(3, args.steps // 2)
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms_e2e], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t)
+        e2e = {"value": world * M / (ms_e2e / n_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": host_in.numel() * 4,
+               "d2h_bytes_per_step": host_out.numel() * 4, "steps": n_e2e,
+               "api": "quantization.Quantizer modules: 4 activation quantizers + 6 QLinear per layer, x12"}
+    except Exception as ex:  # pragma: no cover
+        e2e = {"value": None, "error": repr(ex)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_record(args.cpu_reps)
+
+    if rank == 0:
+        rec = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8 (u8 x s8 -> s32 bins, fp32 I/O)",
+               "data": "synthetic",
+               "config": {"workload": "BERT-base seq512 6-bit twc_fine_gamma (LSQ+ acts / AvgPruneMinMax p=.99, Fixed per-channel weights, gamma folded), "
+                                      "batch 32 per GPU (M=16384), 72 fused QLinear sites per step",
+                          "l2": "inputs/outputs rotate over 4x50MB / 2x201MB buffers (> 126 MB L2) between launches",
+                          "parallelism": "dp%d (independent batches, no collective)" % world},
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * LAYERS * len(SITES),
+               "clocks": clocks}
+        print(json.dumps(rec))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

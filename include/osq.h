@@ -1,0 +1,214 @@
+/*
+ * osq.h -- C ABI of libosq_b200.so: the B200 (sm_100a) fake-quantize / observer / fused
+ * fake-quant+Linear hot path of wimh966/outlier_suppression.
+ *
+ * The reference is pure Python (no FFI); each entry point below replaces the launch sequence of
+ * the reference function it cites (paths relative to /root/reference/quant_transformer).  A
+ * maintainer binds them with ctypes exactly as outlier_suppression_b200/_lib.py does
+ * (INTEGRATION.md shows the stub to drop into quantization/).
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer unless its name ends in _host; the caller owns all
+ *     memory (outputs and workspaces are pre-allocated by the caller);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) and never synchronises the device;
+ *   - return value: 0 on success, a negative OSQ_E* code on failure; the message for the calling
+ *     thread is available through osq_last_error();
+ *   - all floating point data is fp32; quantisation parameters live in device memory so that no
+ *     host<->device sync (the reference's `.item()` calls, fake_quant.py:124) is ever needed.
+ */
+#ifndef OSQ_H_
+#define OSQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSQ_OK 0
+#define OSQ_EINVAL (-1)   /* bad argument / unsupported shape */
+#define OSQ_ECUDA (-2)    /* CUDA runtime / driver error      */
+#define OSQ_EARCH (-3)    /* device is not sm_100             */
+
+#define OSQ_VERSION 100
+
+int osq_version(void);
+const char* osq_last_error(void);
+/* number of SMs of the current device (used to size caller-owned workspaces); <0 on error */
+int osq_sm_count(void);
+/* bytes of caller-owned scratch every reduction entry point needs (partials + ticket counter) */
+int64_t osq_workspace_bytes(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  per-tensor fake-quantize.     replaces util_quant.py:11-15 (fake_quantize_per_tensor_affine)
+ *     and util_quant.py:48-55 (learnable-plus variant) as called from fake_quant.py:107-126,178-209.
+ *
+ *   q = clamp((rint(x/s) - x/s + x/s) + z, qmin, qmax);   y = (q - z) * s        (all fp32, true division)
+ *
+ *   scale/zero_point are device scalars.  lsq_grad_factor > 0 selects the LSQ+ forward: the
+ *   effective parameters  z' = gs(rint(z), g), s' = gs(s, g), gs(t,g) = (t - t*g) + t*g  are
+ *   derived in-kernel with the reference's exact fp32 op order (util_quant.py:49-51,70-71).
+ *   zp_is_int32 != 0: zero_point points at an int32 (FixedFakeQuantize buffer), else at a float.
+ *   codes (optional, may be NULL): int16 bin per element, rint(q)  (debug / parity side output).
+ *   x and y may alias.  n elements, any alignment.
+ * ------------------------------------------------------------------------------------------- */
+int osq_fq_per_tensor_f32(const float* x, float* y, int16_t* codes, int64_t n,
+                          const float* scale, const void* zero_point, int zp_is_int32,
+                          float lsq_grad_factor, int qmin, int qmax, void* stream);
+
+/* K2  per-channel (ch_axis = 0) fake-quantize of a [rows, cols] matrix.
+ *     replaces util_quant.py:18-26 (fake_quantize_per_channel_affine), fake_quant.py:119-122. */
+int osq_fq_per_channel_f32(const float* x, float* y, int16_t* codes, int64_t rows, int64_t cols,
+                           const float* scale, const int32_t* zero_point, int qmin, int qmax,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Token geometry shared by the observer kernels.  replaces observer.py:72-98 (remove_padding /
+ * reshape_batch_embedding): the activation is viewed as [B, S, F1, F2] with element strides
+ * (sb, ss, sf1, sf2); token (b, s) owns the F1*F2 features; it is valid iff s < lens[b]
+ * (lens == NULL: every token valid; b >= n_lens: batch entry skipped -- the reference's zip()).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t B, S, F1, F2;
+  int64_t sb, ss, sf1, sf2;
+} osq_tokens_t;
+
+/* Running-statistics epilogue shared by the observer entry points.
+ *   mode 0: none (only cur_minmax[2] is written)
+ *   mode 1: running average  m <- (m*cnt + cur)/(cnt+1)   observer.py:194-202 (Avg* observers);
+ *           cnt == 0 takes the `first batch` branch (m <- cur).
+ *   mode 2: running extrema  m <- min/max(m, cur)          observer.py:143-144
+ * If scale_out != NULL the quantisation parameters of observer.py:100-119 (calculate_qparams) are
+ * recomputed from the updated state: scale_out[0] (fp32) and zp_out (int32 when zp_out_is_int32,
+ * else fp32 -- the LSQ+ Parameter). */
+typedef struct {
+  int mode;
+  int cnt;
+  float* state_min;    /* [1] device: the observer's min_val buffer (updated in place) */
+  float* state_max;    /* [1] device: the observer's max_val buffer */
+  float* scale_out;    /* [1] device or NULL */
+  void* zp_out;        /* [1] device or NULL */
+  int zp_out_is_int32;
+  int qmin, qmax, symmetric;
+} osq_stat_epilogue_t;
+
+/* K3  masked global min/max.  replaces observer.py:188-193 (+ _aminmax) for AvgMinMaxObserver /
+ *     MinMaxObserver(ch_axis=-1).  cur_minmax[2] device output.  workspace: osq_workspace_bytes(). */
+int osq_minmax_masked_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens,
+                          float* cur_minmax, const osq_stat_epilogue_t* epi, void* workspace,
+                          void* stream);
+
+/* flat (no token geometry) global min/max of n elements: observer.py:227 with seq_pos == -1 */
+int osq_minmax_flat_f32(const float* x, int64_t n, float* cur_minmax,
+                        const osq_stat_epilogue_t* epi, void* workspace, void* stream);
+
+/* K4a per-token min/max over the feature axis.  replaces observer.py:64-65 (value.max(1)/min(1))
+ *     fused with the pad removal.  tmin/tmax have B*S entries indexed b*S+s; invalid tokens get
+ *     (+inf, -inf).  n_valid (device int32[1]) receives the number of valid tokens T. */
+int osq_token_minmax_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens,
+                         float* tmin, float* tmax, int32_t* n_valid, void* stream);
+
+/* K4b token pruning on the per-token vectors.  replaces observer.py:50-70 (quantile_range /
+ *     cac_thres / prune_token) + the clip + _aminmax of :69,:227, which equal (lower, upper).
+ *     abs_tmax_sorted / abs_tmin_sorted: ascending sort of |tmax|, |tmin| over the n_slots entries
+ *     with invalid tokens mapped to +inf (so the first T entries are the valid ones).
+ *     Quantile rank/lerp follow torch.quantile(..., interpolation='linear') in fp32. */
+int osq_prune_select_f32(const float* tmin, const float* tmax, const float* abs_tmin_sorted,
+                         const float* abs_tmax_sorted, int64_t n_slots, const int32_t* n_valid,
+                         float percentile, float* cur_minmax, const osq_stat_epilogue_t* epi,
+                         void* workspace, void* stream);
+
+/* per-row min/max of a [rows, cols] matrix with the running-extrema update of
+ * MinMaxObserver(ch_axis=0) (observer.py:141-144) and per-row calculate_qparams.
+ * state_min/state_max [rows] are updated in place (first = 1 overwrites them). */
+int osq_rowwise_minmax_qparams_f32(const float* w, int64_t rows, int64_t cols, int first,
+                                   float* state_min, float* state_max, float* scale_out,
+                                   int32_t* zp_out, int qmin, int qmax, int symmetric, void* stream);
+
+/* observer.py:100-119 (calculate_qparams) for n independent (min, max) pairs; true fp32 division.
+ * zp_f32 / zp_i32: either may be NULL. */
+int osq_calc_qparams_f32(const float* min_val, const float* max_val, int64_t n, int qmin, int qmax,
+                         int symmetric, float* scale, float* zp_f32, int32_t* zp_i32, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  MSE-grid evaluation.  replaces observer.py:420-432 (MSEFastObserver.loss_fx) evaluated for C
+ *     candidate (min, max) pairs in ONE pass over x:  loss[c] = mean((fq(x; qparams(c)) - x)^2).
+ *     Sums are accumulated in fp64 (the reference's fp32 `.mean()` is order-dependent; tolerance
+ *     stated in tests).  cand_scale[C] (fp32), cand_zp[C] (fp32, integer valued) are the candidates'
+ *     quantisation parameters.  loss_sum[C] (fp64) receives the SUM of squared errors (caller
+ *     divides by the number of valid elements, returned in n_valid (int64 device)).
+ * ------------------------------------------------------------------------------------------- */
+int osq_mse_multi_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens,
+                      const float* cand_scale, const float* cand_zp, int n_cand, int qmin, int qmax,
+                      double* loss_sum, int64_t* n_valid, void* stream);
+
+/* K5b per-row bounded-Brent search of MSEFastObserver(ch_axis=0, symmetric) -- observer.py:483-517
+ *     with scipy.optimize.minimize_scalar(method='Bounded') restated on-chip (one CTA per row, row
+ *     resident in shared memory).  out_min/out_max [rows]; evals [rows] (int32) optional. */
+int osq_mse_brent_rows_f32(const float* w, int64_t rows, int64_t cols, int qmin, int qmax,
+                           int one_side /*0 no,1 pos,2 neg*/, float* out_min, float* out_max,
+                           int32_t* evals, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight preparation for the fused kernel (once per weight version; replaces the per-forward
+ * weight fake-quant of quantized_module.py:72).  W [N, K] fp32 (gamma already folded by
+ * gamma_migration.py:46-76), scale[N]/zp[N] from the weight quantizer.
+ *   codes  [N, K] int8  : q - zp  (the dequantised weight is codes * scale[n])
+ *   rowsum [N]    int32 : sum_k codes[n, k]   (zero-point correction of the u8 x s8 contraction)
+ * Requires qmin - zp >= -128 and qmax - zp <= 127 for every row (true for every symmetric config).
+ * ------------------------------------------------------------------------------------------- */
+int osq_pack_weight_s8(const float* w, int64_t N, int64_t K, const float* scale, const int32_t* zp,
+                       int qmin, int qmax, int8_t* codes, int32_t* rowsum, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  fused activation fake-quant + per-channel weight fake-quant + Linear.
+ *     replaces  fake_quant.py:107-126 / :178-209 (activation quantizer)  ->
+ *               quantized_module.py:71-72 (QLinear.forward: weight fq + F.linear)
+ *
+ *   Y[m, n] = s_a * w_scale[n] * sum_k (qa[m,k] - Z) * wcodes[n,k] + bias[n]
+ *   qa = clamp(rint(A/s_a) + Z, a_qmin, a_qmax)  with  Z = rint(z_a)  (LSQ+ effective s', z' when
+ *   lsq_grad_factor > 0, as in K1).  A [M, K] fp32 row-major (raw, un-quantised, or already
+ *   fake-quantised -- fq is idempotent), Y [M, N] fp32 row-major.
+ *
+ *   One persistent, warp-specialised tcgen05 kernel: A tiles arrive by TMA as fp32, converter
+ *   warps turn them into integer codes in the UMMA shared-memory layout, the packed weight codes
+ *   arrive by TMA, `tcgen05.mma kind::i8` (u8 x s8 -> s32, exact) accumulates in TMEM, the
+ *   epilogue applies the zero-point correction, scales and bias and streams fp32 Y to HBM.
+ *   mma_kind: 0 = auto, 1 = kind::i8, 2 = kind::f16 (bf16 code tiles, exact for a_bit,w_bit <= 7).
+ *
+ *   Shape contract: K % 128 == 0, N % 16 == 0, M >= 1.  a_codes_dbg (optional uint8 [M, K]):
+ *   the activation bins the kernel fed to the tensor core (parity side output).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* A;
+  int64_t M, K;
+  const float* a_scale;  /* device [1] */
+  const void* a_zp;      /* device [1] */
+  int a_zp_is_int32;
+  float lsq_grad_factor; /* 0 for FixedFakeQuantize */
+  int a_qmin, a_qmax;
+  const int8_t* w_codes; /* [N, K] from osq_pack_weight_s8 */
+  const float* w_scale;  /* [N] */
+  const int32_t* w_rowsum; /* [N] */
+  const float* bias;     /* [N] or NULL */
+  float* Y;
+  int64_t N;
+  int mma_kind;
+  uint8_t* a_codes_dbg;  /* optional */
+} osq_fused_linear_t;
+
+int osq_fused_fq_linear(const osq_fused_linear_t* args, void* stream);
+
+/* LSQ+ backward (fine stage `learn_scale`, token_wise_clipping.py:72-108; gradients of
+ * util_quant.py:48-55):  dx = dy * 1[qmin <= q <= qmax];
+ *   dscale += g * sum dy * (inside ? rint(x/s) - x/s : q_clamped - z);  dzp += g * sum dy * (inside ? 0 : -s)
+ * grad_acc (device double[2]) must be zeroed by the caller. */
+int osq_lsqplus_backward_f32(const float* x, const float* dy, float* dx, int64_t n,
+                             const float* scale, const float* zero_point, float lsq_grad_factor,
+                             int qmin, int qmax, double* grad_acc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSQ_H_ */

@@ -1,0 +1,155 @@
+// common.cuh -- shared helpers for libosq_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "osq.h"
+
+namespace osq {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+#define OSQ_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::osq::set_error(__VA_ARGS__);        \
+      return OSQ_EINVAL;                    \
+    }                                       \
+  } while (0)
+
+#define OSQ_CUDA(call)                                                            \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) {                                                     \
+      ::osq::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                       __FILE__, __LINE__);                                       \
+      return OSQ_ECUDA;                                                           \
+    }                                                                             \
+  } while (0)
+
+#define OSQ_LAUNCH_CHECK() OSQ_CUDA(cudaPeekAtLastError())
+
+constexpr int kMaxPartialBlocks = 2048;  // upper bound on the grid of any reduction kernel
+// workspace layout: float partial_min[kMax], float partial_max[kMax], uint32 ticket, pad
+constexpr int64_t kWorkspaceBytes = (2 * kMaxPartialBlocks) * 4 + 64;
+
+// ---------------------------------------------------------------------------------------------
+// Quantisation parameters as the kernels consume them.
+// ---------------------------------------------------------------------------------------------
+struct QParam {
+  float s;  // effective scale
+  float z;  // effective zero point (integer valued except for LSQ+'s 1-ulp drift)
+};
+
+// (t - t*g) + t*g with the reference's op order and NO fma contraction (util_quant.py:70-71)
+__device__ __forceinline__ float grad_scale_value(float t, float g) {
+  float tg = __fmul_rn(t, g);
+  return __fadd_rn(__fsub_rn(t, tg), tg);
+}
+
+// Loads (scale, zero_point) device scalars and derives the effective parameters.
+//   g == 0  : FixedFakeQuantize -- parameters used as stored (fake_quant.py:123-125)
+//   g  > 0  : LSQPlusFakeQuantize -- in-place sanitise (fake_quant.py:188-191: |s| clamped to
+//             eps, z clamped to [qmin,qmax]) then round_ste + grad_scale (util_quant.py:49-51).
+// `writeback` (one thread of the grid) stores the sanitised raw parameters like the reference's
+// in-place ops; sanitise is idempotent so concurrent readers are unaffected.
+__device__ __forceinline__ QParam load_qparam(const float* scale, const void* zp, int zp_is_int32,
+                                              float g, float qmin, float qmax, bool writeback) {
+  float s = *scale;
+  float z = zp_is_int32 ? (float)(*(const int32_t*)zp) : *(const float*)zp;
+  if (g > 0.f) {
+    float s_raw = s, z_raw = z;
+    s = fmaxf(fabsf(s), 1.1920928955078125e-07f);
+    z = fminf(fmaxf(z, qmin), qmax);
+    if (writeback && !zp_is_int32) {
+      if (s != s_raw) *const_cast<float*>(scale) = s;
+      if (z != z_raw) *(float*)const_cast<void*>(zp) = z;
+    }
+    z = grad_scale_value(rintf(z), g);
+    s = grad_scale_value(s, g);
+  }
+  return QParam{s, z};
+}
+
+// One element of util_quant.py:12-14.  Returns y; q receives the clamped bin (fp32).
+// round_ste value (rint(t) - t) + t: rint(t) for finite t, NaN for +-inf, like the reference.
+__device__ __forceinline__ float fq_elem(float x, float s, float z, float qmin, float qmax, float& q) {
+  float t = __fdiv_rn(x, s);
+  float r = rintf(t);
+  r = __fadd_rn(__fsub_rn(r, t), t);
+  float v = __fadd_rn(r, z);
+  q = (v != v) ? v : fminf(fmaxf(v, qmin), qmax);  // torch.clamp propagates NaN
+  return __fmul_rn(__fsub_rn(q, z), s);
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit load that does not allocate in L1 (data is touched once)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// observer.py:100-119 for one (min,max) pair.  Returns scale; zp by reference (fp32, integer valued).
+__device__ __forceinline__ float calc_qparams(float mn, float mx, int qmin, int qmax, int symmetric, float& zp) {
+  float lo = fminf(mn, 0.f), hi = fmaxf(mx, 0.f);
+  float s;
+  if (symmetric) {
+    hi = fmaxf(-lo, hi);
+    s = fmaxf(__fdiv_rn(hi, (float)(qmax - qmin) / 2.f), 1e-8f);
+    zp = 0.f;
+  } else {
+    s = fmaxf(__fdiv_rn(__fsub_rn(hi, lo), (float)(qmax - qmin)), 1e-8f);
+    float z = __fsub_rn((float)qmin, rintf(__fdiv_rn(lo, s)));
+    zp = fminf(fmaxf(z, (float)qmin), (float)qmax);
+  }
+  return s;
+}
+
+// running-statistics epilogue executed by ONE thread (see osq_stat_epilogue_t in osq.h)
+__device__ __forceinline__ void stat_epilogue(const osq_stat_epilogue_t& e, float cur_min, float cur_max) {
+  if (e.mode == 0) return;
+  float mn = *e.state_min, mx = *e.state_max;
+  if (e.mode == 1) {
+    if (isinf(mx)) {  // observer.py:194-196 (`first batch` branch: max_val still +-inf)
+      mn = cur_min;
+      mx = cur_max;
+    } else {
+      mn = __fadd_rn(__fmul_rn(mn, (float)e.cnt), cur_min);
+      mx = __fadd_rn(__fmul_rn(mx, (float)e.cnt), cur_max);
+    }
+    mn = __fdiv_rn(mn, (float)(e.cnt + 1));
+    mx = __fdiv_rn(mx, (float)(e.cnt + 1));
+  } else {
+    mn = fminf(mn, cur_min);
+    mx = fmaxf(mx, cur_max);
+  }
+  *e.state_min = mn;
+  *e.state_max = mx;
+  if (e.scale_out != nullptr) {
+    float zp;
+    float s = calc_qparams(mn, mx, e.qmin, e.qmax, e.symmetric, zp);
+    e.scale_out[0] = s;
+    if (e.zp_out != nullptr) {
+      if (e.zp_out_is_int32) *(int32_t*)e.zp_out = (int32_t)zp;
+      else *(float*)e.zp_out = zp;
+    }
+  }
+}
+
+}  // namespace osq

@@ -1,0 +1,248 @@
+// fq_elementwise.cu -- K1 / K2: per-tensor and per-channel fake-quantize (one read, one write).
+//
+// HBM-bound: 8 algorithmic bytes per element (4 read + 4 written).  Grid = multiple of the SM
+// count, 128-bit streaming loads/stores, device-resident quantisation parameters (no .item()).
+#include "common.cuh"
+
+namespace osq {
+
+constexpr int kFqThreads = 256;
+constexpr int kFqUnroll = 4;  // float4s in flight per thread
+
+template <bool kCodes>
+__global__ void __launch_bounds__(kFqThreads)
+fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, int16_t* __restrict__ codes,
+                     int64_t n, const float* __restrict__ scale, const void* __restrict__ zp,
+                     int zp_is_int32, float g, float qmin, float qmax) {
+  const QParam p = load_qparam(scale, zp, zp_is_int32, g, qmin, qmax,
+                               blockIdx.x == 0 && threadIdx.x == 0);
+  const float s = p.s, z = p.z;
+  // head: elements before the first 16-byte boundary, tail: after the last full float4
+  int64_t head = (int64_t)((16 - ((uintptr_t)x & 15)) & 15) >> 2;
+  if (head > n) head = n;
+  const bool vec_ok = (((uintptr_t)x & 3) == 0) && ((((uintptr_t)x) & 15) == (((uintptr_t)y) & 15));
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  if (!vec_ok) {
+    for (int64_t i = tid; i < n; i += nthreads) {
+      float q;
+      y[i] = fq_elem(x[i], s, z, qmin, qmax, q);
+      if (kCodes) codes[i] = (int16_t)rintf(q);
+    }
+    return;
+  }
+  const int64_t nvec = (n - head) >> 2;
+  const float4* xv = reinterpret_cast<const float4*>(x + head);
+  float4* yv = reinterpret_cast<float4*>(y + head);
+  for (int64_t base = tid; base < nvec; base += nthreads * kFqUnroll) {
+    float4 v[kFqUnroll];
+#pragma unroll
+    for (int u = 0; u < kFqUnroll; ++u) {
+      int64_t i = base + (int64_t)u * nthreads;
+      if (i < nvec) v[u] = ldg_stream(xv + i);
+    }
+#pragma unroll
+    for (int u = 0; u < kFqUnroll; ++u) {
+      int64_t i = base + (int64_t)u * nthreads;
+      if (i < nvec) {
+        float4 o;
+        float q0, q1, q2, q3;
+        o.x = fq_elem(v[u].x, s, z, qmin, qmax, q0);
+        o.y = fq_elem(v[u].y, s, z, qmin, qmax, q1);
+        o.z = fq_elem(v[u].z, s, z, qmin, qmax, q2);
+        o.w = fq_elem(v[u].w, s, z, qmin, qmax, q3);
+        __stcs(yv + i, o);
+        if (kCodes) {
+          int16_t* c = codes + head + (i << 2);
+          c[0] = (int16_t)rintf(q0); c[1] = (int16_t)rintf(q1);
+          c[2] = (int16_t)rintf(q2); c[3] = (int16_t)rintf(q3);
+        }
+      }
+    }
+  }
+  // scalar head + tail
+  const int64_t tail_start = head + (nvec << 2);
+  for (int64_t i = tid; i < head + (n - tail_start); i += nthreads) {
+    int64_t j = i < head ? i : tail_start + (i - head);
+    float q;
+    y[j] = fq_elem(x[j], s, z, qmin, qmax, q);
+    if (kCodes) codes[j] = (int16_t)rintf(q);
+  }
+}
+
+// one CTA per (row, column-slab): scale/zp are per row (ch_axis = 0)
+template <bool kCodes>
+__global__ void __launch_bounds__(kFqThreads)
+fq_per_channel_kernel(const float* __restrict__ x, float* __restrict__ y, int16_t* __restrict__ codes,
+                      int64_t rows, int64_t cols, const float* __restrict__ scale,
+                      const int32_t* __restrict__ zp, float qmin, float qmax) {
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float s = scale[r];
+    const float z = (float)zp[r];
+    const float* xr = x + r * cols;
+    float* yr = y + r * cols;
+    const bool vec_ok = ((cols & 3) == 0) && (((uintptr_t)xr & 15) == 0) && (((uintptr_t)yr & 15) == 0);
+    if (vec_ok) {
+      const float4* xv = reinterpret_cast<const float4*>(xr);
+      float4* yv = reinterpret_cast<float4*>(yr);
+      for (int64_t i = threadIdx.x; i < (cols >> 2); i += blockDim.x) {
+        float4 v = ldg_stream(xv + i), o;
+        float q0, q1, q2, q3;
+        o.x = fq_elem(v.x, s, z, qmin, qmax, q0);
+        o.y = fq_elem(v.y, s, z, qmin, qmax, q1);
+        o.z = fq_elem(v.z, s, z, qmin, qmax, q2);
+        o.w = fq_elem(v.w, s, z, qmin, qmax, q3);
+        yv[i] = o;
+        if (kCodes) {
+          int16_t* c = codes + r * cols + (i << 2);
+          c[0] = (int16_t)rintf(q0); c[1] = (int16_t)rintf(q1);
+          c[2] = (int16_t)rintf(q2); c[3] = (int16_t)rintf(q3);
+        }
+      }
+    } else {
+      for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) {
+        float q;
+        yr[i] = fq_elem(xr[i], s, z, qmin, qmax, q);
+        if (kCodes) codes[r * cols + i] = (int16_t)rintf(q);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSQ+ backward (gradients of util_quant.py:48-55 as autograd derives them)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFqThreads)
+lsqplus_backward_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t n,
+                        const float* __restrict__ scale, const float* __restrict__ zp, float g, float qmin, float qmax,
+                        double* __restrict__ grad_acc) {
+  const QParam p = load_qparam(scale, zp, 0, g, qmin, qmax, false);
+  const float s = p.s, z = p.z;
+  double ds = 0.0, dz = 0.0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n; i += nthreads) {
+    const float xv = x[i], gy = dy[i];
+    const float t = __fdiv_rn(xv, s);
+    float r = rintf(t);
+    r = __fadd_rn(__fsub_rn(r, t), t);
+    const float v = __fadd_rn(r, z);
+    const bool inside = (v >= qmin) && (v <= qmax);
+    const float gq = __fmul_rn(gy, s);  // d/d x_quant
+    if (inside) {
+      dx[i] = __fdiv_rn(gq, s);
+      ds += (double)gy * ((double)__fsub_rn(v, z) - (double)t);
+    } else {
+      dx[i] = 0.f;
+      const float q = fminf(fmaxf(v, qmin), qmax);
+      ds += (double)gy * (double)__fsub_rn(q, z);
+      dz -= (double)gq;
+    }
+  }
+  __shared__ double sds[kFqThreads / 32], sdz[kFqThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dz += __shfl_xor_sync(0xffffffffu, dz, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sds[threadIdx.x >> 5] = ds; sdz[threadIdx.x >> 5] = dz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < kFqThreads / 32; ++i) { a += sds[i]; b += sdz[i]; }
+    atomicAdd(grad_acc + 0, a * (double)g);
+    atomicAdd(grad_acc + 1, b * (double)g);
+  }
+}
+
+__global__ void calc_qparams_kernel(const float* __restrict__ mn, const float* __restrict__ mx, int64_t n, int qmin,
+                                    int qmax, int symmetric, float* __restrict__ scale, float* __restrict__ zp_f32,
+                                    int32_t* __restrict__ zp_i32) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float zp;
+  scale[i] = calc_qparams(mn[i], mx[i], qmin, qmax, symmetric, zp);
+  if (zp_f32) zp_f32[i] = zp;
+  if (zp_i32) zp_i32[i] = (int32_t)zp;
+}
+
+}  // namespace osq
+
+extern "C" {
+
+int osq_calc_qparams_f32(const float* min_val, const float* max_val, int64_t n, int qmin, int qmax, int symmetric,
+                         float* scale, float* zp_f32, int32_t* zp_i32, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(min_val && max_val && scale && n >= 0, "osq_calc_qparams_f32: bad argument");
+  if (n == 0) return OSQ_OK;
+  calc_qparams_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(min_val, max_val, n, qmin, qmax, symmetric,
+                                                                                   scale, zp_f32, zp_i32);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_lsqplus_backward_f32(const float* x, const float* dy, float* dx, int64_t n, const float* scale,
+                             const float* zero_point, float lsq_grad_factor, int qmin, int qmax, double* grad_acc,
+                             void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(x && dy && dx && scale && zero_point && grad_acc && n >= 0, "osq_lsqplus_backward_f32: bad argument");
+  OSQ_CHECK_ARG(lsq_grad_factor > 0.f, "osq_lsqplus_backward_f32: grad factor must be > 0");
+  if (n == 0) return OSQ_OK;
+  int sms = sm_count();
+  if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  int64_t want = (n + kFqThreads * 8 - 1) / (kFqThreads * 8);
+  int grid = (int)(want < (int64_t)sms * 8 ? (want < 1 ? 1 : want) : (int64_t)sms * 8);
+  lsqplus_backward_kernel<<<grid, kFqThreads, 0, (cudaStream_t)stream>>>(x, dy, dx, n, scale, zero_point, lsq_grad_factor,
+                                                                        (float)qmin, (float)qmax, grad_acc);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_fq_per_tensor_f32(const float* x, float* y, int16_t* codes, int64_t n, const float* scale,
+                          const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin,
+                          int qmax, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(n >= 0, "osq_fq_per_tensor_f32: n < 0");
+  if (n == 0) return OSQ_OK;
+  OSQ_CHECK_ARG(x && y && scale && zero_point, "osq_fq_per_tensor_f32: null pointer");
+  OSQ_CHECK_ARG(qmin < qmax, "osq_fq_per_tensor_f32: qmin >= qmax");
+  OSQ_CHECK_ARG(!(lsq_grad_factor > 0.f && zp_is_int32), "osq_fq_per_tensor_f32: LSQ+ needs a float zero_point");
+  int sms = sm_count();
+  if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  int64_t per_block = (int64_t)kFqThreads * 4 * kFqUnroll;
+  int64_t want = (n + per_block - 1) / per_block;
+  int grid = (int)(want < (int64_t)sms * 8 ? (want < 1 ? 1 : want) : (int64_t)sms * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (codes)
+    fq_per_tensor_kernel<true><<<grid, kFqThreads, 0, st>>>(x, y, codes, n, scale, zero_point, zp_is_int32,
+                                                            lsq_grad_factor, (float)qmin, (float)qmax);
+  else
+    fq_per_tensor_kernel<false><<<grid, kFqThreads, 0, st>>>(x, y, nullptr, n, scale, zero_point, zp_is_int32,
+                                                             lsq_grad_factor, (float)qmin, (float)qmax);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_fq_per_channel_f32(const float* x, float* y, int16_t* codes, int64_t rows, int64_t cols,
+                           const float* scale, const int32_t* zero_point, int qmin, int qmax,
+                           void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(rows >= 0 && cols >= 0, "osq_fq_per_channel_f32: negative shape");
+  if (rows == 0 || cols == 0) return OSQ_OK;
+  OSQ_CHECK_ARG(x && y && scale && zero_point, "osq_fq_per_channel_f32: null pointer");
+  OSQ_CHECK_ARG(qmin < qmax, "osq_fq_per_channel_f32: qmin >= qmax");
+  int sms = sm_count();
+  if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  int grid = (int)(rows < (int64_t)sms * 16 ? rows : (int64_t)sms * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (codes)
+    fq_per_channel_kernel<true><<<grid, kFqThreads, 0, st>>>(x, y, codes, rows, cols, scale, zero_point,
+                                                             (float)qmin, (float)qmax);
+  else
+    fq_per_channel_kernel<false><<<grid, kFqThreads, 0, st>>>(x, y, nullptr, rows, cols, scale, zero_point,
+                                                              (float)qmin, (float)qmax);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// observer.cu -- K3 / K4: calibration-observer reductions with the pad-token mask applied in-kernel.
+//
+// All of these read the activation exactly once (4 algorithmic bytes / element) and are HBM-bound.
+// Work unit = one contiguous feature segment (F2 floats) of one token; a warp owns a segment,
+// lanes issue 128-bit streaming loads, results fold through warp shuffles, then per-CTA partials,
+// then the last CTA to finish (ticket counter) folds the partials and runs the running-statistics
+// epilogue (running average / extrema + calculate_qparams) so a whole observer.forward() is ONE
+// launch with no host synchronisation.
+#include "common.cuh"
+
+namespace osq {
+
+constexpr int kObsThreads = 512;
+constexpr int kObsWarps = kObsThreads / 32;
+
+struct Partials {
+  float* pmin;
+  float* pmax;
+  unsigned int* ticket;
+};
+__host__ __device__ inline Partials carve(void* ws) {
+  Partials p;
+  p.pmin = (float*)ws;
+  p.pmax = p.pmin + kMaxPartialBlocks;
+  p.ticket = (unsigned int*)(p.pmax + kMaxPartialBlocks);
+  return p;
+}
+
+__device__ __forceinline__ bool token_valid(const int64_t* lens, int n_lens, int64_t b, int64_t s) {
+  if (lens == nullptr) return true;
+  if (b >= n_lens) return false;  // zip(observation_mask, x) stops at the shorter one (observer.py:82)
+  return s < lens[b];
+}
+
+// min/max over one contiguous run of `len` floats (stride 1) handled by a full warp
+__device__ __forceinline__ void warp_scan_segment(const float* __restrict__ p, int64_t len, int lane,
+                                                  float& mn, float& mx) {
+  if ((((uintptr_t)p) & 15) == 0 && len >= 128) {
+    const float4* v = reinterpret_cast<const float4*>(p);
+    const int64_t nv = len >> 2;
+    int64_t i = lane;
+    for (; i + 96 < nv; i += 128) {  // 4 independent 128-bit loads in flight per lane
+      float4 a = ldg_stream(v + i), b = ldg_stream(v + i + 32), c = ldg_stream(v + i + 64), d = ldg_stream(v + i + 96);
+      mn = fminf(mn, fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w))));
+      mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+      mn = fminf(mn, fminf(fminf(fminf(c.x, c.y), fminf(c.z, c.w)), fminf(fminf(d.x, d.y), fminf(d.z, d.w))));
+      mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w))));
+    }
+    for (; i < nv; i += 32) {
+      float4 a = ldg_stream(v + i);
+      mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
+      mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+    }
+    for (int64_t j = (nv << 2) + lane; j < len; j += 32) {
+      float a = p[j];
+      mn = fminf(mn, a);
+      mx = fmaxf(mx, a);
+    }
+  } else {
+    for (int64_t j = lane; j < len; j += 32) {
+      float a = __ldg(p + j);
+      mn = fminf(mn, a);
+      mx = fmaxf(mx, a);
+    }
+  }
+}
+
+// generic strided segment (sf2 != 1): lanes stride over f2
+__device__ __forceinline__ void warp_scan_strided(const float* __restrict__ p, int64_t len, int64_t stride,
+                                                  int lane, float& mn, float& mx) {
+  for (int64_t j = lane; j < len; j += 32) {
+    float a = __ldg(p + j * stride);
+    mn = fminf(mn, a);
+    mx = fmaxf(mx, a);
+  }
+}
+
+// Folds per-CTA (mn, mx) into the workspace; the last CTA reduces all partials.
+// Returns true in thread 0 of the last CTA with the final values in (mn, mx).
+__device__ __forceinline__ bool grid_fold(float& mn, float& mx, Partials ws) {
+  __shared__ float smn[kObsWarps], smx[kObsWarps];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    mn = lane < (blockDim.x >> 5) ? smn[lane] : INFINITY;
+    mx = lane < (blockDim.x >> 5) ? smx[lane] : -INFINITY;
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+      ws.pmin[blockIdx.x] = mn;
+      ws.pmax[blockIdx.x] = mx;
+      __threadfence();
+      unsigned int t = atomicAdd(ws.ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  mn = INFINITY;
+  mx = -INFINITY;
+  for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    mn = fminf(mn, __ldcg(ws.pmin + i));
+    mx = fmaxf(mx, __ldcg(ws.pmax + i));
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  __syncthreads();
+  if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    mn = lane < (blockDim.x >> 5) ? smn[lane] : INFINITY;
+    mx = lane < (blockDim.x >> 5) ? smx[lane] : -INFINITY;
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+      *ws.ticket = 0;  // re-arm the workspace for the next launch on this stream
+      return true;
+    }
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: masked global min/max
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kObsThreads)
+minmax_masked_kernel(const float* __restrict__ x, osq_tokens_t tk, const int64_t* __restrict__ lens,
+                     int n_lens, float* __restrict__ cur, osq_stat_epilogue_t epi, void* wsp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kObsWarps + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * kObsWarps;
+  const int64_t n_seg = tk.B * tk.S * tk.F1;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t seg = warp_global; seg < n_seg; seg += n_warps) {
+    const int64_t f1 = seg % tk.F1;
+    const int64_t bs = seg / tk.F1;
+    const int64_t s = bs % tk.S, b = bs / tk.S;
+    if (!token_valid(lens, n_lens, b, s)) continue;
+    const float* p = x + b * tk.sb + s * tk.ss + f1 * tk.sf1;
+    if (tk.sf2 == 1) warp_scan_segment(p, tk.F2, lane, mn, mx);
+    else warp_scan_strided(p, tk.F2, tk.sf2, lane, mn, mx);
+  }
+  if (grid_fold(mn, mx, carve(wsp))) {
+    cur[0] = mn;
+    cur[1] = mx;
+    stat_epilogue(epi, mn, mx);
+  }
+}
+
+__global__ void __launch_bounds__(kObsThreads)
+minmax_flat_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ cur,
+                   osq_stat_epilogue_t epi, void* wsp) {
+  // contiguous: every CTA takes an equal slab, warps split the slab
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = 4096;  // floats per warp step (16 KB)
+  const int64_t warp_global = (int64_t)blockIdx.x * kObsWarps + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * kObsWarps;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t off = warp_global * chunk; off < n; off += n_warps * chunk) {
+    int64_t len = n - off < chunk ? n - off : chunk;
+    warp_scan_segment(x + off, len, lane, mn, mx);
+  }
+  if (grid_fold(mn, mx, carve(wsp))) {
+    cur[0] = mn;
+    cur[1] = mx;
+    stat_epilogue(epi, mn, mx);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4a: per-token min/max (one warp per token)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kObsThreads)
+token_minmax_kernel(const float* __restrict__ x, osq_tokens_t tk, const int64_t* __restrict__ lens,
+                    int n_lens, float* __restrict__ tmin, float* __restrict__ tmax,
+                    int32_t* __restrict__ n_valid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kObsWarps + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * kObsWarps;
+  const int64_t n_tok = tk.B * tk.S;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int64_t t = 0;
+    if (lens == nullptr) t = n_tok;
+    else
+      for (int64_t b = 0; b < tk.B && b < n_lens; ++b) {
+        int64_t l = lens[b];
+        t += l < 0 ? 0 : (l > tk.S ? tk.S : l);
+      }
+    *n_valid = (int32_t)t;
+  }
+  for (int64_t t = warp_global; t < n_tok; t += n_warps) {
+    const int64_t s = t % tk.S, b = t / tk.S;
+    float mn = INFINITY, mx = -INFINITY;
+    if (token_valid(lens, n_lens, b, s)) {
+      const float* p = x + b * tk.sb + s * tk.ss;
+      for (int64_t f1 = 0; f1 < tk.F1; ++f1) {
+        if (tk.sf2 == 1) warp_scan_segment(p + f1 * tk.sf1, tk.F2, lane, mn, mx);
+        else warp_scan_strided(p + f1 * tk.sf1, tk.F2, tk.sf2, lane, mn, mx);
+      }
+      mn = warp_min(mn);
+      mx = warp_max(mx);
+    }
+    if (lane == 0) {
+      tmin[t] = mn;
+      tmax[t] = mx;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4b: prune selection on the [T] vectors (single CTA; the vectors are tiny next to the activation)
+// ---------------------------------------------------------------------------------------------
+// torch.quantile(v, p) on an ascending-sorted fp32 vector of n entries ('linear' interpolation):
+// rank = p*(n-1) in fp32, lerp with the fused multiply-add form ATen's CPU kernel uses.
+__device__ __forceinline__ float quantile_sorted(const float* __restrict__ sorted, int n, float p) {
+  float rank = __fmul_rn(p, (float)(n - 1));
+  int lo = (int)rank;  // trunc, like .toType(kLong)
+  int hi = (int)ceilf(rank);
+  float w = __fsub_rn(rank, (float)lo);
+  float a = sorted[lo], b = sorted[hi];
+  float d = __fsub_rn(b, a);
+  return (w < 0.5f) ? fmaf(w, d, a) : fmaf(-d, __fsub_rn(1.f, w), b);
+}
+
+__global__ void __launch_bounds__(1024)
+prune_select_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax,
+                    const float* __restrict__ abs_tmin_sorted, const float* __restrict__ abs_tmax_sorted,
+                    int64_t n_slots, const int32_t* __restrict__ n_valid, float percentile,
+                    float* __restrict__ cur, osq_stat_epilogue_t epi) {
+  __shared__ float smn[32], smx[32];
+  const int T = *n_valid;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float lower = INFINITY, upper = -INFINITY;
+  if (T > 0) {
+    const float up_thr = quantile_sorted(abs_tmax_sorted, T, percentile);
+    const float lo_thr = -quantile_sorted(abs_tmin_sorted, T, percentile);
+    for (int64_t i = threadIdx.x; i < n_slots; i += blockDim.x) {
+      float a = tmin[i], b = tmax[i];
+      if (a <= b) {  // valid token (invalid ones hold +inf / -inf)
+        if (b <= up_thr) upper = fmaxf(upper, b);
+        if (a >= lo_thr) lower = fminf(lower, a);
+      }
+    }
+  }
+  lower = warp_min(lower);
+  upper = warp_max(upper);
+  if (lane == 0) { smn[warp] = lower; smx[warp] = upper; }
+  __syncthreads();
+  if (warp == 0) {
+    lower = lane < (blockDim.x >> 5) ? smn[lane] : INFINITY;
+    upper = lane < (blockDim.x >> 5) ? smx[lane] : -INFINITY;
+    lower = warp_min(lower);
+    upper = warp_max(upper);
+    if (lane == 0) {
+      cur[0] = lower;
+      cur[1] = upper;
+      stat_epilogue(epi, lower, upper);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-row min/max + running extrema + per-row qparams (weights, MinMaxObserver ch_axis=0)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowwise_minmax_qparams_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int first,
+                              float* __restrict__ state_min, float* __restrict__ state_max,
+                              float* __restrict__ scale_out, int32_t* __restrict__ zp_out, int qmin,
+                              int qmax, int symmetric) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp_global; r < rows; r += n_warps) {
+    float mn = INFINITY, mx = -INFINITY;
+    warp_scan_segment(w + r * cols, cols, lane, mn, mx);
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+      if (!first) {
+        mn = fminf(mn, state_min[r]);
+        mx = fmaxf(mx, state_max[r]);
+      }
+      state_min[r] = mn;
+      state_max[r] = mx;
+      if (scale_out != nullptr) {
+        float zp;
+        scale_out[r] = calc_qparams(mn, mx, qmin, qmax, symmetric, zp);
+        if (zp_out != nullptr) zp_out[r] = (int32_t)zp;
+      }
+    }
+  }
+}
+
+static int reduction_grid(int64_t units_of_work) {
+  int sms = sm_count();
+  if (sms <= 0) return -1;
+  int64_t g = (units_of_work + kObsWarps - 1) / kObsWarps;
+  int64_t cap = (int64_t)sms * 4;  // 4 CTAs of 512 threads = 64 warps / SM
+  if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int check_tokens(const osq_tokens_t* t, const char* who) {
+  OSQ_CHECK_ARG(t != nullptr, "%s: null token geometry", who);
+  OSQ_CHECK_ARG(t->B >= 0 && t->S >= 0 && t->F1 >= 0 && t->F2 >= 0, "%s: negative size", who);
+  return OSQ_OK;
+}
+
+}  // namespace osq
+
+extern "C" {
+
+int osq_minmax_masked_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens,
+                          float* cur_minmax, const osq_stat_epilogue_t* epi, void* workspace,
+                          void* stream) {
+  using namespace osq;
+  if (int rc = check_tokens(tok, "osq_minmax_masked_f32")) return rc;
+  OSQ_CHECK_ARG(x && cur_minmax && epi && workspace, "osq_minmax_masked_f32: null pointer");
+  int grid = reduction_grid(tok->B * tok->S * tok->F1);
+  if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  minmax_masked_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, cur_minmax, *epi, workspace);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_minmax_flat_f32(const float* x, int64_t n, float* cur_minmax, const osq_stat_epilogue_t* epi,
+                        void* workspace, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(x && cur_minmax && epi && workspace && n > 0, "osq_minmax_flat_f32: bad argument");
+  int grid = reduction_grid((n + 4095) / 4096);
+  if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  minmax_flat_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, n, cur_minmax, *epi, workspace);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_token_minmax_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens,
+                         float* tmin, float* tmax, int32_t* n_valid, void* stream) {
+  using namespace osq;
+  if (int rc = check_tokens(tok, "osq_token_minmax_f32")) return rc;
+  OSQ_CHECK_ARG(x && tmin && tmax && n_valid, "osq_token_minmax_f32: null pointer");
+  OSQ_CHECK_ARG(tok->B * tok->S < (int64_t)INT32_MAX, "osq_token_minmax_f32: too many tokens");
+  int grid = reduction_grid(tok->B * tok->S);
+  if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_prune_select_f32(const float* tmin, const float* tmax, const float* abs_tmin_sorted,
+                         const float* abs_tmax_sorted, int64_t n_slots, const int32_t* n_valid,
+                         float percentile, float* cur_minmax, const osq_stat_epilogue_t* epi,
+                         void* workspace, void* stream) {
+  using namespace osq;
+  (void)workspace;
+  OSQ_CHECK_ARG(tmin && tmax && abs_tmin_sorted && abs_tmax_sorted && n_valid && cur_minmax && epi,
+                "osq_prune_select_f32: null pointer");
+  OSQ_CHECK_ARG(n_slots > 0, "osq_prune_select_f32: n_slots <= 0");
+  OSQ_CHECK_ARG(percentile >= 0.f && percentile <= 1.f, "osq_prune_select_f32: percentile outside [0,1]");
+  prune_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tmin, tmax, abs_tmin_sorted, abs_tmax_sorted, n_slots,
+                                                           n_valid, percentile, cur_minmax, *epi);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_rowwise_minmax_qparams_f32(const float* w, int64_t rows, int64_t cols, int first,
+                                   float* state_min, float* state_max, float* scale_out,
+                                   int32_t* zp_out, int qmin, int qmax, int symmetric, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(w && state_min && state_max && rows > 0 && cols > 0, "osq_rowwise_minmax_qparams_f32: bad argument");
+  int sms = sm_count();
+  if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  int64_t g = (rows + 7) / 8;
+  if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
+  rowwise_minmax_qparams_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, rows, cols, first, state_min, state_max,
+                                                                       scale_out, zp_out, qmin, qmax, symmetric);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+}  // extern "C"

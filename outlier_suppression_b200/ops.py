@@ -1,0 +1,335 @@
+"""Torch-facing wrappers over the C ABI (include/osq.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic step of the hot path
+runs in libosq_b200.so.  All functions require CUDA tensors and raise otherwise -- there is no CPU
+fallback (the CPU restatement lives in oracle/ and is test infrastructure only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import FusedLinearArgs, StatEpilogue, Tokens, check
+
+_workspaces = {}
+
+STAT_NONE, STAT_AVERAGE, STAT_EXTREMA = 0, 1, 2
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("outlier_suppression_b200 runs on CUDA tensors only (got a %s tensor); "
+                               "there is no CPU fallback" % t.device)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def workspace(device) -> torch.Tensor:
+    """Caller-owned reduction scratch (zeroed ticket counter), one per (device, stream)."""
+    key = (torch.device(device).index, _stream())
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().osq_workspace_bytes()), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _dense_like(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(x', y') such that both cover the same memory layout densely; elementwise kernels run over
+    the flat storage so permuted-but-dense views (q / k^T / v, quant_bert.py:148-186) need no copy."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    if not (x.is_contiguous() or x.is_non_overlapping_and_dense()):
+        x = x.contiguous()
+    return x, torch.empty_like(x)  # preserve_format keeps the dense strides
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 / K2
+# ------------------------------------------------------------------------------------------------
+def fq_per_tensor(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int,
+                  lsq_grad_factor: float = 0.0, want_codes: bool = False):
+    """util_quant.py:11-15 / :48-55 with device-resident qparams. Returns y (and int16 bins)."""
+    _require_cuda(x, scale, zero_point)
+    x, y = _dense_like(x)
+    if x.numel() == 0:
+        return (y, torch.empty_like(x, dtype=torch.int16)) if want_codes else y
+    zp_is_int = zero_point.dtype == torch.int32
+    if not zp_is_int and zero_point.dtype != torch.float32:
+        raise TypeError("zero_point must be int32 or float32")
+    if scale.dtype != torch.float32:
+        raise TypeError("scale must be float32")
+    codes = torch.empty_like(x, dtype=torch.int16) if want_codes else None
+    check(_lib.load().osq_fq_per_tensor_f32(x.data_ptr(), y.data_ptr(), _ptr(codes), x.numel(), scale.data_ptr(),
+                                            zero_point.data_ptr(), int(zp_is_int), float(lsq_grad_factor),
+                                            int(qmin), int(qmax), _stream()), "osq_fq_per_tensor_f32")
+    return (y, codes) if want_codes else y
+
+
+def fq_per_channel(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int,
+                   want_codes: bool = False):
+    """util_quant.py:18-26 for ch_axis = 0; x is viewed as [rows, cols]."""
+    _require_cuda(x, scale, zero_point)
+    x = x.float().contiguous()
+    rows = x.shape[0]
+    cols = x.numel() // max(rows, 1)
+    y = torch.empty_like(x)
+    codes = torch.empty_like(x, dtype=torch.int16) if want_codes else None
+    if x.numel():
+        scale = scale.float().contiguous()
+        zp = zero_point.to(torch.int32).contiguous()
+        if scale.numel() != rows or zp.numel() != rows:
+            raise ValueError("per-channel scale / zero_point must have one entry per row")
+        check(_lib.load().osq_fq_per_channel_f32(x.data_ptr(), y.data_ptr(), _ptr(codes), rows, cols, scale.data_ptr(),
+                                                 zp.data_ptr(), int(qmin), int(qmax), _stream()), "osq_fq_per_channel_f32")
+    return (y, codes) if want_codes else y
+
+
+# ------------------------------------------------------------------------------------------------
+# token geometry (observer.py:72-98)
+# ------------------------------------------------------------------------------------------------
+def token_geometry(x: torch.Tensor, seq_pos: int) -> Tokens:
+    """[B, S, F1, F2] view of a 3-D / 4-D activation with the sequence axis at ``seq_pos``."""
+    nd = x.dim()
+    if seq_pos < 0:
+        seq_pos += nd
+    rest = [d for d in range(nd) if d != seq_pos]
+    if len(rest) not in (2, 3):
+        raise ValueError("expected a 3-D or 4-D activation, got %d-D" % nd)
+    size, stride = x.shape, x.stride()
+    b = rest[0]
+    if len(rest) == 2:
+        f1s, f1st = 1, 0
+        f2 = rest[1]
+    else:
+        f1s, f1st = size[rest[1]], stride[rest[1]]
+        f2 = rest[2]
+    F1, F2, sf1, sf2 = f1s, size[f2], f1st, stride[f2]
+    if F1 > 1 and sf2 == 1 and sf1 == F2:  # token row is one contiguous run (q / k^T / v views)
+        F1, F2, sf1 = 1, F1 * F2, 0
+    if F1 > 1 and sf1 == 1 and sf2 == F1:  # transposed but still contiguous
+        F1, F2, sf1, sf2 = 1, F1 * F2, 0, 1
+    return Tokens(size[b], size[seq_pos], F1, F2, stride[b], stride[seq_pos], sf1, sf2)
+
+
+def _lens_arg(lens: Optional[torch.Tensor], device):
+    if lens is None:
+        return None, 0
+    if not torch.is_tensor(lens):
+        lens = torch.as_tensor(lens)
+    lens = lens.to(device=device, dtype=torch.int64).contiguous()
+    return lens, lens.numel()
+
+
+def _epilogue(mode: int, cnt: int, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric) -> StatEpilogue:
+    e = StatEpilogue()
+    e.mode, e.cnt = mode, int(cnt)
+    e.state_min, e.state_max = _ptr(state_min), _ptr(state_max)
+    e.scale_out, e.zp_out = _ptr(scale_out), _ptr(zp_out)
+    e.zp_out_is_int32 = int(zp_out is not None and zp_out.dtype == torch.int32)
+    e.qmin, e.qmax, e.symmetric = int(qmin), int(qmax), int(bool(symmetric))
+    return e
+
+
+def _prep_act(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x)
+    x = x.detach()
+    return x if x.dtype == torch.float32 else x.float()
+
+
+def observe_minmax(x, lens, seq_pos, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None, scale_out=None,
+                   zp_out=None, qmin=0, qmax=255, symmetric=False) -> torch.Tensor:
+    """Masked global (min,max) + running statistic + qparams in ONE launch (observer.py:184-203)."""
+    x = _prep_act(x)
+    cur = torch.empty(2, dtype=torch.float32, device=x.device)
+    epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
+    ws = workspace(x.device)
+    lib = _lib.load()
+    if lens is None and (seq_pos == -1 or x.dim() < 3):
+        xc = x if (x.is_contiguous() or x.is_non_overlapping_and_dense()) else x.contiguous()
+        check(lib.osq_minmax_flat_f32(xc.data_ptr(), xc.numel(), cur.data_ptr(), C.byref(epi), ws.data_ptr(), _stream()),
+              "osq_minmax_flat_f32")
+        return cur
+    if lens is None and (x.is_contiguous() or x.is_non_overlapping_and_dense()):
+        check(lib.osq_minmax_flat_f32(x.data_ptr(), x.numel(), cur.data_ptr(), C.byref(epi), ws.data_ptr(), _stream()),
+              "osq_minmax_flat_f32")
+        return cur
+    tok = token_geometry(x, seq_pos)
+    lens_t, n_lens = _lens_arg(lens, x.device)
+    check(lib.osq_minmax_masked_f32(x.data_ptr(), C.byref(tok), _ptr(lens_t), n_lens, cur.data_ptr(), C.byref(epi),
+                                    ws.data_ptr(), _stream()), "osq_minmax_masked_f32")
+    return cur
+
+
+def token_minmax(x, lens, seq_pos):
+    """Per-token extrema (observer.py:64-65) with pad removal fused in. Returns (tmin, tmax, n_valid)."""
+    x = _prep_act(x)
+    tok = token_geometry(x, seq_pos)
+    n = tok.B * tok.S
+    tmin = torch.empty(n, dtype=torch.float32, device=x.device)
+    tmax = torch.empty(n, dtype=torch.float32, device=x.device)
+    n_valid = torch.empty(1, dtype=torch.int32, device=x.device)
+    lens_t, n_lens = _lens_arg(lens, x.device)
+    check(_lib.load().osq_token_minmax_f32(x.data_ptr(), C.byref(tok), _ptr(lens_t), n_lens, tmin.data_ptr(),
+                                           tmax.data_ptr(), n_valid.data_ptr(), _stream()), "osq_token_minmax_f32")
+    return tmin, tmax, n_valid
+
+
+def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
+                         scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False) -> torch.Tensor:
+    """AvgPruneMinMaxObserver's token pruning (observer.py:50-70,214-237) as: one pass over the
+    activation (per-token extrema), two sorts of the [T] vectors, one selection launch."""
+    tmin, tmax, n_valid = token_minmax(x, lens, seq_pos)
+    # invalid tokens hold (+inf, -inf): |.| maps both to +inf so they sort behind the T valid entries
+    abs_tmin_sorted = torch.sort(tmin.abs()).values
+    abs_tmax_sorted = torch.sort(tmax.abs()).values
+    cur = torch.empty(2, dtype=torch.float32, device=tmin.device)
+    epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
+    check(_lib.load().osq_prune_select_f32(tmin.data_ptr(), tmax.data_ptr(), abs_tmin_sorted.data_ptr(),
+                                           abs_tmax_sorted.data_ptr(), tmin.numel(), n_valid.data_ptr(),
+                                           float(percentile), cur.data_ptr(), C.byref(epi),
+                                           workspace(tmin.device).data_ptr(), _stream()), "osq_prune_select_f32")
+    return cur
+
+
+def rowwise_minmax_qparams(w, first, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric):
+    """MinMaxObserver(ch_axis=0) + calculate_qparams on a [N, K] weight in one launch."""
+    _require_cuda(w, state_min, state_max)
+    w = w.detach().float().contiguous()
+    rows = w.shape[0]
+    cols = w.numel() // rows
+    check(_lib.load().osq_rowwise_minmax_qparams_f32(w.data_ptr(), rows, cols, int(bool(first)), state_min.data_ptr(),
+                                                     state_max.data_ptr(), _ptr(scale_out), _ptr(zp_out), int(qmin),
+                                                     int(qmax), int(bool(symmetric)), _stream()),
+          "osq_rowwise_minmax_qparams_f32")
+
+
+def calc_qparams(min_val, max_val, qmin, qmax, symmetric):
+    """observer.py:100-119 on device; returns (scale fp32, zero_point: int32 if symmetric else fp32)."""
+    _require_cuda(min_val, max_val)
+    shape = min_val.shape
+    mn = min_val.detach().float().contiguous().reshape(-1)
+    mx = max_val.detach().float().contiguous().reshape(-1)
+    scale = torch.empty_like(mn)
+    zp_f = None if symmetric else torch.empty_like(mn)
+    zp_i = torch.empty(mn.shape, dtype=torch.int32, device=mn.device) if symmetric else None
+    check(_lib.load().osq_calc_qparams_f32(mn.data_ptr(), mx.data_ptr(), mn.numel(), int(qmin), int(qmax),
+                                           int(bool(symmetric)), scale.data_ptr(), _ptr(zp_f), _ptr(zp_i), _stream()),
+          "osq_calc_qparams_f32")
+    zp = zp_i if symmetric else zp_f
+    return scale.reshape(shape), zp.reshape(shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# K5
+# ------------------------------------------------------------------------------------------------
+def mse_multi(x, lens, seq_pos, cand_scale, cand_zp, qmin, qmax):
+    """sum of squared fq error per candidate + number of valid elements (device tensors)."""
+    x = _prep_act(x)
+    if x.dim() >= 3 and seq_pos != -1:
+        tok = token_geometry(x, seq_pos)
+    else:
+        xc = x if x.is_contiguous() else x.contiguous()
+        x = xc
+        tok = Tokens(1, 1, 1, x.numel(), 0, 0, 0, 1)
+        lens = None
+    lens_t, n_lens = _lens_arg(lens, x.device)
+    cand_scale = cand_scale.to(device=x.device, dtype=torch.float32).contiguous()
+    cand_zp = cand_zp.to(device=x.device, dtype=torch.float32).contiguous()
+    n = cand_scale.numel()
+    loss = torch.empty(n, dtype=torch.float64, device=x.device)
+    n_valid = torch.empty(1, dtype=torch.int64, device=x.device)
+    check(_lib.load().osq_mse_multi_f32(x.data_ptr(), C.byref(tok), _ptr(lens_t), n_lens, cand_scale.data_ptr(),
+                                        cand_zp.data_ptr(), n, int(qmin), int(qmax), loss.data_ptr(), n_valid.data_ptr(),
+                                        _stream()), "osq_mse_multi_f32")
+    return loss, n_valid
+
+
+def mse_brent_rows(w, qmin, qmax, one_side: str, want_evals=False):
+    """MSEFastObserver per-channel 1-D search (observer.py:483-517) entirely on-chip."""
+    _require_cuda(w)
+    w = w.detach().float().contiguous()
+    rows = w.shape[0]
+    cols = w.numel() // rows
+    out_min = torch.empty(rows, dtype=torch.float32, device=w.device)
+    out_max = torch.empty(rows, dtype=torch.float32, device=w.device)
+    evals = torch.empty(rows, dtype=torch.int32, device=w.device) if want_evals else None
+    side = {"no": 0, "pos": 1, "neg": 2}[one_side]
+    check(_lib.load().osq_mse_brent_rows_f32(w.data_ptr(), rows, cols, int(qmin), int(qmax), side, out_min.data_ptr(),
+                                             out_max.data_ptr(), _ptr(evals), _stream()), "osq_mse_brent_rows_f32")
+    return (out_min, out_max, evals) if want_evals else (out_min, out_max)
+
+
+# ------------------------------------------------------------------------------------------------
+# K6
+# ------------------------------------------------------------------------------------------------
+def pack_weight(w, scale, zero_point, qmin, qmax):
+    """bins (q - zp) as int8 [N, K] + per-row sums (int32 [N])."""
+    _require_cuda(w, scale, zero_point)
+    w = w.detach().float().contiguous()
+    n, k = w.shape[0], w.numel() // w.shape[0]
+    scale = scale.detach().float().contiguous()
+    zp = zero_point.detach().to(torch.int32).contiguous()
+    codes = torch.empty((n, k), dtype=torch.int8, device=w.device)
+    rowsum = torch.empty(n, dtype=torch.int32, device=w.device)
+    check(_lib.load().osq_pack_weight_s8(w.data_ptr(), n, k, scale.data_ptr(), zp.data_ptr(), int(qmin), int(qmax),
+                                         codes.data_ptr(), rowsum.data_ptr(), _stream()), "osq_pack_weight_s8")
+    return codes, rowsum
+
+
+def fused_linear_supported(k: int, n: int) -> bool:
+    return k >= 128 and k % 128 == 0 and n >= 16 and n % 16 == 0
+
+
+def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum, bias, lsq_grad_factor=0.0,
+                    mma_kind=0, want_codes=False, out=None):
+    """activation fq + weight fq + Linear in one tcgen05 kernel. a: [..., K] fp32 -> [..., N] fp32."""
+    _require_cuda(a, a_scale, a_zp, w_codes, w_scale, w_rowsum, bias)
+    if a.dtype != torch.float32:
+        a = a.float()
+    a2 = a.reshape(-1, a.shape[-1])
+    if not a2.is_contiguous():
+        a2 = a2.contiguous()
+    m, k = a2.shape
+    n = w_codes.shape[0]
+    y = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
+    dbg = torch.empty((m, k), dtype=torch.uint8, device=a.device) if want_codes else None
+    args = FusedLinearArgs()
+    args.A, args.M, args.K = a2.data_ptr(), m, k
+    args.a_scale, args.a_zp = a_scale.data_ptr(), a_zp.data_ptr()
+    args.a_zp_is_int32 = int(a_zp.dtype == torch.int32)
+    args.lsq_grad_factor = float(lsq_grad_factor)
+    args.a_qmin, args.a_qmax = int(a_qmin), int(a_qmax)
+    args.w_codes, args.w_scale, args.w_rowsum = w_codes.data_ptr(), w_scale.data_ptr(), w_rowsum.data_ptr()
+    args.bias = _ptr(bias)
+    args.Y, args.N = y.data_ptr(), n
+    args.mma_kind = int(mma_kind)
+    args.a_codes_dbg = _ptr(dbg)
+    if m > 0:
+        check(_lib.load().osq_fused_fq_linear(C.byref(args), _stream()), "osq_fused_fq_linear")
+    y = y.reshape(*a.shape[:-1], n)
+    return (y, dbg) if want_codes else y
+
+
+def lsqplus_backward(x, dy, scale, zero_point, lsq_grad_factor, qmin, qmax):
+    """gradients of util_quant.py:48-55: returns (dx, dscale[1], dzero_point[1])."""
+    _require_cuda(x, dy, scale, zero_point)
+    x = x.detach().float().contiguous()
+    dy = dy.detach().float().contiguous()
+    dx = torch.empty_like(x)
+    acc = torch.zeros(2, dtype=torch.float64, device=x.device)
+    check(_lib.load().osq_lsqplus_backward_f32(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), scale.data_ptr(),
+                                               zero_point.data_ptr(), float(lsq_grad_factor), int(qmin), int(qmax),
+                                               acc.data_ptr(), _stream()), "osq_lsqplus_backward_f32")
+    g = acc.float()
+    return dx, g[0:1], g[1:2]

@@ -1,0 +1,267 @@
+"""Quantizer modules with the reference's names, flags, buffers / Parameters and state_dict keys
+(quantization/fake_quant.py), running on the sm_100a kernels.
+
+The forward contract is unchanged: ``q(X, observation_mask=None, seq_pos=-1)`` returns the
+fake-quantized fp32 tensor (or X itself when both flags are off).  Additionally the returned
+tensor is *tagged* with the quantizer that produced it so that a downstream ``QLinear`` can run the
+fused fake-quant + Linear tcgen05 kernel (fake-quant is idempotent).
+"""
+from __future__ import annotations
+
+import weakref
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .observer import MinMaxObserver
+from . import util_quant as UQ
+
+_TAG = "_osq_producer"
+
+
+def producer_of(t: torch.Tensor):
+    """The live quantizer whose output ``t`` is, or None."""
+    ref = getattr(t, _TAG, None)
+    return ref() if ref is not None else None
+
+
+class QuantizeBase(nn.Module):
+    """fake_quant.py:15-97."""
+
+    def __init__(self, observer=MinMaxObserver, bit=8, symmetric=False, ch_axis=-1):
+        super().__init__()
+        self.observer = observer(bit=bit, symmetric=symmetric, ch_axis=ch_axis)
+        self.bit, self.symmetric, self.ch_axis = bit, symmetric, ch_axis
+        self.observer_enabled = 0
+        self.fake_quant_enabled = 0
+        self.quant_min, self.quant_max = self.observer.quant_min, self.observer.quant_max
+        self.qparam_epoch = 0  # bumped whenever (scale, zero_point) are rewritten; keys derived caches
+
+    def set_name(self, name):
+        self.name = name
+
+    @torch.jit.export
+    def calculate_qparams(self):
+        return self.observer.calculate_qparams(self.observer.min_val, self.observer.max_val)
+
+    @torch.jit.export
+    def disable_observer(self):
+        self.observer_enabled = 0
+
+    @torch.jit.export
+    def enable_observer(self):
+        self.observer_enabled = 1
+
+    @torch.jit.export
+    def disable_fake_quant(self):
+        self.fake_quant_enabled = 0
+
+    @torch.jit.export
+    def enable_fake_quant(self):
+        self.fake_quant_enabled = 1
+
+    @torch.jit.export
+    def extra_repr(self):
+        return ("fake_quant_enabled={}, observer_enabled={}, symmetric={}, bit={}, ch_axis={}, quant_min={}, "
+                "quant_max={}").format(self.fake_quant_enabled, self.observer_enabled, self.symmetric, self.bit,
+                                       self.ch_axis, self.quant_min, self.quant_max)
+
+    # ---- state_dict glue: scale / zero_point change shape after calibration (fake_quant.py:59-97) ----
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        destination[prefix + "scale"] = self.scale
+        destination[prefix + "zero_point"] = self.zero_point
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for name in ("scale", "zero_point"):
+            key = prefix + name
+            if key in state_dict:
+                val = state_dict[key]
+                cur = getattr(self, name)
+                if isinstance(cur, nn.Parameter):
+                    cur.data = torch.ones_like(val.to(cur.device))
+                else:
+                    cur.resize_(val.shape)
+            elif strict:
+                missing_keys.append(key)
+        self.qparam_epoch += 1
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+    # ---- where the observer kernels may write the refreshed qparams ----
+    def _per_tensor_qparam_targets(self):
+        return None, None
+
+    def _per_channel_qparam_targets(self, rows):
+        return None, None
+
+    def _tag(self, y: torch.Tensor) -> torch.Tensor:
+        try:
+            setattr(y, _TAG, weakref.ref(self))
+        except Exception:  # pragma: no cover  (tensor subclasses that refuse attributes)
+            pass
+        return y
+
+
+class FixedFakeQuantize(QuantizeBase):
+    """Non-learnable scale / zero_point (fake_quant.py:100-126)."""
+
+    def __init__(self, observer, bit=8, symmetric=False, ch_axis=-1):
+        super().__init__(observer, bit=bit, symmetric=symmetric, ch_axis=ch_axis)
+        self.register_buffer("scale", torch.tensor([1.0], dtype=torch.float))
+        self.register_buffer("zero_point", torch.tensor([0], dtype=torch.int))
+
+    def _per_tensor_qparam_targets(self):
+        if self.scale.shape != torch.Size([]):  # the reference resizes to the observer's 0-dim shape (:115-117)
+            self.scale.resize_(())
+            self.zero_point.resize_(())
+        return self.scale, self.zero_point
+
+    def _per_channel_qparam_targets(self, rows):
+        if self.scale.numel() != rows or self.scale.dim() != 1:
+            self.scale.resize_(rows)
+            self.zero_point.resize_(rows)
+        return self.scale, self.zero_point
+
+    def forward(self, X, observation_mask=None, seq_pos=-1):
+        if self.observer_enabled == 1 and X.numel() > 0:
+            fused = self.observer._observe(X.detach(), observation_mask, seq_pos, self)
+            if not fused:
+                _scale, _zero_point = self.observer.calculate_qparams(self.observer.min_val, self.observer.max_val)
+                _scale, _zero_point = _scale.to(self.scale.device), _zero_point.to(self.zero_point.device)
+                if self.scale.shape != _scale.shape:
+                    self.scale.resize_(_scale.shape)
+                    self.zero_point.resize_(_zero_point.shape)
+                self.scale.copy_(_scale)
+                self.zero_point.copy_(_zero_point)
+            self.qparam_epoch += 1
+        if self.fake_quant_enabled == 1:
+            if self.ch_axis != -1:
+                X = UQ.fake_quantize_per_channel_affine(X, self.scale, self.zero_point, self.ch_axis, self.quant_min,
+                                                        self.quant_max) if not _needs_grad(X) else \
+                    _ste_per_channel(X, self.scale, self.zero_point, self.ch_axis, self.quant_min, self.quant_max)
+            elif _needs_grad(X):
+                X = _SteFixedPerTensor.apply(X, self.scale, self.zero_point, self.quant_min, self.quant_max)
+            else:
+                X = self._tag(ops.fq_per_tensor(X, self.scale, self.zero_point, self.quant_min, self.quant_max))
+        return X
+
+
+def _needs_grad(x):
+    return torch.is_grad_enabled() and x.requires_grad
+
+
+class _SteFixedPerTensor(torch.autograd.Function):
+    """straight-through gradient of util_quant.py:11-15: dy where the un-clamped bin is inside [qmin, qmax]."""
+
+    @staticmethod
+    def forward(ctx, x, scale, zero_point, qmin, qmax):
+        ctx.save_for_backward(x, scale, zero_point)
+        ctx.rng = (qmin, qmax)
+        return ops.fq_per_tensor(x, scale, zero_point, qmin, qmax)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale, zero_point = ctx.saved_tensors
+        qmin, qmax = ctx.rng
+        v = torch.round(x / scale.reshape(())) + zero_point.reshape(()).to(x.dtype)
+        return dy * ((v >= qmin) & (v <= qmax)).to(dy.dtype), None, None, None, None
+
+
+def _ste_per_channel(x, scale, zero_point, ch_axis, qmin, qmax):
+    shape = [1] * x.dim()
+    shape[ch_axis] = x.shape[ch_axis]
+    s, z = scale.reshape(shape), zero_point.reshape(shape)
+    q = torch.clamp(UQ.round_ste(x / s) + z, qmin, qmax)
+    return (q - z) * s
+
+
+class LSQPlusFakeQuantize(QuantizeBase):
+    """Learnable scale AND zero point (fake_quant.py:170-209); the fine stage of token-wise clipping
+    feeds ``scale`` / ``zero_point`` (fp32 Parameters of shape [1]) to Adam."""
+
+    def __init__(self, observer, bit=8, symmetric=False, ch_axis=-1, use_grad_scaling=True):
+        super().__init__(observer, bit=bit, symmetric=symmetric, ch_axis=ch_axis)
+        self.scale = torch.nn.Parameter(torch.tensor([1.0], dtype=torch.float))
+        self.zero_point = torch.nn.Parameter(torch.tensor([0.0], dtype=torch.float))
+        self.register_buffer("eps", torch.tensor([torch.finfo(torch.float32).eps]))
+        self.use_grad_scaling = use_grad_scaling
+
+    def _per_tensor_qparam_targets(self):
+        return self.scale.data, self.zero_point.data  # shape [1] is kept (copy_ broadcasts, :186-187)
+
+    def grad_factor(self, X):
+        """fake_quant.py:193-207."""
+        if not self.use_grad_scaling:
+            return 1.0
+        n = X.numel() if self.ch_axis == -1 else X.numel() / X.shape[self.ch_axis]
+        return 1.0 / (n * self.quant_max) ** 0.5
+
+    def forward(self, X, observation_mask=None, seq_pos=-1):
+        sanitized_by_kernel = False
+        if self.observer_enabled == 1 and X.numel() > 0:
+            fused = self.observer._observe(X.detach(), observation_mask, seq_pos, self)
+            if not fused:
+                _scale, _zero_point = self.observer.calculate_qparams(self.observer.min_val, self.observer.max_val)
+                _scale, _zero_point = _scale.to(self.scale.device), _zero_point.to(self.zero_point.device)
+                if self.ch_axis != -1:
+                    self.scale.data = torch.ones_like(_scale, dtype=torch.float32)
+                    self.zero_point.data = torch.zeros_like(_zero_point.float())
+                self.scale.data.copy_(_scale)
+                self.zero_point.data.copy_(_zero_point.float())
+            self.qparam_epoch += 1
+        elif self.fake_quant_enabled == 1 and self.ch_axis == -1 and X.is_cuda:
+            sanitized_by_kernel = True  # K1 / K6 apply fake_quant.py:188-191 in place
+        else:
+            self.scale.data.abs_()
+            self.scale.data.clamp_(min=float(torch.finfo(torch.float32).eps))
+            self.zero_point.data.clamp_(self.quant_min, self.quant_max)
+
+        if self.fake_quant_enabled == 1:
+            g = self.grad_factor(X)
+            if self.ch_axis != -1:
+                X = UQ.fake_quantize_learnableplus_per_channel_affine_training(X, self.scale, self.zero_point, self.ch_axis,
+                                                                              self.quant_min, self.quant_max, g)
+            else:
+                X = UQ.fake_quantize_learnableplus_per_tensor_affine_training(X, self.scale, self.zero_point,
+                                                                             self.quant_min, self.quant_max, g)
+                if not X.requires_grad:
+                    self._tag(X)
+        del sanitized_by_kernel
+        return X
+
+
+class LSQFakeQuantize(QuantizeBase):
+    """Learnable scale, symmetric (fake_quant.py:129-167).  Not used by any shipped config: kept on
+    torch ops (reference formulas) so the registry key resolves."""
+
+    def __init__(self, observer, bit=8, symmetric=False, ch_axis=-1, use_grad_scaling=True):
+        super().__init__(observer, bit=bit, symmetric=symmetric, ch_axis=ch_axis)
+        self.scale = torch.nn.Parameter(torch.tensor([1.0], dtype=torch.float))
+        self.register_buffer("zero_point", torch.tensor([0], dtype=torch.int))
+        self.register_buffer("eps", torch.tensor([torch.finfo(torch.float32).eps]))
+        self.use_grad_scaling = use_grad_scaling
+
+    def forward(self, X, observation_mask=None, seq_pos=-1):
+        if self.observer_enabled == 1 and X.numel() > 0:
+            self.observer._observe(X.detach(), observation_mask, seq_pos, None)
+            _scale, _zero_point = self.observer.calculate_qparams(self.observer.min_val, self.observer.max_val)
+            if self.ch_axis != -1:
+                self.scale.data = torch.ones_like(_scale, dtype=torch.float32)
+                self.zero_point.resize_(_zero_point.shape)
+            self.scale.data.copy_(_scale)
+            self.zero_point.copy_(_zero_point)
+            self.qparam_epoch += 1
+        else:
+            self.scale.data.abs_()
+            self.scale.data.clamp_(min=float(torch.finfo(torch.float32).eps))
+        if self.fake_quant_enabled == 1:
+            n = X.numel() if self.ch_axis == -1 else X.numel() / X.shape[self.ch_axis]
+            g = 1.0 / (n * self.quant_max) ** 0.5 if self.use_grad_scaling else 1.0
+            if self.ch_axis != -1:
+                X = UQ.fake_quantize_learnable_per_channel_affine_training(X, self.scale, self.zero_point.int(), self.ch_axis,
+                                                                          self.quant_min, self.quant_max, g)
+            else:
+                X = UQ.fake_quantize_learnable_per_tensor_affine_training(X, self.scale, self.zero_point.reshape(()).to(X.dtype),
+                                                                         self.quant_min, self.quant_max, g)
+        return X

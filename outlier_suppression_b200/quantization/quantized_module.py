@@ -1,0 +1,196 @@
+"""Operator wrappers, registries and the ``Quantizer`` factory with the reference's names
+(quantization/quantized_module.py).  ``QLinear.forward`` is where the fused fake-quant + Linear
+tcgen05 kernel sits behind the unchanged per-module call."""
+from __future__ import annotations
+
+import os
+
+import torch  # noqa: F401
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from .fake_quant import FixedFakeQuantize, LSQFakeQuantize, LSQPlusFakeQuantize, producer_of
+from .observer import (AvgMinMaxObserver, AvgMSEFastObserver, AvgMSEObserver, AvgPruneMinMaxObserver,
+                       AvgQuantileObserver, LSQPlusObserver, MinMaxObserver, MSEFastObserver, MSEObserver)
+
+ObserverDict = {
+    "MinMaxObserver": MinMaxObserver,
+    "AvgMinMaxObserver": AvgMinMaxObserver,
+    "MSEObserver": MSEObserver,
+    "AvgMSEObserver": AvgMSEObserver,
+    "MSEFastObserver": MSEFastObserver,
+    "AvgMSEFastObserver": AvgMSEFastObserver,
+    "AvgQuantileObserver": AvgQuantileObserver,
+    "LSQPlusObserver": LSQPlusObserver,
+    "AvgPruneMinMaxObserver": AvgPruneMinMaxObserver,
+}
+
+FakeQuantizeDict = {
+    "FixedFakeQuantize": FixedFakeQuantize,
+    "LSQFakeQuantize": LSQFakeQuantize,
+    "LSQPlusFakeQuantize": LSQPlusFakeQuantize,
+}
+
+# statistics for tests / benches: which path QLinear.forward took
+stats = {"fused": 0, "unfused": 0}
+
+
+class QuantizedModule(nn.Module):
+    def __init__(self, backend="academic"):
+        super().__init__()
+        self.backend = backend
+
+
+class QuantizedOperator:
+    """Mixin: derived-state cache for the weight side (never serialised)."""
+
+    def _weight_key(self):
+        wq = self.weight_fake_quant
+        return (self.weight.data_ptr(), self.weight._version, tuple(self.weight.shape), wq.qparam_epoch,
+                wq.scale.data_ptr(), wq.scale._version, wq.zero_point._version, wq.quant_min, wq.quant_max)
+
+    def invalidate_packed(self):
+        """Drop every weight-derived cache.  Call after mutating ``weight.data`` outside torch's
+        version tracking (gamma_migration.py:46-76 does ``w.weight.data *= gamma``); state.py's
+        togglers and the weight observer call it automatically."""
+        self._packed = None
+        self._fq_weight_cache = None
+
+    def _weight_is_static(self):
+        wq = self.weight_fake_quant
+        return (wq.fake_quant_enabled == 1 and wq.observer_enabled == 0 and isinstance(wq, FixedFakeQuantize)
+                and not (torch.is_grad_enabled() and self.weight.requires_grad))
+
+    def _cached_fq_weight(self):
+        """fake-quantized weight, recomputed only when the weight / its qparams changed
+        (the reference re-runs it on every forward, quantized_module.py:72,98)."""
+        key = self._weight_key()
+        c = getattr(self, "_fq_weight_cache", None)
+        if c is None or c[0] != key:
+            c = (key, self.weight_fake_quant(self.weight).detach())
+            self._fq_weight_cache = c
+        return c[1]
+
+
+class QConv2d(QuantizedOperator, nn.Conv2d):
+    """quantized_module.py:38-57."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, padding_mode,
+                 w_qconfig):
+        super().__init__(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size, stride=stride,
+                         padding=padding, dilation=dilation, groups=groups, bias=bias, padding_mode=padding_mode)
+        self.weight_fake_quant = WeightQuantizer(w_qconfig)
+
+    def forward(self, input):
+        w = self._cached_fq_weight() if self._weight_is_static() else self.weight_fake_quant(self.weight)
+        return self._conv_forward(input, w, self.bias)
+
+
+class QLinear(QuantizedOperator, nn.Linear):
+    """quantized_module.py:60-72."""
+
+    def __init__(self, in_features, out_features, bias, w_qconfig):
+        super().__init__(in_features=in_features, out_features=out_features, bias=bias)
+        self.weight_fake_quant = WeightQuantizer(w_qconfig)
+
+    # ---- fused path ----
+    def _fusable_producer(self, input):
+        if os.environ.get("OSQ_DISABLE_FUSION") == "1":
+            return None
+        if not (input.is_cuda and input.dtype == torch.float32 and input.dim() >= 2):
+            return None
+        aq = producer_of(input)
+        if aq is None or aq.fake_quant_enabled != 1 or aq.ch_axis != -1 or aq.quant_max - aq.quant_min > 255:
+            return None
+        wq = self.weight_fake_quant
+        if not self._weight_is_static() or wq.ch_axis != 0 or wq.quant_max - wq.quant_min > 255:
+            return None
+        if torch.is_grad_enabled() and (input.requires_grad or aq.scale.requires_grad or
+                                        (self.bias is not None and self.bias.requires_grad)):
+            return None  # training / learn_scale stage: reference semantics through autograd
+        if not ops.fused_linear_supported(self.in_features, self.out_features):
+            return None
+        return aq
+
+    def _packed_weight(self):
+        key = self._weight_key()
+        c = getattr(self, "_packed", None)
+        if c is None or c[0] != key:
+            wq = self.weight_fake_quant
+            codes, rowsum = ops.pack_weight(self.weight, wq.scale, wq.zero_point, wq.quant_min, wq.quant_max)
+            c = (key, codes, rowsum, wq.scale.detach().float().contiguous())
+            self._packed = c
+        return c[1], c[2], c[3]
+
+    def forward(self, input):
+        aq = self._fusable_producer(input)
+        if aq is not None:
+            codes, rowsum, w_scale = self._packed_weight()
+            g = aq.grad_factor(input) if isinstance(aq, LSQPlusFakeQuantize) else 0.0
+            stats["fused"] += 1
+            return ops.fused_fq_linear(input, aq.scale.detach(), aq.zero_point.detach(), aq.quant_min, aq.quant_max,
+                                       codes, w_scale, rowsum, self.bias, lsq_grad_factor=g)
+        stats["unfused"] += 1
+        w = self._cached_fq_weight() if self._weight_is_static() else self.weight_fake_quant(self.weight)
+        return F.linear(input, w, self.bias)
+
+
+class QEmbedding(QuantizedOperator, nn.Embedding):
+    """quantized_module.py:75-100; the 23 M-element table is fake-quantized once per weight version."""
+
+    def __init__(self, num_embeddings, embedding_dim, padding_idx, max_norm, norm_type, scale_grad_by_freq, sparse,
+                 _weight, w_qconfig):
+        super().__init__(num_embeddings=num_embeddings, embedding_dim=embedding_dim, padding_idx=padding_idx,
+                         max_norm=max_norm, norm_type=norm_type, scale_grad_by_freq=scale_grad_by_freq, sparse=sparse,
+                         _weight=_weight)
+        self.weight_fake_quant = WeightQuantizer(w_qconfig)
+
+    def forward(self, input):
+        w = self._cached_fq_weight() if self._weight_is_static() else self.weight_fake_quant(self.weight)
+        return F.embedding(input, w, self.padding_idx, self.max_norm, self.norm_type, self.scale_grad_by_freq,
+                           self.sparse)
+
+
+module_type_to_quant_weight = {nn.Linear: QLinear, nn.Conv2d: QConv2d, nn.Embedding: QEmbedding}
+
+
+def get_module_args(module):
+    if isinstance(module, nn.Linear):
+        return dict(in_features=module.in_features, out_features=module.out_features, bias=module.bias is not None)
+    if isinstance(module, nn.Conv2d):
+        return dict(in_channels=module.in_channels, out_channels=module.out_channels, kernel_size=module.kernel_size,
+                    stride=module.stride, padding=module.padding, dilation=module.dilation, groups=module.groups,
+                    bias=module.bias is not None, padding_mode=module.padding_mode)
+    if isinstance(module, nn.Embedding):
+        return dict(num_embeddings=module.num_embeddings, embedding_dim=module.embedding_dim,
+                    padding_idx=module.padding_idx, max_norm=module.max_norm, norm_type=module.norm_type,
+                    scale_grad_by_freq=module.scale_grad_by_freq, sparse=module.sparse, _weight=None)
+    raise NotImplementedError
+
+
+def Quantizer(module, config):
+    """quantized_module.py:144-155: ``None`` -> activation quantizer, Linear/Conv2d/Embedding -> Q* operator."""
+    if module is None:
+        return ActivationQuantizer(a_qconfig=config)
+    cls = module_type_to_quant_weight.get(type(module))
+    if cls is None:
+        return module
+    qmodule = cls(**get_module_args(module), w_qconfig=config)
+    qmodule.weight.data = module.weight.data.clone()
+    if getattr(module, "bias", None) is not None:
+        qmodule.bias.data = module.bias.data.clone()
+    return qmodule
+
+
+def _build(qconfig):
+    return FakeQuantizeDict[qconfig.quantizer](ObserverDict[qconfig.observer], bit=qconfig.bit,
+                                               symmetric=qconfig.symmetric, ch_axis=qconfig.ch_axis)
+
+
+def ActivationQuantizer(a_qconfig):
+    return _build(a_qconfig)
+
+
+def WeightQuantizer(w_qconfig):
+    return _build(w_qconfig)

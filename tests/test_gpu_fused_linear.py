@@ -1,0 +1,148 @@
+"""-m gpu: the fused fake-quant + Linear tcgen05 kernel.
+
+Parity bar (BASELINE.json north_star): activation / weight bins BIT-EXACT (checked through the kernel's
+debug side output and the packed weight codes); Y within 1e-3 relative of the reference's fp32
+F.linear path, written as |dY| <= 1e-3*|Y_ref| + 1e-3*max|Y_ref| (the pure elementwise
+relative test is ill-posed at cancellation zeros).  Additionally Y must match the EXACT integer
+contraction of the bins to fp32 rounding (1e-5), which is size independent."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import osq_oracle as O
+from tests.test_host_logic import QC
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+def close(y, ref, rel=1e-3):
+    y, ref = y.detach().double().cpu(), ref.detach().double().cpu()
+    bad = (y - ref).abs() > rel * ref.abs() + rel * ref.abs().max()
+    assert not bool(bad.any()), "%d / %d outside tolerance, max abs diff %g" % (int(bad.sum()), bad.numel(), float((y - ref).abs().max()))
+
+
+def run_case(m, k, n, a_bit, w_bit, lsq, seed, gamma=False):
+    from outlier_suppression_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(m, k, generator=g)
+    a[:, :3] *= 20
+    w, bias = O.synth_linear(n, k, seed=seed + 1, gamma=gamma)
+    a_qmin, a_qmax = O.quant_range(a_bit, False)
+    mn, mx = O.global_minmax(a)
+    a_scale, a_zp = O.qparams_from_minmax(mn * 0.7, mx * 0.7, a_qmin, a_qmax, False)
+    w_scale, w_zp, w_qmin, w_qmax = O.weight_qparams_minmax(w, w_bit, True)
+    if lsq:
+        a_scale_t = a_scale.reshape(1).clone()
+        a_zp_t = a_zp.reshape(1).float() + 0.37
+        a_zp_t = a_zp_t.clamp(a_qmin, a_qmax)
+    else:
+        a_scale_t, a_zp_t = a_scale.reshape(1), a_zp.reshape(1).to(torch.int32)
+    y_ref, qa_ref, qw_ref = O.fused_fq_linear(a, a_scale_t.clone(), a_zp_t.clone(), a_qmin, a_qmax, lsq, w, w_scale, w_zp,
+                                              w_qmin, w_qmax, bias)
+    codes, rowsum = ops.pack_weight(w.cuda(), w_scale.cuda(), w_zp.cuda(), w_qmin, w_qmax)
+    np.testing.assert_array_equal(codes.cpu().numpy(), qw_ref.numpy().astype(np.int8))          # weight bins bit-exact
+    np.testing.assert_array_equal(rowsum.cpu().numpy(), qw_ref.sum(1).numpy().astype(np.int32))
+    gfac = 1.0 / (a.numel() * a_qmax) ** 0.5 if lsq else 0.0
+    y, dbg = ops.fused_fq_linear(a.cuda(), a_scale_t.cuda(), a_zp_t.cuda(), a_qmin, a_qmax, codes, w_scale.cuda(), rowsum,
+                                 bias.cuda(), lsq_grad_factor=gfac, want_codes=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dbg.cpu().numpy(), (qa_ref - a_qmin).numpy().astype(np.uint8))  # activation bins bit-exact
+    close(y, y_ref)
+    # exact contraction of the bins (size-independent property)
+    s_eff = a_scale_t if not lsq else O.lsqplus_effective_qparams(a_scale_t, a_zp_t, a.numel(), a_qmax)[0]
+    z_int = torch.round(a_zp_t.float())
+    acc = (qa_ref.double() - z_int.double()) @ qw_ref.double().t()
+    exact = acc * (s_eff.double() * w_scale.double())[None, :] + bias.double()[None, :]
+    np.testing.assert_allclose(y.double().cpu().numpy(), exact.numpy(), rtol=2e-6, atol=2e-6 * float(exact.abs().max()))
+    return y
+
+
+@pytest.mark.parametrize("m,k,n", [(128, 128, 16), (300, 768, 768), (257, 768, 3072), (515, 3072, 768), (129, 1024, 1024),
+                                   (64, 256, 400), (1, 128, 48)])
+def test_fused_shapes_6bit(m, k, n):
+    run_case(m, k, n, 6, 6, False, seed=m + k + n)
+
+
+@pytest.mark.parametrize("a_bit,w_bit,lsq", [(8, 8, False), (4, 4, False), (6, 4, False), (6, 6, True), (8, 8, True)])
+def test_fused_bits_and_lsqplus(a_bit, w_bit, lsq):
+    run_case(384, 768, 768, a_bit, w_bit, lsq, seed=a_bit * 10 + w_bit, gamma=True)
+
+
+def test_fused_multi_block_persistent():
+    """more 128-row blocks than SMs: every CTA loops over several blocks (ring phases wrap)."""
+    run_case(148 * 128 * 2 + 77, 256, 64, 6, 6, False, seed=5)
+
+
+def test_fused_full_size_bert_base_site():
+    """BASELINE config 2 site 768->768 at M = 32*512 = 16384 against the CPU oracle."""
+    run_case(16384, 768, 768, 6, 6, True, seed=2)
+
+
+def test_qlinear_module_golden(golden):
+    """module-level drop-in: Quantizer(None, a_qconfig) -> Quantizer(linear, w_qconfig) exactly as
+    quant_bert.py wires them; must take the fused path and reproduce the reference's Y."""
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    g = golden("qlinear")
+    for i in range(int(g["n"])):
+        a_bit, w_bit, lsq, aqmin, aqmax, wqmin, wqmax = (int(v) for v in g["p%d" % i])
+        w, b, x = T(g["w%d" % i]), T(g["b%d" % i]), T(g["x%d" % i])
+        lin = torch.nn.Linear(w.shape[1], w.shape[0])
+        lin.weight.data, lin.bias.data = w.clone(), b.clone()
+        ql = qm.Quantizer(lin, QC("FixedFakeQuantize", "MinMaxObserver", w_bit, True, 0)).cuda()
+        aq = qm.Quantizer(None, QC("LSQPlusFakeQuantize" if lsq else "FixedFakeQuantize", "AvgMinMaxObserver", a_bit, False, -1)).cuda()
+        lens = T(g["lens%d" % i]).cuda()
+        xg = x.cuda()
+        ql.weight_fake_quant.enable_observer(); ql(xg); ql.weight_fake_quant.disable_observer()
+        aq.enable_observer(); aq(xg, lens, 1); aq.disable_observer()
+        np.testing.assert_array_equal(ql.weight_fake_quant.scale.cpu().numpy(), g["w_scale%d" % i])
+        if lsq:
+            aq.zero_point.data += 0.37
+        np.testing.assert_array_equal(aq.scale.data.reshape(()).cpu().numpy(), g["a_scale%d" % i])
+        aq.enable_fake_quant(); ql.weight_fake_quant.enable_fake_quant()
+        before = dict(qm.stats)
+        with torch.no_grad():
+            x_fq = aq(xg, lens, 1)
+            y = ql(x_fq)
+        np.testing.assert_array_equal(x_fq.cpu().numpy(), g["x_fq%d" % i])
+        assert qm.stats["fused"] == before["fused"] + 1, "QLinear did not take the fused kernel"
+        close(y, T(g["y%d" % i]))
+        # un-tagged input -> reference semantics (separate kernels), still correct
+        with torch.no_grad():
+            y2 = ql(x_fq.clone())
+        assert qm.stats["unfused"] == before["unfused"] + 1
+        close(y2, T(g["y%d" % i]), rel=1e-5)
+
+
+def test_weight_cache_invalidation_after_gamma_fold():
+    """gamma_migration.py:46-76 rewrites weight.data in place; the togglers drop the packed cache."""
+    from outlier_suppression_b200 import quantization as Q
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(128, 32)
+    net = torch.nn.Module()
+    net.dense = qm.Quantizer(lin, QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0))
+    net.in_act_fake_quant = qm.Quantizer(None, QC("FixedFakeQuantize", "AvgMinMaxObserver", 6, False, -1))
+    net.cuda()
+    x = torch.randn(4, 16, 128, device="cuda")
+
+    def calibrate_and_run():
+        obs = net.dense.weight_fake_quant.observer  # fresh running extrema, as in a real (single) weight calibration
+        obs.min_val = torch.tensor(float("inf"), device="cuda"); obs.max_val = torch.tensor(float("-inf"), device="cuda")
+        Q.enable_calibration_woquantization(net, "weight_fake_quant"); net.dense(x)
+        Q.enable_calibration_woquantization(net, "act_fake_quant"); net.in_act_fake_quant.observer.cnt = 0; net.in_act_fake_quant(x)
+        Q.enable_quantization(net)
+        with torch.no_grad():
+            return net.dense(net.in_act_fake_quant(x))
+
+    def oracle_run():
+        w, b = net.dense.weight.detach().cpu(), net.dense.bias.detach().cpu()
+        ws, wz, wqmin, wqmax = O.weight_qparams_minmax(w, 6, True)
+        mn, mx = O.global_minmax(x.cpu())
+        s, z = O.qparams_from_minmax(mn, mx, 0, 63, False)
+        return O.qlinear(O.fq_per_tensor(x.cpu(), s.item(), int(z.item()), 0, 63), w, ws, wz, wqmin, wqmax, b)
+
+    close(calibrate_and_run(), oracle_run())
+    gamma = torch.rand(128, device="cuda") * 2 + 0.2
+    net.dense.weight.data *= gamma  # not tracked by weight._version
+    close(calibrate_and_run(), oracle_run())

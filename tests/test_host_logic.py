@@ -1,0 +1,157 @@
+"""CPU-only checks: the C-ABI library builds/loads and exports every symbol of include/osq.h, the
+boundary keeps the reference's names / flags / state_dict keys, and the product path refuses to run
+without CUDA (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class QC:
+    def __init__(self, quantizer, observer, bit, symmetric, ch_axis):
+        self.quantizer, self.observer, self.bit, self.symmetric, self.ch_axis = quantizer, observer, bit, symmetric, ch_axis
+
+
+def test_library_exports_every_declared_symbol():
+    from outlier_suppression_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "osq.h")).read()
+    declared = set(re.findall(r"\b(osq_[a-z0-9_]+)\s*\(", header))
+    declared -= {"osq_tokens_t", "osq_stat_epilogue_t", "osq_fused_linear_t"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libosq_b200.so does not export %s" % name
+    assert set(_lib.EXPORTS) == declared
+    assert lib.osq_version() == 100
+    assert lib.osq_workspace_bytes() > 0
+
+
+def test_argument_validation_without_gpu():
+    from outlier_suppression_b200 import _lib
+    lib = _lib.load()
+    rc = lib.osq_fq_per_tensor_f32(None, None, None, 16, None, None, 0, 0.0, 0, 63, None)
+    assert rc == -1 and b"null pointer" in lib.osq_last_error()
+    rc = lib.osq_fused_fq_linear(None, None)
+    assert rc == -1
+
+
+def test_no_cpu_fallback():
+    from outlier_suppression_b200 import ops
+    x = torch.randn(4, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.fq_per_tensor(x, torch.tensor([0.1]), torch.tensor([0], dtype=torch.int32), 0, 63)
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer
+    q = Quantizer(None, QC("FixedFakeQuantize", "AvgMinMaxObserver", 6, False, -1))
+    q.enable_fake_quant()
+    with pytest.raises(RuntimeError):
+        q(x)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "outlier_suppression_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_registries_and_factory(golden):
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    from outlier_suppression_b200.quantization.fake_quant import (FixedFakeQuantize, LSQFakeQuantize, LSQPlusFakeQuantize,
+                                                                  QuantizeBase)
+    assert set(qm.ObserverDict) == {"MinMaxObserver", "AvgMinMaxObserver", "MSEObserver", "AvgMSEObserver", "MSEFastObserver",
+                                    "AvgMSEFastObserver", "AvgQuantileObserver", "LSQPlusObserver", "AvgPruneMinMaxObserver"}
+    assert set(qm.FakeQuantizeDict) == {"FixedFakeQuantize", "LSQFakeQuantize", "LSQPlusFakeQuantize"}
+    lin = torch.nn.Linear(128, 48)
+    ql = qm.Quantizer(lin, QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0))
+    assert isinstance(ql, qm.QLinear) and isinstance(ql.weight_fake_quant, FixedFakeQuantize)
+    assert torch.equal(ql.weight, lin.weight) and ql.weight.data_ptr() != lin.weight.data_ptr()
+    assert (ql.weight_fake_quant.quant_min, ql.weight_fake_quant.quant_max) == (-32, 31)
+    aq = qm.Quantizer(None, QC("FixedFakeQuantize", "AvgMinMaxObserver", 6, False, -1))
+    assert (aq.quant_min, aq.quant_max, aq.observer_enabled, aq.fake_quant_enabled) == (0, 63, 0, 0)
+    g = golden("qlinear")
+    assert sorted(aq.state_dict().keys()) == list(g["keys_fixed"])
+    assert sorted(ql.state_dict().keys()) == list(g["keys_qlinear"])
+    lq = qm.Quantizer(None, QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1))
+    assert sorted(lq.state_dict().keys()) == list(g["keys_lsqplus"])
+    assert isinstance(lq.scale, torch.nn.Parameter) and isinstance(lq.zero_point, torch.nn.Parameter)
+    assert isinstance(lq, QuantizeBase) and isinstance(qm.Quantizer(torch.nn.ReLU(), None), torch.nn.ReLU)
+    emb = qm.Quantizer(torch.nn.Embedding(10, 8), QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0))
+    assert isinstance(emb, qm.QEmbedding)
+    assert isinstance(qm.Quantizer(None, QC("LSQFakeQuantize", "MinMaxObserver", 8, True, -1)), LSQFakeQuantize)
+    assert isinstance(lq, LSQPlusFakeQuantize)
+
+
+def test_state_dict_roundtrip_resizes():
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    cfg = QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)
+    a = qm.Quantizer(torch.nn.Linear(16, 4), cfg)
+    a.weight_fake_quant.scale.resize_(4).copy_(torch.tensor([1., 2., 3., 4.]))
+    a.weight_fake_quant.zero_point.resize_(4).zero_()
+    b = qm.Quantizer(torch.nn.Linear(16, 4), cfg)
+    epoch = b.weight_fake_quant.qparam_epoch
+    b.load_state_dict(a.state_dict())
+    assert torch.equal(b.weight_fake_quant.scale, torch.tensor([1., 2., 3., 4.]))
+    assert b.weight_fake_quant.qparam_epoch > epoch
+
+
+def test_state_togglers():
+    from outlier_suppression_b200 import quantization as Q
+    from outlier_suppression_b200.quantization.state import set_observer_name
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dense = Quantizer(torch.nn.Linear(8, 8), QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0))
+            self.out_act_fake_quant = Quantizer(None, QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1))
+            self.in_act_fake_quant = Quantizer(None, QC("FixedFakeQuantize", "AvgMinMaxObserver", 6, False, -1))
+
+    net = Net()
+    flags = lambda m: (m.observer_enabled, m.fake_quant_enabled)  # noqa: E731
+    Q.enable_calibration_woquantization(net, quantizer_type="weight_fake_quant")
+    assert flags(net.dense.weight_fake_quant) == (1, 0) and flags(net.out_act_fake_quant) == (0, 0)
+    Q.enable_calibration_woquantization(net, quantizer_type="act_fake_quant")
+    assert flags(net.dense.weight_fake_quant) == (0, 0) and flags(net.in_act_fake_quant) == (1, 0)
+    Q.enable_calibration_quantization(net, quantizer_type="act_fake_quant")
+    assert flags(net.out_act_fake_quant) == (0, 1) and flags(net.in_act_fake_quant) == (1, 1)
+    Q.enable_quantization(net)
+    assert flags(net.dense.weight_fake_quant) == (0, 1) and flags(net.in_act_fake_quant) == (0, 1)
+    Q.enable_quantization(net, except_quantizer=["in_act_fake_quant"])
+    assert flags(net.in_act_fake_quant) == (0, 0)
+    Q.disable_all(net)
+    assert flags(net.dense.weight_fake_quant) == (0, 0)
+    set_observer_name(net)
+    assert net.out_act_fake_quant.observer.name == "out_act_fake_quant.observer"
+
+
+def test_token_geometry():
+    from outlier_suppression_b200 import ops
+    x = torch.empty(4, 12, 32)
+    t = ops.token_geometry(x, 1)
+    assert (t.B, t.S, t.F1, t.F2, t.sb, t.ss, t.sf2) == (4, 12, 1, 32, 384, 32, 1)
+    q = torch.empty(4, 12, 3, 8).permute(0, 2, 1, 3)          # [B,h,S,d] view of [B,S,h,d]
+    t = ops.token_geometry(q, 2)
+    assert (t.B, t.S, t.F1, t.F2, t.ss, t.sf2) == (4, 12, 1, 24, 24, 1)
+    kT = q.transpose(-1, -2)                                   # [B,h,d,S]
+    t = ops.token_geometry(kT, 3)
+    assert (t.B, t.S, t.F1, t.F2, t.ss, t.sf2) == (4, 12, 1, 24, 24, 1)
+    p = torch.empty(4, 3, 12, 12)                              # probs: F = h * S_k in h segments
+    t = ops.token_geometry(p, 2)
+    assert (t.B, t.S, t.F1, t.F2, t.sf1, t.ss, t.sf2) == (4, 12, 3, 12, 144, 12, 1)
+
+
+def test_host_qparams_match_golden(golden):
+    from outlier_suppression_b200.quantization.observer import ObserverBase
+    g = golden("qparams")
+    for bit in (4, 6, 8):
+        for sym in (False, True):
+            o = ObserverBase(bit=bit, symmetric=sym)
+            s, z = o.calculate_qparams(torch.from_numpy(g["mins"]), torch.from_numpy(g["maxs"]))
+            np.testing.assert_array_equal(s.numpy(), g["s_%d_%d" % (bit, sym)])
+            np.testing.assert_array_equal(z.numpy(), g["z_%d_%d" % (bit, sym)])
