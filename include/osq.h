@@ -171,14 +171,17 @@ int osq_pack_weight_s8(const float* w, int64_t N, int64_t K, const float* scale,
  *   lsq_grad_factor > 0, as in K1).  A [M, K] fp32 row-major (raw, un-quantised, or already
  *   fake-quantised -- fq is idempotent), Y [M, N] fp32 row-major.
  *
- *   One persistent, warp-specialised tcgen05 kernel: A tiles arrive by TMA as fp32, converter
- *   warps turn them into integer codes in the UMMA shared-memory layout, the packed weight codes
- *   arrive by TMA, `tcgen05.mma kind::i8` (u8 x s8 -> s32, exact) accumulates in TMEM, the
- *   epilogue applies the zero-point correction, scales and bias and streams fp32 Y to HBM.
+ *   One persistent, warp-specialised tcgen05 kernel: converter warps stream fp32 A with 128-bit
+ *   loads and turn it into integer bins in the UMMA shared-memory layout, the packed weight bins
+ *   arrive by TMA, `tcgen05.mma kind::i8` (u8 x s8 -> s32, exact) accumulates in TMEM, the epilogue
+ *   applies the zero-point correction, scales and bias and writes fp32 Y with TMA stores.
  *   mma_kind: 0 = auto, 1 = kind::i8, 2 = kind::f16 (bf16 code tiles, exact for a_bit,w_bit <= 7).
  *
- *   Shape contract: K % 128 == 0, N % 16 == 0, M >= 1.  a_codes_dbg (optional uint8 [M, K]):
- *   the activation bins the kernel fed to the tensor core (parity side output).
+ *   Shape contract: K % 128 == 0, N % 16 == 0, M >= 1.  a_codes (optional uint8 [M, K], 16-byte
+ *   aligned): receives the activation bins (bin - a_qmin) the kernel fed to the tensor core (parity
+ *   side output).  When K > 1024 the converted block no longer fits in shared memory; if a_codes is
+ *   given it doubles as an L2-resident code cache so fp32 A is read and quantised once (otherwise
+ *   A is re-read and re-quantised for every 256-column chunk of N).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* A;
@@ -195,7 +198,7 @@ typedef struct {
   float* Y;
   int64_t N;
   int mma_kind;
-  uint8_t* a_codes_dbg;  /* optional */
+  uint8_t* a_codes;      /* optional [M, K] u8: bins side output AND the kernel's code cache (see above) */
 } osq_fused_linear_t;
 
 int osq_fused_fq_linear(const osq_fused_linear_t* args, void* stream);

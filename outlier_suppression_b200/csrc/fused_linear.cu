@@ -11,17 +11,19 @@
 //
 // Data flow per CTA (one 128-row block of A at a time, all of N for that block):
 //
-//   warp 0  (1 lane)  TMA: fp32 A sub-tiles [32 rows x 128 k]            -> F ring   (f_full / f_empty)
-//   warp 1  (1 lane)  TMA: s8 weight tiles  [BN rows x 128 k], SW128     -> W ring   (w_full / w_empty)
-//   warps 8-15        convert F (fp32) -> integer bins -> A ring in the UMMA K-major SW128 layout
-//                                                                         (a_full / a_empty)
+//   warps 8-15        A path: 128-bit streaming loads of fp32 A straight into registers (16 rows x 512 B
+//                     in flight per warp, software pipelined in two halves) -> integer bins -> A ring in
+//                     the UMMA K-major SW128 shared-memory layout                    (a_full / a_empty)
+//   warp 1  (1 lane)  TMA: s8 weight tiles [BN rows x 128 k], SW128 -> W ring        (w_full / w_empty)
 //   warp 2  (1 lane)  tcgen05.mma  D[tmem] (+)= A[smem] * W[smem]^T, commit -> w_empty/a_empty/acc_full
-//   warps 4-7         epilogue: tcgen05.ld -> zero-point correction, scales, bias -> fp32 Y (st.global.cs.v4)
+//   warps 4-7         epilogue: tcgen05.ld -> zero-point correction, scales, bias -> swizzled smem tile
+//                     -> TMA store (full 128-byte lines) of fp32 Y
 //
-// When all of K fits in the A ring (K/128 <= a_stages: BERT-base 768, BART 1024) the converted A
-// block stays RESIDENT in shared memory and is reused for every N chunk, so each activation element
-// is read from HBM once and quantised once.  Otherwise (K = 3072/4096) A streams through the ring
-// and is re-converted per N chunk (re-reads hit L2).
+// When all of K fits in the A ring (K/128 <= 8: BERT-base 768, BART 1024) the converted A block stays
+// RESIDENT in shared memory and is reused for every N chunk: each activation element is read from HBM
+// once and quantised once.  Otherwise (K = 3072/4096) pass 0 converts A and also spills the bins (1 B per
+// element) to a caller-provided code cache that stays in L2; the remaining N chunks re-load the bins
+// by TMA directly in the UMMA layout -- fp32 A is still read from HBM exactly once.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -32,17 +34,17 @@ constexpr int kBM = 128;            // rows of A per CTA tile (UMMA M)
 constexpr int kBNMax = 256;         // columns per accumulator stage (UMMA N)
 constexpr int kStageK = 128;        // k elements (= bytes, u8/s8) per smem stage row: one 128B swizzle row
 constexpr int kUmmaK = 32;          // k per tcgen05.mma kind::i8
-constexpr int kFRows = 32;          // rows per fp32 staging tile
-constexpr int kFPerA = kBM / kFRows;
 constexpr int kAStageBytes = kBM * kStageK;          // 16 KB
-constexpr int kFStageBytes = kFRows * kStageK * 4;   // 16 KB
 constexpr int kWStageBytes = kBNMax * kStageK;       // 32 KB
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kBNMax;       // 512
 constexpr int kNumThreads = 512;
 constexpr int kConvWarp0 = 8, kNumConvWarps = 8;
 constexpr int kEpiWarp0 = 4, kNumEpiWarps = 4;
-constexpr int kMaxAStages = 8, kMaxFStages = 4, kMaxWStages = 4;
+constexpr int kRowsPerConvWarp = kBM / kNumConvWarps;  // 16
+constexpr int kHalf = kRowsPerConvWarp / 2;            // 8 rows per software-pipeline half
+constexpr int kOutTileBytes = 32 * 128;                // 32 rows x 32 fp32 columns, SW128
+constexpr int kMaxAStages = 8, kMaxWStages = 4;
 constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: fp32 ulp is 1 in [2^23, 2^24)
 
 struct FusedParams {
@@ -51,8 +53,10 @@ struct FusedParams {
   int NC;          // number of N chunks
   int BN;          // chunk width (<= 256, multiple of 16)
   int n_mblocks;
-  int a_stages, f_stages, w_stages;
+  int a_stages, w_stages, out_bufs;
   int resident;    // converted A block stays in smem for all N chunks
+  int cached;      // streaming mode with a code cache: passes >= 1 TMA-load bins instead of re-converting
+  const float* A;
   const float* a_scale;
   const void* a_zp;
   int a_zp_is_int32;
@@ -61,8 +65,8 @@ struct FusedParams {
   const float* w_scale;
   const int32_t* w_rowsum;
   const float* bias;
-  float* Y;
-  uint8_t* a_codes_dbg;
+  uint8_t* a_codes;  // optional [M, K]: bins side output / code cache
+  uint32_t codes_box_bytes;  // bytes one code-cache TMA box delivers
 };
 
 // ------------------------------------------------------------------------------------------
@@ -95,6 +99,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -105,6 +110,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -192,10 +208,10 @@ __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, ui
 }
 
 struct Smem {
-  uint64_t f_full[kMaxFStages], f_empty[kMaxFStages];
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   uint64_t acc_full[kAccStages], acc_empty[kAccStages];
+  uint64_t codes_ready;
   uint32_t tmem_base;
   uint32_t pad;
   alignas(16) float c1[kAccStages][kBNMax];      // s_a * w_scale[n]
@@ -204,28 +220,29 @@ struct Smem {
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
-fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                       const FusedParams p) {
+fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
+                       const __grid_constant__ CUtensorMap tmap_codes, const FusedParams p) {
+  // dynamic shared memory, 1024B aligned by the attribute (SWIZZLE_128B tiles need it):
+  // [A ring][W ring][out staging][Smem bookkeeping]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A ring][W ring][F ring][Smem bookkeeping]; every ring stage is 1024B aligned
-  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_ring = base;
+  uint8_t* a_ring = smem_raw;
   uint8_t* w_ring = a_ring + (size_t)p.a_stages * kAStageBytes;
-  uint8_t* f_ring = w_ring + (size_t)p.w_stages * kWStageBytes;
-  Smem& sm = *reinterpret_cast<Smem*>(f_ring + (size_t)p.f_stages * kFStageBytes);
+  uint8_t* o_ring = w_ring + (size_t)p.w_stages * kWStageBytes;
+  Smem& sm = *reinterpret_cast<Smem*>(o_ring + (size_t)kNumEpiWarps * p.out_bufs * kOutTileBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_y);
+    if (p.cached) tma_prefetch_desc(&tmap_codes);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < p.f_stages; ++i) { mbar_init(&sm.f_full[i], 1); mbar_init(&sm.f_empty[i], kNumConvWarps); }
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&sm.a_full[i], kNumConvWarps); mbar_init(&sm.a_empty[i], 1); }
     for (int i = 0; i < p.w_stages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps); }
+    mbar_init(&sm.codes_ready, kNumConvWarps);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&sm.tmem_base, kTmemCols);
@@ -235,26 +252,9 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const uint32_t tmem_base = sm.tmem_base;
 
   const int n_my_blocks = (p.n_mblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int conv_passes = p.resident ? 1 : p.NC;  // how many times A is converted per m-block
+  const int a_passes = p.resident ? 1 : p.NC;  // how many times the A ring is filled per m-block
 
-  if (warp == 0) {
-    // ===================== TMA producer: fp32 A sub-tiles =====================
-    if (lane == 0) {
-      uint32_t pf = 0;
-      for (int it = 0; it < n_my_blocks; ++it) {
-        const int mb = blockIdx.x + it * gridDim.x;
-        for (int pass = 0; pass < conv_passes; ++pass)
-          for (int kb = 0; kb < p.KB; ++kb)
-            for (int j = 0; j < kFPerA; ++j, ++pf) {
-              const int fs = pf % p.f_stages;
-              mbar_wait(&sm.f_empty[fs], ((pf / p.f_stages) & 1) ^ 1);
-              mbar_arrive_expect_tx(&sm.f_full[fs], kFStageBytes);
-              tma_load_2d(f_ring + (size_t)fs * kFStageBytes, &tmap_a, &sm.f_full[fs], kb * kStageK,
-                          mb * kBM + j * kFRows);
-            }
-      }
-    }
-  } else if (warp == 1) {
+  if (warp == 1) {
     // ===================== TMA producer: packed weight tiles =====================
     if (lane == 0) {
       uint32_t pw = 0;
@@ -305,10 +305,12 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const QParam qp = load_qparam(p.a_scale, p.a_zp, p.a_zp_is_int32, p.g, p.qmin, p.qmax, false);
     const float s_a = qp.s;
     const int zc = (int)(rintf(qp.z) - p.qmin);
-    uint32_t cacc = 0;
+    uint8_t* my_out = o_ring + (size_t)wg * p.out_bufs * kOutTileBytes;
+    const uint32_t sw = ((uint32_t)lane & 7) << 4;  // 128B swizzle phase of this thread's staging row
+    uint32_t cacc = 0, n_stores = 0;
     for (int it = 0; it < n_my_blocks; ++it) {
       const int mb = blockIdx.x + it * gridDim.x;
-      const int row = mb * kBM + wg * 32 + lane;
+      const int row0 = mb * kBM + wg * 32;
       for (int nc = 0; nc < p.NC; ++nc, ++cacc) {
         const int as_ = cacc & 1;
         const int n0 = nc * p.BN;
@@ -316,43 +318,55 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (int c = et; c < p.BN; c += kNumEpiWarps * 32) {
           const int n = n0 + c;
           const bool ok = n < p.N;
-          sm.c1[as_][c] = ok ? __fmul_rn(s_a, p.w_scale[n]) : 0.f;
-          sm.zr[as_][c] = ok ? zc * p.w_rowsum[n] : 0;
-          sm.bias[as_][c] = (ok && p.bias != nullptr) ? p.bias[n] : 0.f;
+          sm.c1[as_][c] = ok ? __fmul_rn(s_a, __ldg(p.w_scale + n)) : 0.f;
+          sm.zr[as_][c] = ok ? zc * __ldg(p.w_rowsum + n) : 0;
+          sm.bias[as_][c] = (ok && p.bias != nullptr) ? __ldg(p.bias + n) : 0.f;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
         mbar_wait(&sm.acc_full[as_], (cacc >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(wg * 32) << 16) + (uint32_t)as_ * kBNMax;
-        float* yrow = p.Y + (size_t)row * p.N + n0;
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        for (int c0 = 0; c0 < p.BN && n0 + c0 < p.N; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (row < p.M) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (n0 + c0 + j < p.N) {
-                const float4 c1 = *reinterpret_cast<const float4*>(&sm.c1[as_][c0 + j]);
-                const int4 zr = *reinterpret_cast<const int4*>(&sm.zr[as_][c0 + j]);
-                const float4 bi = *reinterpret_cast<const float4*>(&sm.bias[as_][c0 + j]);
-                float4 o;
-                o.x = fmaf((float)((int)v[j + 0] - zr.x), c1.x, bi.x);
-                o.y = fmaf((float)((int)v[j + 1] - zr.y), c1.y, bi.y);
-                o.z = fmaf((float)((int)v[j + 2] - zr.z), c1.z, bi.z);
-                o.w = fmaf((float)((int)v[j + 3] - zr.w), c1.w, bi.w);
-                __stcs(reinterpret_cast<float4*>(yrow + c0 + j), o);
-              }
+          // the staging tile must have been read out by its previous TMA store
+          if (n_stores >= (uint32_t)p.out_bufs) {
+            if (lane == 0) {
+              if (p.out_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
             }
+            __syncwarp();
           }
+          uint8_t* tile = my_out + (size_t)(n_stores % p.out_bufs) * kOutTileBytes;
+          uint8_t* trow = tile + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 c1 = *reinterpret_cast<const float4*>(&sm.c1[as_][c0 + j]);
+            const int4 zr = *reinterpret_cast<const int4*>(&sm.zr[as_][c0 + j]);
+            const float4 bi = *reinterpret_cast<const float4*>(&sm.bias[as_][c0 + j]);
+            float4 o;
+            o.x = fmaf((float)((int)v[j + 0] - zr.x), c1.x, bi.x);
+            o.y = fmaf((float)((int)v[j + 1] - zr.y), c1.y, bi.y);
+            o.z = fmaf((float)((int)v[j + 2] - zr.z), c1.z, bi.z);
+            o.w = fmaf((float)((int)v[j + 3] - zr.w), c1.w, bi.w);
+            *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ sw)) = o;  // chunk (j/4) ^ (row & 7)
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_y, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
+            tma_store_commit();
+          }
+          ++n_stores;
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.acc_empty[as_]);
       }
     }
+    if (lane == 0) tma_store_wait_all();
   } else if (warp >= kConvWarp0) {
-    // ===================== converters: fp32 -> bins in the UMMA smem layout =====================
+    // ===================== A path: fp32 -> bins in the UMMA smem layout =====================
     const int cw_ = warp - kConvWarp0;
     const QParam qp = load_qparam(p.a_scale, p.a_zp, p.a_zp_is_int32, p.g, p.qmin, p.qmax,
                                   blockIdx.x == 0 && cw_ == 0 && lane == 0);
@@ -364,42 +378,91 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     cp.mz = kMagic + cp.zc;
     cp.lo = kMagic;
     cp.hi = kMagic + cp.span;
-    uint32_t pf = 0, pa = 0;
-    constexpr int kRowsPerWarp = kFRows / kNumConvWarps;  // 4
+    const int r_base = cw_ * kRowsPerConvWarp;  // this warp's 16 rows of the 128-row block
+    // byte offset of this lane's 4 bins inside a swizzled 128 B stage row (before the row term)
+    const uint32_t lane_chunk = (uint32_t)lane >> 2, lane_in = ((uint32_t)lane & 3) << 2;
+
+    float4 xa[kHalf], xb[kHalf];
+    auto load_half = [&](float4* x, int mb, int kb, int half) {
+      const float* base = p.A + (size_t)kb * kStageK + lane * 4;
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int grow = mb * kBM + r_base + half * kHalf + i;
+        x[i] = (grow < p.M) ? ldg_stream(reinterpret_cast<const float4*>(base + (size_t)grow * p.K))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto convert_half = [&](const float4* x, uint8_t* a_tile, int mb, int kb, int half) {
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const int r = r_base + half * kHalf + i;
+        const uint32_t word = pack4(quant_bin(x[i].x, cp), quant_bin(x[i].y, cp), quant_bin(x[i].z, cp), quant_bin(x[i].w, cp));
+        const uint32_t off = (uint32_t)r * kStageK + ((lane_chunk ^ ((uint32_t)r & 7)) << 4) + lane_in;
+        *reinterpret_cast<uint32_t*>(a_tile + off) = word;
+        if (p.a_codes != nullptr) {
+          const int grow = mb * kBM + r;
+          if (grow < p.M) *reinterpret_cast<uint32_t*>(p.a_codes + (size_t)grow * p.K + kb * kStageK + lane * 4) = word;
+        }
+      }
+    };
+
+    uint32_t pa = 0;
+    if (n_my_blocks > 0) {
+      load_half(xa, blockIdx.x, 0, 0);
+      load_half(xb, blockIdx.x, 0, 1);
+    }
     for (int it = 0; it < n_my_blocks; ++it) {
       const int mb = blockIdx.x + it * gridDim.x;
-      for (int pass = 0; pass < conv_passes; ++pass)
-        for (int kb = 0; kb < p.KB; ++kb, ++pa) {
-          const int a_st = pa % p.a_stages;
-          mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
-          uint8_t* a_tile = a_ring + (size_t)a_st * kAStageBytes;
-          for (int j = 0; j < kFPerA; ++j, ++pf) {
-            const int fs = pf % p.f_stages;
-            mbar_wait(&sm.f_full[fs], (pf / p.f_stages) & 1);
-            const float4* f_tile = reinterpret_cast<const float4*>(f_ring + (size_t)fs * kFStageBytes);
-            float4 x[kRowsPerWarp];
-#pragma unroll
-            for (int i = 0; i < kRowsPerWarp; ++i) x[i] = f_tile[(cw_ * kRowsPerWarp + i) * (kStageK / 4) + lane];
-#pragma unroll
-            for (int i = 0; i < kRowsPerWarp; ++i) {
-              const int r = j * kFRows + cw_ * kRowsPerWarp + i;  // row inside the 128-row block
-              const uint32_t word = pack4(quant_bin(x[i].x, cp), quant_bin(x[i].y, cp), quant_bin(x[i].z, cp),
-                                          quant_bin(x[i].w, cp));
-              const uint32_t off = (uint32_t)r * kStageK + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7)) << 4) + (((uint32_t)lane & 3) << 2);
-              *reinterpret_cast<uint32_t*>(a_tile + off) = word;
-              if (p.a_codes_dbg != nullptr) {
-                const int grow = mb * kBM + r;
-                if (grow < p.M)
-                  *reinterpret_cast<uint32_t*>(p.a_codes_dbg + (size_t)grow * p.K + kb * kStageK + lane * 4) = word;
+      for (int pass = 0; pass < a_passes; ++pass) {
+        if (pass == 0 || !p.cached) {
+          // ---- conversion pass: registers -> bins -> smem (next k-block's loads are issued in between) ----
+          for (int kb = 0; kb < p.KB; ++kb, ++pa) {
+            const int a_st = pa % p.a_stages;
+            mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
+            uint8_t* a_tile = a_ring + (size_t)a_st * kAStageBytes;
+            // what to prefetch next: the following k-block of this pass, the first of the next
+            // conversion pass, or the first k-block of this CTA's next m-block
+            int nmb = mb, nkb = kb + 1;
+            bool more = true;
+            if (nkb == p.KB) {
+              nkb = 0;
+              const bool next_pass_converts = (pass + 1 < a_passes) && !p.cached;
+              if (!next_pass_converts) { nmb = mb + gridDim.x; more = (it + 1 < n_my_blocks); }
+            }
+            convert_half(xa, a_tile, mb, kb, 0);
+            if (more) load_half(xa, nmb, nkb, 0);
+            convert_half(xb, a_tile, mb, kb, 1);
+            if (more) load_half(xb, nmb, nkb, 1);
+            fence_proxy_async_smem();  // generic-proxy smem stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.a_full[a_st]);
+          }
+          if (p.cached && pass == 0) {
+            // bins of this m-block are in the code cache: publish them to the async proxy (TMA) of this CTA
+            __threadfence();
+            fence_proxy_async_all();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.codes_ready);
+          }
+        } else {
+          // ---- cached pass: bins come back from the (L2 resident) code cache by TMA, already in UMMA layout ----
+          if (pass == 1) mbar_wait(&sm.codes_ready, it & 1);
+          for (int kb = 0; kb < p.KB; ++kb, ++pa) {
+            const int a_st = pa % p.a_stages;
+            // every warp paces itself on a_empty so that at most one arrival per warp lands in a phase
+            mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
+            if (lane == 0) {
+              if (cw_ == 0) {
+                mbar_arrive_expect_tx(&sm.a_full[a_st], p.codes_box_bytes);
+                tma_load_2d(a_ring + (size_t)a_st * kAStageBytes, &tmap_codes, &sm.a_full[a_st], kb * kStageK, mb * kBM);
+              } else {
+                mbar_arrive(&sm.a_full[a_st]);  // keeps the arrival count of a_full uniform across pass kinds
               }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.f_empty[fs]);
           }
-          fence_proxy_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.a_full[a_st]);
         }
+      }
     }
   }
 
@@ -516,7 +579,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   OSQ_CHECK_ARG((((uintptr_t)a->A) & 15) == 0 && (((uintptr_t)a->Y) & 15) == 0 && (((uintptr_t)a->w_codes) & 15) == 0,
                 "osq_fused_fq_linear: A, Y and w_codes must be 16-byte aligned");
   OSQ_CHECK_ARG(!(a->lsq_grad_factor > 0.f && a->a_zp_is_int32), "osq_fused_fq_linear: LSQ+ needs a float zero_point");
-  OSQ_CHECK_ARG(a->a_codes_dbg == nullptr || (((uintptr_t)a->a_codes_dbg) & 3) == 0, "osq_fused_fq_linear: a_codes_dbg alignment");
+  OSQ_CHECK_ARG(a->a_codes == nullptr || (((uintptr_t)a->a_codes) & 15) == 0, "osq_fused_fq_linear: a_codes must be 16-byte aligned");
 
   int dev = 0, cc_major = 0, sms = sm_count();
   OSQ_CUDA(cudaGetDevice(&dev));
@@ -532,35 +595,47 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   p.BN = p.N < kBNMax ? p.N : kBNMax;
   p.NC = (p.N + p.BN - 1) / p.BN;
   p.n_mblocks = (p.M + kBM - 1) / kBM;
-  // shared-memory plan (227 KB): resident A when the whole K fits next to >= 2 weight and >= 2 fp32 stages
-  const int budget = 227 * 1024 - 1024 /*align slack*/ - (int)sizeof(Smem);
-  if (p.KB <= kMaxAStages && p.KB * kAStageBytes + 2 * kWStageBytes + 2 * kFStageBytes <= budget) {
+  // shared-memory plan (227 KB / CTA): [A ring][W ring][out staging][bookkeeping]
+  const int budget = 227 * 1024 - (int)sizeof(Smem);
+  const int out1 = kNumEpiWarps * kOutTileBytes;  // one 4 KB staging tile per epilogue warp
+  if (p.KB <= kMaxAStages && p.KB * kAStageBytes + 2 * kWStageBytes + out1 <= budget) {
     p.resident = 1;
     p.a_stages = p.KB;
   } else {
     p.resident = 0;
     p.a_stages = 4;
   }
-  int rest = budget - p.a_stages * kAStageBytes;
+  p.cached = (!p.resident && p.NC > 1 && a->a_codes != nullptr) ? 1 : 0;
+  int rest = budget - p.a_stages * kAStageBytes - 2 * kWStageBytes - out1;
   p.w_stages = 2;
-  p.f_stages = 2;
-  rest -= p.w_stages * kWStageBytes + p.f_stages * kFStageBytes;
-  while (p.f_stages < kMaxFStages && rest >= kFStageBytes) { ++p.f_stages; rest -= kFStageBytes; }
+  p.out_bufs = 1;
+  if (rest >= out1) { p.out_bufs = 2; rest -= out1; }
   while (p.w_stages < kMaxWStages && rest >= kWStageBytes) { ++p.w_stages; rest -= kWStageBytes; }
+  if (!p.resident)
+    while (p.a_stages < kMaxAStages && rest >= kAStageBytes) { ++p.a_stages; rest -= kAStageBytes; }
   const size_t smem_bytes = (size_t)p.a_stages * kAStageBytes + (size_t)p.w_stages * kWStageBytes +
-                            (size_t)p.f_stages * kFStageBytes + sizeof(Smem) + 1024;
+                            (size_t)p.out_bufs * out1 + sizeof(Smem);
 
+  p.A = a->A;
   p.a_scale = a->a_scale; p.a_zp = a->a_zp; p.a_zp_is_int32 = a->a_zp_is_int32; p.g = a->lsq_grad_factor;
   p.qmin = (float)a->a_qmin; p.qmax = (float)a->a_qmax;
-  p.w_scale = a->w_scale; p.w_rowsum = a->w_rowsum; p.bias = a->bias; p.Y = a->Y; p.a_codes_dbg = a->a_codes_dbg;
+  p.w_scale = a->w_scale; p.w_rowsum = a->w_rowsum; p.bias = a->bias; p.a_codes = a->a_codes;
+  p.codes_box_bytes = (uint32_t)(p.M < kBM ? p.M : kBM) * kStageK;
 
-  CUtensorMap map_a, map_w;
-  if (int rc = make_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->A, (uint64_t)p.K, (uint64_t)p.M, kStageK, kFRows,
-                           CU_TENSOR_MAP_SWIZZLE_NONE))
-    return rc;
+  CUtensorMap map_w, map_y, map_c;
   if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->w_codes, (uint64_t)p.K, (uint64_t)p.N, kStageK,
                            (uint32_t)p.BN, CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
+  if (int rc = make_map_2d(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
+                           p.M < 32 ? (uint32_t)p.M : 32u, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
+  if (p.cached) {
+    if (int rc = make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->a_codes, (uint64_t)p.K, (uint64_t)p.M, kStageK,
+                             p.M < kBM ? (uint32_t)p.M : (uint32_t)kBM, CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  } else {
+    map_c = map_w;  // unused by the kernel
+  }
 
   static bool attr_set[64] = {false};
   if (!attr_set[dev & 63]) {
@@ -568,7 +643,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
     attr_set[dev & 63] = true;
   }
   int grid = p.n_mblocks < sms ? p.n_mblocks : sms;
-  fused_fq_linear_kernel<<<grid, kNumThreads, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, p);
+  fused_fq_linear_kernel<<<grid, kNumThreads, smem_bytes, (cudaStream_t)stream>>>(map_w, map_y, map_c, p);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

@@ -44,12 +44,24 @@ def workspace(device) -> torch.Tensor:
     return ws
 
 
+def _is_dense(x: torch.Tensor) -> bool:
+    """non-overlapping and dense: some permutation of the dims is contiguous"""
+    if x.is_contiguous():
+        return True
+    expect = 1
+    for size, stride in sorted(((sz, st) for sz, st in zip(x.shape, x.stride()) if sz != 1), key=lambda p: p[1]):
+        if stride != expect:
+            return False
+        expect *= size
+    return True
+
+
 def _dense_like(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """(x', y') such that both cover the same memory layout densely; elementwise kernels run over
     the flat storage so permuted-but-dense views (q / k^T / v, quant_bert.py:148-186) need no copy."""
     if x.dtype != torch.float32:
         x = x.float()
-    if not (x.is_contiguous() or x.is_non_overlapping_and_dense()):
+    if not (_is_dense(x)):
         x = x.contiguous()
     return x, torch.empty_like(x)  # preserve_format keeps the dense strides
 
@@ -147,20 +159,27 @@ def _prep_act(x: torch.Tensor) -> torch.Tensor:
     return x if x.dtype == torch.float32 else x.float()
 
 
+def _cur_out(out, device):
+    if out is None:
+        return torch.empty(2, dtype=torch.float32, device=device)
+    assert out.is_cuda and out.dtype == torch.float32 and out.numel() == 2 and out.is_contiguous()
+    return out
+
+
 def observe_minmax(x, lens, seq_pos, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None, scale_out=None,
-                   zp_out=None, qmin=0, qmax=255, symmetric=False) -> torch.Tensor:
+                   zp_out=None, qmin=0, qmax=255, symmetric=False, out=None) -> torch.Tensor:
     """Masked global (min,max) + running statistic + qparams in ONE launch (observer.py:184-203)."""
     x = _prep_act(x)
-    cur = torch.empty(2, dtype=torch.float32, device=x.device)
+    cur = _cur_out(out, x.device)
     epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
     ws = workspace(x.device)
     lib = _lib.load()
     if lens is None and (seq_pos == -1 or x.dim() < 3):
-        xc = x if (x.is_contiguous() or x.is_non_overlapping_and_dense()) else x.contiguous()
+        xc = x if (_is_dense(x)) else x.contiguous()
         check(lib.osq_minmax_flat_f32(xc.data_ptr(), xc.numel(), cur.data_ptr(), C.byref(epi), ws.data_ptr(), _stream()),
               "osq_minmax_flat_f32")
         return cur
-    if lens is None and (x.is_contiguous() or x.is_non_overlapping_and_dense()):
+    if lens is None and (_is_dense(x)):
         check(lib.osq_minmax_flat_f32(x.data_ptr(), x.numel(), cur.data_ptr(), C.byref(epi), ws.data_ptr(), _stream()),
               "osq_minmax_flat_f32")
         return cur
@@ -186,14 +205,14 @@ def token_minmax(x, lens, seq_pos):
 
 
 def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
-                         scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False) -> torch.Tensor:
+                         scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None) -> torch.Tensor:
     """AvgPruneMinMaxObserver's token pruning (observer.py:50-70,214-237) as: one pass over the
     activation (per-token extrema), two sorts of the [T] vectors, one selection launch."""
     tmin, tmax, n_valid = token_minmax(x, lens, seq_pos)
     # invalid tokens hold (+inf, -inf): |.| maps both to +inf so they sort behind the T valid entries
     abs_tmin_sorted = torch.sort(tmin.abs()).values
     abs_tmax_sorted = torch.sort(tmax.abs()).values
-    cur = torch.empty(2, dtype=torch.float32, device=tmin.device)
+    cur = _cur_out(out, tmin.device)
     epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
     check(_lib.load().osq_prune_select_f32(tmin.data_ptr(), tmax.data_ptr(), abs_tmin_sorted.data_ptr(),
                                            abs_tmax_sorted.data_ptr(), tmin.numel(), n_valid.data_ptr(),
@@ -292,7 +311,7 @@ def fused_linear_supported(k: int, n: int) -> bool:
 
 
 def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum, bias, lsq_grad_factor=0.0,
-                    mma_kind=0, want_codes=False, out=None):
+                    mma_kind=0, want_codes=False, out=None, use_code_cache=True):
     """activation fq + weight fq + Linear in one tcgen05 kernel. a: [..., K] fp32 -> [..., N] fp32."""
     _require_cuda(a, a_scale, a_zp, w_codes, w_scale, w_rowsum, bias)
     if a.dtype != torch.float32:
@@ -303,7 +322,9 @@ def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum
     m, k = a2.shape
     n = w_codes.shape[0]
     y = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
-    dbg = torch.empty((m, k), dtype=torch.uint8, device=a.device) if want_codes else None
+    # K > 1024: the bins do not fit in shared memory -> give the kernel an (L2 resident) code cache
+    need_cache = use_code_cache and k > 1024 and n > 256
+    dbg = torch.empty((m, k), dtype=torch.uint8, device=a.device) if (want_codes or need_cache) else None
     args = FusedLinearArgs()
     args.A, args.M, args.K = a2.data_ptr(), m, k
     args.a_scale, args.a_zp = a_scale.data_ptr(), a_zp.data_ptr()
@@ -314,7 +335,7 @@ def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum
     args.bias = _ptr(bias)
     args.Y, args.N = y.data_ptr(), n
     args.mma_kind = int(mma_kind)
-    args.a_codes_dbg = _ptr(dbg)
+    args.a_codes = _ptr(dbg)
     if m > 0:
         check(_lib.load().osq_fused_fq_linear(C.byref(args), _stream()), "osq_fused_fq_linear")
     y = y.reshape(*a.shape[:-1], n)

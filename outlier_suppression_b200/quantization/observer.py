@@ -144,6 +144,10 @@ class AvgMinMaxObserver(ObserverBase):
     def _observe(self, x, observation_mask, seq_pos, quantizer=None):
         assert self.ch_axis == -1
         self._ensure_scalar_state(x.device)
+        if getattr(self, "_shard", None) is not None:  # rank-sharded pass (dist.py): record this batch's pair only
+            ctl, idx = self._shard
+            ops.observe_minmax(x, observation_mask, seq_pos, out=ctl.table.slot(idx, ctl.batch))
+            return True
         s_out, z_out = self._fused_targets(quantizer)
         ops.observe_minmax(x, observation_mask, seq_pos, mode=ops.STAT_AVERAGE, cnt=self.cnt, state_min=self.min_val,
                            state_max=self.max_val, scale_out=s_out, zp_out=z_out, qmin=self.quant_min,
@@ -165,11 +169,16 @@ class AvgPruneMinMaxObserver(ObserverBase):
         s_out, z_out = self._fused_targets(quantizer)
         kw = dict(mode=ops.STAT_AVERAGE, cnt=self.cnt, state_min=self.min_val, state_max=self.max_val, scale_out=s_out,
                   zp_out=z_out, qmin=self.quant_min, qmax=self.quant_max, symmetric=self.symmetric)
+        shard = getattr(self, "_shard", None)
+        if shard is not None:  # rank-sharded pass (dist.py): record this batch's pair only
+            kw = dict(out=shard[0].table.slot(shard[1], shard[0].batch))
         tokenwise = observation_mask is not None or seq_pos != -1
         if tokenwise and "attention_probs" not in self.name:  # observer.py:62-63
             ops.observe_prune_minmax(x, observation_mask, seq_pos, self.percentile, **kw)
         else:
             ops.observe_minmax(x, observation_mask, seq_pos, **kw)
+        if shard is not None:
+            return True
         self.cnt += 1
         return s_out is not None
 

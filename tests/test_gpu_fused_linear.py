@@ -22,7 +22,7 @@ def close(y, ref, rel=1e-3):
     assert not bool(bad.any()), "%d / %d outside tolerance, max abs diff %g" % (int(bad.sum()), bad.numel(), float((y - ref).abs().max()))
 
 
-def run_case(m, k, n, a_bit, w_bit, lsq, seed, gamma=False):
+def run_case(m, k, n, a_bit, w_bit, lsq, seed, gamma=False, use_code_cache=True):
     from outlier_suppression_b200 import ops
     g = torch.Generator().manual_seed(seed)
     a = torch.randn(m, k, generator=g)
@@ -45,7 +45,7 @@ def run_case(m, k, n, a_bit, w_bit, lsq, seed, gamma=False):
     np.testing.assert_array_equal(rowsum.cpu().numpy(), qw_ref.sum(1).numpy().astype(np.int32))
     gfac = 1.0 / (a.numel() * a_qmax) ** 0.5 if lsq else 0.0
     y, dbg = ops.fused_fq_linear(a.cuda(), a_scale_t.cuda(), a_zp_t.cuda(), a_qmin, a_qmax, codes, w_scale.cuda(), rowsum,
-                                 bias.cuda(), lsq_grad_factor=gfac, want_codes=True)
+                                 bias.cuda(), lsq_grad_factor=gfac, want_codes=True, use_code_cache=use_code_cache)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(dbg.cpu().numpy(), (qa_ref - a_qmin).numpy().astype(np.uint8))  # activation bins bit-exact
     close(y, y_ref)
@@ -67,6 +67,17 @@ def test_fused_shapes_6bit(m, k, n):
 @pytest.mark.parametrize("a_bit,w_bit,lsq", [(8, 8, False), (4, 4, False), (6, 4, False), (6, 6, True), (8, 8, True)])
 def test_fused_bits_and_lsqplus(a_bit, w_bit, lsq):
     run_case(384, 768, 768, a_bit, w_bit, lsq, seed=a_bit * 10 + w_bit, gamma=True)
+
+
+def test_fused_streaming_k_with_and_without_code_cache():
+    """K = 3072 does not fit in shared memory: pass 0 spills the bins to the L2 code cache and later N chunks
+    TMA-load them; without a cache every chunk re-converts.  Both must give identical results.  The
+    multi-block case makes every CTA run the cached protocol several times (barrier phases wrap)."""
+    y1 = run_case(515, 3072, 768, 6, 6, False, seed=11, use_code_cache=True)
+    y2 = run_case(515, 3072, 768, 6, 6, False, seed=11, use_code_cache=False)
+    assert torch.equal(y1, y2)
+    run_case(148 * 128 + 300, 2048, 512, 8, 8, False, seed=12, use_code_cache=True)
+    run_case(100, 4096, 1024, 6, 6, True, seed=13, use_code_cache=True)
 
 
 def test_fused_multi_block_persistent():
