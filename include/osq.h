@@ -199,6 +199,7 @@ typedef struct {
   int64_t N;
   int mma_kind;
   uint8_t* a_codes;      /* optional [M, K] u8: bins side output AND the kernel's code cache (see above) */
+  void* debug_trace;     /* optional device int64[2048]: clock64 timeline of CTA 0 + per-CTA globaltimer start/end (profiling aid), else NULL */
 } osq_fused_linear_t;
 
 int osq_fused_fq_linear(const osq_fused_linear_t* args, void* stream);

@@ -11,13 +11,14 @@
 //
 // Data flow per CTA (one 128-row block of A at a time, all of N for that block):
 //
-//   warps 8-15        A path: 128-bit streaming loads of fp32 A straight into registers (16 rows x 512 B
-//                     in flight per warp, software pipelined in two halves) -> integer bins -> A ring in
-//                     the UMMA K-major SW128 shared-memory layout                    (a_full / a_empty)
-//   warp 1  (1 lane)  TMA: s8 weight tiles [BN rows x 128 k], SW128 -> W ring        (w_full / w_empty)
-//   warp 2  (1 lane)  tcgen05.mma  D[tmem] (+)= A[smem] * W[smem]^T, commit -> w_empty/a_empty/acc_full
-//   warps 4-7         epilogue: tcgen05.ld -> zero-point correction, scales, bias -> swizzled smem tile
-//                     -> TMA store (full 128-byte lines) of fp32 Y
+//   warps 4-19  (16)  workers, phase A: 128-bit streaming loads of fp32 A straight into registers (8 rows x
+//                     512 B in flight per warp, software pipelined in two halves) -> integer bins -> A ring
+//                     in the UMMA K-major SW128 shared-memory layout               (a_full / a_empty)
+//   warp 0  (1 lane)  TMA: s8 weight tiles [BN rows x 128 k], SW128 -> W ring      (w_full / w_empty)
+//   warp 1  (1 lane)  tcgen05.mma  D[tmem] (+)= A[smem] * W[smem]^T, commit -> w_empty/a_empty/acc_full
+//   warp 2            TMEM allocation; (1 lane) TMA re-load of cached bins for N chunks >= 1 when K > 1024
+//   warps 4-11 (8)    workers, phase B (epilogue): tcgen05.ld -> zero-point correction, scales, bias ->
+//                     swizzled smem tile -> TMA store (full 128-byte lines) of fp32 Y
 //
 // When all of K fits in the A ring (K/128 <= 8: BERT-base 768, BART 1024) the converted A block stays
 // RESIDENT in shared memory and is reused for every N chunk: each activation element is read from HBM
@@ -25,37 +26,41 @@
 // element) to a caller-provided code cache that stays in L2; the remaining N chunks re-load the bins
 // by TMA directly in the UMMA layout -- fp32 A is still read from HBM exactly once.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
 namespace osq {
 
 constexpr int kBM = 128;            // rows of A per CTA tile (UMMA M)
-constexpr int kBNMax = 256;         // columns per accumulator stage (UMMA N)
+constexpr int kBNMax = 256;         // widest N chunk (UMMA N); the resident-A mode uses 128
 constexpr int kStageK = 128;        // k elements (= bytes, u8/s8) per smem stage row: one 128B swizzle row
 constexpr int kUmmaK = 32;          // k per tcgen05.mma kind::i8
 constexpr int kAStageBytes = kBM * kStageK;          // 16 KB
-constexpr int kWStageBytes = kBNMax * kStageK;       // 32 KB
-constexpr int kAccStages = 2;
-constexpr int kTmemCols = kAccStages * kBNMax;       // 512
-constexpr int kNumThreads = 512;
-constexpr int kConvWarp0 = 8, kNumConvWarps = 8;
-constexpr int kEpiWarp0 = 4, kNumEpiWarps = 4;
-constexpr int kRowsPerConvWarp = kBM / kNumConvWarps;  // 16
-constexpr int kHalf = kRowsPerConvWarp / 2;            // 8 rows per software-pipeline half
-constexpr int kOutTileBytes = 32 * 128;                // 32 rows x 32 fp32 columns, SW128
-constexpr int kMaxAStages = 8, kMaxWStages = 4;
+constexpr int kTmemCols = 512;                       // acc stages x BN: 4 x 128 or 2 x 256
+constexpr int kWorkerWarp0 = 4, kNumWorkers = 16;    // warps 4..19 convert A (phase A); warps 4..11 also run the epilogue
+constexpr int kNumEpiWarps = 8;                      // four TMEM lane quarters x two column halves of a chunk
+constexpr int kNumThreads = (kWorkerWarp0 + kNumWorkers) * 32;  // 640
+constexpr int kRowsPerWorker = kBM / kNumWorkers;    // 8
+constexpr int kOutTileBytes = 32 * 128;              // TMA-store staging tile: 32 rows x 32 fp32 columns, SW128
+constexpr int kMaxAStages = 8, kMaxWStages = 6, kMaxAccStages = 4;
 constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: fp32 ulp is 1 in [2^23, 2^24)
 
 struct FusedParams {
   int M, K, N;
-  int KB;          // K / 128
-  int NC;          // number of N chunks
-  int BN;          // chunk width (<= 256, multiple of 16)
+  int KB;             // K / 128
+  int NC;             // number of N chunks
+  int BN;             // chunk width: 128 (resident A) or 256 (streamed A), or N when N is smaller
+  int acc_stages;     // TMEM accumulator stages (512 / BN, at most 4)
   int n_mblocks;
+  int csz;            // thread-block cluster size (1, 2 or 4): the W stream is TMA-multicast across the cluster
+  int n_iters;        // tiles per CTA (identical for every CTA; out-of-range tiles are phantoms that only keep the W protocol alive)
+  int rows_per_tile;  // valid rows per CTA tile (<= 128, multiple of 16): chosen so the tile count fills all SMs
   int a_stages, w_stages, out_bufs;
-  int resident;    // converted A block stays in smem for all N chunks
-  int cached;      // streaming mode with a code cache: passes >= 1 TMA-load bins instead of re-converting
+  int w_stage_bytes;  // BN * 128
+  int resident;       // converted A block stays in smem for all N chunks
+  int cached;         // streaming mode with a code cache: passes >= 1 TMA-load bins instead of re-converting
   const float* A;
   const float* a_scale;
   const void* a_zp;
@@ -67,6 +72,8 @@ struct FusedParams {
   const float* bias;
   uint8_t* a_codes;  // optional [M, K]: bins side output / code cache
   uint32_t codes_box_bytes;  // bytes one code-cache TMA box delivers
+  int dbg;                   // profiling experiments (OSQ_FUSED_DBG): 1 = W tile pinned, 2 = no Y stores, 4 = A rows pinned
+  long long* trace;          // optional debug timeline: CTA 0 clock64 stamps [0,1024), per-CTA globaltimer start/end [1024, 1024+2*grid)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -79,6 +86,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -97,6 +107,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// same primitives on precomputed 32-bit shared addresses (the single-thread issue loops must stay lean:
+// their own instruction latency, not the tensor core, was the bottleneck with generic addressing)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast_u32(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -109,6 +155,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
@@ -149,6 +207,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// same, arriving on the barrier at this offset in every CTA of `mask` (W stages are filled by cluster multicast)
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -158,6 +223,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -207,28 +281,62 @@ __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, ui
   return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
+// four bins -> one packed word.  The fast path of the four elements is straight-line code (full ILP);
+// ONE branch per float4 sends the whole group through the exact path when any element is near a tie.
+__device__ __noinline__ uint32_t quant_bin4_exact(float x0, float x1, float x2, float x3, float s, float zc, float span) {
+  // exact path (true division), taken by ~0.1 % of the float4 groups: kept out of line so the unrolled
+  // conversion loop stays a few KB of straight-line code
+  float v0 = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(x0, s)), zc), 0.f), span);
+  float v1 = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(x1, s)), zc), 0.f), span);
+  float v2 = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(x2, s)), zc), 0.f), span);
+  float v3 = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(x3, s)), zc), 0.f), span);
+  return (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+}
+
+__device__ __forceinline__ uint32_t quant_bin4(const float4 x, const ConvParam& c) {
+  float u0 = fmaf(x.x, c.rinv, c.mz), u1 = fmaf(x.y, c.rinv, c.mz), u2 = fmaf(x.z, c.rinv, c.mz), u3 = fmaf(x.w, c.rinv, c.mz);
+  const float e0 = fmaf(x.x, c.rinv, -__fsub_rn(u0, c.mz)), e1 = fmaf(x.y, c.rinv, -__fsub_rn(u1, c.mz));
+  const float e2 = fmaf(x.z, c.rinv, -__fsub_rn(u2, c.mz)), e3 = fmaf(x.w, c.rinv, -__fsub_rn(u3, c.mz));
+  const float worst = fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fmaxf(fabsf(e2), fabsf(e3)));
+  const bool nan_in = (e0 != e0) | (e1 != e1) | (e2 != e2) | (e3 != e3);
+  if (!(worst <= 0.4999f) | nan_in) return quant_bin4_exact(x.x, x.y, x.z, x.w, c.s, c.zc, c.span);
+  u0 = fminf(fmaxf(u0, c.lo), c.hi); u1 = fminf(fmaxf(u1, c.lo), c.hi);
+  u2 = fminf(fmaxf(u2, c.lo), c.hi); u3 = fminf(fmaxf(u3, c.lo), c.hi);
+  return pack4(__float_as_uint(u0), __float_as_uint(u1), __float_as_uint(u2), __float_as_uint(u3));
+}
+
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#ifdef OSQ_ENABLE_TRACE
+#define OSQ_TRACE(slot) do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[(slot)] = clock64(); } while (0)
+#else
+#define OSQ_TRACE(slot) do { } while (0)
+#endif
+
 struct Smem {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
-  uint64_t acc_full[kAccStages], acc_empty[kAccStages];
-  uint64_t codes_ready;
+  uint64_t acc_full[kMaxAccStages], acc_empty[kMaxAccStages];
+  uint64_t codes_ready, passes_issued;
   uint32_t tmem_base;
   uint32_t pad;
-  alignas(16) float c1[kAccStages][kBNMax];      // s_a * w_scale[n]
-  alignas(16) int32_t zr[kAccStages][kBNMax];    // Zc * rowsum[n]
-  alignas(16) float bias[kAccStages][kBNMax];
+  uint32_t pad2[2];  // keeps sizeof(Smem) a multiple of 16: the per-column constants follow it
 };
+// after Smem: per-column epilogue constants of a chunk, double buffered by chunk parity (4 * BN floats):
+//   y = acc * c1[n] + c0[n],  c1 = s_a * w_scale[n],  c0 = bias[n] - Zc * rowsum[n] * c1
+static_assert(sizeof(Smem) % 16 == 0, "constants must stay 16-byte aligned");
 
 __global__ void __launch_bounds__(kNumThreads, 1)
 fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
                        const __grid_constant__ CUtensorMap tmap_codes, const FusedParams p) {
   // dynamic shared memory, 1024B aligned by the attribute (SWIZZLE_128B tiles need it):
-  // [A ring][W ring][out staging][Smem bookkeeping]
+  // [A ring][W ring][TMA-store staging tiles][Smem bookkeeping]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* a_ring = smem_raw;
   uint8_t* w_ring = a_ring + (size_t)p.a_stages * kAStageBytes;
-  uint8_t* o_ring = w_ring + (size_t)p.w_stages * kWStageBytes;
+  uint8_t* o_ring = w_ring + (size_t)p.w_stages * p.w_stage_bytes;
   Smem& sm = *reinterpret_cast<Smem*>(o_ring + (size_t)kNumEpiWarps * p.out_bufs * kOutTileBytes);
+  float* sm_c1 = reinterpret_cast<float*>(&sm + 1);  // [2][BN]
+  float* sm_c0 = sm_c1 + 2 * p.BN;                   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -239,137 +347,109 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     if (p.cached) tma_prefetch_desc(&tmap_codes);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&sm.a_full[i], kNumConvWarps); mbar_init(&sm.a_empty[i], 1); }
-    for (int i = 0; i < p.w_stages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps); }
-    mbar_init(&sm.codes_ready, kNumConvWarps);
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&sm.a_full[i], kNumWorkers); mbar_init(&sm.a_empty[i], 1); }
+    for (int i = 0; i < p.w_stages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], p.csz); }
+    for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps); }
+    mbar_init(&sm.codes_ready, kNumWorkers);
+    mbar_init(&sm.passes_issued, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&sm.tmem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (p.csz > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
+  const uint32_t crank = (p.csz > 1) ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << p.csz) - 1u);
+  if (threadIdx.x == 0) OSQ_TRACE(1020);
+  if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x] = gtimer();
 
-  const int n_my_blocks = (p.n_mblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_my_blocks = p.n_iters;
   const int a_passes = p.resident ? 1 : p.NC;  // how many times the A ring is filled per m-block
 
-  if (warp == 1) {
+  if (warp == 0) {
     // ===================== TMA producer: packed weight tiles =====================
     if (lane == 0) {
-      uint32_t pw = 0;
-      const uint32_t w_bytes = (uint32_t)p.BN * kStageK;
+      const uint32_t w_bytes = (uint32_t)p.w_stage_bytes;
+      const uint32_t w_base = smem_u32(w_ring), full0 = smem_u32(&sm.w_full[0]), empty0 = smem_u32(&sm.w_empty[0]);
+      const int slice = p.BN / p.csz;  // rows of the tile this CTA fetches (and multicasts when csz > 1)
+      uint32_t ws = 0, wph = 0;        // ring stage and its phase parity
       for (int it = 0; it < n_my_blocks; ++it)
         for (int nc = 0; nc < p.NC; ++nc)
-          for (int kb = 0; kb < p.KB; ++kb, ++pw) {
-            const int ws = pw % p.w_stages;
-            mbar_wait(&sm.w_empty[ws], ((pw / p.w_stages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&sm.w_full[ws], w_bytes);
-            tma_load_2d(w_ring + (size_t)ws * kWStageBytes, &tmap_w, &sm.w_full[ws], kb * kStageK, nc * p.BN);
+          for (int kb = 0; kb < p.KB; ++kb) {
+            mbar_wait_u32(empty0 + ws * 8, wph ^ 1);
+            mbar_arrive_expect_tx_u32(full0 + ws * 8, w_bytes);  // the whole stage: every CTA of the cluster delivers its slice
+            if (p.csz == 1)
+              tma_load_2d_u32(w_base + ws * w_bytes, &tmap_w, full0 + ws * 8, (p.dbg & 1) ? 0 : kb * kStageK, (p.dbg & 1) ? 0 : nc * p.BN);
+            else
+              tma_load_2d_mcast_u32(w_base + ws * w_bytes + crank * (uint32_t)(slice * kStageK), &tmap_w, full0 + ws * 8,
+                                    kb * kStageK, nc * p.BN + (int)crank * slice, cmask);
+            if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
           }
     }
-  } else if (warp == 2) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // One thread; everything it touches is a precomputed 32-bit shared address or a running counter --
+    // no divisions, no generic->shared conversions inside the loop.
     if (lane == 0) {
       const uint32_t idesc = make_idesc_i8(p.BN);
-      uint32_t cw = 0, cacc = 0;
+      const uint32_t a_base = smem_u32(a_ring), w_base = smem_u32(w_ring);
+      const uint32_t a_full0 = smem_u32(&sm.a_full[0]), a_empty0 = smem_u32(&sm.a_empty[0]);
+      const uint32_t w_full0 = smem_u32(&sm.w_full[0]), w_empty0 = smem_u32(&sm.w_empty[0]);
+      const uint32_t acc_full0 = smem_u32(&sm.acc_full[0]), acc_empty0 = smem_u32(&sm.acc_empty[0]);
+      const uint64_t desc_hi = make_smem_desc(0);  // everything but the 14-bit start address
+      const uint32_t w_bytes = (uint32_t)p.w_stage_bytes;
+      uint32_t ws = 0, wph = 0, as_ = 0, aph = 0, st_a = 0, sph_a = 0;
       for (int it = 0; it < n_my_blocks; ++it)
-        for (int nc = 0; nc < p.NC; ++nc, ++cacc) {
-          const int as_ = cacc & 1;
-          mbar_wait(&sm.acc_empty[as_], ((cacc >> 1) & 1) ^ 1);
+        for (int nc = 0; nc < p.NC; ++nc) {
+          mbar_wait_u32(acc_empty0 + as_ * 8, aph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)as_ * kBNMax;
-          for (int kb = 0; kb < p.KB; ++kb, ++cw) {
-            const uint32_t ca = p.resident ? (uint32_t)(it * p.KB + kb) : (uint32_t)((it * p.NC + nc) * p.KB + kb);
-            const int a_st = ca % p.a_stages;
-            const int ws = cw % p.w_stages;
-            mbar_wait(&sm.a_full[a_st], (ca / p.a_stages) & 1);
-            mbar_wait(&sm.w_full[ws], (cw / p.w_stages) & 1);
+          const uint32_t d_tmem = tmem_base + as_ * (uint32_t)p.BN;
+          if (p.resident) { st_a = 0; sph_a = (uint32_t)it & 1; }
+          const bool wait_a = !p.resident || nc == 0;         // resident A: filled once per m-block
+          const bool free_a = !p.resident || nc == p.NC - 1;  // ... and released after its last chunk
+          for (int kb = 0; kb < p.KB; ++kb) {
+            if (wait_a) mbar_wait_u32(a_full0 + st_a * 8, sph_a);
+            mbar_wait_u32(w_full0 + ws * 8, wph);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(a_ring + (size_t)a_st * kAStageBytes);
-            const uint32_t w_addr = smem_u32(w_ring + (size_t)ws * kWStageBytes);
+            const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)kAStageBytes) >> 4);
+            const uint64_t db = desc_hi | (uint64_t)((w_base + ws * w_bytes) >> 4);
 #pragma unroll
             for (int k = 0; k < kStageK / kUmmaK; ++k)
-              umma_i8(d_tmem, make_smem_desc(a_addr + k * kUmmaK), make_smem_desc(w_addr + k * kUmmaK), idesc,
-                      (kb | k) != 0);
-            umma_commit(&sm.w_empty[ws]);
-            if (!p.resident || nc == p.NC - 1) umma_commit(&sm.a_empty[a_st]);
+              umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
+            if (p.csz == 1) umma_commit_u32(w_empty0 + ws * 8); else umma_commit_mcast_u32(w_empty0 + ws * 8, cmask);
+            if (free_a) umma_commit_u32(a_empty0 + st_a * 8);
+            if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
+            if (++st_a == (uint32_t)p.a_stages) { st_a = 0; sph_a ^= 1; }
           }
-          umma_commit(&sm.acc_full[as_]);
+          umma_commit_u32(acc_full0 + as_ * 8);
+          if (++as_ == (uint32_t)p.acc_stages) { as_ = 0; aph ^= 1; }
         }
     }
-  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kNumEpiWarps) {
-    // ===================== epilogue =====================
-    const int wg = warp - kEpiWarp0;  // == warp % 4: TMEM lanes [32*wg, 32*wg+32)
-    const int et = threadIdx.x - kEpiWarp0 * 32;
-    const QParam qp = load_qparam(p.a_scale, p.a_zp, p.a_zp_is_int32, p.g, p.qmin, p.qmax, false);
-    const float s_a = qp.s;
-    const int zc = (int)(rintf(qp.z) - p.qmin);
-    uint8_t* my_out = o_ring + (size_t)wg * p.out_bufs * kOutTileBytes;
-    const uint32_t sw = ((uint32_t)lane & 7) << 4;  // 128B swizzle phase of this thread's staging row
-    uint32_t cacc = 0, n_stores = 0;
-    for (int it = 0; it < n_my_blocks; ++it) {
-      const int mb = blockIdx.x + it * gridDim.x;
-      const int row0 = mb * kBM + wg * 32;
-      for (int nc = 0; nc < p.NC; ++nc, ++cacc) {
-        const int as_ = cacc & 1;
-        const int n0 = nc * p.BN;
-        // stage the per-column constants of this chunk (double buffered with the accumulator stage)
-        for (int c = et; c < p.BN; c += kNumEpiWarps * 32) {
-          const int n = n0 + c;
-          const bool ok = n < p.N;
-          sm.c1[as_][c] = ok ? __fmul_rn(s_a, __ldg(p.w_scale + n)) : 0.f;
-          sm.zr[as_][c] = ok ? zc * __ldg(p.w_rowsum + n) : 0;
-          sm.bias[as_][c] = (ok && p.bias != nullptr) ? __ldg(p.bias + n) : 0.f;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
-        mbar_wait(&sm.acc_full[as_], (cacc >> 1) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(wg * 32) << 16) + (uint32_t)as_ * kBNMax;
-        for (int c0 = 0; c0 < p.BN && n0 + c0 < p.N; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld_wait();
-          // the staging tile must have been read out by its previous TMA store
-          if (n_stores >= (uint32_t)p.out_bufs) {
-            if (lane == 0) {
-              if (p.out_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-            }
-            __syncwarp();
+  } else if (warp == 2) {
+    // ===================== TMA producer: cached bins for N chunks >= 1 (K > 1024 only) =====================
+    if (lane == 0 && p.cached) {
+      for (int it = 0; it < n_my_blocks; ++it) {
+        const int mb = blockIdx.x + it * gridDim.x;
+        mbar_wait(&sm.codes_ready, it & 1);  // every worker has published this block's bins
+        for (int pass = 1; pass < a_passes; ++pass)
+          for (int kb = 0; kb < p.KB; ++kb) {
+            const uint32_t pa = (uint32_t)((it * p.NC + pass) * p.KB + kb);
+            const int a_st = pa % p.a_stages;
+            mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&sm.a_full[a_st], p.codes_box_bytes);
+            mbar_arrive_n(&sm.a_full[a_st], kNumWorkers - 1);  // a_full always counts kNumWorkers arrivals
+            tma_load_2d(a_ring + (size_t)a_st * kAStageBytes, &tmap_codes, &sm.a_full[a_st], kb * kStageK, mb * p.rows_per_tile);
           }
-          uint8_t* tile = my_out + (size_t)(n_stores % p.out_bufs) * kOutTileBytes;
-          uint8_t* trow = tile + lane * 128;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 c1 = *reinterpret_cast<const float4*>(&sm.c1[as_][c0 + j]);
-            const int4 zr = *reinterpret_cast<const int4*>(&sm.zr[as_][c0 + j]);
-            const float4 bi = *reinterpret_cast<const float4*>(&sm.bias[as_][c0 + j]);
-            float4 o;
-            o.x = fmaf((float)((int)v[j + 0] - zr.x), c1.x, bi.x);
-            o.y = fmaf((float)((int)v[j + 1] - zr.y), c1.y, bi.y);
-            o.z = fmaf((float)((int)v[j + 2] - zr.z), c1.z, bi.z);
-            o.w = fmaf((float)((int)v[j + 3] - zr.w), c1.w, bi.w);
-            *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ sw)) = o;  // chunk (j/4) ^ (row & 7)
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmap_y, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
-            tma_store_commit();
-          }
-          ++n_stores;
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.acc_empty[as_]);
+        mbar_arrive(&sm.passes_issued);  // workers may start filling the ring for the next m-block
       }
     }
-    if (lane == 0) tma_store_wait_all();
-  } else if (warp >= kConvWarp0) {
-    // ===================== A path: fp32 -> bins in the UMMA smem layout =====================
-    const int cw_ = warp - kConvWarp0;
+  } else if (warp >= kWorkerWarp0) {
+    // ===================== workers: A path (all 16) + epilogue (first 8) =====================
+    const int w = warp - kWorkerWarp0;
     const QParam qp = load_qparam(p.a_scale, p.a_zp, p.a_zp_is_int32, p.g, p.qmin, p.qmax,
-                                  blockIdx.x == 0 && cw_ == 0 && lane == 0);
+                                  blockIdx.x == 0 && w == 0 && lane == 0);
     ConvParam cp;
     cp.s = qp.s;
     cp.rinv = __frcp_rn(qp.s);
@@ -378,101 +458,170 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     cp.mz = kMagic + cp.zc;
     cp.lo = kMagic;
     cp.hi = kMagic + cp.span;
-    const int r_base = cw_ * kRowsPerConvWarp;  // this warp's 16 rows of the 128-row block
-    // byte offset of this lane's 4 bins inside a swizzled 128 B stage row (before the row term)
-    const uint32_t lane_chunk = (uint32_t)lane >> 2, lane_in = ((uint32_t)lane & 3) << 2;
+    const int r_base = w * kRowsPerWorker;  // this warp's 8 rows of the 128-row block
+    const uint32_t lc16 = ((uint32_t)lane >> 2) << 4, lane_in = ((uint32_t)lane & 3) << 2;
+    uint32_t cacc = 0, n_stores = 0;
 
-    float4 xa[kHalf], xb[kHalf];
-    auto load_half = [&](float4* x, int mb, int kb, int half) {
-      const float* base = p.A + (size_t)kb * kStageK + lane * 4;
+    float4 x[kRowsPerWorker];
+    // one conversion pass over all k-blocks of m-block `mb`; ring positions start at pa0.
+    // Row i of the next k-block is re-issued right after row i of the current one is consumed, so every
+    // register stays in flight for a whole iteration (iteration time = max(latency, convert), not the sum).
+    // All addressing is strength-reduced to one base pointer per array + compile-time row offsets.
+    auto convert_pass = [&](int mb, uint32_t pa0) {
+      const int row_first = mb * p.rows_per_tile + r_base;
+      const int nvalid = (r_base < p.rows_per_tile) ? min(kRowsPerWorker, p.M - row_first) : 0;  // warp uniform
+      const size_t rs = (size_t)p.K;
+      const float* aptr = p.A + ((p.dbg & 4) ? (size_t)0 : (size_t)row_first * rs) + lane * 4;
+      uint8_t* cptr = (p.a_codes != nullptr) ? p.a_codes + (size_t)row_first * rs + lane * 4 : nullptr;
+      const bool full = nvalid == kRowsPerWorker;
+      if (full) {
 #pragma unroll
-      for (int i = 0; i < kHalf; ++i) {
-        const int grow = mb * kBM + r_base + half * kHalf + i;
-        x[i] = (grow < p.M) ? ldg_stream(reinterpret_cast<const float4*>(base + (size_t)grow * p.K))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < kRowsPerWorker; ++i) x[i] = ldg_stream(reinterpret_cast<const float4*>(aptr + i * rs));
       }
-    };
-    auto convert_half = [&](const float4* x, uint8_t* a_tile, int mb, int kb, int half) {
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const uint32_t pa = pa0 + kb;
+        const int a_st = pa % p.a_stages;
+        mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
+        uint8_t* st = a_ring + (size_t)a_st * kAStageBytes + r_base * kStageK + lane_in;
+        if (full) {
+          const bool more = kb + 1 < p.KB;
+          const float* nxt = aptr + (size_t)(kb + 1) * kStageK;
 #pragma unroll
-      for (int i = 0; i < kHalf; ++i) {
-        const int r = r_base + half * kHalf + i;
-        const uint32_t word = pack4(quant_bin(x[i].x, cp), quant_bin(x[i].y, cp), quant_bin(x[i].z, cp), quant_bin(x[i].w, cp));
-        const uint32_t off = (uint32_t)r * kStageK + ((lane_chunk ^ ((uint32_t)r & 7)) << 4) + lane_in;
-        *reinterpret_cast<uint32_t*>(a_tile + off) = word;
-        if (p.a_codes != nullptr) {
-          const int grow = mb * kBM + r;
-          if (grow < p.M) *reinterpret_cast<uint32_t*>(p.a_codes + (size_t)grow * p.K + kb * kStageK + lane * 4) = word;
-        }
-      }
-    };
-
-    uint32_t pa = 0;
-    if (n_my_blocks > 0) {
-      load_half(xa, blockIdx.x, 0, 0);
-      load_half(xb, blockIdx.x, 0, 1);
-    }
-    for (int it = 0; it < n_my_blocks; ++it) {
-      const int mb = blockIdx.x + it * gridDim.x;
-      for (int pass = 0; pass < a_passes; ++pass) {
-        if (pass == 0 || !p.cached) {
-          // ---- conversion pass: registers -> bins -> smem (next k-block's loads are issued in between) ----
-          for (int kb = 0; kb < p.KB; ++kb, ++pa) {
-            const int a_st = pa % p.a_stages;
-            mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
-            uint8_t* a_tile = a_ring + (size_t)a_st * kAStageBytes;
-            // what to prefetch next: the following k-block of this pass, the first of the next
-            // conversion pass, or the first k-block of this CTA's next m-block
-            int nmb = mb, nkb = kb + 1;
-            bool more = true;
-            if (nkb == p.KB) {
-              nkb = 0;
-              const bool next_pass_converts = (pass + 1 < a_passes) && !p.cached;
-              if (!next_pass_converts) { nmb = mb + gridDim.x; more = (it + 1 < n_my_blocks); }
-            }
-            convert_half(xa, a_tile, mb, kb, 0);
-            if (more) load_half(xa, nmb, nkb, 0);
-            convert_half(xb, a_tile, mb, kb, 1);
-            if (more) load_half(xb, nmb, nkb, 1);
-            fence_proxy_async_smem();  // generic-proxy smem stores -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.a_full[a_st]);
-          }
-          if (p.cached && pass == 0) {
-            // bins of this m-block are in the code cache: publish them to the async proxy (TMA) of this CTA
-            __threadfence();
-            fence_proxy_async_all();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.codes_ready);
+          for (int i = 0; i < kRowsPerWorker; ++i) {  // r & 7 == i & 7 because r_base is a multiple of 8
+            const uint32_t word = quant_bin4(x[i], cp);
+            if (more) x[i] = ldg_stream(reinterpret_cast<const float4*>(nxt + i * rs));
+            *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
+            if (cptr != nullptr) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word;
           }
         } else {
-          // ---- cached pass: bins come back from the (L2 resident) code cache by TMA, already in UMMA layout ----
-          if (pass == 1) mbar_wait(&sm.codes_ready, it & 1);
-          for (int kb = 0; kb < p.KB; ++kb, ++pa) {
-            const int a_st = pa % p.a_stages;
-            // every warp paces itself on a_empty so that at most one arrival per warp lands in a phase
-            mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
-            if (lane == 0) {
-              if (cw_ == 0) {
-                mbar_arrive_expect_tx(&sm.a_full[a_st], p.codes_box_bytes);
-                tma_load_2d(a_ring + (size_t)a_st * kAStageBytes, &tmap_codes, &sm.a_full[a_st], kb * kStageK, mb * kBM);
-              } else {
-                mbar_arrive(&sm.a_full[a_st]);  // keeps the arrival count of a_full uniform across pass kinds
-              }
-            }
-            __syncwarp();
+          // ragged tail of the last tile (or a warp past rows_per_tile): simple predicated path
+#pragma unroll 1
+          for (int i = 0; i < kRowsPerWorker; ++i) {
+            const bool ok = i < nvalid;
+            const float4 v = ok ? ldg_stream(reinterpret_cast<const float4*>(aptr + i * rs + (size_t)kb * kStageK))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t word = quant_bin4(v, cp);
+            *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
+            if (ok && cptr != nullptr) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word;
           }
         }
+        fence_proxy_async_smem();  // generic-proxy smem stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.a_full[a_st]);
+        if (w == 0 && lane == 0 && pa < 250) OSQ_TRACE(pa);
+      }
+    };
+
+    // ---- epilogue (workers 0..7): TMEM -> registers (thread = row) -> y = acc*c1 + c0 -> swizzled staging
+    //      tile -> TMA store.  The TMA unit writes full 128-byte lines and bypasses the (1 KB) L1.
+    const int q = w & 3;                 // TMEM lane quarter (= warp % 4, a hardware rule)
+    const int half = w >> 2;             // column half of the chunk (epilogue warps only: 0 or 1)
+    const float s_a = qp.s;
+    const float zcf = cp.zc;
+    uint8_t* my_tiles = o_ring + (size_t)w * p.out_bufs * kOutTileBytes;
+    const uint32_t sw = ((uint32_t)lane & 7) << 4;  // 128B swizzle phase of this thread's staging row
+    const int et = threadIdx.x - kWorkerWarp0 * 32;  // 0..255 among the epilogue threads
+    auto stage_consts = [&](int nc) {  // per-column constants of chunk nc -> smem buffer nc & 1
+      const int buf = nc & 1;
+      for (int c = et; c < p.BN; c += kNumEpiWarps * 32) {
+        const int n = nc * p.BN + c;
+        float c1 = 0.f, c0 = 0.f;
+        if (n < p.N) {
+          c1 = __fmul_rn(s_a, __ldg(p.w_scale + n));
+          const float b = (p.bias != nullptr) ? __ldg(p.bias + n) : 0.f;
+          c0 = fmaf(-zcf * (float)__ldg(p.w_rowsum + n), c1, b);
+        }
+        sm_c1[buf * p.BN + c] = c1;
+        sm_c0[buf * p.BN + c] = c0;
+      }
+    };
+    auto epilogue_chunk = [&](int mb, int nc) {
+      const int as_ = cacc % p.acc_stages;
+      const int buf = nc & 1;
+      const int n0 = nc * p.BN;
+      if (nc + 1 < p.NC) stage_consts(nc + 1);  // next chunk's constants: their L2 latency hides under this chunk
+      mbar_wait(&sm.acc_full[as_], (cacc / p.acc_stages) & 1);
+      tc_fence_after();
+      if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as_ * p.BN);
+      const int row0 = mb * p.rows_per_tile + q * 32;
+      const int cols_per_half = p.BN >> 1;
+      const int c_end = min(min((half + 1) * cols_per_half, p.BN), p.N - n0);
+      const bool any_rows = (q * 32 < p.rows_per_tile) && (row0 < p.M);
+      for (int c0 = half * cols_per_half; c0 < c_end; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (!any_rows) continue;  // warp uniform: phantom tile / quarter past the tile's rows
+        if (n_stores >= (uint32_t)p.out_bufs) {  // the staging tile must have been read out by its previous TMA store
+          if (lane == 0) { if (p.out_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          __syncwarp();
+        }
+        uint8_t* tile = my_tiles + (size_t)(n_stores % p.out_bufs) * kOutTileBytes;
+        uint8_t* trow = tile + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 c1 = *reinterpret_cast<const float4*>(sm_c1 + buf * p.BN + c0 + j);
+          const float4 k0 = *reinterpret_cast<const float4*>(sm_c0 + buf * p.BN + c0 + j);
+          float4 o;
+          o.x = fmaf((float)(int)v[j + 0], c1.x, k0.x);
+          o.y = fmaf((float)(int)v[j + 1], c1.y, k0.y);
+          o.z = fmaf((float)(int)v[j + 2], c1.z, k0.z);
+          o.w = fmaf((float)(int)v[j + 3], c1.w, k0.w);
+          *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ sw)) = o;  // 16B chunk (j/4) ^ (row & 7): conflict free
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(p.dbg & 2)) {
+          tma_store_2d(&tmap_y, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
+          tma_store_commit();
+        }
+        ++n_stores;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.acc_empty[as_]);
+      // constants of chunk nc+1 are complete in smem before any epilogue warp starts reading them
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+      if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4 + 1);
+      ++cacc;
+    };
+
+    for (int it = 0; it < n_my_blocks; ++it) {
+      const int mb = blockIdx.x + it * gridDim.x;
+      const uint32_t pa_block = (uint32_t)it * (uint32_t)(a_passes * p.KB);
+      // cached mode: the TMA thread must have issued every re-load pass of the previous block before this
+      // warp runs ahead on the same ring (two producers may never be more than one ring cycle apart)
+      if (p.cached && it > 0) mbar_wait(&sm.passes_issued, (it - 1) & 1);
+      if (w < kNumEpiWarps) stage_consts(0);
+      convert_pass(mb, pa_block);
+      if (p.cached) {
+        // bins of this m-block are in the code cache: publish them to the async proxy (TMA) of this CTA
+        __threadfence();
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.codes_ready);
+      }
+      if (w < kNumEpiWarps) asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");  // chunk 0 constants staged
+      for (int nc = 0; nc < p.NC; ++nc) {
+        // no code cache and K too large for residency: re-convert A for the next N chunk first
+        if (!p.resident && !p.cached && nc + 1 < p.NC) convert_pass(mb, pa_block + (uint32_t)(nc + 1) * p.KB);
+        if (w < kNumEpiWarps) epilogue_chunk(mb, nc);
       }
     }
+    if (w < kNumEpiWarps && lane == 0) tma_store_wait_all();
+    if (w == 0 && lane == 0) OSQ_TRACE(1021);
   }
 
   // ===================== teardown =====================
   tc_fence_before();
   __syncthreads();
+  if (p.csz > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x + 1] = gtimer();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -590,41 +739,63 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   }
 
   FusedParams p;
+  memset(&p, 0, sizeof(p));
   p.M = (int)a->M; p.K = (int)a->K; p.N = (int)a->N;
   p.KB = p.K / kStageK;
-  p.BN = p.N < kBNMax ? p.N : kBNMax;
+  // shared-memory plan (227 KB / CTA): [A ring][W ring][TMA-store staging: 8 warps x out_bufs x 4 KB][bookkeeping]
+  const int out1 = kNumEpiWarps * kOutTileBytes;  // 32 KB per buffer set
+  int budget = 227 * 1024 - (int)sizeof(Smem) - 16 * 128;  // barriers + constants of a 128-column chunk
+  // resident A (K <= 1024): 128-column chunks, 16 KB W stages, four TMEM accumulator stages
+  p.resident = (p.KB <= kMaxAStages && p.KB * kAStageBytes + 4 * (128 * kStageK) + out1 <= budget) ? 1 : 0;
+  const int bn_pref = p.resident ? 128 : 256;
+  p.BN = p.N < bn_pref ? p.N : bn_pref;
   p.NC = (p.N + p.BN - 1) / p.BN;
-  p.n_mblocks = (p.M + kBM - 1) / kBM;
-  // shared-memory plan (227 KB / CTA): [A ring][W ring][out staging][bookkeeping]
-  const int budget = 227 * 1024 - (int)sizeof(Smem);
-  const int out1 = kNumEpiWarps * kOutTileBytes;  // one 4 KB staging tile per epilogue warp
-  if (p.KB <= kMaxAStages && p.KB * kAStageBytes + 2 * kWStageBytes + out1 <= budget) {
-    p.resident = 1;
-    p.a_stages = p.KB;
-  } else {
-    p.resident = 0;
-    p.a_stages = 4;
-  }
+  p.acc_stages = kTmemCols / p.BN;
+  if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
+  const int const_bytes = 4 * p.BN * (int)sizeof(float);
+  budget = 227 * 1024 - (int)sizeof(Smem) - const_bytes;
+  p.w_stage_bytes = p.BN * kStageK;
+  if (p.w_stage_bytes % 1024 != 0) p.w_stage_bytes = (p.w_stage_bytes + 1023) / 1024 * 1024;
+  p.a_stages = p.resident ? p.KB : 4;
   p.cached = (!p.resident && p.NC > 1 && a->a_codes != nullptr) ? 1 : 0;
-  int rest = budget - p.a_stages * kAStageBytes - 2 * kWStageBytes - out1;
+  int rest = budget - p.a_stages * kAStageBytes - 2 * p.w_stage_bytes - out1;
   p.w_stages = 2;
   p.out_bufs = 1;
-  if (rest >= out1) { p.out_bufs = 2; rest -= out1; }
-  while (p.w_stages < kMaxWStages && rest >= kWStageBytes) { ++p.w_stages; rest -= kWStageBytes; }
+  static int env_ob = -1;
+  if (env_ob < 0) { const char* e = getenv("OSQ_FUSED_OUTBUFS"); env_ob = e ? atoi(e) : 0; }
+  if (env_ob != 1 && rest >= out1 + 2 * p.w_stage_bytes) { p.out_bufs = 2; rest -= out1; }  // double-buffered stores once W has 4 stages
+  while (p.w_stages < 4 && rest >= p.w_stage_bytes) { ++p.w_stages; rest -= p.w_stage_bytes; }
+  if (env_ob != 1 && p.out_bufs == 1 && rest >= out1) { p.out_bufs = 2; rest -= out1; }
+  while (p.w_stages < kMaxWStages && rest >= p.w_stage_bytes) { ++p.w_stages; rest -= p.w_stage_bytes; }
   if (!p.resident)
     while (p.a_stages < kMaxAStages && rest >= kAStageBytes) { ++p.a_stages; rest -= kAStageBytes; }
-  const size_t smem_bytes = (size_t)p.a_stages * kAStageBytes + (size_t)p.w_stages * kWStageBytes +
-                            (size_t)p.out_bufs * out1 + sizeof(Smem);
+  const size_t smem_bytes = (size_t)p.a_stages * kAStageBytes + (size_t)p.w_stages * p.w_stage_bytes +
+                            (size_t)p.out_bufs * out1 + sizeof(Smem) + (size_t)const_bytes;
+
+  // cluster size: the W stream is identical for every CTA, so it can be multicast across a thread-block cluster
+  // (each CTA fetches 1/csz of every tile); measured neutral on B200 (L2 already merges the requests) -> default 1
+  static int env_csz = -1;
+  if (env_csz < 0) {
+    const char* e = getenv("OSQ_FUSED_CLUSTER");
+    env_csz = e ? atoi(e) : 0;
+  }
+  p.csz = env_csz > 0 ? env_csz : 1;
+  if (p.csz != 1 && p.csz != 2 && p.csz != 4) p.csz = 1;
+  while (p.csz > 1 && (p.BN % (8 * p.csz) != 0 || (p.M + kBM - 1) / kBM < p.csz)) p.csz >>= 1;
 
   p.A = a->A;
   p.a_scale = a->a_scale; p.a_zp = a->a_zp; p.a_zp_is_int32 = a->a_zp_is_int32; p.g = a->lsq_grad_factor;
   p.qmin = (float)a->a_qmin; p.qmax = (float)a->a_qmax;
   p.w_scale = a->w_scale; p.w_rowsum = a->w_rowsum; p.bias = a->bias; p.a_codes = a->a_codes;
-  p.codes_box_bytes = (uint32_t)(p.M < kBM ? p.M : kBM) * kStageK;
+  p.trace = (long long*)a->debug_trace;
+  {
+    const char* e = getenv("OSQ_FUSED_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
 
   CUtensorMap map_w, map_y, map_c;
   if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->w_codes, (uint64_t)p.K, (uint64_t)p.N, kStageK,
-                           (uint32_t)p.BN, CU_TENSOR_MAP_SWIZZLE_128B))
+                           (uint32_t)(p.BN / p.csz), CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
   if (int rc = make_map_2d(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
                            p.M < 32 ? (uint32_t)p.M : 32u, CU_TENSOR_MAP_SWIZZLE_128B))
@@ -642,8 +813,49 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  int grid = p.n_mblocks < sms ? p.n_mblocks : sms;
-  fused_fq_linear_kernel<<<grid, kNumThreads, smem_bytes, (cudaStream_t)stream>>>(map_w, map_y, map_c, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.csz;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // how many CTAs can be co-resident (1 CTA / SM; clusters of 4 cannot use every SM)
+  static int max_ctas[64][5] = {{0}};
+  if (max_ctas[dev & 63][p.csz] == 0) {
+    int n_clusters = 0;
+    cfg.gridDim = dim3((unsigned)(sms / p.csz * p.csz));
+    if (p.csz > 1) {
+      OSQ_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, fused_fq_linear_kernel, &cfg));
+      max_ctas[dev & 63][p.csz] = n_clusters * p.csz;
+    } else {
+      max_ctas[dev & 63][p.csz] = sms;
+    }
+    if (max_ctas[dev & 63][p.csz] <= 0) { set_error("osq_fused_fq_linear: no resident cluster of %d CTAs", p.csz); return OSQ_ECUDA; }
+  }
+  const int G = max_ctas[dev & 63][p.csz];
+  // rows per CTA tile: the 128-row MMA tile is filled with as many rows as make the tile count a multiple of
+  // the resident CTA count (M = 16384 on 148 SMs: 147 tiles of 112 rows instead of 128 tiles of 128 rows)
+  {
+    const int64_t waves = (p.M + (int64_t)kBM * G - 1) / ((int64_t)kBM * G);
+    int64_t rpt = (p.M + waves * G - 1) / (waves * G);
+    rpt = (rpt + 15) / 16 * 16;
+    if (rpt > kBM) rpt = kBM;
+    if (rpt < 16) rpt = 16;
+    p.rows_per_tile = (int)rpt;
+  }
+  p.n_mblocks = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
+  int grid = p.n_mblocks < G ? p.n_mblocks : G;
+  grid = (grid + p.csz - 1) / p.csz * p.csz;
+  p.n_iters = (p.n_mblocks + grid - 1) / grid;
+  p.codes_box_bytes = (uint32_t)(p.M < kBM ? p.M : kBM) * kStageK;
+  cfg.gridDim = dim3((unsigned)grid);
+  OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel, map_w, map_y, map_c, p));
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

@@ -311,7 +311,7 @@ def fused_linear_supported(k: int, n: int) -> bool:
 
 
 def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum, bias, lsq_grad_factor=0.0,
-                    mma_kind=0, want_codes=False, out=None, use_code_cache=True):
+                    mma_kind=0, want_codes=False, out=None, use_code_cache=True, trace=None):
     """activation fq + weight fq + Linear in one tcgen05 kernel. a: [..., K] fp32 -> [..., N] fp32."""
     _require_cuda(a, a_scale, a_zp, w_codes, w_scale, w_rowsum, bias)
     if a.dtype != torch.float32:
@@ -336,6 +336,7 @@ def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum
     args.Y, args.N = y.data_ptr(), n
     args.mma_kind = int(mma_kind)
     args.a_codes = _ptr(dbg)
+    args.debug_trace = _ptr(trace)
     if m > 0:
         check(_lib.load().osq_fused_fq_linear(C.byref(args), _stream()), "osq_fused_fq_linear")
     y = y.reshape(*a.shape[:-1], n)
