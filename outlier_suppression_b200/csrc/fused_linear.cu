@@ -40,7 +40,7 @@ constexpr int kUmmaK = 32;          // k per tcgen05.mma kind::i8
 constexpr int kAStageBytes = kBM * kStageK;          // 16 KB
 constexpr int kTmemCols = 512;                       // acc stages x BN: 4 x 128 or 2 x 256
 constexpr int kWorkerWarp0 = 4, kNumWorkers = 16;    // warps 4..19 convert A (phase A); warps 4..11 also run the epilogue
-constexpr int kNumEpiWarps = 8;                      // four TMEM lane quarters x two column halves of a chunk
+constexpr int kNumEpiWarps = 8;                      // workers 0..7: four TMEM lane quarters x two column halves of a chunk
 constexpr int kNumThreads = (kWorkerWarp0 + kNumWorkers) * 32;  // 640
 constexpr int kRowsPerWorker = kBM / kNumWorkers;    // 8
 constexpr int kOutTileBytes = 32 * 128;              // TMA-store staging tile: 32 rows x 32 fp32 columns, SW128
@@ -72,6 +72,7 @@ struct FusedParams {
   const float* bias;
   uint8_t* a_codes;  // optional [M, K]: bins side output / code cache
   uint32_t codes_box_bytes;  // bytes one code-cache TMA box delivers
+  int pdl;                   // launched with programmatic stream serialization
   int dbg;                   // profiling experiments (OSQ_FUSED_DBG): 1 = W tile pinned, 2 = no Y stores, 4 = A rows pinned
   long long* trace;          // optional debug timeline: CTA 0 clock64 stamps [0,1024), per-CTA globaltimer start/end [1024, 1024+2*grid)
 };
@@ -143,6 +144,10 @@ __device__ __forceinline__ void tma_load_2d_mcast_u32(uint32_t smem_dst, const C
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// programmatic dependent launch: let the next kernel of the stream start its prologue / weight stream
+// while this one drains, and order this kernel's first dependent access after the previous grid
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -306,6 +311,32 @@ __device__ __forceinline__ uint32_t quant_bin4(const float4 x, const ConvParam& 
 }
 
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// two rows at once: 8 independent fast-path chains and ONE branch (the conversion loop is bound by
+// fixed-latency dependencies, so instruction-level parallelism is what buys throughput)
+__device__ __forceinline__ void quant_bin4x2(const float4 a, const float4 b, const ConvParam& c, uint32_t& wa, uint32_t& wb) {
+  float u0 = fmaf(a.x, c.rinv, c.mz), u1 = fmaf(a.y, c.rinv, c.mz), u2 = fmaf(a.z, c.rinv, c.mz), u3 = fmaf(a.w, c.rinv, c.mz);
+  float v0 = fmaf(b.x, c.rinv, c.mz), v1 = fmaf(b.y, c.rinv, c.mz), v2 = fmaf(b.z, c.rinv, c.mz), v3 = fmaf(b.w, c.rinv, c.mz);
+  const float e0 = fmaf(a.x, c.rinv, -__fsub_rn(u0, c.mz)), e1 = fmaf(a.y, c.rinv, -__fsub_rn(u1, c.mz));
+  const float e2 = fmaf(a.z, c.rinv, -__fsub_rn(u2, c.mz)), e3 = fmaf(a.w, c.rinv, -__fsub_rn(u3, c.mz));
+  const float f0 = fmaf(b.x, c.rinv, -__fsub_rn(v0, c.mz)), f1 = fmaf(b.y, c.rinv, -__fsub_rn(v1, c.mz));
+  const float f2 = fmaf(b.z, c.rinv, -__fsub_rn(v2, c.mz)), f3 = fmaf(b.w, c.rinv, -__fsub_rn(v3, c.mz));
+  // NaN-safe: !(x <= t) is true for NaN residuals
+  const float worst = fmaxf(fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fmaxf(fabsf(e2), fabsf(e3))),
+                            fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(f2), fabsf(f3))));
+  const float nan_probe = ((e0 + e1) + (e2 + e3)) + ((f0 + f1) + (f2 + f3));  // NaN if any residual is NaN (fmaxf drops NaNs)
+  if (!(worst <= 0.4999f) | (nan_probe != nan_probe)) {
+    wa = quant_bin4_exact(a.x, a.y, a.z, a.w, c.s, c.zc, c.span);
+    wb = quant_bin4_exact(b.x, b.y, b.z, b.w, c.s, c.zc, c.span);
+    return;
+  }
+  u0 = fminf(fmaxf(u0, c.lo), c.hi); u1 = fminf(fmaxf(u1, c.lo), c.hi);
+  u2 = fminf(fmaxf(u2, c.lo), c.hi); u3 = fminf(fmaxf(u3, c.lo), c.hi);
+  v0 = fminf(fmaxf(v0, c.lo), c.hi); v1 = fminf(fmaxf(v1, c.lo), c.hi);
+  v2 = fminf(fmaxf(v2, c.lo), c.hi); v3 = fminf(fmaxf(v3, c.lo), c.hi);
+  wa = pack4(__float_as_uint(u0), __float_as_uint(u1), __float_as_uint(u2), __float_as_uint(u3));
+  wb = pack4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+}
+
 #ifdef OSQ_ENABLE_TRACE
 #define OSQ_TRACE(slot) do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[(slot)] = clock64(); } while (0)
 #else
@@ -321,13 +352,14 @@ struct Smem {
   uint32_t pad;
   uint32_t pad2[2];  // keeps sizeof(Smem) a multiple of 16: the per-column constants follow it
 };
-// after Smem: per-column epilogue constants of a chunk, double buffered by chunk parity (4 * BN floats):
+// after Smem: per-column epilogue constants of the current chunk (2 * BN floats):
 //   y = acc * c1[n] + c0[n],  c1 = s_a * w_scale[n],  c0 = bias[n] - Zc * rowsum[n] * c1
 static_assert(sizeof(Smem) % 16 == 0, "constants must stay 16-byte aligned");
 
 __global__ void __launch_bounds__(kNumThreads, 1)
 fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
-                       const __grid_constant__ CUtensorMap tmap_codes, const FusedParams p) {
+                       const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,
+                       const FusedParams p) {
   // dynamic shared memory, 1024B aligned by the attribute (SWIZZLE_128B tiles need it):
   // [A ring][W ring][TMA-store staging tiles][Smem bookkeeping]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -335,8 +367,8 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   uint8_t* w_ring = a_ring + (size_t)p.a_stages * kAStageBytes;
   uint8_t* o_ring = w_ring + (size_t)p.w_stages * p.w_stage_bytes;
   Smem& sm = *reinterpret_cast<Smem*>(o_ring + (size_t)kNumEpiWarps * p.out_bufs * kOutTileBytes);
-  float* sm_c1 = reinterpret_cast<float*>(&sm + 1);  // [2][BN]
-  float* sm_c0 = sm_c1 + 2 * p.BN;                   // [2][BN]
+  float* sm_c1 = reinterpret_cast<float*>(&sm + 1);  // [BN]
+  float* sm_c0 = sm_c1 + p.BN;                       // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -344,6 +376,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_y);
+    tma_prefetch_desc(&tmap_y16);
     if (p.cached) tma_prefetch_desc(&tmap_codes);
   }
   if (warp == 1 && lane == 0) {
@@ -366,11 +399,15 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x] = gtimer();
 
   const int n_my_blocks = p.n_iters;
+  if (p.pdl && threadIdx.x == 0) pdl_launch_dependents();
   const int a_passes = p.resident ? 1 : p.NC;  // how many times the A ring is filled per m-block
 
   if (warp == 0) {
     // ===================== TMA producer: packed weight tiles =====================
     if (lane == 0) {
+      // the packed weights may have been written by the kernel right before this one (first call after a
+      // re-pack): like every other global access they are ordered after the previous grid
+      if (p.pdl) pdl_wait_prior_grids();
       const uint32_t w_bytes = (uint32_t)p.w_stage_bytes;
       const uint32_t w_base = smem_u32(w_ring), full0 = smem_u32(&sm.w_full[0]), empty0 = smem_u32(&sm.w_empty[0]);
       const int slice = p.BN / p.csz;  // rows of the tile this CTA fetches (and multicasts when csz > 1)
@@ -385,6 +422,9 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
             else
               tma_load_2d_mcast_u32(w_base + ws * w_bytes + crank * (uint32_t)(slice * kStageK), &tmap_w, full0 + ws * 8,
                                     kb * kStageK, nc * p.BN + (int)crank * slice, cmask);
+#ifdef OSQ_ENABLE_TRACE
+            { const int ps = (it * p.NC + nc) * p.KB + kb; if (ps >= 36 && ps < 76) OSQ_TRACE(1600 + ps - 36); }
+#endif
             if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
           }
     }
@@ -411,7 +451,14 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
           const bool free_a = !p.resident || nc == p.NC - 1;  // ... and released after its last chunk
           for (int kb = 0; kb < p.KB; ++kb) {
             if (wait_a) mbar_wait_u32(a_full0 + st_a * 8, sph_a);
+#ifdef OSQ_ENABLE_TRACE
+            const int tslot = (it * p.NC + nc) * p.KB + kb;
+            if (tslot >= 36 && tslot < 72) OSQ_TRACE(1400 + 3 * (tslot - 36));
+#endif
             mbar_wait_u32(w_full0 + ws * 8, wph);
+#ifdef OSQ_ENABLE_TRACE
+            if (tslot >= 36 && tslot < 72) OSQ_TRACE(1401 + 3 * (tslot - 36));
+#endif
             tc_fence_after();
             const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)kAStageBytes) >> 4);
             const uint64_t db = desc_hi | (uint64_t)((w_base + ws * w_bytes) >> 4);
@@ -420,6 +467,9 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
               umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
             if (p.csz == 1) umma_commit_u32(w_empty0 + ws * 8); else umma_commit_mcast_u32(w_empty0 + ws * 8, cmask);
             if (free_a) umma_commit_u32(a_empty0 + st_a * 8);
+#ifdef OSQ_ENABLE_TRACE
+            if (tslot >= 36 && tslot < 72) OSQ_TRACE(1402 + 3 * (tslot - 36));
+#endif
             if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
             if (++st_a == (uint32_t)p.a_stages) { st_a = 0; sph_a ^= 1; }
           }
@@ -430,6 +480,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   } else if (warp == 2) {
     // ===================== TMA producer: cached bins for N chunks >= 1 (K > 1024 only) =====================
     if (lane == 0 && p.cached) {
+      if (p.pdl) pdl_wait_prior_grids();
       for (int it = 0; it < n_my_blocks; ++it) {
         const int mb = blockIdx.x + it * gridDim.x;
         mbar_wait(&sm.codes_ready, it & 1);  // every worker has published this block's bins
@@ -448,6 +499,9 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   } else if (warp >= kWorkerWarp0) {
     // ===================== workers: A path (all 16) + epilogue (first 8) =====================
     const int w = warp - kWorkerWarp0;
+    // A, the quantisation parameters, Y and the code cache may be produced / still be read by the previous
+    // kernel of the stream: every global access is ordered after it; only the prologue above overlaps
+    if (p.pdl) pdl_wait_prior_grids();
     const QParam qp = load_qparam(p.a_scale, p.a_zp, p.a_zp_is_int32, p.g, p.qmin, p.qmax,
                                   blockIdx.x == 0 && w == 0 && lane == 0);
     ConvParam cp;
@@ -481,17 +535,25 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       for (int kb = 0; kb < p.KB; ++kb) {
         const uint32_t pa = pa0 + kb;
         const int a_st = pa % p.a_stages;
-        mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
+        if (pa >= (uint32_t)p.a_stages) mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);  // first fill: ring is empty
         uint8_t* st = a_ring + (size_t)a_st * kAStageBytes + r_base * kStageK + lane_in;
         if (full) {
           const bool more = kb + 1 < p.KB;
           const float* nxt = aptr + (size_t)(kb + 1) * kStageK;
 #pragma unroll
-          for (int i = 0; i < kRowsPerWorker; ++i) {  // r & 7 == i & 7 because r_base is a multiple of 8
-            const uint32_t word = quant_bin4(x[i], cp);
-            if (more) x[i] = ldg_stream(reinterpret_cast<const float4*>(nxt + i * rs));
-            *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
-            if (cptr != nullptr) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word;
+          for (int i = 0; i < kRowsPerWorker; i += 2) {  // r & 7 == i & 7 because r_base is a multiple of 8
+            uint32_t w0, w1;
+            quant_bin4x2(x[i], x[i + 1], cp, w0, w1);
+            if (more) {
+              x[i] = ldg_stream(reinterpret_cast<const float4*>(nxt + i * rs));
+              x[i + 1] = ldg_stream(reinterpret_cast<const float4*>(nxt + (i + 1) * rs));
+            }
+            *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = w0;
+            *reinterpret_cast<uint32_t*>(st + (i + 1) * kStageK + (lc16 ^ (uint32_t)(((i + 1) & 7) << 4))) = w1;
+            if (cptr != nullptr) {
+              *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = w0;
+              *reinterpret_cast<uint32_t*>(cptr + (i + 1) * rs + (size_t)kb * kStageK) = w1;
+            }
           }
         } else {
           // ragged tail of the last tile (or a warp past rows_per_tile): simple predicated path
@@ -515,40 +577,47 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     // ---- epilogue (workers 0..7): TMEM -> registers (thread = row) -> y = acc*c1 + c0 -> swizzled staging
     //      tile -> TMA store.  The TMA unit writes full 128-byte lines and bypasses the (1 KB) L1.
     const int q = w & 3;                 // TMEM lane quarter (= warp % 4, a hardware rule)
-    const int half = w >> 2;             // column half of the chunk (epilogue warps only: 0 or 1)
+    const int slice = w >> 2;            // column slice of the chunk (epilogue warps: 0 or 1)
     const float s_a = qp.s;
     const float zcf = cp.zc;
     uint8_t* my_tiles = o_ring + (size_t)w * p.out_bufs * kOutTileBytes;
     const uint32_t sw = ((uint32_t)lane & 7) << 4;  // 128B swizzle phase of this thread's staging row
     const int et = threadIdx.x - kWorkerWarp0 * 32;  // 0..255 among the epilogue threads
-    auto stage_consts = [&](int nc) {  // per-column constants of chunk nc -> smem buffer nc & 1
-      const int buf = nc & 1;
-      for (int c = et; c < p.BN; c += kNumEpiWarps * 32) {
-        const int n = nc * p.BN + c;
-        float c1 = 0.f, c0 = 0.f;
-        if (n < p.N) {
-          c1 = __fmul_rn(s_a, __ldg(p.w_scale + n));
-          const float b = (p.bias != nullptr) ? __ldg(p.bias + n) : 0.f;
-          c0 = fmaf(-zcf * (float)__ldg(p.w_rowsum + n), c1, b);
-        }
-        sm_c1[buf * p.BN + c] = c1;
-        sm_c0[buf * p.BN + c] = c0;
+    // per-column constants: each epilogue thread owns column `et` of the chunk (BN <= 256 = epilogue threads);
+    // they are fetched into registers early (L2 latency hides under the previous chunk) and published to
+    // shared memory between two barriers
+    float pc1 = 0.f, pc0 = 0.f;
+    auto fetch_consts = [&](int nc) {
+      const int n = nc * p.BN + et;
+      pc1 = 0.f; pc0 = 0.f;
+      if (et < p.BN && n < p.N) {
+        pc1 = __fmul_rn(s_a, __ldg(p.w_scale + n));
+        const float b = (p.bias != nullptr) ? __ldg(p.bias + n) : 0.f;
+        pc0 = fmaf(-zcf * (float)__ldg(p.w_rowsum + n), pc1, b);
       }
+    };
+    auto publish_consts = [&]() {  // all epilogue warps; previous chunk's readers are done (barrier before)
+      if (et < p.BN) { sm_c1[et] = pc1; sm_c0[et] = pc0; }
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
     };
     auto epilogue_chunk = [&](int mb, int nc) {
       const int as_ = cacc % p.acc_stages;
-      const int buf = nc & 1;
       const int n0 = nc * p.BN;
-      if (nc + 1 < p.NC) stage_consts(nc + 1);  // next chunk's constants: their L2 latency hides under this chunk
+      if (nc + 1 < p.NC) fetch_consts(nc + 1);
       mbar_wait(&sm.acc_full[as_], (cacc / p.acc_stages) & 1);
       tc_fence_after();
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as_ * p.BN);
       const int row0 = mb * p.rows_per_tile + q * 32;
-      const int cols_per_half = p.BN >> 1;
-      const int c_end = min(min((half + 1) * cols_per_half, p.BN), p.N - n0);
-      const bool any_rows = (q * 32 < p.rows_per_tile) && (row0 < p.M);
-      for (int c0 = half * cols_per_half; c0 < c_end; c0 += 32) {
+      const int cols_per_slice = ((p.BN + 1) >> 1) + 31 & ~31;  // 128 for BN = 256; smaller BN: the second slice may stay idle
+      const int c_lo = slice * cols_per_slice;
+      const int c_end = min(min(c_lo + cols_per_slice, p.BN), p.N - n0);
+      // rows_per_tile is a multiple of 16: the tile's last lane quarter may own only 16 rows, which go out
+      // through the 16-row box so that the neighbouring tile's rows are never touched
+      const int rows_q = min(32, p.rows_per_tile - q * 32);
+      const bool any_rows = (rows_q > 0) && (row0 < p.M);
+      const CUtensorMap* ymap = (rows_q == 32) ? &tmap_y : &tmap_y16;
+      for (int c0 = c_lo; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
@@ -561,8 +630,8 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         uint8_t* trow = tile + lane * 128;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 c1 = *reinterpret_cast<const float4*>(sm_c1 + buf * p.BN + c0 + j);
-          const float4 k0 = *reinterpret_cast<const float4*>(sm_c0 + buf * p.BN + c0 + j);
+          const float4 c1 = *reinterpret_cast<const float4*>(sm_c1 + c0 + j);
+          const float4 k0 = *reinterpret_cast<const float4*>(sm_c0 + c0 + j);
           float4 o;
           o.x = fmaf((float)(int)v[j + 0], c1.x, k0.x);
           o.y = fmaf((float)(int)v[j + 1], c1.y, k0.y);
@@ -573,7 +642,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.dbg & 2)) {
-          tma_store_2d(&tmap_y, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
+          tma_store_2d(ymap, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
           tma_store_commit();
         }
         ++n_stores;
@@ -581,10 +650,10 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.acc_empty[as_]);
-      // constants of chunk nc+1 are complete in smem before any epilogue warp starts reading them
-      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4 + 1);
       ++cacc;
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");  // every reader of this chunk's constants is done
+      if (nc + 1 < p.NC) publish_consts();
     };
 
     for (int it = 0; it < n_my_blocks; ++it) {
@@ -593,7 +662,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       // cached mode: the TMA thread must have issued every re-load pass of the previous block before this
       // warp runs ahead on the same ring (two producers may never be more than one ring cycle apart)
       if (p.cached && it > 0) mbar_wait(&sm.passes_issued, (it - 1) & 1);
-      if (w < kNumEpiWarps) stage_consts(0);
+      if (w < kNumEpiWarps) fetch_consts(0);
       convert_pass(mb, pa_block);
       if (p.cached) {
         // bins of this m-block are in the code cache: publish them to the async proxy (TMA) of this CTA
@@ -602,7 +671,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.codes_ready);
       }
-      if (w < kNumEpiWarps) asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");  // chunk 0 constants staged
+      if (w < kNumEpiWarps) publish_consts();  // chunk 0 constants
       for (int nc = 0; nc < p.NC; ++nc) {
         // no code cache and K too large for residency: re-convert A for the next N chunk first
         if (!p.resident && !p.cached && nc + 1 < p.NC) convert_pass(mb, pa_block + (uint32_t)(nc + 1) * p.KB);
@@ -744,15 +813,15 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   p.KB = p.K / kStageK;
   // shared-memory plan (227 KB / CTA): [A ring][W ring][TMA-store staging: 8 warps x out_bufs x 4 KB][bookkeeping]
   const int out1 = kNumEpiWarps * kOutTileBytes;  // 32 KB per buffer set
-  int budget = 227 * 1024 - (int)sizeof(Smem) - 16 * 128;  // barriers + constants of a 128-column chunk
+  int budget = 227 * 1024 - (int)sizeof(Smem) - 8 * 256;  // barriers + constants of a 256-column chunk
   // resident A (K <= 1024): 128-column chunks, 16 KB W stages, four TMEM accumulator stages
-  p.resident = (p.KB <= kMaxAStages && p.KB * kAStageBytes + 4 * (128 * kStageK) + out1 <= budget) ? 1 : 0;
-  const int bn_pref = p.resident ? 128 : 256;
+  p.resident = (p.KB <= kMaxAStages && p.KB * kAStageBytes + 2 * (256 * kStageK) + out1 <= budget) ? 1 : 0;
+  const int bn_pref = 256;  // SS-mode kind::i8 MMAs read A and B from shared memory: N = 256 halves the A re-reads per MAC
   p.BN = p.N < bn_pref ? p.N : bn_pref;
   p.NC = (p.N + p.BN - 1) / p.BN;
   p.acc_stages = kTmemCols / p.BN;
   if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
-  const int const_bytes = 4 * p.BN * (int)sizeof(float);
+  const int const_bytes = 2 * p.BN * (int)sizeof(float);
   budget = 227 * 1024 - (int)sizeof(Smem) - const_bytes;
   p.w_stage_bytes = p.BN * kStageK;
   if (p.w_stage_bytes % 1024 != 0) p.w_stage_bytes = (p.w_stage_bytes + 1023) / 1024 * 1024;
@@ -763,8 +832,10 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   p.out_bufs = 1;
   static int env_ob = -1;
   if (env_ob < 0) { const char* e = getenv("OSQ_FUSED_OUTBUFS"); env_ob = e ? atoi(e) : 0; }
-  if (env_ob != 1 && rest >= out1 + 2 * p.w_stage_bytes) { p.out_bufs = 2; rest -= out1; }  // double-buffered stores once W has 4 stages
-  while (p.w_stages < 4 && rest >= p.w_stage_bytes) { ++p.w_stages; rest -= p.w_stage_bytes; }
+  // the W stream needs ~2.5 stages of 32 KB in flight to cover the L2 latency at the chunk rate the epilogue
+  // sustains; a third stage therefore comes before double-buffered stores
+  if (env_ob == 2 && rest >= out1) { p.out_bufs = 2; rest -= out1; }  // experiment: stores before W depth
+  if (rest >= p.w_stage_bytes) { ++p.w_stages; rest -= p.w_stage_bytes; }
   if (env_ob != 1 && p.out_bufs == 1 && rest >= out1) { p.out_bufs = 2; rest -= out1; }
   while (p.w_stages < kMaxWStages && rest >= p.w_stage_bytes) { ++p.w_stages; rest -= p.w_stage_bytes; }
   if (!p.resident)
@@ -793,12 +864,15 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
     p.dbg = e ? atoi(e) : 0;
   }
 
-  CUtensorMap map_w, map_y, map_c;
+  CUtensorMap map_w, map_y, map_y16, map_c;
   if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->w_codes, (uint64_t)p.K, (uint64_t)p.N, kStageK,
                            (uint32_t)(p.BN / p.csz), CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
   if (int rc = make_map_2d(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
                            p.M < 32 ? (uint32_t)p.M : 32u, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
+  if (int rc = make_map_2d(&map_y16, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
+                           p.M < 16 ? (uint32_t)p.M : 16u, CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
   if (p.cached) {
     if (int rc = make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->a_codes, (uint64_t)p.K, (uint64_t)p.M, kStageK,
@@ -818,13 +892,18 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  static int env_pdl = -1;
+  if (env_pdl < 0) { const char* e = getenv("OSQ_FUSED_PDL"); env_pdl = e ? atoi(e) : 1; }
+  p.pdl = env_pdl ? 1 : 0;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)p.csz;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = p.pdl ? 2 : 1;
   // how many CTAs can be co-resident (1 CTA / SM; clusters of 4 cannot use every SM)
   static int max_ctas[64][5] = {{0}};
   if (max_ctas[dev & 63][p.csz] == 0) {
@@ -855,7 +934,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   p.n_iters = (p.n_mblocks + grid - 1) / grid;
   p.codes_box_bytes = (uint32_t)(p.M < kBM ? p.M : kBM) * kStageK;
   cfg.gridDim = dim3((unsigned)grid);
-  OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel, map_w, map_y, map_c, p));
+  OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel, map_w, map_y, map_y16, map_c, p));
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

@@ -32,8 +32,8 @@ for K, N in SHAPES:
     g0 = min(st)
     print("ctas=%d start spread %.1f us; end min/median/max %.1f/%.1f/%.1f us after first start; cta0 %.1f..%.1f" % (len(st), (max(st) - g0) / 1e3, (min(en) - g0) / 1e3, (sorted(en)[len(en) // 2] - g0) / 1e3, (max(en) - g0) / 1e3, (st[0] - g0) / 1e3, (en[0] - g0) / 1e3))
     print("conv a_full arrivals:", [rel(v) for v in t[0:256] if v][:40])
-    print("wprod issues [36:72]:", [rel(v) for v in t[1636:1672] if v])
-    print("mma operands ready [36:72]:", [rel(v) for v in t[1436:1472] if v])
+    print("wprod issue times, uses 36..75:", [rel(v) for v in t[1600:1640] if v])
+    print("mma per k-block uses 36..71 (a ready, w ready, issued):", [tuple(rel(t[1400 + 3 * i + k]) for k in range(3)) for i in range(36) if t[1400 + 3 * i]])
     print("mma  (start, first operands, commit issued):", [(rel(t[256 + 4 * i]), rel(t[257 + 4 * i]), rel(t[258 + 4 * i])) for i in range(60) if t[256 + 4 * i]][:14])
     print("epi group detail (ld issue, ld done, sts+sync done, consts ready, stores issued):", [rel(t[900 + i]) for i in range(5)])
     print("epi  (acc_full acquired, chunk done):", [(rel(t[512 + 4 * i]), rel(t[513 + 4 * i])) for i in range(60) if t[512 + 4 * i]][:14])
