@@ -310,9 +310,19 @@ def main():
         per_site[name] = {"K": k, "N": n, "us": ms * 1e3, "bytes": by, "gbs": by / (ms * 1e-3) / 1e9, "frac": by / (ms * 1e-3) / 1e9 / peak}
         mult = LAYERS
         tot_bytes += by * mult; tot_ms += ms * mult; n_launch += mult
+    # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/*_traffic.json), launch-weighted
+    traffic = None
+    try:
+        import glob
+        tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+        if tf:
+            t = json.load(open(tf[-1]))
+            traffic = sum(t[name] for name, *_ in SITES) / len(SITES)
+    except Exception:
+        traffic = None
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fused_fq_linear_kernel (kind::i8)", "bytes_per_launch_avg": tot_bytes / n_launch,
+                "traffic": traffic, "kernel": "fused_fq_linear_kernel (kind::i8)", "bytes_per_launch_avg": tot_bytes / n_launch,
                 "us_per_launch_avg": tot_ms * 1e3 / n_launch, "sites": per_site}
 
     # ---- e2e: module-level API, batch from pinned host memory, result read back to the host ----

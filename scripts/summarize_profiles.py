@@ -1,0 +1,66 @@
+"""Turns the raw ncu artefacts of a gpurun call (gpurun_out/) into the tracked summaries under profiles/.
+
+    python scripts/summarize_profiles.py r01
+
+  profiles/<round>_launches.md     per-kernel launch count / total device time / share (ncu --metrics gpu__time_duration.sum)
+  profiles/<round>_fused_full.md   key metrics of the `ncu --set full` capture of the fused kernel, per launch
+  profiles/<round>_traffic.json    DRAM bytes per launch per site shape (read by bench.py for roofline.traffic)
+  profiles/<round>_bench.json      the bench line of the same call
+"""
+import collections, csv, json, os, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(PROF, exist_ok=True)
+
+# ---- launch list
+rows = [r for r in csv.reader(open(os.path.join(OUT, "launches.csv"))) if len(r) > 10]
+hdr = rows[0]; ci = {h: i for i, h in enumerate(hdr)}
+agg = collections.OrderedDict()
+for r in rows[1:]:
+    try:
+        v = float(r[ci["Metric Value"]])
+    except ValueError:
+        continue
+    name = r[ci["Kernel Name"]].split("(")[0]
+    key = (name, r[ci["Grid Size"]], r[ci["Block Size"]])
+    a = agg.setdefault(key, [0, 0.0, 1e30, 0.0])
+    a[0] += 1; a[1] += v; a[2] = min(a[2], v); a[3] = max(a[3], v)
+tot = sum(a[1] for a in agg.values())
+with open(os.path.join(PROF, tag + "_launches.md"), "w") as f:
+    f.write("# %s: ncu launch list of `bench.py --steps 2 --warmup 3 --only-value` (-k regex:osq, --clock-control none)\n\n" % tag)
+    f.write("Per-launch times are cold-cache and serialised by ncu: compare SHARES, not absolutes.\n\n")
+    f.write("| kernel | grid | block | launches | total us | min us | max us | share |\n|---|---|---|---|---|---|---|---|\n")
+    for (name, grid, block), a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write("| %s | %s | %s | %d | %.1f | %.1f | %.1f | %.1f %% |\n" % (name, grid, block, a[0], a[1] / 1e3, a[2] / 1e3, a[3] / 1e3, 100 * a[1] / tot))
+print(open(os.path.join(PROF, tag + "_launches.md")).read())
+
+# ---- full capture
+rep = os.path.join(OUT, "prof_fused.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr = rows[0]; units = rows[1]; body = rows[2:]
+keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum"]
+idx = {k: hdr.index(k) for k in keys if k in hdr}
+traffic = {}
+with open(os.path.join(PROF, tag + "_fused_full.md"), "w") as f:
+    f.write("# %s: `ncu --set full --clock-control none --import-source on -k regex:fused_fq_linear` (6 launches of one encoder layer)\n\n" % tag)
+    f.write("| metric | unit | " + " | ".join("launch %d" % i for i in range(len(body))) + " |\n|---|---|" + "---|" * len(body) + "\n")
+    for k, i in idx.items():
+        f.write("| %s | %s | %s |\n" % (k, units[i], " | ".join(r[i] for r in body)))
+    f.write("\nLaunch order inside a layer: q, k, v, attn_out (768->768), ffn_up (768->3072), ffn_down (3072->768); the capture starts at a layer boundary.\n")
+names = ["q", "k", "v", "attn_out", "ffn_up", "ffn_down"]
+for j, r in enumerate(body[:6]):
+    rd, wr = float(r[idx["dram__bytes_read.sum"]]), float(r[idx["dram__bytes_write.sum"]])
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    traffic[names[j]] = rd * scale[units[idx["dram__bytes_read.sum"]]] + wr * scale[units[idx["dram__bytes_write.sum"]]]
+json.dump(traffic, open(os.path.join(PROF, tag + "_traffic.json"), "w"), indent=1)
+print(open(os.path.join(PROF, tag + "_fused_full.md")).read())
+if os.path.exists(os.path.join(OUT, "bench.json")):
+    open(os.path.join(PROF, tag + "_bench.json"), "w").write(open(os.path.join(OUT, "bench.json")).read())
