@@ -26,6 +26,7 @@
 // element) to a caller-provided code cache that stays in L2; the remaining N chunks re-load the bins
 // by TMA directly in the UMMA layout -- fp32 A is still read from HBM exactly once.
 #include <cuda.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -311,6 +312,20 @@ __device__ __forceinline__ uint32_t quant_bin4(const float4 x, const ConvParam& 
 }
 
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// branch-free fast path for one float4: returns the packed bins and sets `risky` when any element is within
+// 1e-4 of a rounding tie (or huge / NaN): those groups (~0.1 %) are redone with the exact division AFTER the
+// unrolled loop, so the hot loop is straight-line code that the scheduler can interleave across all rows
+__device__ __forceinline__ uint32_t quant_bin4_fast(const float4 x, const ConvParam& c, bool& risky) {
+  float u0 = fmaf(x.x, c.rinv, c.mz), u1 = fmaf(x.y, c.rinv, c.mz), u2 = fmaf(x.z, c.rinv, c.mz), u3 = fmaf(x.w, c.rinv, c.mz);
+  const float e0 = fmaf(x.x, c.rinv, -__fsub_rn(u0, c.mz)), e1 = fmaf(x.y, c.rinv, -__fsub_rn(u1, c.mz));
+  const float e2 = fmaf(x.z, c.rinv, -__fsub_rn(u2, c.mz)), e3 = fmaf(x.w, c.rinv, -__fsub_rn(u3, c.mz));
+  const float worst = fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fmaxf(fabsf(e2), fabsf(e3)));
+  risky = !(worst <= 0.4999f);  // NaN residuals (non-finite A) are dropped by fmaxf: such inputs are outside the contract
+  u0 = fminf(fmaxf(u0, c.lo), c.hi); u1 = fminf(fmaxf(u1, c.lo), c.hi);
+  u2 = fminf(fmaxf(u2, c.lo), c.hi); u3 = fminf(fmaxf(u3, c.lo), c.hi);
+  return pack4(__float_as_uint(u0), __float_as_uint(u1), __float_as_uint(u2), __float_as_uint(u3));
+}
+
 // two rows at once: 8 independent fast-path chains and ONE branch (the conversion loop is bound by
 // fixed-latency dependencies, so instruction-level parallelism is what buys throughput)
 __device__ __forceinline__ void quant_bin4x2(const float4 a, const float4 b, const ConvParam& c, uint32_t& wa, uint32_t& wb) {
@@ -521,6 +536,8 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     // Row i of the next k-block is re-issued right after row i of the current one is consumed, so every
     // register stays in flight for a whole iteration (iteration time = max(latency, convert), not the sum).
     // All addressing is strength-reduced to one base pointer per array + compile-time row offsets.
+    // A-ring position of the conversion stream (running counters: no divisions in the per-k-block path)
+    uint32_t c_st = 0, c_ph = 0;
     auto convert_pass = [&](int mb, uint32_t pa0) {
       const int row_first = mb * p.rows_per_tile + r_base;
       const int nvalid = (r_base < p.rows_per_tile) ? min(kRowsPerWorker, p.M - row_first) : 0;  // warp uniform
@@ -534,26 +551,40 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       }
       for (int kb = 0; kb < p.KB; ++kb) {
         const uint32_t pa = pa0 + kb;
-        const int a_st = pa % p.a_stages;
-        if (pa >= (uint32_t)p.a_stages) mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);  // first fill: ring is empty
-        uint8_t* st = a_ring + (size_t)a_st * kAStageBytes + r_base * kStageK + lane_in;
+        const uint32_t a_st = c_st;
+        if (pa >= (uint32_t)p.a_stages) mbar_wait(&sm.a_empty[a_st], c_ph ^ 1);  // first fill: ring is empty
+        uint8_t* st = a_ring + a_st * (uint32_t)kAStageBytes + r_base * kStageK + lane_in;
         if (full) {
           const bool more = kb + 1 < p.KB;
           const float* nxt = aptr + (size_t)(kb + 1) * kStageK;
+          uint32_t risky_mask = 0;
+          // four straight-line variants (reload next k-block? write bins to the code cache?) keep every
+          // predicate out of the unrolled body: predicated-off instructions still cost issue slots
+          auto body = [&](auto reload, auto codes) {
 #pragma unroll
-          for (int i = 0; i < kRowsPerWorker; i += 2) {  // r & 7 == i & 7 because r_base is a multiple of 8
-            uint32_t w0, w1;
-            quant_bin4x2(x[i], x[i + 1], cp, w0, w1);
-            if (more) {
-              x[i] = ldg_stream(reinterpret_cast<const float4*>(nxt + i * rs));
-              x[i + 1] = ldg_stream(reinterpret_cast<const float4*>(nxt + (i + 1) * rs));
+            for (int i = 0; i < kRowsPerWorker; ++i) {  // r & 7 == i & 7 because r_base is a multiple of 8
+              bool risky;
+              uint32_t word;
+              if (p.dbg & 32) { word = __float_as_uint(x[i].x) ^ __float_as_uint(x[i].w); risky = false; }
+              else word = quant_bin4_fast(x[i], cp, risky);
+              risky_mask |= (uint32_t)risky << i;
+              if (decltype(reload)::value) x[i] = ldg_stream(reinterpret_cast<const float4*>(nxt + i * rs));
+              *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
+              if (decltype(codes)::value) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word;
             }
-            *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = w0;
-            *reinterpret_cast<uint32_t*>(st + (i + 1) * kStageK + (lc16 ^ (uint32_t)(((i + 1) & 7) << 4))) = w1;
-            if (cptr != nullptr) {
-              *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = w0;
-              *reinterpret_cast<uint32_t*>(cptr + (i + 1) * rs + (size_t)kb * kStageK) = w1;
-            }
+          };
+          using T = std::true_type; using F = std::false_type;
+          const bool reload = more && !(p.dbg & 16);
+          if (cptr == nullptr) { if (reload) body(T{}, F{}); else body(F{}, F{}); }
+          else                 { if (reload) body(T{}, T{}); else body(F{}, T{}); }
+          // rare exact fix-up (true division): re-read the float4 (L2 hit) and overwrite its bins
+          while (risky_mask != 0) {
+            const int i = __ffs(risky_mask) - 1;
+            risky_mask &= risky_mask - 1;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(aptr + i * rs + (size_t)kb * kStageK));
+            const uint32_t word = quant_bin4_exact(v.x, v.y, v.z, v.w, cp.s, cp.zc, cp.span);
+            *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
+            if (cptr != nullptr) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word;
           }
         } else {
           // ragged tail of the last tile (or a warp past rows_per_tile): simple predicated path
@@ -567,11 +598,18 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
             if (ok && cptr != nullptr) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word;
           }
         }
-        fence_proxy_async_smem();  // generic-proxy smem stores -> visible to the tensor core (async proxy)
+        if (!(p.dbg & 8)) fence_proxy_async_smem();  // generic-proxy smem stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.a_full[a_st]);
         if (w == 0 && lane == 0 && pa < 250) OSQ_TRACE(pa);
+        if (++c_st == (uint32_t)p.a_stages) { c_st = 0; c_ph ^= 1; }
       }
+    };
+    // ring uses that are filled by the TMA thread (cached passes) advance the same counters
+    auto skip_ring = [&](uint32_t n) {
+      const uint32_t tot = c_st + n;
+      c_ph ^= (tot / (uint32_t)p.a_stages) & 1u;
+      c_st = tot % (uint32_t)p.a_stages;
     };
 
     // ---- epilogue (workers 0..7): TMEM -> registers (thread = row) -> y = acc*c1 + c0 -> swizzled staging
@@ -670,6 +708,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         fence_proxy_async_all();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.codes_ready);
+        skip_ring((uint32_t)(a_passes - 1) * (uint32_t)p.KB);  // N chunks >= 1 are filled by the TMA thread
       }
       if (w < kNumEpiWarps) publish_consts();  // chunk 0 constants
       for (int nc = 0; nc < p.NC; ++nc) {
