@@ -119,6 +119,13 @@ int osq_prune_select_f32(const float* tmin, const float* tmax, const float* abs_
                          float percentile, float* cur_minmax, const osq_stat_epilogue_t* epi,
                          void* workspace, void* stream);
 
+/* K4b' the same selection without any sort: the two order statistics torch.quantile interpolates between are
+ *      found by an exact radix select on the fp32 bit patterns of |tmax| / |tmin| (one CTA, one launch);
+ *      bit-identical to osq_prune_select_f32 on sorted inputs.  No workspace needed. */
+int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t n_slots,
+                                  const int32_t* n_valid, float percentile, float* cur_minmax,
+                                  const osq_stat_epilogue_t* epi, void* stream);
+
 /* per-row min/max of a [rows, cols] matrix with the running-extrema update of
  * MinMaxObserver(ch_axis=0) (observer.py:141-144) and per-row calculate_qparams.
  * state_min/state_max [rows] are updated in place (first = 1 overwrites them). */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libosq_b200.so")
 EXPORTS = [
     "osq_version", "osq_last_error", "osq_sm_count", "osq_workspace_bytes",
     "osq_fq_per_tensor_f32", "osq_fq_per_channel_f32",
-    "osq_minmax_masked_f32", "osq_minmax_flat_f32", "osq_token_minmax_f32", "osq_prune_select_f32",
+    "osq_minmax_masked_f32", "osq_minmax_flat_f32", "osq_token_minmax_f32", "osq_prune_select_f32", "osq_prune_select_unsorted_f32",
     "osq_rowwise_minmax_qparams_f32", "osq_calc_qparams_f32",
     "osq_mse_multi_f32", "osq_mse_brent_rows_f32",
     "osq_pack_weight_s8", "osq_fused_fq_linear", "osq_lsqplus_backward_f32",
@@ -64,6 +64,7 @@ def _declare(lib):
         "osq_minmax_flat_f32": [vp, i64, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_token_minmax_f32": [vp, C.POINTER(Tokens), vp, i32, vp, vp, vp, vp],
         "osq_prune_select_f32": [vp, vp, vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp, vp],
+        "osq_prune_select_unsorted_f32": [vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp],
         "osq_rowwise_minmax_qparams_f32": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp],
         "osq_calc_qparams_f32": [vp, vp, i64, i32, i32, i32, vp, vp, vp, vp],
         "osq_mse_multi_f32": [vp, C.POINTER(Tokens), vp, i32, vp, vp, i32, i32, i32, vp, vp, vp],

@@ -265,6 +265,145 @@ prune_select_kernel(const float* __restrict__ tmin, const float* __restrict__ tm
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4b': the same selection WITHOUT a sort: exact order statistics of |tmax| and |tmin| by an 8-bit-per-pass
+// radix select on the fp32 bit patterns (monotone for non-negative floats), one CTA, one launch.
+// Replaces two torch.abs + two torch.sort (>= 10 launches) of the first version.
+// ---------------------------------------------------------------------------------------------
+// single-CTA sweep over a small vector with 8 independent loads in flight per thread (the [T] vectors live in L2;
+// with one dependent load per iteration every pass would cost 64 L2 round trips)
+template <class F>
+__device__ __forceinline__ void sweep8(const float* __restrict__ v, int64_t n, F&& f) {
+  const int64_t stride = blockDim.x;
+  for (int64_t base = threadIdx.x; base < n; base += stride * 8) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (base + j * stride < n) ? __ldg(v + base + j * stride) : __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f(x[j], base + j * stride < n);
+  }
+}
+
+struct SelectScratch {
+  unsigned int hist[256];
+  unsigned int prefix, k_rem;
+  float fmin_above;
+  unsigned int cnt_le;
+};
+
+// value of rank k (0-based, ascending) of {|v[i]|}; also the value of rank k+1 (needed by the lerp)
+template <bool kIsMax>
+__device__ void select_two(const float* __restrict__ v, int64_t n, int k, int n_valid, SelectScratch& sc, float& a, float& b) {
+  unsigned int prefix = 0, mask = 0, krem = (unsigned int)k;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sc.hist[i] = 0;
+    __syncthreads();
+    sweep8(v, n, [&](float xv, bool ok) {
+      const unsigned int u = __float_as_uint(fabsf(xv));
+      const bool in = ok && (u & mask) == prefix;
+      // warp-aggregated histogram update: lanes with the same digit elect one leader (the leading digits of
+      // fp32 magnitudes are nearly constant, a plain atomicAdd would serialise the whole warp on one bin)
+      const unsigned int digit = in ? ((u >> (8 * pass)) & 255u) : 256u;
+      const unsigned int peers = __match_any_sync(__activemask(), digit);
+      if (in && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sc.hist[digit], (unsigned int)__popc(peers));
+    });
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int acc = 0, bin = 0;
+      for (; bin < 256; ++bin) {
+        if (acc + sc.hist[bin] > krem) break;
+        acc += sc.hist[bin];
+      }
+      sc.prefix = prefix | (bin << (8 * pass));
+      sc.k_rem = krem - acc;
+    }
+    __syncthreads();
+    prefix = sc.prefix;
+    krem = sc.k_rem;
+    mask |= 0xFFu << (8 * pass);
+    __syncthreads();
+  }
+  a = __uint_as_float(prefix);
+  // rank k+1: a again if it has duplicates beyond rank k, else the smallest value above a
+  if (threadIdx.x == 0) { sc.cnt_le = 0; sc.fmin_above = INFINITY; }
+  __syncthreads();
+  unsigned int cnt = 0;
+  float above = INFINITY;
+  sweep8(v, n, [&](float xv, bool ok) {
+    const float x = fabsf(xv);
+    if (ok) { if (x <= a) ++cnt; else above = fminf(above, x); }
+  });
+  above = warp_min(above);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sc.cnt_le, cnt);
+    atomicMin(reinterpret_cast<unsigned int*>(&sc.fmin_above), __float_as_uint(above));  // non-negative floats order like uints
+  }
+  __syncthreads();
+  b = (sc.cnt_le >= (unsigned int)k + 2u || k + 1 >= n_valid) ? a : sc.fmin_above;
+  __syncthreads();
+}
+
+__device__ __forceinline__ float quantile_from_pair(float a, float b, float rank, int lo) {
+  const float w = __fsub_rn(rank, (float)lo);
+  const float d = __fsub_rn(b, a);
+  return (w < 0.5f) ? fmaf(w, d, a) : fmaf(-d, __fsub_rn(1.f, w), b);
+}
+
+__global__ void __launch_bounds__(1024)
+prune_select_unsorted_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
+                             const int32_t* __restrict__ n_valid, float percentile, float* __restrict__ cur,
+                             osq_stat_epilogue_t epi) {
+  __shared__ SelectScratch sc;
+  __shared__ float smn[32], smx[32];
+  const int T = *n_valid;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float lower = INFINITY, upper = -INFINITY;
+  if (T > 0) {
+    // torch.quantile: rank = p * (T - 1) in fp32, below = trunc(rank), above = ceil(rank), lerp
+    const float rank = __fmul_rn(percentile, (float)(T - 1));
+    const int lo = (int)rank;
+    const bool need_pair = (int)ceilf(rank) != lo;
+    float a, b;
+    select_two<true>(tmax, n_slots, lo, T, sc, a, b);
+    const float up_thr = need_pair ? quantile_from_pair(a, b, rank, lo) : quantile_from_pair(a, a, rank, lo);
+    select_two<false>(tmin, n_slots, lo, T, sc, a, b);
+    const float lo_thr = -(need_pair ? quantile_from_pair(a, b, rank, lo) : quantile_from_pair(a, a, rank, lo));
+    const int64_t stride = blockDim.x;
+    for (int64_t base = threadIdx.x; base < n_slots; base += stride * 4) {  // 8 independent loads in flight
+      float mn[4], mx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = base + j * stride < n_slots;
+        mn[j] = ok ? __ldg(tmin + base + j * stride) : INFINITY;
+        mx[j] = ok ? __ldg(tmax + base + j * stride) : -INFINITY;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (mn[j] <= mx[j]) {  // valid token (invalid ones hold +inf / -inf)
+          if (mx[j] <= up_thr) upper = fmaxf(upper, mx[j]);
+          if (mn[j] >= lo_thr) lower = fminf(lower, mn[j]);
+        }
+    }
+  }
+  lower = warp_min(lower);
+  upper = warp_max(upper);
+  if (lane == 0) { smn[warp] = lower; smx[warp] = upper; }
+  __syncthreads();
+  if (warp == 0) {
+    lower = lane < (blockDim.x >> 5) ? smn[lane] : INFINITY;
+    upper = lane < (blockDim.x >> 5) ? smx[lane] : -INFINITY;
+    lower = warp_min(lower);
+    upper = warp_max(upper);
+    if (lane == 0) {
+      cur[0] = lower;
+      cur[1] = upper;
+      stat_epilogue(epi, lower, upper);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-row min/max + running extrema + per-row qparams (weights, MinMaxObserver ch_axis=0)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -366,6 +505,17 @@ int osq_prune_select_f32(const float* tmin, const float* tmax, const float* abs_
   OSQ_CHECK_ARG(percentile >= 0.f && percentile <= 1.f, "osq_prune_select_f32: percentile outside [0,1]");
   prune_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tmin, tmax, abs_tmin_sorted, abs_tmax_sorted, n_slots,
                                                            n_valid, percentile, cur_minmax, *epi);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t n_slots, const int32_t* n_valid,
+                                  float percentile, float* cur_minmax, const osq_stat_epilogue_t* epi, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(tmin && tmax && n_valid && cur_minmax && epi, "osq_prune_select_unsorted_f32: null pointer");
+  OSQ_CHECK_ARG(n_slots > 0, "osq_prune_select_unsorted_f32: n_slots <= 0");
+  OSQ_CHECK_ARG(percentile >= 0.f && percentile <= 1.f, "osq_prune_select_unsorted_f32: percentile outside [0,1]");
+  prune_select_unsorted_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tmin, tmax, n_slots, n_valid, percentile, cur_minmax, *epi);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

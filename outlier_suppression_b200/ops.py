@@ -205,19 +205,24 @@ def token_minmax(x, lens, seq_pos):
 
 
 def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
-                         scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None) -> torch.Tensor:
-    """AvgPruneMinMaxObserver's token pruning (observer.py:50-70,214-237) as: one pass over the
-    activation (per-token extrema), two sorts of the [T] vectors, one selection launch."""
+                         scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None, use_sort=False) -> torch.Tensor:
+    """AvgPruneMinMaxObserver's token pruning (observer.py:50-70,214-237) in TWO launches: one pass over the
+    activation (per-token extrema) and one radix-select + selection + running-statistics launch."""
     tmin, tmax, n_valid = token_minmax(x, lens, seq_pos)
-    # invalid tokens hold (+inf, -inf): |.| maps both to +inf so they sort behind the T valid entries
-    abs_tmin_sorted = torch.sort(tmin.abs()).values
-    abs_tmax_sorted = torch.sort(tmax.abs()).values
     cur = _cur_out(out, tmin.device)
     epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
-    check(_lib.load().osq_prune_select_f32(tmin.data_ptr(), tmax.data_ptr(), abs_tmin_sorted.data_ptr(),
-                                           abs_tmax_sorted.data_ptr(), tmin.numel(), n_valid.data_ptr(),
-                                           float(percentile), cur.data_ptr(), C.byref(epi),
-                                           workspace(tmin.device).data_ptr(), _stream()), "osq_prune_select_f32")
+    if use_sort:
+        # first version: invalid tokens hold (+inf, -inf): |.| maps both to +inf so they sort behind the T valid entries
+        abs_tmin_sorted = torch.sort(tmin.abs()).values
+        abs_tmax_sorted = torch.sort(tmax.abs()).values
+        check(_lib.load().osq_prune_select_f32(tmin.data_ptr(), tmax.data_ptr(), abs_tmin_sorted.data_ptr(),
+                                               abs_tmax_sorted.data_ptr(), tmin.numel(), n_valid.data_ptr(),
+                                               float(percentile), cur.data_ptr(), C.byref(epi),
+                                               workspace(tmin.device).data_ptr(), _stream()), "osq_prune_select_f32")
+    else:
+        check(_lib.load().osq_prune_select_unsorted_f32(tmin.data_ptr(), tmax.data_ptr(), tmin.numel(), n_valid.data_ptr(),
+                                                        float(percentile), cur.data_ptr(), C.byref(epi), _stream()),
+              "osq_prune_select_unsorted_f32")
     return cur
 
 

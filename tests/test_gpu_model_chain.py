@@ -1,0 +1,129 @@
+"""-m gpu: a miniature encoder block wired exactly like quant_bert.py:134-349 (LN-output quantizer -> q/k/v
+QLinear, permuted 4-D query quantizer, context quantizer -> output QLinear, GELU quantizer -> FFN QLinear) run through
+the schedule of ptq_glue_quant.py:230-253 (gamma fold -> weight calibration -> token-wise-clipping style activation
+calibration over two masked batches -> quantized forward) on the drop-in modules, against the CPU oracle doing the
+same steps.  Observer states / qparams / fake-quantized activations: bit-exact.  Linear outputs: 1e-3 tolerance."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import osq_oracle as O
+from tests.test_host_logic import QC
+
+pytestmark = pytest.mark.gpu
+B, S, H, HEADS, FF = 4, 48, 256, 4, 512
+P = 0.9
+
+
+def close(y, ref, rel=1e-3):
+    y, ref = y.detach().double().cpu(), ref.detach().double().cpu()
+    bad = (y - ref).abs() > rel * ref.abs() + rel * ref.abs().max()
+    assert not bool(bad.any()), "%d / %d outside tolerance, max abs diff %g" % (int(bad.sum()), bad.numel(), float((y - ref).abs().max()))
+
+
+def same(a, b):
+    np.testing.assert_array_equal(a.detach().cpu().numpy(), b.detach().cpu().numpy())
+
+
+def test_mini_encoder_block_matches_oracle():
+    from outlier_suppression_b200 import quantization as Q
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    from outlier_suppression_b200.quantization.state import set_observer_name
+    g = torch.Generator().manual_seed(7)
+    a_cfg = QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1)
+    w_cfg = QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)
+
+    def lin(k, n):
+        m = torch.nn.Linear(k, n)
+        m.weight.data = torch.randn(n, k, generator=g) * 0.05
+        m.bias.data = torch.randn(n, generator=g) * 0.02
+        return m
+
+    net = torch.nn.Module()
+    net.query, net.value, net.dense, net.ffn = (qm.Quantizer(lin(H, H), w_cfg), qm.Quantizer(lin(H, H), w_cfg),
+                                                qm.Quantizer(lin(H, H), w_cfg), qm.Quantizer(lin(H, FF), w_cfg))
+    for nme in ("ln_post_act_fake_quantize", "query_permute_post_act_fake_quantize", "context_view_post_act_fake_quantize",
+                "gelu_post_act_fake_quantize"):
+        setattr(net, nme, qm.Quantizer(None, a_cfg))
+    net.cuda()
+    set_observer_name(net)
+    gamma = torch.rand(H, generator=g) * 2 + 0.2
+    xs = [torch.randn(B, S, H, generator=g) for _ in range(2)]
+    for x in xs:
+        x[..., :3] *= 15
+    lens = torch.tensor([S, S // 2, 5, S - 1])
+
+    # ---- schedule on the GPU modules ----
+    net.query.weight.data *= gamma.cuda()                 # gamma_migration.py:46-76 (rewrites weight.data)
+    net.ffn.weight.data *= gamma.cuda()
+    Q.enable_calibration_woquantization(net, quantizer_type="weight_fake_quant")
+
+    def forward(x, mask):
+        h = net.ln_post_act_fake_quantize(x, mask, 1)
+        q = net.query(h)
+        qp = net.query_permute_post_act_fake_quantize(q.view(B, S, HEADS, H // HEADS).permute(0, 2, 1, 3), mask, 2)
+        v = net.value(h)
+        ctx = net.context_view_post_act_fake_quantize(v, mask, 1)
+        o = net.dense(ctx)
+        gl = net.gelu_post_act_fake_quantize(F.gelu(o), mask, 1)
+        return net.ffn(gl), h, qp, ctx, gl
+
+    with torch.no_grad():
+        forward(xs[0].cuda(), lens.cuda())                 # weight observers see one batch (ptq_glue_quant.py:234-235)
+        Q.disable_all(net)
+        for m in net.modules():                            # token_wise_clipping.set_ratio (token_wise_clipping.py:12-19)
+            if isinstance(m, Q.quantized_module.LSQPlusFakeQuantize):
+                m.observer.set_percentile(P); m.observer.cnt = 0; m.enable_observer(); m.disable_fake_quant()
+        for x in xs:
+            forward(x.cuda(), lens.cuda())
+        Q.enable_quantization(net)
+        before = dict(qm.stats)
+        y, h, qp, ctx, gl = forward(xs[0].cuda(), lens.cuda())
+    assert qm.stats["fused"] - before["fused"] == 4, "all four QLinear calls must take the fused kernel"
+
+    # ---- the same schedule on the CPU oracle ----
+    W = {n: (getattr(net, n).weight.detach().cpu(), getattr(net, n).bias.detach().cpu()) for n in ("query", "value", "dense", "ffn")}
+    wq = {n: O.weight_qparams_minmax(W[n][0], 6, True) for n in W}
+    for n in W:
+        same(getattr(net, n).weight_fake_quant.scale, wq[n][0])
+    st = {n: O.ObserverState() for n in ("ln", "qp", "ctx", "gl")}
+    ll = lens.tolist()
+
+    def o_lin(x, n):
+        s, z, qmin, qmax = wq[n]
+        return O.qlinear(x, W[n][0], s, z, qmin, qmax, W[n][1])
+
+    def o_forward(x, observe):
+        def aq(name, t, seq_pos):
+            if observe:
+                O.observe_avg_prune_minmax(st[name], t, P, name, ll, seq_pos)
+                return t
+            s, z = O.qparams_from_minmax(st[name].min_val, st[name].max_val, 0, 63, False)
+            return O.fq_lsqplus_per_tensor(t, s.reshape(1), z.reshape(1), 0, 63)
+        h = aq("ln", x, 1)
+        # calibration runs with weight fake-quant DISABLED (disable_all), the final forward with it enabled
+        lin_ = (lambda t, n: F.linear(t, W[n][0], W[n][1])) if observe else o_lin
+        q = lin_(h, "query")
+        qp = aq("qp", q.view(B, S, HEADS, H // HEADS).permute(0, 2, 1, 3), 2)
+        v = lin_(h, "value")
+        ctx = aq("ctx", v, 1)
+        o = lin_(ctx, "dense")
+        gl = aq("gl", F.gelu(o), 1)
+        return lin_(gl, "ffn"), h, qp, ctx, gl
+
+    for x in xs:
+        o_forward(x, True)
+    # calibration inputs of downstream observers come from cuBLAS fp32 GEMMs on the GPU vs MKL on the CPU (FP passes,
+    # outside the hot path): their min/max agree to fp32 GEMM rounding, not bit-for-bit -- the first observer does.
+    same(torch.stack([net.ln_post_act_fake_quantize.observer.min_val, net.ln_post_act_fake_quantize.observer.max_val]),
+         torch.stack([st["ln"].min_val, st["ln"].max_val]))
+    for name, mod in (("qp", net.query_permute_post_act_fake_quantize), ("ctx", net.context_view_post_act_fake_quantize),
+                      ("gl", net.gelu_post_act_fake_quantize)):
+        np.testing.assert_allclose(float(mod.observer.max_val), float(st[name].max_val), rtol=1e-4)
+        np.testing.assert_allclose(float(mod.observer.min_val), float(st[name].min_val), rtol=1e-4, atol=1e-5)
+        st[name].min_val, st[name].max_val = mod.observer.min_val.cpu(), mod.observer.max_val.cpu()  # continue from identical state
+    y_ref, h_ref, qp_ref, ctx_ref, gl_ref = o_forward(xs[0], False)
+    same(h, h_ref)                      # LN-output fake-quant: bit-exact
+    close(y, y_ref)
+    close(ctx, ctx_ref); close(gl, gl_ref); close(qp, qp_ref)
