@@ -120,11 +120,13 @@ int osq_prune_select_f32(const float* tmin, const float* tmax, const float* abs_
                          void* workspace, void* stream);
 
 /* K4b' the same selection without any sort: the two order statistics torch.quantile interpolates between are
- *      found by an exact radix select on the fp32 bit patterns of |tmax| / |tmin| (one CTA, one launch);
- *      bit-identical to osq_prune_select_f32 on sorted inputs.  No workspace needed. */
+ *      found by an exact radix select on the fp32 bit patterns of |tmax| / |tmin|; bit-identical to
+ *      osq_prune_select_f32 on sorted inputs.  Up to 32768 slots: one CTA, one launch.  Above: six launches
+ *      spread over the SMs (four digit passes, the rank+1 value, clip + aminmax + running statistics) with
+ *      their state in `workspace` (osq_workspace_bytes(), zero-initialised once; re-armed by the kernels). */
 int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t n_slots,
                                   const int32_t* n_valid, float percentile, float* cur_minmax,
-                                  const osq_stat_epilogue_t* epi, void* stream);
+                                  const osq_stat_epilogue_t* epi, void* workspace, void* stream);
 
 /* per-row min/max of a [rows, cols] matrix with the running-extrema update of
  * MinMaxObserver(ch_axis=0) (observer.py:141-144) and per-row calculate_qparams.

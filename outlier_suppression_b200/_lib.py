@@ -64,7 +64,7 @@ def _declare(lib):
         "osq_minmax_flat_f32": [vp, i64, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_token_minmax_f32": [vp, C.POINTER(Tokens), vp, i32, vp, vp, vp, vp],
         "osq_prune_select_f32": [vp, vp, vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp, vp],
-        "osq_prune_select_unsorted_f32": [vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp],
+        "osq_prune_select_unsorted_f32": [vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_rowwise_minmax_qparams_f32": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp],
         "osq_calc_qparams_f32": [vp, vp, i64, i32, i32, i32, vp, vp, vp, vp],
         "osq_mse_multi_f32": [vp, C.POINTER(Tokens), vp, i32, vp, vp, i32, i32, i32, vp, vp, vp],

@@ -34,7 +34,8 @@ int sm_count();
 
 constexpr int kMaxPartialBlocks = 2048;  // upper bound on the grid of any reduction kernel
 // workspace layout: float partial_min[kMax], float partial_max[kMax], uint32 ticket, pad
-constexpr int64_t kWorkspaceBytes = (2 * kMaxPartialBlocks) * 4 + 64;
+constexpr int64_t kSelectWsOffset = (2 * kMaxPartialBlocks) * 4 + 64;  // multi-CTA radix select state (observer.cu)
+constexpr int64_t kWorkspaceBytes = kSelectWsOffset + 2 * 256 * 4 + 64;
 
 // ---------------------------------------------------------------------------------------------
 // Quantisation parameters as the kernels consume them.

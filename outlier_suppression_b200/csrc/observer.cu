@@ -272,9 +272,9 @@ prune_select_kernel(const float* __restrict__ tmin, const float* __restrict__ tm
 // single-CTA sweep over a small vector with 8 independent loads in flight per thread (the [T] vectors live in L2;
 // with one dependent load per iteration every pass would cost 64 L2 round trips)
 template <class F>
-__device__ __forceinline__ void sweep8(const float* __restrict__ v, int64_t n, F&& f) {
-  const int64_t stride = blockDim.x;
-  for (int64_t base = threadIdx.x; base < n; base += stride * 8) {
+__device__ __forceinline__ void sweep8(const float* __restrict__ v, int64_t n, F&& f, int64_t first = -1, int64_t stride = 0) {
+  if (first < 0) { first = threadIdx.x; stride = blockDim.x; }
+  for (int64_t base = first; base < n; base += stride * 8) {
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = (base + j * stride < n) ? __ldg(v + base + j * stride) : __int_as_float(0x7fc00000);
@@ -290,6 +290,42 @@ struct SelectScratch {
   unsigned int cnt_le;
 };
 
+// warp-aggregated histogram update: lanes with the same digit elect one leader (the leading digits of fp32
+// magnitudes are nearly constant, a plain atomicAdd would serialise the whole warp on one bin)
+__device__ __forceinline__ void hist_add(unsigned int* hist, float xv, bool ok, unsigned int mask, unsigned int prefix, int pass) {
+  const unsigned int u = __float_as_uint(fabsf(xv));
+  const bool in = ok && (u & mask) == prefix;
+  const unsigned int digit = in ? ((u >> (8 * pass)) & 255u) : 256u;
+  const unsigned int peers = __match_any_sync(__activemask(), digit);
+  if (in && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+}
+
+// one full warp: first bin with (count of all lower bins) + hist[bin] > krem, and that count of lower bins
+__device__ __forceinline__ void warp_pick_bin(const unsigned int* hist, unsigned int krem, unsigned int& bin, unsigned int& below) {
+  const int lane = threadIdx.x & 31;
+  unsigned int h[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { h[j] = hist[lane * 8 + j]; sum += h[j]; }
+  unsigned int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned int vote = __ballot_sync(0xffffffffu, incl > krem);
+  const int src = vote ? __ffs(vote) - 1 : 31;
+  unsigned int acc = incl - sum, pick = lane * 8 + 7;
+#pragma unroll
+  for (int j = 7; j >= 0; --j) {  // descending so the smallest qualifying j wins
+    unsigned int lower = incl - sum;
+#pragma unroll
+    for (int i = 0; i < j; ++i) lower += h[i];
+    if (lower + h[j] > krem) { pick = lane * 8 + j; acc = lower; }
+  }
+  bin = __shfl_sync(0xffffffffu, pick, src);
+  below = __shfl_sync(0xffffffffu, acc, src);
+}
+
 // value of rank k (0-based, ascending) of {|v[i]|}; also the value of rank k+1 (needed by the lerp)
 template <bool kIsMax>
 __device__ void select_two(const float* __restrict__ v, int64_t n, int k, int n_valid, SelectScratch& sc, float& a, float& b) {
@@ -297,24 +333,15 @@ __device__ void select_two(const float* __restrict__ v, int64_t n, int k, int n_
   for (int pass = 3; pass >= 0; --pass) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sc.hist[i] = 0;
     __syncthreads();
-    sweep8(v, n, [&](float xv, bool ok) {
-      const unsigned int u = __float_as_uint(fabsf(xv));
-      const bool in = ok && (u & mask) == prefix;
-      // warp-aggregated histogram update: lanes with the same digit elect one leader (the leading digits of
-      // fp32 magnitudes are nearly constant, a plain atomicAdd would serialise the whole warp on one bin)
-      const unsigned int digit = in ? ((u >> (8 * pass)) & 255u) : 256u;
-      const unsigned int peers = __match_any_sync(__activemask(), digit);
-      if (in && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sc.hist[digit], (unsigned int)__popc(peers));
-    });
+    sweep8(v, n, [&](float xv, bool ok) { hist_add(sc.hist, xv, ok, mask, prefix, pass); });
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int acc = 0, bin = 0;
-      for (; bin < 256; ++bin) {
-        if (acc + sc.hist[bin] > krem) break;
-        acc += sc.hist[bin];
+    if (threadIdx.x < 32) {
+      unsigned int bin, below;
+      warp_pick_bin(sc.hist, krem, bin, below);
+      if (threadIdx.x == 0) {
+        sc.prefix = prefix | (bin << (8 * pass));
+        sc.k_rem = krem - below;
       }
-      sc.prefix = prefix | (bin << (8 * pass));
-      sc.k_rem = krem - acc;
     }
     __syncthreads();
     prefix = sc.prefix;
@@ -400,6 +427,150 @@ prune_select_unsorted_kernel(const float* __restrict__ tmin, const float* __rest
       cur[1] = upper;
       stat_epilogue(epi, lower, upper);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4b'': the same radix select spread over many CTAs for long token vectors (T >> 64K: a calibration batch
+// of 1024 x 512 tokens has 4 MB of per-token extrema, one CTA would crawl through it ten times).
+// One launch per 8-bit digit (both sides at once), one for the rank-(k+1) value, one for clip + aminmax +
+// running statistics.  State lives in the caller's workspace; the last CTA of every launch (ticket) folds the
+// global histogram and re-arms it, so the whole sequence needs no host synchronisation and no memset.
+// ---------------------------------------------------------------------------------------------
+constexpr int64_t kSelectSingleCtaMax = 32768;
+
+struct SelectWs {
+  unsigned int hist[2][256];
+  unsigned int prefix[2], krem[2];
+  unsigned int cnt_le[2], above_s[2];  // above_s = 0x7f800000 - bits(min value above a): atomicMax, zero = +inf
+  float thr[2];                        // up_thr, lo_thr
+  unsigned int ticket;
+};
+static_assert(sizeof(SelectWs) <= 2 * 256 * 4 + 64, "workspace too small");
+
+__device__ __forceinline__ bool last_cta(unsigned int* ticket) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+__global__ void __launch_bounds__(1024)
+select_pass_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n,
+                   const int32_t* __restrict__ n_valid, float percentile, int pass, SelectWs* __restrict__ ws) {
+  __shared__ unsigned int hist[2][256];
+  const int T = *n_valid;
+  if (T <= 0) return;
+  unsigned int prefix[2], krem[2];
+  const unsigned int mask = pass == 3 ? 0u : (0xFFFFFFFFu << (8 * (pass + 1)));
+  if (pass == 3) {
+    prefix[0] = prefix[1] = 0;
+    krem[0] = krem[1] = (unsigned int)(int)__fmul_rn(percentile, (float)(T - 1));
+  } else {
+    prefix[0] = __ldcg(&ws->prefix[0]); prefix[1] = __ldcg(&ws->prefix[1]);
+    krem[0] = __ldcg(&ws->krem[0]); krem[1] = __ldcg(&ws->krem[1]);
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  sweep8(tmax, n, [&](float xv, bool ok) { hist_add(hist[0], xv, ok, mask, prefix[0], pass); }, first, stride);
+  sweep8(tmin, n, [&](float xv, bool ok) { hist_add(hist[1], xv, ok, mask, prefix[1], pass); }, first, stride);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const unsigned int c = (&hist[0][0])[i];
+    if (c) atomicAdd(&ws->hist[0][0] + i, c);
+  }
+  if (!last_cta(&ws->ticket)) return;
+  if (threadIdx.x < 64) {
+    const int side = threadIdx.x >> 5;
+    for (int i = threadIdx.x & 31; i < 256; i += 32) hist[side][i] = __ldcg(&ws->hist[side][i]);
+    __syncwarp();
+    unsigned int bin, below;
+    warp_pick_bin(hist[side], krem[side], bin, below);
+    if ((threadIdx.x & 31) == 0) {
+      ws->prefix[side] = prefix[side] | (bin << (8 * pass));
+      ws->krem[side] = krem[side] - below;
+    }
+  }
+  __syncthreads();  // the two scanning warps have read the global histogram; now re-arm it
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&ws->hist[0][0])[i] = 0;
+  if (threadIdx.x == 0) ws->ticket = 0;
+}
+
+__global__ void __launch_bounds__(1024)
+select_final_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n,
+                    const int32_t* __restrict__ n_valid, float percentile, SelectWs* __restrict__ ws) {
+  const int T = *n_valid;
+  if (T <= 0) return;
+  const float a0 = __uint_as_float(__ldcg(&ws->prefix[0])), a1 = __uint_as_float(__ldcg(&ws->prefix[1]));
+  unsigned int cnt[2] = {0, 0};
+  float above[2] = {INFINITY, INFINITY};
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  sweep8(tmax, n, [&](float xv, bool ok) { const float x = fabsf(xv); if (ok) { if (x <= a0) ++cnt[0]; else above[0] = fminf(above[0], x); } }, first, stride);
+  sweep8(tmin, n, [&](float xv, bool ok) { const float x = fabsf(xv); if (ok) { if (x <= a1) ++cnt[1]; else above[1] = fminf(above[1], x); } }, first, stride);
+#pragma unroll
+  for (int sd = 0; sd < 2; ++sd) {
+    above[sd] = warp_min(above[sd]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt[sd] += __shfl_xor_sync(0xffffffffu, cnt[sd], o);
+    if ((threadIdx.x & 31) == 0) {
+      if (cnt[sd]) atomicAdd(&ws->cnt_le[sd], cnt[sd]);
+      if (above[sd] < INFINITY) atomicMax(&ws->above_s[sd], 0x7f800000u - __float_as_uint(above[sd]));
+    }
+  }
+  if (!last_cta(&ws->ticket)) return;
+  if (threadIdx.x == 0) {
+    const float rank = __fmul_rn(percentile, (float)(T - 1));
+    const int lo = (int)rank;
+    const bool need_pair = (int)ceilf(rank) != lo;
+    float thr[2];
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+      const float a = sd ? a1 : a0;
+      const unsigned int c = __ldcg(&ws->cnt_le[sd]);
+      const float nxt = __uint_as_float(0x7f800000u - __ldcg(&ws->above_s[sd]));
+      const float b = (c >= (unsigned int)lo + 2u || lo + 1 >= T) ? a : nxt;
+      thr[sd] = quantile_from_pair(a, need_pair ? b : a, rank, lo);
+      ws->cnt_le[sd] = 0;
+      ws->above_s[sd] = 0;
+    }
+    ws->thr[0] = thr[0];
+    ws->thr[1] = -thr[1];
+    ws->ticket = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kObsThreads)
+prune_apply_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n,
+                   const int32_t* __restrict__ n_valid, const SelectWs* __restrict__ sw, float* __restrict__ cur,
+                   osq_stat_epilogue_t epi, void* wsp) {
+  float lower = INFINITY, upper = -INFINITY;
+  if (*n_valid > 0) {
+    const float up_thr = __ldcg(&sw->thr[0]), lo_thr = __ldcg(&sw->thr[1]);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * 4) {
+      float mn[4], mx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = base + j * stride < n;
+        mn[j] = ok ? __ldg(tmin + base + j * stride) : INFINITY;
+        mx[j] = ok ? __ldg(tmax + base + j * stride) : -INFINITY;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (mn[j] <= mx[j]) {
+          if (mx[j] <= up_thr) upper = fmaxf(upper, mx[j]);
+          if (mn[j] >= lo_thr) lower = fminf(lower, mn[j]);
+        }
+    }
+  }
+  if (grid_fold(lower, upper, carve(wsp))) {
+    cur[0] = lower;
+    cur[1] = upper;
+    stat_epilogue(epi, lower, upper);
   }
 }
 
@@ -510,12 +681,29 @@ int osq_prune_select_f32(const float* tmin, const float* tmax, const float* abs_
 }
 
 int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t n_slots, const int32_t* n_valid,
-                                  float percentile, float* cur_minmax, const osq_stat_epilogue_t* epi, void* stream) {
+                                  float percentile, float* cur_minmax, const osq_stat_epilogue_t* epi,
+                                  void* workspace, void* stream) {
   using namespace osq;
-  OSQ_CHECK_ARG(tmin && tmax && n_valid && cur_minmax && epi, "osq_prune_select_unsorted_f32: null pointer");
+  OSQ_CHECK_ARG(tmin && tmax && n_valid && cur_minmax && epi && workspace, "osq_prune_select_unsorted_f32: null pointer");
   OSQ_CHECK_ARG(n_slots > 0, "osq_prune_select_unsorted_f32: n_slots <= 0");
   OSQ_CHECK_ARG(percentile >= 0.f && percentile <= 1.f, "osq_prune_select_unsorted_f32: percentile outside [0,1]");
-  prune_select_unsorted_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tmin, tmax, n_slots, n_valid, percentile, cur_minmax, *epi);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_slots <= kSelectSingleCtaMax) {
+    prune_select_unsorted_kernel<<<1, 1024, 0, st>>>(tmin, tmax, n_slots, n_valid, percentile, cur_minmax, *epi);
+    OSQ_LAUNCH_CHECK();
+    return OSQ_OK;
+  }
+  int sms = sm_count();
+  if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  int64_t g = (n_slots + 8191) / 8192;  // 8 slots per thread and side
+  if (g > sms) g = sms;
+  SelectWs* sw = reinterpret_cast<SelectWs*>(static_cast<char*>(workspace) + kSelectWsOffset);
+  for (int pass = 3; pass >= 0; --pass)
+    select_pass_kernel<<<(int)g, 1024, 0, st>>>(tmin, tmax, n_slots, n_valid, percentile, pass, sw);
+  select_final_kernel<<<(int)g, 1024, 0, st>>>(tmin, tmax, n_slots, n_valid, percentile, sw);
+  int64_t g2 = (n_slots + kObsThreads * 4 - 1) / (kObsThreads * 4);
+  if (g2 > sms) g2 = sms;
+  prune_apply_kernel<<<(int)g2, kObsThreads, 0, st>>>(tmin, tmax, n_slots, n_valid, sw, cur_minmax, *epi, workspace);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

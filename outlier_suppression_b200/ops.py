@@ -221,7 +221,8 @@ def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0,
                                                workspace(tmin.device).data_ptr(), _stream()), "osq_prune_select_f32")
     else:
         check(_lib.load().osq_prune_select_unsorted_f32(tmin.data_ptr(), tmax.data_ptr(), tmin.numel(), n_valid.data_ptr(),
-                                                        float(percentile), cur.data_ptr(), C.byref(epi), _stream()),
+                                                        float(percentile), cur.data_ptr(), C.byref(epi),
+                                                        workspace(tmin.device).data_ptr(), _stream()),
               "osq_prune_select_unsorted_f32")
     return cur
 

@@ -18,23 +18,27 @@ os.makedirs(PROF, exist_ok=True)
 # ---- launch list
 rows = [r for r in csv.reader(open(os.path.join(OUT, "launches.csv"))) if len(r) > 10]
 hdr = rows[0]; ci = {h: i for i, h in enumerate(hdr)}
-agg = collections.OrderedDict()
-for r in rows[1:]:
+first_fused = next(i for i, r in enumerate(rows[1:]) if r[ci["Kernel Name"]].startswith("fused_fq_linear"))
+agg = {"setup": collections.OrderedDict(), "step": collections.OrderedDict()}
+for i, r in enumerate(rows[1:]):
     try:
         v = float(r[ci["Metric Value"]])
     except ValueError:
         continue
     name = r[ci["Kernel Name"]].split("(")[0]
     key = (name, r[ci["Grid Size"]], r[ci["Block Size"]])
-    a = agg.setdefault(key, [0, 0.0, 1e30, 0.0])
+    a = agg["setup" if i < first_fused else "step"].setdefault(key, [0, 0.0, 1e30, 0.0])
     a[0] += 1; a[1] += v; a[2] = min(a[2], v); a[3] = max(a[3], v)
-tot = sum(a[1] for a in agg.values())
 with open(os.path.join(PROF, tag + "_launches.md"), "w") as f:
-    f.write("# %s: ncu launch list of `bench.py --steps 2 --warmup 3 --only-value` (-k regex:osq, --clock-control none)\n\n" % tag)
-    f.write("Per-launch times are cold-cache and serialised by ncu: compare SHARES, not absolutes.\n\n")
-    f.write("| kernel | grid | block | launches | total us | min us | max us | share |\n|---|---|---|---|---|---|---|---|\n")
-    for (name, grid, block), a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        f.write("| %s | %s | %s | %d | %.1f | %.1f | %.1f | %.1f %% |\n" % (name, grid, block, a[0], a[1] / 1e3, a[2] / 1e3, a[3] / 1e3, 100 * a[1] / tot))
+    f.write("# %s: ncu launch list of `bench.py --steps 2 --warmup 3 --only-value --no-graph`\n\n" % tag)
+    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fused_fq|pack_weight|minmax|prune_select|fq_per`.\n"
+            "Per-launch times are cold-cache and serialised by ncu: compare SHARES, not absolutes.\n")
+    for part, title in (("step", "Warm-up + timed steps (5 steps x 72 launches): the region `value` is measured on"),
+                        ("setup", "Setup before the first step (untimed): per-channel weight qparams + s8 packing, one calibration batch per activation quantizer")):
+        tot = sum(a[1] for a in agg[part].values()) or 1.0
+        f.write("\n## %s\n\n| kernel | grid | block | launches | total us | min us | max us | share |\n|---|---|---|---|---|---|---|---|\n" % title)
+        for (name, grid, block), a in sorted(agg[part].items(), key=lambda kv: -kv[1][1]):
+            f.write("| %s | %s | %s | %d | %.1f | %.1f | %.1f | %.1f %% |\n" % (name, grid, block, a[0], a[1] / 1e3, a[2] / 1e3, a[3] / 1e3, 100 * a[1] / tot))
 print(open(os.path.join(PROF, tag + "_launches.md")).read())
 
 # ---- full capture

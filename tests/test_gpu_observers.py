@@ -85,6 +85,33 @@ def test_permuted_views_and_large_vs_oracle():
                 same(ops.observe_prune_minmax(xg, None if lz is None else lz.cuda(), sp, p), torch.stack([lo, hi]))
 
 
+def test_long_token_vectors_multi_cta_select():
+    """> 32768 tokens: the radix select runs as six multi-CTA launches; must equal the oracle (= torch.quantile on
+    the CPU), the sort-based first version, and itself when the workspace is reused back to back."""
+    from outlier_suppression_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    for (b, s_, f), ties in (((160, 512, 32), False), ((96, 512, 64), True), ((300, 333, 16), False)):
+        x = torch.randn(b, s_, f, generator=g) * torch.rand(b, s_, 1, generator=g).mul(4).exp()
+        if ties:  # heavy duplicates around the selected rank: quantise the magnitudes coarsely
+            x = (x * 2).round() / 2
+        lens = torch.randint(1, s_ + 1, (b,), generator=g)
+        lens[0] = s_
+        xg = x.cuda()
+        for lz in (lens, None):
+            tok = O.token_matrix(x, None if lz is None else lz.tolist(), 1)
+            tmin, tmax = O.token_minmax(tok)
+            for p in (0.99, 0.9, 0.5, 1.0, 0.0):
+                lo, hi = O.prune_bounds(tmin, tmax, p)
+                lg = None if lz is None else lz.cuda()
+                first = ops.observe_prune_minmax(xg, lg, 1, p).clone()
+                same(first, torch.stack([lo, hi]))
+                same(ops.observe_prune_minmax(xg, lg, 1, p), first)
+                same(ops.observe_prune_minmax(xg, lg, 1, p, use_sort=True), first)
+    # all tokens masked out on the long path
+    z = ops.observe_prune_minmax(xg, torch.zeros(300, dtype=torch.int64, device="cuda"), 1, 0.99)
+    assert float(z[0]) == float("inf") and float(z[1]) == float("-inf")
+
+
 def test_fp16_input_and_empty():
     from outlier_suppression_b200.quantization.observer import AvgMinMaxObserver
     o = AvgMinMaxObserver(bit=8).cuda()
