@@ -45,6 +45,7 @@ constexpr int kNumEpiWarps = 8;                      // workers 0..7: four TMEM 
 constexpr int kNumThreads = (kWorkerWarp0 + kNumWorkers) * 32;  // 640
 constexpr int kRowsPerWorker = kBM / kNumWorkers;    // 8
 constexpr int kOutTileBytes = 32 * 128;              // TMA-store staging tile: 32 rows x 32 fp32 columns, SW128
+constexpr int kXSlotBytes = kRowsPerWorker * kStageK * 4;  // fp32 landing slot of one worker: 8 rows x 128 floats = 4 KB
 constexpr int kMaxAStages = 8, kMaxWStages = 6, kMaxAccStages = 4;
 constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: fp32 ulp is 1 in [2^23, 2^24)
 
@@ -59,6 +60,9 @@ struct FusedParams {
   int n_iters;        // tiles per CTA (identical for every CTA; out-of-range tiles are phantoms that only keep the W protocol alive)
   int rows_per_tile;  // valid rows per CTA tile (<= 128, multiple of 16): chosen so the tile count fills all SMs
   int a_stages, w_stages, out_bufs;
+  int a_stage_bytes;  // rows_per_tile * 128
+  int x_tma;          // fp32 A arrives by TMA into per-worker landing slots (else: 128-bit loads into registers)
+  int alias_xo;       // the TMA-store staging tiles share the landing slots' memory
   int w_stage_bytes;  // BN * 128
   int resident;       // converted A block stays in smem for all N chunks
   int cached;         // streaming mode with a code cache: passes >= 1 TMA-load bins instead of re-converting
@@ -74,6 +78,7 @@ struct FusedParams {
   uint8_t* a_codes;  // optional [M, K]: bins side output / code cache
   uint32_t codes_box_bytes;  // bytes one code-cache TMA box delivers
   int pdl;                   // launched with programmatic stream serialization
+  int prefetch;              // L2 prefetch distance of the fp32 activation in k-blocks (0 = off)
   int dbg;                   // profiling experiments (OSQ_FUSED_DBG): 1 = W tile pinned, 2 = no Y stores, 4 = A rows pinned
   long long* trace;          // optional debug timeline: CTA 0 clock64 stamps [0,1024), per-CTA globaltimer start/end [1024, 1024+2*grid)
 };
@@ -185,6 +190,9 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -363,25 +371,29 @@ struct Smem {
   uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   uint64_t acc_full[kMaxAccStages], acc_empty[kMaxAccStages];
   uint64_t codes_ready, passes_issued;
+  uint64_t x_full[kNumWorkers];  // per-worker fp32 landing slot filled (TMA complete_tx)
   uint32_t tmem_base;
-  uint32_t pad;
+  volatile uint32_t converted;  // k-blocks worker 0 has converted so far (paces the L2 prefetcher)
   uint32_t pad2[2];  // keeps sizeof(Smem) a multiple of 16: the per-column constants follow it
 };
 // after Smem: per-column epilogue constants of the current chunk (2 * BN floats):
 //   y = acc * c1[n] + c0[n],  c1 = s_a * w_scale[n],  c0 = bias[n] - Zc * rowsum[n] * c1
 static_assert(sizeof(Smem) % 16 == 0, "constants must stay 16-byte aligned");
 
+template <bool kXTma>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
                        const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,
-                       const FusedParams p) {
+                       const __grid_constant__ CUtensorMap tmap_a, const FusedParams p) {
   // dynamic shared memory, 1024B aligned by the attribute (SWIZZLE_128B tiles need it):
-  // [A ring][W ring][TMA-store staging tiles][Smem bookkeeping]
+  // [A ring][W ring][fp32 landing slots][TMA-store staging tiles (may alias the slots)][Smem bookkeeping]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* a_ring = smem_raw;
-  uint8_t* w_ring = a_ring + (size_t)p.a_stages * kAStageBytes;
-  uint8_t* o_ring = w_ring + (size_t)p.w_stages * p.w_stage_bytes;
-  Smem& sm = *reinterpret_cast<Smem*>(o_ring + (size_t)kNumEpiWarps * p.out_bufs * kOutTileBytes);
+  uint8_t* w_ring = a_ring + (size_t)p.a_stages * p.a_stage_bytes;
+  uint8_t* x_ring = w_ring + (size_t)p.w_stages * p.w_stage_bytes;  // 16 fp32 landing slots of 4 KB (x_tma only)
+  uint8_t* o_ring = p.alias_xo ? x_ring : x_ring + (kXTma ? kNumWorkers * kXSlotBytes : 0);
+  Smem& sm = *reinterpret_cast<Smem*>(p.alias_xo ? x_ring + kNumWorkers * kXSlotBytes
+                                                 : o_ring + (size_t)kNumEpiWarps * p.out_bufs * kOutTileBytes);
   float* sm_c1 = reinterpret_cast<float*>(&sm + 1);  // [BN]
   float* sm_c0 = sm_c1 + p.BN;                       // [BN]
 
@@ -393,12 +405,15 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     tma_prefetch_desc(&tmap_y);
     tma_prefetch_desc(&tmap_y16);
     if (p.cached) tma_prefetch_desc(&tmap_codes);
+    if (p.prefetch) tma_prefetch_desc(&tmap_a);
+    sm.converted = 0;
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&sm.a_full[i], kNumWorkers); mbar_init(&sm.a_empty[i], 1); }
     for (int i = 0; i < p.w_stages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], p.csz); }
     for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps); }
     mbar_init(&sm.codes_ready, kNumWorkers);
+    for (int i = 0; i < kNumWorkers; ++i) mbar_init(&sm.x_full[i], 1);
     mbar_init(&sm.passes_issued, 1);
     fence_barrier_init();
   }
@@ -475,7 +490,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
             if (tslot >= 36 && tslot < 72) OSQ_TRACE(1401 + 3 * (tslot - 36));
 #endif
             tc_fence_after();
-            const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)kAStageBytes) >> 4);
+            const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)p.a_stage_bytes) >> 4);
             const uint64_t db = desc_hi | (uint64_t)((w_base + ws * w_bytes) >> 4);
 #pragma unroll
             for (int k = 0; k < kStageK / kUmmaK; ++k)
@@ -506,9 +521,28 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
             mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
             mbar_arrive_expect_tx(&sm.a_full[a_st], p.codes_box_bytes);
             mbar_arrive_n(&sm.a_full[a_st], kNumWorkers - 1);  // a_full always counts kNumWorkers arrivals
-            tma_load_2d(a_ring + (size_t)a_st * kAStageBytes, &tmap_codes, &sm.a_full[a_st], kb * kStageK, mb * p.rows_per_tile);
+            tma_load_2d(a_ring + (size_t)a_st * p.a_stage_bytes, &tmap_codes, &sm.a_full[a_st], kb * kStageK, mb * p.rows_per_tile);
           }
         mbar_arrive(&sm.passes_issued);  // workers may start filling the ring for the next m-block
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== L2 prefetcher for the fp32 activation =====================
+    // The conversion warps can keep only 8 x 512 B per warp in flight (registers), too little to cover DRAM
+    // latency at this CTA's share of the HBM bandwidth.  One thread pulls the tile's [rows x 128] fp32 boxes into
+    // L2 a bounded distance ahead (in the order the workers consume them), so their loads see L2 latency.
+    if (lane == 0 && p.prefetch > 0) {
+      if (p.pdl) pdl_wait_prior_grids();
+      const int passes_per_block = (p.resident || p.cached) ? 1 : p.NC;  // fp32 A is re-read per chunk only without a cache
+      uint32_t done = 0;
+      for (int it = 0; it < n_my_blocks; ++it) {
+        const int mb = blockIdx.x + it * gridDim.x;
+        if (mb >= p.n_mblocks) break;
+        for (int pass = 0; pass < passes_per_block; ++pass)
+          for (int kb = 0; kb < p.KB; ++kb, ++done) {
+            while (done >= sm.converted + (uint32_t)p.prefetch) __nanosleep(64);
+            tma_prefetch_l2_2d(&tmap_a, kb * kStageK, mb * p.rows_per_tile);
+          }
       }
     }
   } else if (warp >= kWorkerWarp0) {
@@ -553,7 +587,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         const uint32_t pa = pa0 + kb;
         const uint32_t a_st = c_st;
         if (pa >= (uint32_t)p.a_stages) mbar_wait(&sm.a_empty[a_st], c_ph ^ 1);  // first fill: ring is empty
-        uint8_t* st = a_ring + a_st * (uint32_t)kAStageBytes + r_base * kStageK + lane_in;
+        uint8_t* st = a_ring + a_st * (uint32_t)p.a_stage_bytes + r_base * kStageK + lane_in;
         if (full) {
           const bool more = kb + 1 < p.KB;
           const float* nxt = aptr + (size_t)(kb + 1) * kStageK;
@@ -594,11 +628,80 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
             const float4 v = ok ? ldg_stream(reinterpret_cast<const float4*>(aptr + i * rs + (size_t)kb * kStageK))
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             const uint32_t word = quant_bin4(v, cp);
-            *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
+            if (r_base < p.rows_per_tile) *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
             if (ok && cptr != nullptr) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word;
           }
         }
         if (!(p.dbg & 8)) fence_proxy_async_smem();  // generic-proxy smem stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.a_full[a_st]);
+        if (w == 0 && lane == 0) sm.converted = sm.converted + 1;
+        if (w == 0 && lane == 0 && pa < 250) OSQ_TRACE(pa);
+        if (++c_st == (uint32_t)p.a_stages) { c_st = 0; c_ph ^= 1; }
+      }
+    };
+    // The same pass with the fp32 rows arriving by TMA: each worker owns one 4 KB landing slot (its 8 rows x one
+    // k-block).  Slot -> registers (8 LDS.128 per lane), then lane 0 immediately re-arms the slot with the next
+    // k-block, so 16 x 4 KB stay in flight per SM no matter what the warps are doing, without going through the L1
+    // (whose capacity bounds plain loads in flight once 227 KB are carved out as shared memory).  Rows past M are
+    // zero-filled by the TMA unit: no ragged path.
+    uint32_t x_ph = 0;
+    auto convert_pass_tma = [&](int mb, uint32_t pa0) {
+      const uint32_t x_bar = smem_u32(&sm.x_full[w]);
+      uint8_t* const x_slot = x_ring + (size_t)w * kXSlotBytes;
+      const uint32_t x_box_bytes = (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker) * (uint32_t)(kStageK * 4);
+      const int row_first = mb * p.rows_per_tile + r_base;
+      const bool active = r_base < p.rows_per_tile && row_first < p.M;  // warp uniform
+      const int nvalid = active ? min(kRowsPerWorker, p.M - row_first) : 0;
+      const size_t rs = (size_t)p.K;
+      uint8_t* cptr = (p.a_codes != nullptr && active) ? p.a_codes + (size_t)row_first * rs + lane * 4 : nullptr;
+      if (active && lane == 0) {
+        mbar_arrive_expect_tx_u32(x_bar, x_box_bytes);
+        tma_load_2d_u32(smem_u32(x_slot), &tmap_a, x_bar, 0, row_first);
+      }
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const uint32_t pa = pa0 + kb;
+        const uint32_t a_st = c_st;
+        if (pa >= (uint32_t)p.a_stages) mbar_wait(&sm.a_empty[a_st], c_ph ^ 1);  // first fill: ring is empty
+        if (active) {
+          uint8_t* st = a_ring + a_st * (uint32_t)p.a_stage_bytes + r_base * kStageK + lane_in;
+          mbar_wait_u32(x_bar, x_ph);
+          x_ph ^= 1;
+#pragma unroll
+          for (int i = 0; i < kRowsPerWorker; ++i)
+            x[i] = *reinterpret_cast<const float4*>(x_slot + i * (kStageK * 4) + lane * 16);
+          if (kb + 1 < p.KB) {
+            // the slot's contents are in registers: order these generic-proxy reads before the async-proxy refill
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_expect_tx_u32(x_bar, x_box_bytes);
+              tma_load_2d_u32(smem_u32(x_slot), &tmap_a, x_bar, (kb + 1) * kStageK, row_first);
+            }
+          }
+          uint32_t risky_mask = 0;
+          auto body = [&](auto codes) {
+#pragma unroll
+            for (int i = 0; i < kRowsPerWorker; ++i) {
+              bool risky;
+              const uint32_t word = quant_bin4_fast(x[i], cp, risky);
+              risky_mask |= (uint32_t)risky << i;
+              *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
+              if (decltype(codes)::value) { if (i < nvalid) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word; }
+            }
+          };
+          if (cptr == nullptr) body(std::false_type{}); else body(std::true_type{});
+          if (risky_mask != 0) {  // rare exact fix-up (true division) of the float4 groups near a rounding tie
+#pragma unroll
+            for (int i = 0; i < kRowsPerWorker; ++i)
+              if (risky_mask & (1u << i)) {
+                const uint32_t word = quant_bin4_exact(x[i].x, x[i].y, x[i].z, x[i].w, cp.s, cp.zc, cp.span);
+                *reinterpret_cast<uint32_t*>(st + i * kStageK + (lc16 ^ (uint32_t)((i & 7) << 4))) = word;
+                if (cptr != nullptr && i < nvalid) *reinterpret_cast<uint32_t*>(cptr + i * rs + (size_t)kb * kStageK) = word;
+              }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.a_full[a_st]);
         if (w == 0 && lane == 0 && pa < 250) OSQ_TRACE(pa);
@@ -638,6 +741,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       if (et < p.BN) { sm_c1[et] = pc1; sm_c0[et] = pc0; }
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
     };
+    int obufs = p.out_bufs;  // store tiles this warp may cycle through in the current m-block
     auto epilogue_chunk = [&](int mb, int nc) {
       const int as_ = cacc % p.acc_stages;
       const int n0 = nc * p.BN;
@@ -660,11 +764,14 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
         if (!any_rows) continue;  // warp uniform: phantom tile / quarter past the tile's rows
-        if (n_stores >= (uint32_t)p.out_bufs) {  // the staging tile must have been read out by its previous TMA store
-          if (lane == 0) { if (p.out_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+        if (n_stores >= (uint32_t)obufs) {  // the staging tile must have been read out by its previous TMA store
+          if (lane == 0) { if (obufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
           __syncwarp();
         }
-        uint8_t* tile = my_tiles + (size_t)(n_stores % p.out_bufs) * kOutTileBytes;
+        // aliased mode: this warp's own landing slot, plus (last tile only) the slot of worker w + 8, whose owner is
+        // through with it once the tile's last MMA has been committed
+        uint8_t* tile = p.alias_xo ? x_ring + (size_t)(((n_stores & 1u) & (uint32_t)(obufs - 1)) * kNumEpiWarps + w) * kXSlotBytes
+                                   : my_tiles + (size_t)(n_stores % (uint32_t)obufs) * kOutTileBytes;
         uint8_t* trow = tile + lane * 128;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -701,7 +808,11 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       // warp runs ahead on the same ring (two producers may never be more than one ring cycle apart)
       if (p.cached && it > 0) mbar_wait(&sm.passes_issued, (it - 1) & 1);
       if (w < kNumEpiWarps) fetch_consts(0);
-      convert_pass(mb, pa_block);
+      if (p.alias_xo && it > 0 && w < kNumEpiWarps) {  // this warp's landing slot was its store tile: reads must be done
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
+      if constexpr (kXTma) convert_pass_tma(mb, pa_block); else convert_pass(mb, pa_block);
       if (p.cached) {
         // bins of this m-block are in the code cache: publish them to the async proxy (TMA) of this CTA
         __threadfence();
@@ -710,10 +821,13 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         if (lane == 0) mbar_arrive(&sm.codes_ready);
         skip_ring((uint32_t)(a_passes - 1) * (uint32_t)p.KB);  // N chunks >= 1 are filled by the TMA thread
       }
+      if (p.alias_xo) { obufs = (it == n_my_blocks - 1) ? p.out_bufs : 1; n_stores = 0; }
       if (w < kNumEpiWarps) publish_consts();  // chunk 0 constants
       for (int nc = 0; nc < p.NC; ++nc) {
         // no code cache and K too large for residency: re-convert A for the next N chunk first
-        if (!p.resident && !p.cached && nc + 1 < p.NC) convert_pass(mb, pa_block + (uint32_t)(nc + 1) * p.KB);
+        if (!p.resident && !p.cached && nc + 1 < p.NC) {
+          if constexpr (kXTma) convert_pass_tma(mb, pa_block + (uint32_t)(nc + 1) * p.KB); else convert_pass(mb, pa_block + (uint32_t)(nc + 1) * p.KB);
+        }
         if (w < kNumEpiWarps) epilogue_chunk(mb, nc);
       }
     }
@@ -850,90 +964,42 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   memset(&p, 0, sizeof(p));
   p.M = (int)a->M; p.K = (int)a->K; p.N = (int)a->N;
   p.KB = p.K / kStageK;
-  // shared-memory plan (227 KB / CTA): [A ring][W ring][TMA-store staging: 8 warps x out_bufs x 4 KB][bookkeeping]
-  const int out1 = kNumEpiWarps * kOutTileBytes;  // 32 KB per buffer set
-  int budget = 227 * 1024 - (int)sizeof(Smem) - 8 * 256;  // barriers + constants of a 256-column chunk
-  // resident A (K <= 1024): 128-column chunks, 16 KB W stages, four TMEM accumulator stages
-  p.resident = (p.KB <= kMaxAStages && p.KB * kAStageBytes + 2 * (256 * kStageK) + out1 <= budget) ? 1 : 0;
-  const int bn_pref = 256;  // SS-mode kind::i8 MMAs read A and B from shared memory: N = 256 halves the A re-reads per MAC
-  p.BN = p.N < bn_pref ? p.N : bn_pref;
-  p.NC = (p.N + p.BN - 1) / p.BN;
-  p.acc_stages = kTmemCols / p.BN;
-  if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
-  const int const_bytes = 2 * p.BN * (int)sizeof(float);
-  budget = 227 * 1024 - (int)sizeof(Smem) - const_bytes;
-  p.w_stage_bytes = p.BN * kStageK;
-  if (p.w_stage_bytes % 1024 != 0) p.w_stage_bytes = (p.w_stage_bytes + 1023) / 1024 * 1024;
-  p.a_stages = p.resident ? p.KB : 4;
-  p.cached = (!p.resident && p.NC > 1 && a->a_codes != nullptr) ? 1 : 0;
-  int rest = budget - p.a_stages * kAStageBytes - 2 * p.w_stage_bytes - out1;
-  p.w_stages = 2;
-  p.out_bufs = 1;
-  static int env_ob = -1;
-  if (env_ob < 0) { const char* e = getenv("OSQ_FUSED_OUTBUFS"); env_ob = e ? atoi(e) : 0; }
-  // the W stream needs ~2.5 stages of 32 KB in flight to cover the L2 latency at the chunk rate the epilogue
-  // sustains; a third stage therefore comes before double-buffered stores
-  if (env_ob == 2 && rest >= out1) { p.out_bufs = 2; rest -= out1; }  // experiment: stores before W depth
-  if (rest >= p.w_stage_bytes) { ++p.w_stages; rest -= p.w_stage_bytes; }
-  if (env_ob != 1 && p.out_bufs == 1 && rest >= out1) { p.out_bufs = 2; rest -= out1; }
-  while (p.w_stages < kMaxWStages && rest >= p.w_stage_bytes) { ++p.w_stages; rest -= p.w_stage_bytes; }
-  if (!p.resident)
-    while (p.a_stages < kMaxAStages && rest >= kAStageBytes) { ++p.a_stages; rest -= kAStageBytes; }
-  const size_t smem_bytes = (size_t)p.a_stages * kAStageBytes + (size_t)p.w_stages * p.w_stage_bytes +
-                            (size_t)p.out_bufs * out1 + sizeof(Smem) + (size_t)const_bytes;
-
-  // cluster size: the W stream is identical for every CTA, so it can be multicast across a thread-block cluster
-  // (each CTA fetches 1/csz of every tile); measured neutral on B200 (L2 already merges the requests) -> default 1
-  static int env_csz = -1;
-  if (env_csz < 0) {
-    const char* e = getenv("OSQ_FUSED_CLUSTER");
-    env_csz = e ? atoi(e) : 0;
-  }
-  p.csz = env_csz > 0 ? env_csz : 1;
-  if (p.csz != 1 && p.csz != 2 && p.csz != 4) p.csz = 1;
-  while (p.csz > 1 && (p.BN % (8 * p.csz) != 0 || (p.M + kBM - 1) / kBM < p.csz)) p.csz >>= 1;
-
   p.A = a->A;
   p.a_scale = a->a_scale; p.a_zp = a->a_zp; p.a_zp_is_int32 = a->a_zp_is_int32; p.g = a->lsq_grad_factor;
   p.qmin = (float)a->a_qmin; p.qmax = (float)a->a_qmax;
   p.w_scale = a->w_scale; p.w_rowsum = a->w_rowsum; p.bias = a->bias; p.a_codes = a->a_codes;
   p.trace = (long long*)a->debug_trace;
-  {
-    const char* e = getenv("OSQ_FUSED_DBG");
-    p.dbg = e ? atoi(e) : 0;
+  static int env_dbg = -1, env_ob = -1, env_kb = -1, env_csz = -1, env_pdl = -1, env_pf = -1, env_xtma = -1, env_bn = -1;
+  if (env_dbg < 0) {
+    auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    env_dbg = geti("OSQ_FUSED_DBG", 0);
+    env_ob = geti("OSQ_FUSED_OUTBUFS", 0);
+    env_kb = geti("OSQ_FUSED_SMEM_KB", 227);
+    if (env_kb < 100 || env_kb > 227) env_kb = 227;
+    env_csz = geti("OSQ_FUSED_CLUSTER", 1);
+    env_pdl = geti("OSQ_FUSED_PDL", 1);
+    env_pf = geti("OSQ_FUSED_PREFETCH", 0);
+    env_xtma = geti("OSQ_FUSED_XTMA", 1);
+    env_bn = geti("OSQ_FUSED_BN", 0);
   }
+  p.dbg = env_dbg;
+  p.pdl = env_pdl ? 1 : 0;
 
-  CUtensorMap map_w, map_y, map_y16, map_c;
-  if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->w_codes, (uint64_t)p.K, (uint64_t)p.N, kStageK,
-                           (uint32_t)(p.BN / p.csz), CU_TENSOR_MAP_SWIZZLE_128B))
-    return rc;
-  if (int rc = make_map_2d(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
-                           p.M < 32 ? (uint32_t)p.M : 32u, CU_TENSOR_MAP_SWIZZLE_128B))
-    return rc;
-  if (int rc = make_map_2d(&map_y16, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
-                           p.M < 16 ? (uint32_t)p.M : 16u, CU_TENSOR_MAP_SWIZZLE_128B))
-    return rc;
-  if (p.cached) {
-    if (int rc = make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->a_codes, (uint64_t)p.K, (uint64_t)p.M, kStageK,
-                             p.M < kBM ? (uint32_t)p.M : (uint32_t)kBM, CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
-  } else {
-    map_c = map_w;  // unused by the kernel
-  }
+  // cluster size: the W stream is identical for every CTA, so it can be multicast across a thread-block cluster
+  // (each CTA fetches 1/csz of every tile); measured neutral on B200 (L2 already merges the requests) -> default 1
+  p.csz = (env_csz == 2 || env_csz == 4) ? env_csz : 1;
+  while (p.csz > 1 && (p.M + kBM - 1) / kBM < p.csz) p.csz >>= 1;
 
   static bool attr_set[64] = {false};
   if (!attr_set[dev & 63]) {
-    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = (cudaStream_t)stream;
-  static int env_pdl = -1;
-  if (env_pdl < 0) { const char* e = getenv("OSQ_FUSED_PDL"); env_pdl = e ? atoi(e) : 1; }
-  p.pdl = env_pdl ? 1 : 0;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)p.csz;
@@ -948,8 +1014,9 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   if (max_ctas[dev & 63][p.csz] == 0) {
     int n_clusters = 0;
     cfg.gridDim = dim3((unsigned)(sms / p.csz * p.csz));
+    cfg.dynamicSmemBytes = 227 * 1024;
     if (p.csz > 1) {
-      OSQ_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, fused_fq_linear_kernel, &cfg));
+      OSQ_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, fused_fq_linear_kernel<true>, &cfg));
       max_ctas[dev & 63][p.csz] = n_clusters * p.csz;
     } else {
       max_ctas[dev & 63][p.csz] = sms;
@@ -971,9 +1038,111 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   int grid = p.n_mblocks < G ? p.n_mblocks : G;
   grid = (grid + p.csz - 1) / p.csz * p.csz;
   p.n_iters = (p.n_mblocks + grid - 1) / grid;
-  p.codes_box_bytes = (uint32_t)(p.M < kBM ? p.M : kBM) * kStageK;
   cfg.gridDim = dim3((unsigned)grid);
-  OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel, map_w, map_y, map_y16, map_c, p));
+
+  // ---- shared-memory plan (<= 227 KB / CTA):
+  //   [A ring: a_stages x (rows_per_tile x 128 B)] [W ring: w_stages x (BN x 128 B)] [X: 16 x 4 KB fp32 landing slots]
+  //   [O: 8 x out_bufs x 4 KB TMA-store staging, aliased onto X when space is short] [barriers + 2 BN constants]
+  // A stages hold only the tile's valid rows: the MMA (M = 128) reads past them into the next stage / the W ring,
+  // which only produces accumulator rows nobody stores.
+  p.a_stage_bytes = p.rows_per_tile * kStageK;
+  const int x_bytes = kNumWorkers * kXSlotBytes;          // 64 KB
+  const int out1 = kNumEpiWarps * kOutTileBytes;          // 32 KB per buffer set
+  const int total = env_kb * 1024 - (int)sizeof(Smem);
+  struct Plan { int ok, bn, resident, cached, a_stages, w_stages, out_bufs, x_tma, alias, score; };
+  auto make_plan = [&](int bn, int x_tma) {
+    Plan pl; memset(&pl, 0, sizeof(pl));
+    pl.bn = bn; pl.x_tma = x_tma;
+    const int nc = (p.N + bn - 1) / bn;
+    const int w_stage = (bn * kStageK + 1023) / 1024 * 1024;
+    const int budget = total - 2 * bn * (int)sizeof(float);
+    const int xo_min = x_tma ? x_bytes : out1;            // aliased X/O region, or one set of store tiles
+    pl.resident = (p.KB <= kMaxAStages && p.KB * p.a_stage_bytes + 2 * w_stage + xo_min <= budget) ? 1 : 0;
+    pl.cached = (!pl.resident && nc > 1 && a->a_codes != nullptr) ? 1 : 0;
+    pl.a_stages = pl.resident ? p.KB : 4;
+    // X and O can share memory only when conversion and epilogue never interleave inside a tile
+    const bool can_alias = pl.resident || pl.cached || nc == 1;
+    int rest = budget - pl.a_stages * p.a_stage_bytes - 2 * w_stage;
+    pl.w_stages = 2;
+    if (x_tma) {
+      if (can_alias && rest >= x_bytes) { pl.alias = 1; pl.out_bufs = 2; rest -= x_bytes; }
+      else if (rest >= x_bytes + out1) { pl.alias = 0; pl.out_bufs = 1; rest -= x_bytes + out1; }
+      else return pl;                                     // does not fit
+    } else {
+      if (rest < out1) return pl;
+      pl.out_bufs = 1; rest -= out1;
+    }
+    if (env_ob == 1 && !pl.alias) { /* keep one */ }
+    // the W stream needs ~2.5 stages of 32 KB in flight to cover the L2 latency: a third stage comes first
+    if (rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
+    if (!pl.alias && pl.out_bufs == 1 && env_ob != 1 && rest >= out1) { pl.out_bufs = 2; rest -= out1; }
+    while (pl.w_stages < kMaxWStages && rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
+    if (!pl.resident)
+      while (pl.a_stages < kMaxAStages && rest >= p.a_stage_bytes) { ++pl.a_stages; rest -= p.a_stage_bytes; }
+    pl.ok = 1;
+    // preference: three W stages and double-buffered stores matter more than the chunk width
+    pl.score = (pl.w_stages >= 3 ? 4 : 0) + (pl.out_bufs >= 2 ? 2 : 0) + (bn == 256 ? 1 : 0);
+    return pl;
+  };
+  const bool x_ok = env_xtma != 0 && p.K % 4 == 0;
+  Plan best; memset(&best, 0, sizeof(best));
+  const int bn_cands[3] = {256, 192, 128};
+  for (int xt = x_ok ? 1 : 0; xt >= 0 && !best.ok; --xt)
+    for (int i = 0; i < 3; ++i) {
+      int bn = bn_cands[i];
+      if (env_bn > 0 && bn != env_bn) continue;
+      if (p.N < bn) { if (i == 0) bn = p.N; else continue; }   // narrow layers: one chunk of N columns
+      else if (p.N % bn != 0 && i != 0) continue;               // 192 / 128 only when they tile N exactly
+      if (bn % (8 * p.csz) != 0) continue;
+      Plan pl = make_plan(bn, xt);
+      if (pl.ok && (!best.ok || pl.score > best.score)) best = pl;
+    }
+  if (!best.ok) { set_error("osq_fused_fq_linear: no shared-memory plan for K=%d N=%d", p.K, p.N); return OSQ_EINVAL; }
+  p.BN = best.bn;
+  p.NC = (p.N + p.BN - 1) / p.BN;
+  p.acc_stages = kTmemCols / p.BN;
+  if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
+  p.w_stage_bytes = (p.BN * kStageK + 1023) / 1024 * 1024;
+  p.resident = best.resident; p.cached = best.cached;
+  p.a_stages = best.a_stages; p.w_stages = best.w_stages; p.out_bufs = best.out_bufs;
+  p.x_tma = best.x_tma; p.alias_xo = best.alias;
+  const int const_bytes = 2 * p.BN * (int)sizeof(float);
+  const size_t smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes +
+                            (p.x_tma ? (size_t)x_bytes : 0) + (p.alias_xo ? 0 : (size_t)p.out_bufs * out1) +
+                            sizeof(Smem) + (size_t)const_bytes;
+  cfg.dynamicSmemBytes = smem_bytes;
+  p.codes_box_bytes = (uint32_t)(p.M < p.rows_per_tile ? p.M : p.rows_per_tile) * kStageK;
+
+  CUtensorMap map_w, map_y, map_y16, map_c, map_a;
+  if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->w_codes, (uint64_t)p.K, (uint64_t)p.N, kStageK,
+                           (uint32_t)(p.BN / p.csz), CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
+  if (int rc = make_map_2d(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
+                           p.M < 32 ? (uint32_t)p.M : 32u, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
+  if (int rc = make_map_2d(&map_y16, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
+                           p.M < 16 ? (uint32_t)p.M : 16u, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
+  if (p.cached) {
+    if (int rc = make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->a_codes, (uint64_t)p.K, (uint64_t)p.M, kStageK,
+                             (uint32_t)(p.M < p.rows_per_tile ? p.M : p.rows_per_tile), CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  } else {
+    map_c = map_w;  // unused by the kernel
+  }
+  // fp32 activation: [8 rows x 128 floats] boxes (one worker's rows of one k-block) for the landing slots; the
+  // same map serves the optional L2 prefetcher (OSQ_FUSED_PREFETCH = distance in k-blocks; measured: 3 is neutral,
+  // 6 and 12 are 3-8 % slower -> off by default)
+  p.prefetch = (p.x_tma == 0 && p.K % 4 == 0) ? env_pf : 0;
+  if (p.x_tma || p.prefetch > 0) {
+    if (int rc = make_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->A, (uint64_t)p.K, (uint64_t)p.M, kStageK,
+                             (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker), CU_TENSOR_MAP_SWIZZLE_NONE))
+      return rc;
+  } else {
+    map_a = map_w;  // unused by the kernel
+  }
+  if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel<true>, map_w, map_y, map_y16, map_c, map_a, p));
+  else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel<false>, map_w, map_y, map_y16, map_c, map_a, p));
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }
