@@ -376,8 +376,11 @@ struct Smem {
   volatile uint32_t converted;  // k-blocks worker 0 has converted so far (paces the L2 prefetcher)
   uint32_t pad2[2];  // keeps sizeof(Smem) a multiple of 16: the per-column constants follow it
 };
-// after Smem: per-column epilogue constants of the current chunk (2 * BN floats):
+// after Smem: per-column epilogue constants of the current chunk (2 * BN floats, padded to 32 columns):
 //   y = acc * c1[n] + c0[n],  c1 = s_a * w_scale[n],  c0 = bias[n] - Zc * rowsum[n] * c1
+// (measured: an exact integer zero-point correction + magic-number int->float instead of I2F is not faster --
+//  the epilogue is bound by shared-memory bandwidth, which the MMA operand reads share -- and a third constant
+//  array costs 3 %)
 static_assert(sizeof(Smem) % 16 == 0, "constants must stay 16-byte aligned");
 
 template <bool kXTma>
@@ -394,8 +397,10 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   uint8_t* o_ring = p.alias_xo ? x_ring : x_ring + (kXTma ? kNumWorkers * kXSlotBytes : 0);
   Smem& sm = *reinterpret_cast<Smem*>(p.alias_xo ? x_ring + kNumWorkers * kXSlotBytes
                                                  : o_ring + (size_t)kNumEpiWarps * p.out_bufs * kOutTileBytes);
-  float* sm_c1 = reinterpret_cast<float*>(&sm + 1);  // [BN]
-  float* sm_c0 = sm_c1 + p.BN;                       // [BN]
+  // per-column constants; the arrays are padded to a multiple of 32 columns (the epilogue reads 32-column groups)
+  const int bn_pad = (p.BN + 31) & ~31;
+  float* sm_c1 = reinterpret_cast<float*>(&sm + 1);  // s_a * w_scale[n]
+  float* sm_c0 = sm_c1 + bn_pad;                     // bias[n] - Zc * rowsum[n] * c1[n]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -727,18 +732,25 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     // per-column constants: each epilogue thread owns column `et` of the chunk (BN <= 256 = epilogue threads);
     // they are fetched into registers early (L2 latency hides under the previous chunk) and published to
     // shared memory between two barriers
-    float pc1 = 0.f, pc0 = 0.f;
+    // The three loads are issued early and only CONSUMED at publish time (one chunk later): using them right away
+    // would park the warp on an L2 round trip (1-2 K cycles under store traffic) in front of every chunk.
+    float raw_ws = 0.f, raw_b = 0.f;
+    int raw_rs = 0;
     auto fetch_consts = [&](int nc) {
       const int n = nc * p.BN + et;
-      pc1 = 0.f; pc0 = 0.f;
+      raw_ws = 0.f; raw_b = 0.f; raw_rs = 0;
       if (et < p.BN && n < p.N) {
-        pc1 = __fmul_rn(s_a, __ldg(p.w_scale + n));
-        const float b = (p.bias != nullptr) ? __ldg(p.bias + n) : 0.f;
-        pc0 = fmaf(-zcf * (float)__ldg(p.w_rowsum + n), pc1, b);
+        raw_ws = __ldg(p.w_scale + n);
+        raw_rs = __ldg(p.w_rowsum + n);
+        if (p.bias != nullptr) raw_b = __ldg(p.bias + n);
       }
     };
     auto publish_consts = [&]() {  // all epilogue warps; previous chunk's readers are done (barrier before)
-      if (et < p.BN) { sm_c1[et] = pc1; sm_c0[et] = pc0; }
+      if (et < p.BN) {
+        const float pc1 = __fmul_rn(s_a, raw_ws);
+        sm_c1[et] = pc1;
+        sm_c0[et] = fmaf(-zcf * (float)raw_rs, pc1, raw_b);
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
     };
     int obufs = p.out_bufs;  // store tiles this warp may cycle through in the current m-block
@@ -761,35 +773,67 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       const CUtensorMap* ymap = (rows_q == 32) ? &tmap_y : &tmap_y16;
       for (int c0 = c_lo; c0 < c_end; c0 += 32) {
         uint32_t v[32];
+#ifdef OSQ_ENABLE_TRACE
+        const bool probe = (w == 0 && lane == 0 && cacc == 2);
+        const int pslot = 900 + ((c0 - c_lo) >> 5) * 6;
+        if (probe) OSQ_TRACE(pslot + 0);
+#endif
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
+#ifdef OSQ_ENABLE_TRACE
+        if (probe) OSQ_TRACE(pslot + 1);
+#endif
         if (!any_rows) continue;  // warp uniform: phantom tile / quarter past the tile's rows
         if (n_stores >= (uint32_t)obufs) {  // the staging tile must have been read out by its previous TMA store
           if (lane == 0) { if (obufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
           __syncwarp();
         }
+#ifdef OSQ_ENABLE_TRACE
+        if (probe) OSQ_TRACE(pslot + 2);
+#endif
         // aliased mode: this warp's own landing slot, plus (last tile only) the slot of worker w + 8, whose owner is
         // through with it once the tile's last MMA has been committed
         uint8_t* tile = p.alias_xo ? x_ring + (size_t)(((n_stores & 1u) & (uint32_t)(obufs - 1)) * kNumEpiWarps + w) * kXSlotBytes
                                    : my_tiles + (size_t)(n_stores % (uint32_t)obufs) * kOutTileBytes;
         uint8_t* trow = tile + lane * 128;
+        // The constants of the NEXT four columns are loaded before the current four are stored: the compiler
+        // cannot move a shared-memory load above an earlier shared-memory store (possible alias), so without this
+        // every iteration would expose a full LDS latency.
+        // the constants of the NEXT four columns are loaded before the current four are stored: the compiler cannot
+        // move a shared-memory load above an earlier shared-memory store (possible alias)
+        {
+          float4 c1n = *reinterpret_cast<const float4*>(sm_c1 + c0);
+          float4 k0n = *reinterpret_cast<const float4*>(sm_c0 + c0);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 c1 = *reinterpret_cast<const float4*>(sm_c1 + c0 + j);
-          const float4 k0 = *reinterpret_cast<const float4*>(sm_c0 + c0 + j);
-          float4 o;
-          o.x = fmaf((float)(int)v[j + 0], c1.x, k0.x);
-          o.y = fmaf((float)(int)v[j + 1], c1.y, k0.y);
-          o.z = fmaf((float)(int)v[j + 2], c1.z, k0.z);
-          o.w = fmaf((float)(int)v[j + 3], c1.w, k0.w);
-          *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ sw)) = o;  // 16B chunk (j/4) ^ (row & 7): conflict free
+          for (int j = 0; j < 32; j += 4) {
+            const float4 c1 = c1n, k0 = k0n;
+            if (j + 4 < 32) {
+              c1n = *reinterpret_cast<const float4*>(sm_c1 + c0 + j + 4);
+              k0n = *reinterpret_cast<const float4*>(sm_c0 + c0 + j + 4);
+            }
+            float4 o;
+            o.x = fmaf((float)(int)v[j + 0], c1.x, k0.x);
+            o.y = fmaf((float)(int)v[j + 1], c1.y, k0.y);
+            o.z = fmaf((float)(int)v[j + 2], c1.z, k0.z);
+            o.w = fmaf((float)(int)v[j + 3], c1.w, k0.w);
+            *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ sw)) = o;  // 16B chunk (j/4) ^ (row & 7): conflict free
+          }
         }
+#ifdef OSQ_ENABLE_TRACE
+        if (probe) OSQ_TRACE(pslot + 3);
+#endif
         fence_proxy_async_smem();
         __syncwarp();
+#ifdef OSQ_ENABLE_TRACE
+        if (probe) OSQ_TRACE(pslot + 4);
+#endif
         if (lane == 0 && !(p.dbg & 2)) {
           tma_store_2d(ymap, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
           tma_store_commit();
         }
+#ifdef OSQ_ENABLE_TRACE
+        if (probe) OSQ_TRACE(pslot + 5);
+#endif
         ++n_stores;
       }
       tc_fence_before();
@@ -798,7 +842,9 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4 + 1);
       ++cacc;
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");  // every reader of this chunk's constants is done
+      if (w == 0 && lane == 0 && cacc <= 60) OSQ_TRACE(512 + (cacc - 1) * 4 + 2);
       if (nc + 1 < p.NC) publish_consts();
+      if (w == 0 && lane == 0 && cacc <= 60) OSQ_TRACE(512 + (cacc - 1) * 4 + 3);
     };
 
     for (int it = 0; it < n_my_blocks; ++it) {
@@ -943,7 +989,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   OSQ_CHECK_ARG(a->A && a->a_scale && a->a_zp && a->w_codes && a->w_scale && a->w_rowsum && a->Y,
                 "osq_fused_fq_linear: null pointer");
   OSQ_CHECK_ARG(a->M >= 1 && a->M < (1ll << 31) - 256, "osq_fused_fq_linear: M out of range");
-  OSQ_CHECK_ARG(a->K >= kStageK && a->K % kStageK == 0 && a->K <= (1 << 20), "osq_fused_fq_linear: K must be a multiple of 128");
+  OSQ_CHECK_ARG(a->K >= kStageK && a->K % kStageK == 0 && a->K <= 32768, "osq_fused_fq_linear: K must be a multiple of 128, at most 32768 (int32 accumulators)");
   OSQ_CHECK_ARG(a->N >= 16 && a->N % 16 == 0 && a->N <= (1 << 20), "osq_fused_fq_linear: N must be a multiple of 16");
   OSQ_CHECK_ARG(a->a_qmax - a->a_qmin <= 255 && a->a_qmin < a->a_qmax, "osq_fused_fq_linear: activation bits > 8");
   OSQ_CHECK_ARG(a->mma_kind == 0 || a->mma_kind == 1, "osq_fused_fq_linear: mma_kind %d not built", a->mma_kind);
@@ -1055,7 +1101,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
     pl.bn = bn; pl.x_tma = x_tma;
     const int nc = (p.N + bn - 1) / bn;
     const int w_stage = (bn * kStageK + 1023) / 1024 * 1024;
-    const int budget = total - 2 * bn * (int)sizeof(float);
+    const int budget = total - 2 * ((bn + 31) & ~31) * (int)sizeof(float);
     const int xo_min = x_tma ? x_bytes : out1;            // aliased X/O region, or one set of store tiles
     pl.resident = (p.KB <= kMaxAStages && p.KB * p.a_stage_bytes + 2 * w_stage + xo_min <= budget) ? 1 : 0;
     pl.cached = (!pl.resident && nc > 1 && a->a_codes != nullptr) ? 1 : 0;
@@ -1106,7 +1152,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   p.resident = best.resident; p.cached = best.cached;
   p.a_stages = best.a_stages; p.w_stages = best.w_stages; p.out_bufs = best.out_bufs;
   p.x_tma = best.x_tma; p.alias_xo = best.alias;
-  const int const_bytes = 2 * p.BN * (int)sizeof(float);
+  const int const_bytes = 2 * ((p.BN + 31) & ~31) * (int)sizeof(float);
   const size_t smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes +
                             (p.x_tma ? (size_t)x_bytes : 0) + (p.alias_xo ? 0 : (size_t)p.out_bufs * out1) +
                             sizeof(Smem) + (size_t)const_bytes;

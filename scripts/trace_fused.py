@@ -35,5 +35,5 @@ for K, N in SHAPES:
     print("wprod issue times, uses 36..75:", [rel(v) for v in t[1600:1640] if v])
     print("mma per k-block uses 36..71 (a ready, w ready, issued):", [tuple(rel(t[1400 + 3 * i + k]) for k in range(3)) for i in range(36) if t[1400 + 3 * i]])
     print("mma  (start, first operands, commit issued):", [(rel(t[256 + 4 * i]), rel(t[257 + 4 * i]), rel(t[258 + 4 * i])) for i in range(60) if t[256 + 4 * i]][:14])
-    print("epi group detail (ld issue, ld done, sts+sync done, consts ready, stores issued):", [rel(t[900 + i]) for i in range(5)])
-    print("epi  (acc_full acquired, chunk done):", [(rel(t[512 + 4 * i]), rel(t[513 + 4 * i])) for i in range(60) if t[512 + 4 * i]][:14])
+    print("epi groups of chunk 2 (start, tmem ld done, tile free, math+sts done, fence done, store issued):", [[rel(t[900 + 6 * g + i]) for i in range(6)] for g in range(4)])
+    print("epi  (acc_full acquired, chunk done, all warps done, consts published):", [tuple(rel(t[512 + 4 * i + j]) for j in range(4)) for i in range(60) if t[512 + 4 * i]][:14])
