@@ -3,9 +3,11 @@
 
 One step = one pass of the hot path over one synthetic batch [32, 512, 768]: the 72 QLinear sites of
 the BERT-base encoder stack (12 layers x {q, k, v, attn-out: 768->768, FFN-up 768->3072, FFN-down
-3072->768}), each executed as ONE fused activation-fake-quant + weight-fake-quant + Linear launch
+3072->768}), executed as fused activation-fake-quant + weight-fake-quant + Linear launches
 (LSQ+ 6-bit asymmetric activations calibrated by AvgPruneMinMax p=0.99, Fixed 6-bit symmetric
-per-channel weights, gamma folded at load).  tokens/s = 16384 / step time.
+per-channel weights, gamma folded at load).  q, k and v read the same quantized tensor (quant_bert.py
+self-attention) and share ONE launch over their concatenated weights (QLinearGroup; bit-identical outputs),
+so a step is 48 launches; --no-group launches all 72 separately.  tokens/s = 16384 / step time.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -178,11 +180,12 @@ def run_reference_arm(args):
 def build_stack(device):
     """72 calibrated (activation quantizer, QLinear) module pairs + device-resident activations."""
     from outlier_suppression_b200 import ops
-    from outlier_suppression_b200.quantization.quantized_module import Quantizer
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer, QLinearGroup
     lens = synth_lens().to(device)
     # inputs larger than L2 (126 MB): 4 x 50 MB for K=768, 2 x 201 MB for K=3072, rotated per launch
     acts = {H: [synth_act(H, 11 + i, device) for i in range(4)], FF: [synth_act(FF, 21 + i, device) for i in range(2)]}
-    outs = {H: [torch.empty(M, H, device=device) for _ in range(4)], FF: [torch.empty(M, FF, device=device) for _ in range(2)]}
+    outs = {H: [torch.empty(M, H, device=device) for _ in range(4)], FF: [torch.empty(M, FF, device=device) for _ in range(2)],
+            3 * H: [torch.empty(M, 3 * H, device=device) for _ in range(2)]}
     layers = []
     for layer in range(LAYERS):
         mods = []
@@ -200,7 +203,14 @@ def build_stack(device):
             aq.enable_fake_quant(); ql.weight_fake_quant.enable_fake_quant()
             codes, rowsum, w_scale = ql._packed_weight()
             mods.append({"name": name, "k": k, "n": n, "aq": aq, "ql": ql, "codes": codes, "rowsum": rowsum, "w_scale": w_scale,
-                         "g": aq.grad_factor(acts[k][0])})
+                         "bias": ql.bias, "g": aq.grad_factor(acts[k][0])})
+        # q | k | v consume the same quantized tensor (the e2e leg feeds them q's quantizer output, as quant_bert.py does)
+        grp = QLinearGroup([m["ql"] for m in mods[:3]])
+        for m in mods[:3]:
+            m["ql"]._sibling_group = grp
+        gcodes, growsum, gscale, gbias = grp._packed_weight()
+        mods.append({"name": "qkv", "k": H, "n": 3 * H, "aq": mods[0]["aq"], "ql": None, "codes": gcodes, "rowsum": growsum,
+                     "w_scale": gscale, "bias": gbias, "g": mods[0]["g"]})
         layers.append(mods)
     torch.cuda.synchronize()
     return layers, acts, outs, ops
@@ -215,6 +225,7 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python launch loop instead of CUDA graph replay")
+    ap.add_argument("--no-group", action="store_true", help="launch q, k and v separately (72 launches per step)")
     ap.add_argument("--only-value", action="store_true", help="profiling runs: timed stack only, no roofline/e2e/cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -236,8 +247,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
 
+    if args.no_group:
+        os.environ["OSQ_DISABLE_GROUPING"] = "1"
     layers, acts, outs, ops = build_stack(device)
-    counters = {H: 0, FF: 0}
+    counters = {H: 0, FF: 0, 3 * H: 0}
 
     def launch(site, a=None):
         k, n = site["k"], site["n"]
@@ -247,11 +260,16 @@ def main():
         out = outs[n][counters[n] % len(outs[n])]
         aq = site["aq"]
         return ops.fused_fq_linear(a, aq.scale.data, aq.zero_point.data, aq.quant_min, aq.quant_max, site["codes"],
-                                   site["w_scale"], site["rowsum"], site["ql"].bias, lsq_grad_factor=site["g"], out=out)
+                                   site["w_scale"], site["rowsum"], site["bias"], lsq_grad_factor=site["g"], out=out)
+
+    # launch list of one layer
+    order = [n for n, *_ in SITES] if args.no_group else ["qkv", "attn_out", "ffn_up", "ffn_down"]
+    plan = [[next(s for s in mods if s["name"] == n) for n in order] for mods in layers]
+    shape_of = {s["name"]: (s["k"], s["n"]) for s in layers[0]}
 
     def step():
-        for mods in layers:
-            for site in mods:
+        for sites in plan:
+            for site in sites:
                 launch(site)
 
     def barrier():
@@ -279,7 +297,7 @@ def main():
     run_step, launch_mode = step, "eager loop"
     if not args.no_graph:
         step_graph = make_graph(step)
-        run_step, launch_mode = step_graph.replay, "one CUDA graph per step (72 kernel nodes, PDL edges)"
+        run_step, launch_mode = step_graph.replay, "one CUDA graph per step (%d kernel nodes, PDL edges)" % (LAYERS * len(order))
     for _ in range(args.warmup):
         run_step()
     barrier()
@@ -318,7 +336,8 @@ def main():
             pass
     per_site, tot_bytes, tot_ms, n_launch = {}, 0.0, 0.0, 0
     reps, per_graph = 5, 24
-    for name, k, n, _ in SITES:
+    for name in order:
+        k, n = shape_of[name]
         chain = [[s for s in mods if s["name"] == name][0] for mods in layers[:6]] * (per_graph // 6)
 
         def site_chain():
@@ -344,7 +363,7 @@ def main():
         tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
         if tf:
             t = json.load(open(tf[-1]))
-            traffic = sum(t[name] for name, *_ in SITES) / len(SITES)
+            traffic = sum(t[name] for name in order) / len(order)
     except Exception:
         traffic = None
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
@@ -406,11 +425,12 @@ def main():
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8 (u8 x s8 -> s32 bins, fp32 I/O)",
                "data": "synthetic",
                "config": {"workload": "BERT-base seq512 6-bit twc_fine_gamma (LSQ+ acts / AvgPruneMinMax p=.99, Fixed per-channel weights, gamma folded), "
-                                      "batch 32 per GPU (M=16384), 72 fused QLinear sites per step",
+                                      "batch 32 per GPU (M=16384), 72 QLinear sites per step in %d fused launches%s" % (
+                                          LAYERS * len(order), "" if args.no_group else " (q|k|v of a layer share one launch)"),
                           "launch": launch_mode, "host_issue_ms_per_step": host_issue_ms,
                           "l2": "inputs/outputs rotate over 4x50MB / 2x201MB buffers (> 126 MB L2) between launches",
                           "parallelism": "dp%d (independent batches, no collective)" % world},
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * LAYERS * len(SITES),
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * LAYERS * len(order),
                "clocks": clocks}
         print(json.dumps(rec))
     if dist is not None:

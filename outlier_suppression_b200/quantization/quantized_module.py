@@ -33,7 +33,7 @@ FakeQuantizeDict = {
 }
 
 # statistics for tests / benches: which path QLinear.forward took
-stats = {"fused": 0, "unfused": 0}
+stats = {"fused": 0, "unfused": 0, "grouped_launch": 0, "grouped_hit": 0}
 
 
 class QuantizedModule(nn.Module):
@@ -56,6 +56,10 @@ class QuantizedOperator:
         togglers and the weight observer call it automatically."""
         self._packed = None
         self._fq_weight_cache = None
+        grp = getattr(self, "_sibling_group", None)
+        if grp is not None:
+            grp._packed = None
+            grp._pending = None
 
     def _weight_is_static(self):
         wq = self.weight_fake_quant
@@ -93,6 +97,7 @@ class QLinear(QuantizedOperator, nn.Linear):
     def __init__(self, in_features, out_features, bias, w_qconfig):
         super().__init__(in_features=in_features, out_features=out_features, bias=bias)
         self.weight_fake_quant = WeightQuantizer(w_qconfig)
+        self._sibling_group = None  # set by group_sibling_linears()
 
     # ---- fused path ----
     def _fusable_producer(self, input):
@@ -126,6 +131,11 @@ class QLinear(QuantizedOperator, nn.Linear):
     def forward(self, input):
         aq = self._fusable_producer(input)
         if aq is not None:
+            group = getattr(self, "_sibling_group", None)
+            if group is not None:
+                out = group.forward_member(self, input, aq)
+                if out is not None:
+                    return out
             codes, rowsum, w_scale = self._packed_weight()
             g = aq.grad_factor(input) if isinstance(aq, LSQPlusFakeQuantize) else 0.0
             stats["fused"] += 1
@@ -134,6 +144,92 @@ class QLinear(QuantizedOperator, nn.Linear):
         stats["unfused"] += 1
         w = self._cached_fq_weight() if self._weight_is_static() else self.weight_fake_quant(self.weight)
         return F.linear(input, w, self.bias)
+
+
+class QLinearGroup:
+    """Sibling QLinears that consume the SAME quantized activation -- BERT / RoBERTa ``query | key | value``
+    (quant_bert.py / quant_roberta.py self-attention), BART ``q_proj | k_proj | v_proj`` -- served by ONE fused
+    launch over their concatenated packed weights: the activation is read from HBM and quantised once instead of
+    once per sibling.  The first sibling called with a tensor launches and hands the others views of the shared
+    ``[..., sum(N_i)]`` output when they are called with the very same tensor object; every output element is
+    bit-identical to the ungrouped launch (same integer accumulator, same per-column constants).  Not a module on
+    purpose: it must not show up in ``state_dict`` / ``named_modules``."""
+
+    def __init__(self, members):
+        self.members = list(members)
+        self._packed = None
+        self._pending = None  # (input tensor, its version, {id(member): output view})
+
+    def _packed_weight(self):
+        key = tuple((m._weight_key(), None if m.bias is None else (m.bias.data_ptr(), m.bias._version)) for m in self.members)
+        c = self._packed
+        if c is None or c[0] != key:
+            parts = [m._packed_weight() for m in self.members]
+            dev = parts[0][0].device
+            bias = None
+            if any(m.bias is not None for m in self.members):
+                bias = torch.cat([m.bias.detach().float() if m.bias is not None else
+                                  torch.zeros(m.out_features, device=dev) for m in self.members]).contiguous()
+            c = (key, torch.cat([p[0] for p in parts]).contiguous(), torch.cat([p[1] for p in parts]).contiguous(),
+                 torch.cat([p[2] for p in parts]).contiguous(), bias)
+            self._packed = c
+        return c[1:]
+
+    def forward_member(self, member, input, aq):
+        pend = self._pending
+        if pend is not None and pend[0] is input and pend[1] == input._version and id(member) in pend[2]:
+            out = pend[2].pop(id(member))
+            if not pend[2]:
+                self._pending = None
+            stats["grouped_hit"] += 1
+            return out
+        self._pending = None
+        if os.environ.get("OSQ_DISABLE_GROUPING") == "1":
+            return None
+        for m in self.members:  # every sibling must be on the fused path with this very producer
+            if m is not member and m._fusable_producer(input) is not aq:
+                return None
+        if not ops.fused_linear_supported(member.in_features, sum(m.out_features for m in self.members)):
+            return None
+        codes, rowsum, w_scale, bias = self._packed_weight()
+        g = aq.grad_factor(input) if isinstance(aq, LSQPlusFakeQuantize) else 0.0
+        y = ops.fused_fq_linear(input, aq.scale.detach(), aq.zero_point.detach(), aq.quant_min, aq.quant_max,
+                                codes, w_scale, rowsum, bias, lsq_grad_factor=g)
+        stats["grouped_launch"] += 1
+        stats["fused"] += 1
+        outs, col = {}, 0
+        for m in self.members:
+            outs[id(m)] = y[..., col:col + m.out_features]
+            col += m.out_features
+        mine = outs.pop(id(member))
+        self._pending = (input, input._version, outs)
+        return mine
+
+
+SIBLING_NAME_SETS = (("query", "key", "value"), ("q_proj", "k_proj", "v_proj"))
+
+
+def group_sibling_linears(model):
+    """Finds the sibling projections of every self-attention block (children named like SIBLING_NAME_SETS, all QLinear
+    with the same in_features) and ties them into a QLinearGroup.  Idempotent; returns the number of groups.  Called
+    by the state togglers, so a reference driver gets it without any change."""
+    n = 0
+    for parent in model.modules():
+        kids = dict(parent.named_children())
+        for names in SIBLING_NAME_SETS:
+            members = [kids.get(k) for k in names]
+            if any(not isinstance(m, QLinear) for m in members):
+                continue
+            if len({m.in_features for m in members}) != 1:
+                continue
+            n += 1
+            cur = getattr(members[0], "_sibling_group", None)
+            if cur is not None and cur.members == members:
+                continue
+            grp = QLinearGroup(members)
+            for m in members:
+                m._sibling_group = grp
+    return n
 
 
 class QEmbedding(QuantizedOperator, nn.Embedding):

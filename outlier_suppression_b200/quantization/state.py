@@ -14,6 +14,9 @@ def _drop_weight_caches(model):
         inv = getattr(m, "invalidate_packed", None)
         if inv is not None:
             inv()
+    # query | key | value style siblings share one fused launch from here on (quantized_module.QLinearGroup)
+    from .quantized_module import group_sibling_linears
+    group_sibling_linears(model)
 
 
 def _apply(model, quantizer_type, except_quantizer, observer_on, fq_on, lsq_observer_off=False):

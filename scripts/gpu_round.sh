@@ -18,8 +18,8 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:fused_fq|pack_weight|minmax|prune_select|fq_per" -c 700 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --only-value --no-graph > gpurun_out/ncu_list.log 2>&1 ; echo "rc=$?"
-echo "== ncu full (fused kernel, 3 launches: 768->768 q, then skip to ffn sites)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_fq_linear -s 216 -c 6 -o gpurun_out/prof_fused \
+echo "== ncu full (fused kernel, the 4 launches of one encoder layer: qkv, attn_out, ffn_up, ffn_down)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_fq_linear -s 144 -c 4 -o gpurun_out/prof_fused \
     python bench.py --steps 2 --warmup 3 --only-value --no-graph > gpurun_out/ncu_full.log 2>&1 ; echo "rc=$?"
 fi
 ls -la gpurun_out | head -30

@@ -33,7 +33,7 @@ with open(os.path.join(PROF, tag + "_launches.md"), "w") as f:
     f.write("# %s: ncu launch list of `bench.py --steps 2 --warmup 3 --only-value --no-graph`\n\n" % tag)
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fused_fq|pack_weight|minmax|prune_select|fq_per`.\n"
             "Per-launch times are cold-cache and serialised by ncu: compare SHARES, not absolutes.\n")
-    for part, title in (("step", "Warm-up + timed steps (5 steps x 72 launches): the region `value` is measured on"),
+    for part, title in (("step", "Warm-up + timed steps (5 steps x 48 launches): the region `value` is measured on"),
                         ("setup", "Setup before the first step (untimed): per-channel weight qparams + s8 packing, one calibration batch per activation quantizer")):
         tot = sum(a[1] for a in agg[part].values()) or 1.0
         f.write("\n## %s\n\n| kernel | grid | block | launches | total us | min us | max us | share |\n|---|---|---|---|---|---|---|---|\n" % title)
@@ -54,13 +54,13 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 idx = {k: hdr.index(k) for k in keys if k in hdr}
 traffic = {}
 with open(os.path.join(PROF, tag + "_fused_full.md"), "w") as f:
-    f.write("# %s: `ncu --set full --clock-control none --import-source on -k regex:fused_fq_linear` (6 launches of one encoder layer)\n\n" % tag)
+    f.write("# %s: `ncu --set full --clock-control none --import-source on -k regex:fused_fq_linear` (the 4 launches of one encoder layer)\n\n" % tag)
     f.write("| metric | unit | " + " | ".join("launch %d" % i for i in range(len(body))) + " |\n|---|---|" + "---|" * len(body) + "\n")
     for k, i in idx.items():
         f.write("| %s | %s | %s |\n" % (k, units[i], " | ".join(r[i] for r in body)))
-    f.write("\nLaunch order inside a layer: q, k, v, attn_out (768->768), ffn_up (768->3072), ffn_down (3072->768); the capture starts at a layer boundary.\n")
-names = ["q", "k", "v", "attn_out", "ffn_up", "ffn_down"]
-for j, r in enumerate(body[:6]):
+    f.write("\nLaunch order inside a layer: qkv (768->2304, one launch for the three projections), attn_out (768->768), ffn_up (768->3072), ffn_down (3072->768); the capture starts at a layer boundary.\n")
+names = ["qkv", "attn_out", "ffn_up", "ffn_down"]
+for j, r in enumerate(body[:4]):
     rd, wr = float(r[idx["dram__bytes_read.sum"]]), float(r[idx["dram__bytes_write.sum"]])
     scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
     traffic[names[j]] = rd * scale[units[idx["dram__bytes_read.sum"]]] + wr * scale[units[idx["dram__bytes_write.sum"]]]

@@ -127,3 +127,62 @@ def test_mini_encoder_block_matches_oracle():
     same(h, h_ref)                      # LN-output fake-quant: bit-exact
     close(y, y_ref)
     close(ctx, ctx_ref); close(gl, gl_ref); close(qp, qp_ref)
+
+
+def test_query_key_value_share_one_launch_bit_identical(monkeypatch):
+    """BERT's query | key | value QLinears read the same quantized tensor: grouped they run as ONE fused launch
+    (quantized_module.QLinearGroup); every output must be bit-identical to the three separate launches."""
+    from outlier_suppression_b200 import quantization as Q
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    g = torch.Generator().manual_seed(3)
+    a_cfg = QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1)
+    w_cfg = QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)
+    net = torch.nn.Module()
+    for name, has_bias in (("query", True), ("key", False), ("value", True)):
+        m = torch.nn.Linear(H, H if name != "value" else 2 * H, bias=has_bias)
+        m.weight.data = torch.randn(m.out_features, H, generator=g) * 0.05
+        setattr(net, name, qm.Quantizer(m, w_cfg))
+    net.in_post_act_fake_quantize = qm.Quantizer(None, a_cfg)
+    net.cuda()
+    x = (torch.randn(B, S, H, generator=g) * 2).cuda()
+    Q.enable_calibration_woquantization(net, quantizer_type="fake_quant")
+    net.in_post_act_fake_quantize(x)
+    for m in (net.query, net.key, net.value):
+        m.weight_fake_quant(m.weight)
+    Q.enable_quantization(net)
+    assert net.query._sibling_group is not None
+
+    @torch.no_grad()                                           # eval path (HF Trainer.evaluate); with grad the LSQ+ scale
+    def run():                                                 # is a learnable Parameter and the modules stay unfused
+        xq = net.in_post_act_fake_quantize(x)
+        return [net.query(xq), net.key(xq), net.value(xq)]
+
+    before = dict(qm.stats)
+    grouped = run()
+    assert qm.stats["grouped_launch"] == before["grouped_launch"] + 1 and qm.stats["grouped_hit"] == before["grouped_hit"] + 2
+    again = run()                                              # a fresh input tensor object: launches again
+    assert qm.stats["grouped_launch"] == before["grouped_launch"] + 2
+    with torch.no_grad():
+        only_key = net.key(net.in_post_act_fake_quantize(x))   # a sibling called first / alone still works
+    monkeypatch.setenv("OSQ_DISABLE_GROUPING", "1")
+    single = run()
+    assert qm.stats["grouped_launch"] == before["grouped_launch"] + 3
+    for a, b, c in zip(grouped, again, single):
+        assert a.shape == c.shape
+        same(a, c)
+        same(b, c)
+    same(only_key, single[1])
+    # the views survive the usual head split of quant_bert.py:transpose_for_scores
+    q4 = grouped[0].view(B, S, HEADS, H // HEADS).permute(0, 2, 1, 3)
+    same(q4, single[0].view(B, S, HEADS, H // HEADS).permute(0, 2, 1, 3))
+    # a weight rewrite through .data + toggler drops the concatenated pack
+    net.key.weight.data *= 0.5
+    Q.enable_quantization(net)
+    net.key.weight_fake_quant.enable_observer(); net.key.weight_fake_quant(net.key.weight); net.key.weight_fake_quant.disable_observer()
+    monkeypatch.delenv("OSQ_DISABLE_GROUPING")
+    g2 = run()
+    monkeypatch.setenv("OSQ_DISABLE_GROUPING", "1")
+    s2 = run()
+    for a, c in zip(g2, s2):
+        same(a, c)
+    assert not torch.equal(g2[1], grouped[1])

@@ -155,3 +155,32 @@ def test_host_qparams_match_golden(golden):
             s, z = o.calculate_qparams(torch.from_numpy(g["mins"]), torch.from_numpy(g["maxs"]))
             np.testing.assert_array_equal(s.numpy(), g["s_%d_%d" % (bit, sym)])
             np.testing.assert_array_equal(z.numpy(), g["z_%d_%d" % (bit, sym)])
+
+
+def test_sibling_linear_grouping_discovery():
+    """query | key | value QLinears of one parent are tied into one QLinearGroup by the state togglers
+    (no GPU needed: only the module graph is inspected); unrelated or mismatching children are left alone."""
+    from outlier_suppression_b200 import quantization as Q
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    w_cfg = QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)
+
+    class Attn(torch.nn.Module):
+        def __init__(self, names, widths):
+            super().__init__()
+            for n, k in zip(names, widths):
+                setattr(self, n, qm.Quantizer(torch.nn.Linear(k, 16), w_cfg))
+
+    net = torch.nn.Module()
+    net.a = Attn(("query", "key", "value"), (32, 32, 32))
+    net.b = Attn(("q_proj", "k_proj", "v_proj"), (32, 32, 32))
+    net.c = Attn(("query", "key", "value"), (32, 32, 64))      # different in_features: not grouped
+    net.d = Attn(("query", "key"), (32, 32))                    # incomplete set: not grouped
+    assert qm.group_sibling_linears(net) == 2
+    ga = net.a.query._sibling_group
+    assert ga is not None and ga is net.a.key._sibling_group is net.a.value._sibling_group
+    assert ga.members == [net.a.query, net.a.key, net.a.value]
+    assert net.b.q_proj._sibling_group is net.b.v_proj._sibling_group and net.b.q_proj._sibling_group is not ga
+    assert net.c.query._sibling_group is None and net.d.query._sibling_group is None
+    Q.enable_quantization(net)                                   # idempotent through the togglers
+    assert net.a.query._sibling_group is ga
+    assert all("_sibling_group" not in k for k in net.state_dict())
