@@ -61,6 +61,8 @@ struct FusedParams {
   int rows_per_tile;  // valid rows per CTA tile (<= 128, multiple of 16): chosen so the tile count fills all SMs
   int a_stages, w_stages, out_bufs;
   int a_stage_bytes;  // rows_per_tile * 128
+  int a_passes;       // sweeps over K per m-block: 1 (resident A), ceil(NC / cpp) (streamed A)
+  int cpp;            // N chunks accumulated concurrently in TMEM per sweep (streamed A with a code cache: all acc stages)
   int x_tma;          // fp32 A arrives by TMA into per-worker landing slots (else: 128-bit loads into registers)
   int alias_xo;       // the TMA-store staging tiles share the landing slots' memory
   int w_stage_bytes;  // BN * 128
@@ -435,7 +437,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 
   const int n_my_blocks = p.n_iters;
   if (p.pdl && threadIdx.x == 0) pdl_launch_dependents();
-  const int a_passes = p.resident ? 1 : p.NC;  // how many times the A ring is filled per m-block
+  const int a_passes = p.a_passes;  // how many times the A ring is filled per m-block
 
   if (warp == 0) {
     // ===================== TMA producer: packed weight tiles =====================
@@ -447,9 +449,11 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       const uint32_t w_base = smem_u32(w_ring), full0 = smem_u32(&sm.w_full[0]), empty0 = smem_u32(&sm.w_empty[0]);
       const int slice = p.BN / p.csz;  // rows of the tile this CTA fetches (and multicasts when csz > 1)
       uint32_t ws = 0, wph = 0;        // ring stage and its phase parity
+      // tile order = the MMA issuer's: resident A: chunk-major; streamed A: per sweep, k-block-major over its chunks
+      const int n_tiles = p.NC * p.KB;
       for (int it = 0; it < n_my_blocks; ++it)
-        for (int nc = 0; nc < p.NC; ++nc)
-          for (int kb = 0; kb < p.KB; ++kb) {
+        for (int t = 0, nc = 0, kb = 0, c_lo = 0, j = 0; t < n_tiles; ++t) {
+          {
             mbar_wait_u32(empty0 + ws * 8, wph ^ 1);
             mbar_arrive_expect_tx_u32(full0 + ws * 8, w_bytes);  // the whole stage: every CTA of the cluster delivers its slice
             if (p.csz == 1)
@@ -462,6 +466,14 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 #endif
             if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
           }
+          if (p.resident) {
+            if (++kb == p.KB) { kb = 0; ++nc; }
+          } else {
+            const int n_c = min(p.cpp, p.NC - c_lo);
+            if (++j == n_c) { j = 0; if (++kb == p.KB) { kb = 0; c_lo += n_c; } }
+            nc = c_lo + j;
+          }
+        }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -476,41 +488,80 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       const uint64_t desc_hi = make_smem_desc(0);  // everything but the 14-bit start address
       const uint32_t w_bytes = (uint32_t)p.w_stage_bytes;
       uint32_t ws = 0, wph = 0, as_ = 0, aph = 0, st_a = 0, sph_a = 0;
-      for (int it = 0; it < n_my_blocks; ++it)
-        for (int nc = 0; nc < p.NC; ++nc) {
-          mbar_wait_u32(acc_empty0 + as_ * 8, aph ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as_ * (uint32_t)p.BN;
-          if (p.resident) { st_a = 0; sph_a = (uint32_t)it & 1; }
-          const bool wait_a = !p.resident || nc == 0;         // resident A: filled once per m-block
-          const bool free_a = !p.resident || nc == p.NC - 1;  // ... and released after its last chunk
-          for (int kb = 0; kb < p.KB; ++kb) {
-            if (wait_a) mbar_wait_u32(a_full0 + st_a * 8, sph_a);
-#ifdef OSQ_ENABLE_TRACE
-            const int tslot = (it * p.NC + nc) * p.KB + kb;
-            if (tslot >= 36 && tslot < 72) OSQ_TRACE(1400 + 3 * (tslot - 36));
-#endif
-            mbar_wait_u32(w_full0 + ws * 8, wph);
-#ifdef OSQ_ENABLE_TRACE
-            if (tslot >= 36 && tslot < 72) OSQ_TRACE(1401 + 3 * (tslot - 36));
-#endif
+      const uint32_t n_acc = (uint32_t)p.acc_stages;
+      for (int it = 0; it < n_my_blocks; ++it) {
+        if (p.resident) {
+          // resident A: chunk-major, the converted block is filled once per m-block and released after its last chunk
+          for (int nc = 0; nc < p.NC; ++nc) {
+            mbar_wait_u32(acc_empty0 + as_ * 8, aph ^ 1);
             tc_fence_after();
-            const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)p.a_stage_bytes) >> 4);
-            const uint64_t db = desc_hi | (uint64_t)((w_base + ws * w_bytes) >> 4);
-#pragma unroll
-            for (int k = 0; k < kStageK / kUmmaK; ++k)
-              umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
-            if (p.csz == 1) umma_commit_u32(w_empty0 + ws * 8); else umma_commit_mcast_u32(w_empty0 + ws * 8, cmask);
-            if (free_a) umma_commit_u32(a_empty0 + st_a * 8);
+            const uint32_t d_tmem = tmem_base + as_ * (uint32_t)p.BN;
+            st_a = 0; sph_a = (uint32_t)it & 1;
+            const bool wait_a = nc == 0, free_a = nc == p.NC - 1;
+            for (int kb = 0; kb < p.KB; ++kb) {
+              if (wait_a) mbar_wait_u32(a_full0 + st_a * 8, sph_a);
 #ifdef OSQ_ENABLE_TRACE
-            if (tslot >= 36 && tslot < 72) OSQ_TRACE(1402 + 3 * (tslot - 36));
+              const int tslot = (it * p.NC + nc) * p.KB + kb;
+              if (tslot >= 36 && tslot < 72) OSQ_TRACE(1400 + 3 * (tslot - 36));
 #endif
-            if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
-            if (++st_a == (uint32_t)p.a_stages) { st_a = 0; sph_a ^= 1; }
+              mbar_wait_u32(w_full0 + ws * 8, wph);
+#ifdef OSQ_ENABLE_TRACE
+              if (tslot >= 36 && tslot < 72) OSQ_TRACE(1401 + 3 * (tslot - 36));
+#endif
+              tc_fence_after();
+              const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)p.a_stage_bytes) >> 4);
+              const uint64_t db = desc_hi | (uint64_t)((w_base + ws * w_bytes) >> 4);
+#pragma unroll
+              for (int k = 0; k < kStageK / kUmmaK; ++k)
+                umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
+              if (p.csz == 1) umma_commit_u32(w_empty0 + ws * 8); else umma_commit_mcast_u32(w_empty0 + ws * 8, cmask);
+              if (free_a) umma_commit_u32(a_empty0 + st_a * 8);
+#ifdef OSQ_ENABLE_TRACE
+              if (tslot >= 36 && tslot < 72) OSQ_TRACE(1402 + 3 * (tslot - 36));
+#endif
+              if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
+              ++st_a;
+            }
+            umma_commit_u32(acc_full0 + as_ * 8);
+            if (++as_ == n_acc) { as_ = 0; aph ^= 1; }
           }
-          umma_commit_u32(acc_full0 + as_ * 8);
-          if (++as_ == (uint32_t)p.acc_stages) { as_ = 0; aph ^= 1; }
+        } else {
+          // streamed A: every sweep over K feeds `cpp` accumulators at once (k-block-major), so the bins pass
+          // through the ring ceil(NC / cpp) times instead of NC times
+          for (int c_lo = 0; c_lo < p.NC; c_lo += p.cpp) {
+            const int n_c = min(p.cpp, p.NC - c_lo);
+            for (int j = 0; j < n_c; ++j) {  // the sweep's accumulator stages must have been drained
+              uint32_t s = as_ + (uint32_t)j, ph = aph;
+              if (s >= n_acc) { s -= n_acc; ph ^= 1; }
+              mbar_wait_u32(acc_empty0 + s * 8, ph ^ 1);
+            }
+            tc_fence_after();
+            for (int kb = 0; kb < p.KB; ++kb) {
+              mbar_wait_u32(a_full0 + st_a * 8, sph_a);
+              const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)p.a_stage_bytes) >> 4);
+              for (int j = 0; j < n_c; ++j) {
+                mbar_wait_u32(w_full0 + ws * 8, wph);
+                tc_fence_after();
+                uint32_t s = as_ + (uint32_t)j;
+                if (s >= n_acc) s -= n_acc;
+                const uint32_t d_tmem = tmem_base + s * (uint32_t)p.BN;
+                const uint64_t db = desc_hi | (uint64_t)((w_base + ws * w_bytes) >> 4);
+#pragma unroll
+                for (int k = 0; k < kStageK / kUmmaK; ++k)
+                  umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
+                if (p.csz == 1) umma_commit_u32(w_empty0 + ws * 8); else umma_commit_mcast_u32(w_empty0 + ws * 8, cmask);
+                if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
+              }
+              umma_commit_u32(a_empty0 + st_a * 8);
+              if (++st_a == (uint32_t)p.a_stages) { st_a = 0; sph_a ^= 1; }
+            }
+            for (int j = 0; j < n_c; ++j) {
+              umma_commit_u32(acc_full0 + as_ * 8);
+              if (++as_ == n_acc) { as_ = 0; aph ^= 1; }
+            }
+          }
         }
+      }
     }
   } else if (warp == 2) {
     // ===================== TMA producer: cached bins for N chunks >= 1 (K > 1024 only) =====================
@@ -521,7 +572,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         mbar_wait(&sm.codes_ready, it & 1);  // every worker has published this block's bins
         for (int pass = 1; pass < a_passes; ++pass)
           for (int kb = 0; kb < p.KB; ++kb) {
-            const uint32_t pa = (uint32_t)((it * p.NC + pass) * p.KB + kb);
+            const uint32_t pa = (uint32_t)((it * a_passes + pass) * p.KB + kb);
             const int a_st = pa % p.a_stages;
             mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
             mbar_arrive_expect_tx(&sm.a_full[a_st], p.codes_box_bytes);
@@ -1152,6 +1203,11 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   p.resident = best.resident; p.cached = best.cached;
   p.a_stages = best.a_stages; p.w_stages = best.w_stages; p.out_bufs = best.out_bufs;
   p.x_tma = best.x_tma; p.alias_xo = best.alias;
+  // streamed A with a code cache: all accumulator stages are fed in one sweep over K (the later sweeps re-load the
+  // bins by TMA).  Without a cache the workers re-convert per chunk and must keep one stage free for the epilogue
+  // they run in between, so they stay at one chunk per sweep.
+  p.cpp = p.cached ? p.acc_stages : 1;
+  p.a_passes = p.resident ? 1 : (p.NC + p.cpp - 1) / p.cpp;
   const int const_bytes = 2 * ((p.BN + 31) & ~31) * (int)sizeof(float);
   const size_t smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes +
                             (p.x_tma ? (size_t)x_bytes : 0) + (p.alias_xo ? 0 : (size_t)p.out_bufs * out1) +
