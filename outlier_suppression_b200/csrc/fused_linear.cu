@@ -56,7 +56,7 @@ struct FusedParams {
   int BN;             // chunk width: 128 (resident A) or 256 (streamed A), or N when N is smaller
   int acc_stages;     // TMEM accumulator stages (512 / BN, at most 4)
   int n_mblocks;
-  int csz;            // thread-block cluster size (1, 2 or 4): the W stream is TMA-multicast across the cluster
+  int csz;            // 1, or 2 = CTA pair: tcgen05 cta_group::2 (M = 256 over two SMs, each CTA stages half of every W tile)
   int n_iters;        // tiles per CTA (identical for every CTA; out-of-range tiles are phantoms that only keep the W protocol alive)
   int rows_per_tile;  // valid rows per CTA tile (<= 128, multiple of 16): chosen so the tile count fills all SMs
   int a_stages, w_stages, out_bufs;
@@ -137,8 +137,31 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar, uint32_t
 __device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_commit_mcast_u32(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+// ---- CTA pair (cta_group::2): the leader CTA issues the MMAs for both SMs; barriers the leader waits on collect
+// arrivals from both CTAs, barriers both CTAs wait on are signalled by multicast commits
+__device__ __forceinline__ void umma_commit_pair_u32(uint32_t bar) {  // arrives on `bar` at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {  // shared::cta address -> shared::cluster address in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_u32(uint32_t bar, uint32_t parity) {  // acquire at cluster scope: the peer's writes are visible
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -146,10 +169,11 @@ __device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtenso
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mcast_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+// pair mode: lands in this CTA's shared memory, completes transaction bytes on the LEADER's barrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
 // programmatic dependent launch: let the next kernel of the stream start its prologue / weight stream
@@ -167,13 +191,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           smem_u32(smem_dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -207,6 +224,26 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {  // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// pair: D (256 x N: rows 0..127 in this CTA's TMEM, 128..255 in the peer's) (+)= A (each CTA's own 128 rows) * B^T
+// (each CTA holds N/2 rows of the B tile at the same shared-memory offset)
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T,  u8 x s8 -> s32
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -221,13 +258,6 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 // arrives on `bar` once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// same, arriving on the barrier at this offset in every CTA of `mask` (W stages are filled by cluster multicast)
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(mask)
-               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
@@ -263,9 +293,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
   return d;
 }
-// cute::UMMA::InstrDescriptor for kind::i8: D=s32, A=u8, B=s8, both K-major, M=128
-__host__ __device__ inline uint32_t make_idesc_i8(int n) {
-  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+// cute::UMMA::InstrDescriptor for kind::i8: D=s32, A=u8, B=s8, both K-major; M = 128 (one CTA) or 256 (CTA pair)
+__host__ __device__ inline uint32_t make_idesc_i8(int n, int m) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -385,11 +415,12 @@ struct Smem {
 //  array costs 3 %)
 static_assert(sizeof(Smem) % 16 == 0, "constants must stay 16-byte aligned");
 
-template <bool kXTma>
-__global__ void __launch_bounds__(kNumThreads, 1)
-fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
-                       const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,
-                       const __grid_constant__ CUtensorMap tmap_a, const FusedParams p) {
+// One body, three entry points (below): <registers path>, <TMA landing slots>, <TMA landing slots + CTA pair>.
+// Only the pair variant contains cta_group::2 instructions: the driver refuses to launch a kernel that uses them
+// without a cluster of two.
+template <bool kXTma, bool kPair>
+__device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, const CUtensorMap& tmap_y, const CUtensorMap& tmap_y16,
+                                                     const CUtensorMap& tmap_codes, const CUtensorMap& tmap_a, const FusedParams& p) {
   // dynamic shared memory, 1024B aligned by the attribute (SWIZZLE_128B tiles need it):
   // [A ring][W ring][fp32 landing slots][TMA-store staging tiles (may alias the slots)][Smem bookkeeping]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -406,6 +437,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool pair = kPair;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -416,22 +448,23 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     sm.converted = 0;
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&sm.a_full[i], kNumWorkers); mbar_init(&sm.a_empty[i], 1); }
-    for (int i = 0; i < p.w_stages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], p.csz); }
-    for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps); }
+    // pair mode: the leader's a_full / acc_empty collect the arrivals of both CTAs (the peer's copies stay unused);
+    // a_empty / w_empty / acc_full of each CTA receive the leader's multicast commits
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&sm.a_full[i], kNumWorkers * p.csz); mbar_init(&sm.a_empty[i], 1); }
+    for (int i = 0; i < p.w_stages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+    for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps * p.csz); }
     mbar_init(&sm.codes_ready, kNumWorkers);
     for (int i = 0; i < kNumWorkers; ++i) mbar_init(&sm.x_full[i], 1);
     mbar_init(&sm.passes_issued, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&sm.tmem_base, kTmemCols);
+  if (warp == 2) { if (pair) tmem_alloc_pair(&sm.tmem_base, kTmemCols); else tmem_alloc(&sm.tmem_base, kTmemCols); }
   tc_fence_before();
   __syncthreads();
-  if (p.csz > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
+  if (p.csz > 1) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
   const uint32_t crank = (p.csz > 1) ? cluster_ctarank() : 0u;
-  const uint16_t cmask = (uint16_t)((1u << p.csz) - 1u);
   if (threadIdx.x == 0) OSQ_TRACE(1020);
   if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x] = gtimer();
 
@@ -447,7 +480,8 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       if (p.pdl) pdl_wait_prior_grids();
       const uint32_t w_bytes = (uint32_t)p.w_stage_bytes;
       const uint32_t w_base = smem_u32(w_ring), full0 = smem_u32(&sm.w_full[0]), empty0 = smem_u32(&sm.w_empty[0]);
-      const int slice = p.BN / p.csz;  // rows of the tile this CTA fetches (and multicasts when csz > 1)
+      const int slice = p.BN / p.csz;  // rows of the tile this CTA stages (pair: half, the MMA reads both halves)
+      const uint32_t leader_full0 = pair ? mapa_u32(full0, 0) : full0;
       uint32_t ws = 0, wph = 0;        // ring stage and its phase parity
       // tile order = the MMA issuer's: resident A: chunk-major; streamed A: per sweep, k-block-major over its chunks
       const int n_tiles = p.NC * p.KB;
@@ -455,12 +489,14 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         for (int t = 0, nc = 0, kb = 0, c_lo = 0, j = 0; t < n_tiles; ++t) {
           {
             mbar_wait_u32(empty0 + ws * 8, wph ^ 1);
-            mbar_arrive_expect_tx_u32(full0 + ws * 8, w_bytes);  // the whole stage: every CTA of the cluster delivers its slice
-            if (p.csz == 1)
+            if (!pair) {
+              mbar_arrive_expect_tx_u32(full0 + ws * 8, w_bytes);
               tma_load_2d_u32(w_base + ws * w_bytes, &tmap_w, full0 + ws * 8, (p.dbg & 1) ? 0 : kb * kStageK, (p.dbg & 1) ? 0 : nc * p.BN);
-            else
-              tma_load_2d_mcast_u32(w_base + ws * w_bytes + crank * (uint32_t)(slice * kStageK), &tmap_w, full0 + ws * 8,
-                                    kb * kStageK, nc * p.BN + (int)crank * slice, cmask);
+            } else {
+              // the leader's barrier expects both halves; each CTA's TMA completes its bytes there
+              if (crank == 0) mbar_arrive_expect_tx_u32(full0 + ws * 8, 2 * w_bytes);
+              tma_load_2d_pair_u32(w_base + ws * w_bytes, &tmap_w, leader_full0 + ws * 8, kb * kStageK, nc * p.BN + (int)crank * slice);
+            }
 #ifdef OSQ_ENABLE_TRACE
             { const int ps = (it * p.NC + nc) * p.KB + kb; if (ps >= 36 && ps < 76) OSQ_TRACE(1600 + ps - 36); }
 #endif
@@ -479,8 +515,8 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     // ===================== MMA issuer =====================
     // One thread; everything it touches is a precomputed 32-bit shared address or a running counter --
     // no divisions, no generic->shared conversions inside the loop.
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_i8(p.BN);
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = make_idesc_i8(p.BN, pair ? 256 : 128);
       const uint32_t a_base = smem_u32(a_ring), w_base = smem_u32(w_ring);
       const uint32_t a_full0 = smem_u32(&sm.a_full[0]), a_empty0 = smem_u32(&sm.a_empty[0]);
       const uint32_t w_full0 = smem_u32(&sm.w_full[0]), w_empty0 = smem_u32(&sm.w_empty[0]);
@@ -493,13 +529,13 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         if (p.resident) {
           // resident A: chunk-major, the converted block is filled once per m-block and released after its last chunk
           for (int nc = 0; nc < p.NC; ++nc) {
-            mbar_wait_u32(acc_empty0 + as_ * 8, aph ^ 1);
+            if (pair) mbar_wait_cluster_u32(acc_empty0 + as_ * 8, aph ^ 1); else mbar_wait_u32(acc_empty0 + as_ * 8, aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as_ * (uint32_t)p.BN;
             st_a = 0; sph_a = (uint32_t)it & 1;
             const bool wait_a = nc == 0, free_a = nc == p.NC - 1;
             for (int kb = 0; kb < p.KB; ++kb) {
-              if (wait_a) mbar_wait_u32(a_full0 + st_a * 8, sph_a);
+              if (wait_a) { if (pair) mbar_wait_cluster_u32(a_full0 + st_a * 8, sph_a); else mbar_wait_u32(a_full0 + st_a * 8, sph_a); }
 #ifdef OSQ_ENABLE_TRACE
               const int tslot = (it * p.NC + nc) * p.KB + kb;
               if (tslot >= 36 && tslot < 72) OSQ_TRACE(1400 + 3 * (tslot - 36));
@@ -511,18 +547,26 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
               tc_fence_after();
               const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)p.a_stage_bytes) >> 4);
               const uint64_t db = desc_hi | (uint64_t)((w_base + ws * w_bytes) >> 4);
+              if (!pair) {
 #pragma unroll
-              for (int k = 0; k < kStageK / kUmmaK; ++k)
-                umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
-              if (p.csz == 1) umma_commit_u32(w_empty0 + ws * 8); else umma_commit_mcast_u32(w_empty0 + ws * 8, cmask);
-              if (free_a) umma_commit_u32(a_empty0 + st_a * 8);
+                for (int k = 0; k < kStageK / kUmmaK; ++k)
+                  umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
+                umma_commit_u32(w_empty0 + ws * 8);
+                if (free_a) umma_commit_u32(a_empty0 + st_a * 8);
+              } else {
+#pragma unroll
+                for (int k = 0; k < kStageK / kUmmaK; ++k)
+                  umma_i8_pair(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
+                umma_commit_pair_u32(w_empty0 + ws * 8);
+                if (free_a) umma_commit_pair_u32(a_empty0 + st_a * 8);
+              }
 #ifdef OSQ_ENABLE_TRACE
               if (tslot >= 36 && tslot < 72) OSQ_TRACE(1402 + 3 * (tslot - 36));
 #endif
               if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
               ++st_a;
             }
-            umma_commit_u32(acc_full0 + as_ * 8);
+            if (pair) umma_commit_pair_u32(acc_full0 + as_ * 8); else umma_commit_u32(acc_full0 + as_ * 8);
             if (++as_ == n_acc) { as_ = 0; aph ^= 1; }
           }
         } else {
@@ -549,7 +593,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 #pragma unroll
                 for (int k = 0; k < kStageK / kUmmaK; ++k)
                   umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
-                if (p.csz == 1) umma_commit_u32(w_empty0 + ws * 8); else umma_commit_mcast_u32(w_empty0 + ws * 8, cmask);
+                umma_commit_u32(w_empty0 + ws * 8);
                 if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
               }
               umma_commit_u32(a_empty0 + st_a * 8);
@@ -702,6 +746,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     // (whose capacity bounds plain loads in flight once 227 KB are carved out as shared memory).  Rows past M are
     // zero-filled by the TMA unit: no ragged path.
     uint32_t x_ph = 0;
+    const uint32_t leader_a_full0 = pair ? mapa_u32(smem_u32(&sm.a_full[0]), 0) : 0u;
     auto convert_pass_tma = [&](int mb, uint32_t pa0) {
       const uint32_t x_bar = smem_u32(&sm.x_full[w]);
       uint8_t* const x_slot = x_ring + (size_t)w * kXSlotBytes;
@@ -759,7 +804,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         }
         fence_proxy_async_smem();  // generic-proxy smem stores -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.a_full[a_st]);
+        if (lane == 0) { if (pair) mbar_arrive_cluster_u32(leader_a_full0 + a_st * 8); else mbar_arrive(&sm.a_full[a_st]); }
         if (w == 0 && lane == 0 && pa < 250) OSQ_TRACE(pa);
         if (++c_st == (uint32_t)p.a_stages) { c_st = 0; c_ph ^= 1; }
       }
@@ -889,7 +934,7 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.acc_empty[as_]);
+      if (lane == 0) { if (pair) mbar_arrive_cluster_u32(mapa_u32(smem_u32(&sm.acc_empty[as_]), 0)); else mbar_arrive(&sm.acc_empty[as_]); }
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4 + 1);
       ++cacc;
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");  // every reader of this chunk's constants is done
@@ -935,13 +980,24 @@ fused_fq_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   // ===================== teardown =====================
   tc_fence_before();
   __syncthreads();
-  if (p.csz > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / arrive on its barriers
+  if (p.csz > 1) cluster_sync_all();  // no CTA exits while the pair's MMAs / commits / remote arrives may still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (pair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
   if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x + 1] = gtimer();
 }
+
+#define OSQ_FUSED_ENTRY(name, XTMA, PAIR)                                                                              \
+  __global__ void __launch_bounds__(kNumThreads, 1)                                                                    \
+  name(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,                         \
+       const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,                   \
+       const __grid_constant__ CUtensorMap tmap_a, const FusedParams p) {                                              \
+    fused_fq_linear_body<XTMA, PAIR>(tmap_w, tmap_y, tmap_y16, tmap_codes, tmap_a, p);                                 \
+  }
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel_ldg, false, false)
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel, true, false)
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel_pair, true, true)
 
 // ------------------------------------------------------------------------------------------
 // weight packing: bins (q - zp) as s8 + per-row sums
@@ -1082,15 +1138,11 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   p.dbg = env_dbg;
   p.pdl = env_pdl ? 1 : 0;
 
-  // cluster size: the W stream is identical for every CTA, so it can be multicast across a thread-block cluster
-  // (each CTA fetches 1/csz of every tile); measured neutral on B200 (L2 already merges the requests) -> default 1
-  p.csz = (env_csz == 2 || env_csz == 4) ? env_csz : 1;
-  while (p.csz > 1 && (p.M + kBM - 1) / kBM < p.csz) p.csz >>= 1;
-
   static bool attr_set[64] = {false};
   if (!attr_set[dev & 63]) {
-    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_ldg, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
   cudaLaunchConfig_t cfg;
@@ -1099,107 +1151,116 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)p.csz;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 2 : 1;
-  // how many CTAs can be co-resident (1 CTA / SM; clusters of 4 cannot use every SM)
-  static int max_ctas[64][5] = {{0}};
-  if (max_ctas[dev & 63][p.csz] == 0) {
-    int n_clusters = 0;
-    cfg.gridDim = dim3((unsigned)(sms / p.csz * p.csz));
-    cfg.dynamicSmemBytes = 227 * 1024;
-    if (p.csz > 1) {
-      OSQ_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, fused_fq_linear_kernel<true>, &cfg));
-      max_ctas[dev & 63][p.csz] = n_clusters * p.csz;
-    } else {
-      max_ctas[dev & 63][p.csz] = sms;
-    }
-    if (max_ctas[dev & 63][p.csz] <= 0) { set_error("osq_fused_fq_linear: no resident cluster of %d CTAs", p.csz); return OSQ_ECUDA; }
-  }
-  const int G = max_ctas[dev & 63][p.csz];
-  // rows per CTA tile: the 128-row MMA tile is filled with as many rows as make the tile count a multiple of
-  // the resident CTA count (M = 16384 on 148 SMs: 147 tiles of 112 rows instead of 128 tiles of 128 rows)
-  {
-    const int64_t waves = (p.M + (int64_t)kBM * G - 1) / ((int64_t)kBM * G);
-    int64_t rpt = (p.M + waves * G - 1) / (waves * G);
-    rpt = (rpt + 15) / 16 * 16;
-    if (rpt > kBM) rpt = kBM;
-    if (rpt < 16) rpt = 16;
-    p.rows_per_tile = (int)rpt;
-  }
-  p.n_mblocks = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
-  int grid = p.n_mblocks < G ? p.n_mblocks : G;
-  grid = (grid + p.csz - 1) / p.csz * p.csz;
-  p.n_iters = (p.n_mblocks + grid - 1) / grid;
-  cfg.gridDim = dim3((unsigned)grid);
 
   // ---- shared-memory plan (<= 227 KB / CTA):
-  //   [A ring: a_stages x (rows_per_tile x 128 B)] [W ring: w_stages x (BN x 128 B)] [X: 16 x 4 KB fp32 landing slots]
+  //   [A ring: a_stages x (rows_per_tile x 128 B)] [W ring: w_stages x (BN / csz x 128 B)] [X: 16 x 4 KB fp32 landing slots]
   //   [O: 8 x out_bufs x 4 KB TMA-store staging, aliased onto X when space is short] [barriers + 2 BN constants]
   // A stages hold only the tile's valid rows: the MMA (M = 128) reads past them into the next stage / the W ring,
   // which only produces accumulator rows nobody stores.
-  p.a_stage_bytes = p.rows_per_tile * kStageK;
+  // CTA pair (csz = 2, cta_group::2): two CTAs on neighbouring SMs run their two row tiles against ONE copy of every
+  // W tile (each stages half of its rows), which halves the W traffic into and out of shared memory -- the
+  // resource that bounds the epilogue phase.  Tried first; needs resident A, the TMA landing slots and >= 2 tiles.
   const int x_bytes = kNumWorkers * kXSlotBytes;          // 64 KB
   const int out1 = kNumEpiWarps * kOutTileBytes;          // 32 KB per buffer set
   const int total = env_kb * 1024 - (int)sizeof(Smem);
   struct Plan { int ok, bn, resident, cached, a_stages, w_stages, out_bufs, x_tma, alias, score; };
-  auto make_plan = [&](int bn, int x_tma) {
-    Plan pl; memset(&pl, 0, sizeof(pl));
-    pl.bn = bn; pl.x_tma = x_tma;
-    const int nc = (p.N + bn - 1) / bn;
-    const int w_stage = (bn * kStageK + 1023) / 1024 * 1024;
-    const int budget = total - 2 * ((bn + 31) & ~31) * (int)sizeof(float);
-    const int xo_min = x_tma ? x_bytes : out1;            // aliased X/O region, or one set of store tiles
-    pl.resident = (p.KB <= kMaxAStages && p.KB * p.a_stage_bytes + 2 * w_stage + xo_min <= budget) ? 1 : 0;
-    pl.cached = (!pl.resident && nc > 1 && a->a_codes != nullptr) ? 1 : 0;
-    pl.a_stages = pl.resident ? p.KB : 4;
-    // X and O can share memory only when conversion and epilogue never interleave inside a tile
-    const bool can_alias = pl.resident || pl.cached || nc == 1;
-    int rest = budget - pl.a_stages * p.a_stage_bytes - 2 * w_stage;
-    pl.w_stages = 2;
-    if (x_tma) {
-      if (can_alias && rest >= x_bytes) { pl.alias = 1; pl.out_bufs = 2; rest -= x_bytes; }
-      else if (rest >= x_bytes + out1) { pl.alias = 0; pl.out_bufs = 1; rest -= x_bytes + out1; }
-      else return pl;                                     // does not fit
-    } else {
-      if (rest < out1) return pl;
-      pl.out_bufs = 1; rest -= out1;
-    }
-    if (env_ob == 1 && !pl.alias) { /* keep one */ }
-    // the W stream needs ~2.5 stages of 32 KB in flight to cover the L2 latency: a third stage comes first
-    if (rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
-    if (!pl.alias && pl.out_bufs == 1 && env_ob != 1 && rest >= out1) { pl.out_bufs = 2; rest -= out1; }
-    while (pl.w_stages < kMaxWStages && rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
-    if (!pl.resident)
-      while (pl.a_stages < kMaxAStages && rest >= p.a_stage_bytes) { ++pl.a_stages; rest -= p.a_stage_bytes; }
-    pl.ok = 1;
-    // preference: three W stages and double-buffered stores matter more than the chunk width
-    pl.score = (pl.w_stages >= 3 ? 4 : 0) + (pl.out_bufs >= 2 ? 2 : 0) + (bn == 256 ? 1 : 0);
-    return pl;
-  };
-  const bool x_ok = env_xtma != 0 && p.K % 4 == 0;
   Plan best; memset(&best, 0, sizeof(best));
-  const int bn_cands[3] = {256, 192, 128};
-  for (int xt = x_ok ? 1 : 0; xt >= 0 && !best.ok; --xt)
-    for (int i = 0; i < 3; ++i) {
-      int bn = bn_cands[i];
-      if (env_bn > 0 && bn != env_bn) continue;
-      if (p.N < bn) { if (i == 0) bn = p.N; else continue; }   // narrow layers: one chunk of N columns
-      else if (p.N % bn != 0 && i != 0) continue;               // 192 / 128 only when they tile N exactly
-      if (bn % (8 * p.csz) != 0) continue;
-      Plan pl = make_plan(bn, xt);
-      if (pl.ok && (!best.ok || pl.score > best.score)) best = pl;
+  static int max_ctas[64][3] = {{0}};
+  int grid = 0;
+  for (int csz = (env_csz == 2 && p.KB <= kMaxAStages) ? 2 : 1; csz >= 1 && !best.ok; --csz) {
+    p.csz = csz;
+    attr[0].val.clusterDim.x = (unsigned)csz;
+    // how many CTAs can be co-resident (1 CTA / SM)
+    if (max_ctas[dev & 63][csz] == 0) {
+      if (csz > 1) {
+        int n_clusters = 0;
+        cfg.gridDim = dim3((unsigned)(sms / csz * csz));
+        cfg.dynamicSmemBytes = 227 * 1024;
+        OSQ_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, fused_fq_linear_kernel_pair, &cfg));
+        if (n_clusters <= 0) n_clusters = sms / csz;  // the query is only a hint; the launch itself reports a real problem
+        max_ctas[dev & 63][csz] = n_clusters * csz;
+      } else {
+        max_ctas[dev & 63][csz] = sms;
+      }
+      if (max_ctas[dev & 63][csz] <= 0) { if (csz > 1) continue; set_error("osq_fused_fq_linear: no resident CTA"); return OSQ_ECUDA; }
     }
+    const int G = max_ctas[dev & 63][csz];
+    // rows per CTA tile: the 128-row MMA tile is filled with as many rows as make the tile count a multiple of
+    // the resident CTA count (M = 16384 on 148 SMs: 147 tiles of 112 rows instead of 128 tiles of 128 rows)
+    {
+      const int64_t waves = (p.M + (int64_t)kBM * G - 1) / ((int64_t)kBM * G);
+      int64_t rpt = (p.M + waves * G - 1) / (waves * G);
+      rpt = (rpt + 15) / 16 * 16;
+      if (rpt > kBM) rpt = kBM;
+      if (rpt < 16) rpt = 16;
+      p.rows_per_tile = (int)rpt;
+    }
+    p.n_mblocks = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
+    if (csz > 1 && p.n_mblocks < 2) continue;
+    grid = p.n_mblocks < G ? p.n_mblocks : G;
+    grid = (grid + csz - 1) / csz * csz;
+    p.n_iters = (p.n_mblocks + grid - 1) / grid;
+    p.a_stage_bytes = p.rows_per_tile * kStageK;
+
+    auto make_plan = [&](int bn, int x_tma) {
+      Plan pl; memset(&pl, 0, sizeof(pl));
+      pl.bn = bn; pl.x_tma = x_tma;
+      const int nc = (p.N + bn - 1) / bn;
+      const int w_stage = (bn / csz * kStageK + 1023) / 1024 * 1024;
+      const int budget = total - 2 * ((bn + 31) & ~31) * (int)sizeof(float);
+      const int xo_min = x_tma ? x_bytes : out1;            // aliased X/O region, or one set of store tiles
+      pl.resident = (p.KB <= kMaxAStages && p.KB * p.a_stage_bytes + 2 * w_stage + xo_min <= budget) ? 1 : 0;
+      if (csz > 1 && !(pl.resident && x_tma)) return pl;
+      pl.cached = (!pl.resident && nc > 1 && a->a_codes != nullptr) ? 1 : 0;
+      pl.a_stages = pl.resident ? p.KB : 4;
+      // X and O can share memory only when conversion and epilogue never interleave inside a tile
+      const bool can_alias = pl.resident || pl.cached || nc == 1;
+      int rest = budget - pl.a_stages * p.a_stage_bytes - 2 * w_stage;
+      pl.w_stages = 2;
+      if (x_tma) {
+        if (can_alias && rest >= x_bytes) { pl.alias = 1; pl.out_bufs = 2; rest -= x_bytes; }
+        else if (rest >= x_bytes + out1) { pl.alias = 0; pl.out_bufs = 1; rest -= x_bytes + out1; }
+        else return pl;                                     // does not fit
+      } else {
+        if (rest < out1) return pl;
+        pl.out_bufs = 1; rest -= out1;
+      }
+      // the W stream needs ~2.5 stages of 32 KB in flight to cover the L2 latency: a third stage comes first
+      if (rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
+      if (!pl.alias && pl.out_bufs == 1 && env_ob != 1 && rest >= out1) { pl.out_bufs = 2; rest -= out1; }
+      while (pl.w_stages < kMaxWStages && rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
+      if (!pl.resident)
+        while (pl.a_stages < kMaxAStages && rest >= p.a_stage_bytes) { ++pl.a_stages; rest -= p.a_stage_bytes; }
+      pl.ok = 1;
+      // preference: three W stages and double-buffered stores matter more than the chunk width
+      pl.score = (pl.w_stages >= 3 ? 4 : 0) + (pl.out_bufs >= 2 ? 2 : 0) + (bn == 256 ? 1 : 0);
+      return pl;
+    };
+    const bool x_ok = env_xtma != 0 && p.K % 4 == 0;
+    const int bn_cands[3] = {256, 192, 128};
+    for (int xt = x_ok ? 1 : 0; xt >= 0 && !best.ok; --xt)
+      for (int i = 0; i < 3; ++i) {
+        int bn = bn_cands[i];
+        if (env_bn > 0 && bn != env_bn) continue;
+        if (p.N < bn) { if (i == 0) bn = p.N; else continue; }   // narrow layers: one chunk of N columns
+        else if (p.N % bn != 0 && i != 0) continue;               // 192 / 128 only when they tile N exactly
+        if (bn % (16 * csz) != 0) continue;
+        Plan pl = make_plan(bn, xt);
+        if (pl.ok && (!best.ok || pl.score > best.score)) best = pl;
+      }
+  }
   if (!best.ok) { set_error("osq_fused_fq_linear: no shared-memory plan for K=%d N=%d", p.K, p.N); return OSQ_EINVAL; }
   p.BN = best.bn;
   p.NC = (p.N + p.BN - 1) / p.BN;
   p.acc_stages = kTmemCols / p.BN;
   if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
-  p.w_stage_bytes = (p.BN * kStageK + 1023) / 1024 * 1024;
+  p.w_stage_bytes = (p.BN / p.csz * kStageK + 1023) / 1024 * 1024;  // pair: each CTA stages half of the tile's rows
   p.resident = best.resident; p.cached = best.cached;
   p.a_stages = best.a_stages; p.w_stages = best.w_stages; p.out_bufs = best.out_bufs;
   p.x_tma = best.x_tma; p.alias_xo = best.alias;
@@ -1213,6 +1274,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
                             (p.x_tma ? (size_t)x_bytes : 0) + (p.alias_xo ? 0 : (size_t)p.out_bufs * out1) +
                             sizeof(Smem) + (size_t)const_bytes;
   cfg.dynamicSmemBytes = smem_bytes;
+  cfg.gridDim = dim3((unsigned)grid);
   p.codes_box_bytes = (uint32_t)(p.M < p.rows_per_tile ? p.M : p.rows_per_tile) * kStageK;
 
   CUtensorMap map_w, map_y, map_y16, map_c, map_a;
@@ -1243,8 +1305,23 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   } else {
     map_a = map_w;  // unused by the kernel
   }
-  if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel<true>, map_w, map_y, map_y16, map_c, map_a, p));
-  else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel<false>, map_w, map_y, map_y16, map_c, map_a, p));
+  static int env_verbose = -1;
+  if (env_verbose < 0) { const char* e = getenv("OSQ_FUSED_VERBOSE"); env_verbose = e ? atoi(e) : 0; }
+  if (env_verbose) {
+    static int seen[16][3]; static int n_seen = 0;
+    bool known = false;
+    for (int i = 0; i < n_seen; ++i) known |= (seen[i][0] == p.M && seen[i][1] == p.K && seen[i][2] == p.N);
+    if (!known && n_seen < 16) {
+      seen[n_seen][0] = p.M; seen[n_seen][1] = p.K; seen[n_seen][2] = p.N; ++n_seen;
+      fprintf(stderr, "[osq] fused M=%d K=%d N=%d: grid=%d cluster=%d rows/tile=%d tiles/cta=%d BN=%d chunks=%d mode=%s a_stages=%d(%d B) "
+                      "w_stages=%d(%d B) acc_stages=%d out_bufs=%d x_tma=%d alias=%d sweeps=%d smem=%zu\n",
+              p.M, p.K, p.N, grid, p.csz, p.rows_per_tile, p.n_iters, p.BN, p.NC, p.resident ? "resident" : (p.cached ? "streamed+cache" : "streamed"),
+              p.a_stages, p.a_stage_bytes, p.w_stages, p.w_stage_bytes, p.acc_stages, p.out_bufs, p.x_tma, p.alias_xo, p.a_passes, smem_bytes);
+    }
+  }
+  if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair, map_w, map_y, map_y16, map_c, map_a, p));
+  else if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel, map_w, map_y, map_y16, map_c, map_a, p));
+  else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_ldg, map_w, map_y, map_y16, map_c, map_a, p));
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

@@ -157,3 +157,25 @@ def test_weight_cache_invalidation_after_gamma_fold():
     gamma = torch.rand(128, device="cuda") * 2 + 0.2
     net.dense.weight.data *= gamma  # not tracked by weight._version
     close(calibrate_and_run(), oracle_run())
+
+
+PAIR_CASES = "[(256, 768, 768), (1000, 768, 2304), (16384, 768, 768), (300, 1024, 512), (4096, 256, 3072)]"
+
+
+def test_cta_pair_mode_and_register_path_in_subprocess():
+    """The launch plan is read from the environment once per process, so the two non-default kernel variants run in
+    child processes: OSQ_FUSED_CLUSTER=2 (tcgen05 cta_group::2: one W tile copy per CTA pair) and OSQ_FUSED_XTMA=0
+    (fp32 A through 128-bit register loads instead of TMA landing slots).  Same parity bar as every other case."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch; from tests.test_gpu_fused_linear import run_case\n"
+            "for i, (m, k, n) in enumerate(%s):\n"
+            "    run_case(m, k, n, 6, 6, True, 100 + i, gamma=bool(i & 1))\n"
+            "    run_case(m, k, n, 8, 8, False, 200 + i)\n"
+            "print('variant ok')\n" % PAIR_CASES)
+    for env in ({"OSQ_FUSED_CLUSTER": "2"}, {"OSQ_FUSED_XTMA": "0"}):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
+                           timeout=240)
+        assert r.returncode == 0 and "variant ok" in r.stdout, "%s failed:\n%s\n%s" % (env, r.stdout[-2000:], r.stderr[-3000:])
