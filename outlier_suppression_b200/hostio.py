@@ -1,0 +1,59 @@
+"""Host <-> device plumbing for callers whose batches live in host memory (the reference's DataLoader path).
+
+``HostStepRunner`` runs ``fn(device_batch) -> device_result`` for a stream of pinned host batches and lands every
+result in pinned host memory.  Copies run on their own CUDA streams and are double-buffered, so the upload of
+batch i+1 and the download of result i-1 overlap the kernels of batch i; nothing here synchronises the host
+except ``result()`` / ``drain()``.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class HostStepRunner:
+    def __init__(self, fn, in_shape, out_shape, device, depth: int = 2, dtype=torch.float32):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("HostStepRunner needs a CUDA device (no CPU fallback)")
+        self.fn, self.depth, self.device = fn, int(depth), torch.device(device)
+        self.h2d, self.d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.dev_in = [torch.empty(in_shape, dtype=dtype, device=self.device) for _ in range(self.depth)]
+        self.host_out = [torch.empty(out_shape, dtype=dtype).pin_memory() for _ in range(self.depth)]
+        mk = lambda: [torch.cuda.Event() for _ in range(self.depth)]  # noqa: E731
+        self.in_ready, self.in_free, self.out_ready, self.done = mk(), mk(), mk(), mk()
+        self.step = 0
+        self.h2d_bytes = self.dev_in[0].numel() * self.dev_in[0].element_size()
+        self.d2h_bytes = self.host_out[0].numel() * self.host_out[0].element_size()
+
+    def submit(self, host_batch: torch.Tensor) -> int:
+        """Enqueues upload -> fn -> download for one pinned host batch; returns the step index."""
+        i, s = self.step, self.step % self.depth
+        compute = torch.cuda.current_stream(self.device)
+        if i >= self.depth:
+            self.h2d.wait_event(self.in_free[s])     # the kernels of step i-depth have consumed this device buffer
+            self.done[s].synchronize()               # ... and its host result slot has been written (caller may have read it)
+        with torch.cuda.stream(self.h2d):
+            self.dev_in[s].copy_(host_batch, non_blocking=True)
+            self.in_ready[s].record(self.h2d)
+        compute.wait_event(self.in_ready[s])
+        out = self.fn(self.dev_in[s])
+        self.in_free[s].record(compute)
+        self.out_ready[s].record(compute)
+        self.d2h.wait_event(self.out_ready[s])
+        with torch.cuda.stream(self.d2h):
+            self.host_out[s].copy_(out.reshape(self.host_out[s].shape), non_blocking=True)
+            self.done[s].record(self.d2h)
+        out.record_stream(self.d2h)
+        self.step += 1
+        return i
+
+    def result(self, i: int) -> torch.Tensor:
+        """Pinned host tensor holding the result of step i (valid until step i+depth is submitted)."""
+        if not (self.step - self.depth <= i < self.step):
+            raise IndexError("result %d is no longer (or not yet) buffered" % i)
+        self.done[i % self.depth].synchronize()
+        return self.host_out[i % self.depth]
+
+    def drain(self) -> None:
+        self.h2d.synchronize()
+        self.d2h.synchronize()
+        torch.cuda.current_stream(self.device).synchronize()

@@ -186,3 +186,26 @@ def test_query_key_value_share_one_launch_bit_identical(monkeypatch):
     for a, c in zip(g2, s2):
         same(a, c)
     assert not torch.equal(g2[1], grouped[1])
+
+
+def test_host_step_runner_matches_direct_calls():
+    """hostio.HostStepRunner: pinned upload -> fn -> pinned download on side streams, double-buffered; results must
+    equal the plain synchronous calls for every step (buffer reuse across more steps than the pipeline depth)."""
+    from outlier_suppression_b200.hostio import HostStepRunner
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(64, 64, generator=g).cuda()
+    fn = lambda x: torch.tanh(x @ w) * 3.0  # noqa: E731
+    batches = [torch.randn(128, 64, generator=g).pin_memory() for _ in range(7)]
+    runner = HostStepRunner(fn, (128, 64), (128, 64), "cuda", depth=2)
+    got = []
+    for b in batches:
+        i = runner.submit(b)
+        if i >= 1:
+            got.append(runner.result(i - 1).clone())
+    got.append(runner.result(len(batches) - 1).clone())
+    runner.drain()
+    for b, y in zip(batches, got):
+        same(y, fn(b.cuda()))
+    with pytest.raises(IndexError):
+        runner.result(0)
+    assert runner.h2d_bytes == 128 * 64 * 4 and runner.d2h_bytes == 128 * 64 * 4
