@@ -394,7 +394,7 @@ def main():
     # every step uploads its batch from pinned host memory and downloads its result (both inside the timed region);
     # the copies run on side streams, double-buffered, so they overlap the previous / next step's kernels
     from outlier_suppression_b200.hostio import HostStepRunner
-    runner = HostStepRunner(layer_stack, (B, S, H), (M, H), device)
+    runner = HostStepRunner(layer_stack, (B, S, H), (M, H), device, graph=not args.no_graph)
 
     def e2e_step():
         return runner.submit(host_in)
@@ -424,7 +424,7 @@ def main():
         e2e = {"value": world * M / (ms_e2e / n_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": host_in.numel() * 4,
                "d2h_bytes_per_step": runner.d2h_bytes, "steps": n_e2e, "host_issue_ms_per_step": e2e_issue_ms,
                "api": "hostio.HostStepRunner over quantization.Quantizer modules: 4 activation quantizers + 6 QLinear per layer, x12; "
-                      "pinned H2D / D2H on side streams, double-buffered; CUDA-event time up to the last download"}
+                      "pinned H2D / D2H on side streams, double-buffered, module stack %s; CUDA-event time up to the last download" % ("eager" if args.no_graph else "replayed as a CUDA graph") + ""}
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "error": repr(ex)}
 

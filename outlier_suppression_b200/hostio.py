@@ -11,7 +11,7 @@ import torch
 
 
 class HostStepRunner:
-    def __init__(self, fn, in_shape, out_shape, device, depth: int = 2, dtype=torch.float32):
+    def __init__(self, fn, in_shape, out_shape, device, depth: int = 2, dtype=torch.float32, graph: bool = False):
         if torch.device(device).type != "cuda":
             raise RuntimeError("HostStepRunner needs a CUDA device (no CPU fallback)")
         self.fn, self.depth, self.device = fn, int(depth), torch.device(device)
@@ -21,6 +21,12 @@ class HostStepRunner:
         mk = lambda: [torch.cuda.Event() for _ in range(self.depth)]  # noqa: E731
         self.in_ready, self.in_free, self.out_ready, self.done = mk(), mk(), mk(), mk()
         self.step = 0
+        # graph=True: fn is captured once per device buffer into a CUDA graph (after one eager call) and replayed, which
+        # takes the Python issue cost of the module stack off the critical path.  fn must then be capture-safe: no host
+        # synchronisation, no data-dependent Python control flow, parameters unchanged between steps.
+        self.use_graph = bool(graph)
+        self.graphs = [None] * self.depth
+        self.static_out = [None] * self.depth
         self.h2d_bytes = self.dev_in[0].numel() * self.dev_in[0].element_size()
         self.d2h_bytes = self.host_out[0].numel() * self.host_out[0].element_size()
 
@@ -35,14 +41,26 @@ class HostStepRunner:
             self.dev_in[s].copy_(host_batch, non_blocking=True)
             self.in_ready[s].record(self.h2d)
         compute.wait_event(self.in_ready[s])
-        out = self.fn(self.dev_in[s])
+        if not self.use_graph:
+            out = self.fn(self.dev_in[s])
+        else:
+            if self.graphs[s] is None:
+                self.fn(self.dev_in[s])                  # eager warm-up (lazy initialisation, weight packing, allocator)
+                compute.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.static_out[s] = self.fn(self.dev_in[s])
+                self.graphs[s] = g
+            self.graphs[s].replay()
+            out = self.static_out[s]
         self.in_free[s].record(compute)
         self.out_ready[s].record(compute)
         self.d2h.wait_event(self.out_ready[s])
         with torch.cuda.stream(self.d2h):
             self.host_out[s].copy_(out.reshape(self.host_out[s].shape), non_blocking=True)
             self.done[s].record(self.d2h)
-        out.record_stream(self.d2h)
+        if not self.use_graph:
+            out.record_stream(self.d2h)
         self.step += 1
         return i
 

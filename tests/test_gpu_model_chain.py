@@ -196,16 +196,17 @@ def test_host_step_runner_matches_direct_calls():
     w = torch.randn(64, 64, generator=g).cuda()
     fn = lambda x: torch.tanh(x @ w) * 3.0  # noqa: E731
     batches = [torch.randn(128, 64, generator=g).pin_memory() for _ in range(7)]
-    runner = HostStepRunner(fn, (128, 64), (128, 64), "cuda", depth=2)
-    got = []
-    for b in batches:
-        i = runner.submit(b)
-        if i >= 1:
-            got.append(runner.result(i - 1).clone())
-    got.append(runner.result(len(batches) - 1).clone())
-    runner.drain()
-    for b, y in zip(batches, got):
-        same(y, fn(b.cuda()))
+    for graph in (False, True):
+        runner = HostStepRunner(fn, (128, 64), (128, 64), "cuda", depth=2, graph=graph)
+        got = []
+        for b in batches:
+            i = runner.submit(b)
+            if i >= 1:
+                got.append(runner.result(i - 1).clone())
+        got.append(runner.result(len(batches) - 1).clone())
+        runner.drain()
+        for b, y in zip(batches, got):
+            same(y, fn(b.cuda()))
     with pytest.raises(IndexError):
         runner.result(0)
     assert runner.h2d_bytes == 128 * 64 * 4 and runner.d2h_bytes == 128 * 64 * 4
