@@ -440,7 +440,7 @@ def main():
                                       "batch 32 per GPU (M=16384), 72 QLinear sites per step in %d fused launches%s" % (
                                           LAYERS * len(order), "" if args.no_group else " (q|k|v of a layer share one launch)"),
                           "launch": launch_mode, "host_issue_ms_per_step": host_issue_ms,
-                          "l2": "inputs/outputs rotate over 4x50MB / 2x201MB buffers (> 126 MB L2) between launches",
+                          "l2": "inputs/outputs rotate over 4x50MB / 2x151MB / 2x201MB buffers (> 126 MB L2) between launches",
                           "parallelism": "dp%d (independent batches, no collective)" % world},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * LAYERS * len(order),
                "clocks": clocks}
