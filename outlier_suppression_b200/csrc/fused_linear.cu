@@ -402,11 +402,10 @@ struct Smem {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   uint64_t acc_full[kMaxAccStages], acc_empty[kMaxAccStages];
-  uint64_t codes_ready, passes_issued;
+  uint64_t codes_ready, passes_issued, tmem_ready;
   uint64_t x_full[kNumWorkers];  // per-worker fp32 landing slot filled (TMA complete_tx)
   uint32_t tmem_base;
   volatile uint32_t converted;  // k-blocks worker 0 has converted so far (paces the L2 prefetcher)
-  uint32_t pad2[2];  // keeps sizeof(Smem) a multiple of 16: the per-column constants follow it
 };
 // after Smem: per-column epilogue constants of the current chunk (2 * BN floats, padded to 32 columns):
 //   y = acc * c1[n] + c0[n],  c1 = s_a * w_scale[n],  c0 = bias[n] - Zc * rowsum[n] * c1
@@ -456,14 +455,33 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     mbar_init(&sm.codes_ready, kNumWorkers);
     for (int i = 0; i < kNumWorkers; ++i) mbar_init(&sm.x_full[i], 1);
     mbar_init(&sm.passes_issued, 1);
+    mbar_init(&sm.tmem_ready, 1);
     fence_barrier_init();
   }
-  if (warp == 2) { if (pair) tmem_alloc_pair(&sm.tmem_base, kTmemCols); else tmem_alloc(&sm.tmem_base, kTmemCols); }
-  tc_fence_before();
-  __syncthreads();
-  if (p.csz > 1) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit
-  tc_fence_after();
-  const uint32_t tmem_base = sm.tmem_base;
+  if constexpr (pair) {
+    if (warp == 2) tmem_alloc_pair(&sm.tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+  } else {
+    // only the barrier initialisation gates the producers: the TMEM allocation runs behind it and is published
+    // through its own mbarrier to the two consumers of the address (MMA issuer, epilogue warps)
+    __syncthreads();
+    if (warp == 2) {
+      tmem_alloc(&sm.tmem_base, kTmemCols);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.tmem_ready);
+    }
+  }
+  auto tmem_address = [&]() -> uint32_t {
+    if constexpr (!pair) {
+      mbar_wait(&sm.tmem_ready, 0);
+      tc_fence_after();
+    }
+    return *reinterpret_cast<volatile uint32_t*>(&sm.tmem_base);
+  };
   const uint32_t crank = (p.csz > 1) ? cluster_ctarank() : 0u;
   if (threadIdx.x == 0) OSQ_TRACE(1020);
   if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x] = gtimer();
@@ -517,6 +535,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     // no divisions, no generic->shared conversions inside the loop.
     if (lane == 0 && crank == 0) {
       const uint32_t idesc = make_idesc_i8(p.BN, pair ? 256 : 128);
+      const uint32_t tmem_base = tmem_address();
       const uint32_t a_base = smem_u32(a_ring), w_base = smem_u32(w_ring);
       const uint32_t a_full0 = smem_u32(&sm.a_full[0]), a_empty0 = smem_u32(&sm.a_empty[0]);
       const uint32_t w_full0 = smem_u32(&sm.w_full[0]), w_empty0 = smem_u32(&sm.w_empty[0]);
@@ -651,6 +670,15 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     // A, the quantisation parameters, Y and the code cache may be produced / still be read by the previous
     // kernel of the stream: every global access is ordered after it; only the prologue above overlaps
     if (p.pdl) pdl_wait_prior_grids();
+    if constexpr (kXTma) {
+      // the first landing-slot fill of the first tile goes out before the quantisation parameters are even read
+      const int row0 = (int)blockIdx.x * p.rows_per_tile + w * kRowsPerWorker;
+      if (lane == 0 && w * kRowsPerWorker < p.rows_per_tile && row0 < p.M) {
+        const uint32_t bar = smem_u32(&sm.x_full[w]);
+        mbar_arrive_expect_tx_u32(bar, (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker) * (uint32_t)(kStageK * 4));
+        tma_load_2d_u32(smem_u32(x_ring + (size_t)w * kXSlotBytes), &tmap_a, bar, 0, row0);
+      }
+    }
     const QParam qp = load_qparam(p.a_scale, p.a_zp, p.a_zp_is_int32, p.g, p.qmin, p.qmax,
                                   blockIdx.x == 0 && w == 0 && lane == 0);
     ConvParam cp;
@@ -747,7 +775,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     // zero-filled by the TMA unit: no ragged path.
     uint32_t x_ph = 0;
     const uint32_t leader_a_full0 = pair ? mapa_u32(smem_u32(&sm.a_full[0]), 0) : 0u;
-    auto convert_pass_tma = [&](int mb, uint32_t pa0) {
+    auto convert_pass_tma = [&](int mb, uint32_t pa0, bool first_issued) {
       const uint32_t x_bar = smem_u32(&sm.x_full[w]);
       uint8_t* const x_slot = x_ring + (size_t)w * kXSlotBytes;
       const uint32_t x_box_bytes = (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker) * (uint32_t)(kStageK * 4);
@@ -756,7 +784,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       const int nvalid = active ? min(kRowsPerWorker, p.M - row_first) : 0;
       const size_t rs = (size_t)p.K;
       uint8_t* cptr = (p.a_codes != nullptr && active) ? p.a_codes + (size_t)row_first * rs + lane * 4 : nullptr;
-      if (active && lane == 0) {
+      if (active && lane == 0 && !first_issued) {
         mbar_arrive_expect_tx_u32(x_bar, x_box_bytes);
         tma_load_2d_u32(smem_u32(x_slot), &tmap_a, x_bar, 0, row_first);
       }
@@ -850,6 +878,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
     };
     int obufs = p.out_bufs;  // store tiles this warp may cycle through in the current m-block
+    uint32_t tmem_base = 0;   // fetched right before the first epilogue chunk
     auto epilogue_chunk = [&](int mb, int nc) {
       const int as_ = cacc % p.acc_stages;
       const int n0 = nc * p.BN;
@@ -954,7 +983,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
       }
-      if constexpr (kXTma) convert_pass_tma(mb, pa_block); else convert_pass(mb, pa_block);
+      if constexpr (kXTma) convert_pass_tma(mb, pa_block, it == 0); else convert_pass(mb, pa_block);
       if (p.cached) {
         // bins of this m-block are in the code cache: publish them to the async proxy (TMA) of this CTA
         __threadfence();
@@ -964,11 +993,12 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         skip_ring((uint32_t)(a_passes - 1) * (uint32_t)p.KB);  // N chunks >= 1 are filled by the TMA thread
       }
       if (p.alias_xo) { obufs = (it == n_my_blocks - 1) ? p.out_bufs : 1; n_stores = 0; }
+      if (w < kNumEpiWarps && it == 0) tmem_base = tmem_address();
       if (w < kNumEpiWarps) publish_consts();  // chunk 0 constants
       for (int nc = 0; nc < p.NC; ++nc) {
         // no code cache and K too large for residency: re-convert A for the next N chunk first
         if (!p.resident && !p.cached && nc + 1 < p.NC) {
-          if constexpr (kXTma) convert_pass_tma(mb, pa_block + (uint32_t)(nc + 1) * p.KB); else convert_pass(mb, pa_block + (uint32_t)(nc + 1) * p.KB);
+          if constexpr (kXTma) convert_pass_tma(mb, pa_block + (uint32_t)(nc + 1) * p.KB, false); else convert_pass(mb, pa_block + (uint32_t)(nc + 1) * p.KB);
         }
         if (w < kNumEpiWarps) epilogue_chunk(mb, nc);
       }
@@ -983,6 +1013,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
   if (p.csz > 1) cluster_sync_all();  // no CTA exits while the pair's MMAs / commits / remote arrives may still touch it
   if (warp == 2) {
     tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm.tmem_base);
     if (pair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
   if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x + 1] = gtimer();
