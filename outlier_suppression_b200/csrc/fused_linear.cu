@@ -1221,7 +1221,12 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
       }
       if (max_ctas[dev & 63][csz] <= 0) { if (csz > 1) continue; set_error("osq_fused_fq_linear: no resident CTA"); return OSQ_ECUDA; }
     }
-    const int G = max_ctas[dev & 63][csz];
+    int G = max_ctas[dev & 63][csz];
+    {  // experiment knob: leave SMs free for a second stream (two half-batches out of phase)
+      static int env_cap = -1;
+      if (env_cap < 0) { const char* e = getenv("OSQ_FUSED_MAX_CTAS"); env_cap = e ? atoi(e) : 0; }
+      if (env_cap > 0 && env_cap < G) G = env_cap / csz * csz;
+    }
     // rows per CTA tile: the 128-row MMA tile is filled with as many rows as make the tile count a multiple of
     // the resident CTA count (M = 16384 on 148 SMs: 147 tiles of 112 rows instead of 128 tiles of 128 rows)
     {

@@ -206,8 +206,9 @@ def token_minmax(x, lens, seq_pos):
 
 def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
                          scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None, use_sort=False) -> torch.Tensor:
-    """AvgPruneMinMaxObserver's token pruning (observer.py:50-70,214-237) in TWO launches: one pass over the
-    activation (per-token extrema) and one radix-select + selection + running-statistics launch."""
+    """AvgPruneMinMaxObserver's token pruning (observer.py:50-70,214-237): one pass over the activation (per-token
+    extrema), then the exact radix select + clip selection + running statistics on the [T] vectors (one launch up
+    to 32768 tokens, six small multi-CTA launches above)."""
     tmin, tmax, n_valid = token_minmax(x, lens, seq_pos)
     cur = _cur_out(out, tmin.device)
     epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)

@@ -1,0 +1,134 @@
+// storebench.cu -- what the store path of one SM sustains in the shape the fused kernel's epilogue uses:
+// E epilogue warps per CTA, each cycling through T staging tiles of 32 rows x 128 B (SWIZZLE_128B) that leave through
+// cp.async.bulk.tensor stores (mode 0), through one 128-byte cp.async.bulk per row issued by every lane (mode 1), or
+// through plain st.global.v4 from registers (mode 2: thread = row, 8 x 16 B per 32-column group; mode 3: the warp
+// transposes through shared memory and writes 512 contiguous bytes per row).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o storebench storebench.cu -lcuda
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s failed: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// CTA owns `rows` rows (multiple of 32) x N columns; warp w: quarter = w % 4 (32 rows), column slice = w / 4
+__global__ void __launch_bounds__(1024, 1)
+store_kernel(const __grid_constant__ CUtensorMap tmap, float* Y, int N, int rows, int E, int T, int mode, int do_sts, int hint) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= E) return;
+  uint64_t policy = 0;
+  if (hint == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  if (hint == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  if (hint == 3) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(policy));
+  const int q = warp & 3, slices = E >> 2, slice = warp >> 2;
+  uint8_t* mine = smem + (size_t)warp * T * 4096;
+  const int cols_per_slice = N / slices;
+  const int row0 = blockIdx.x * rows + q * 32;
+  int n = 0;
+  for (int rb = 0; rb < rows; rb += 128)
+    for (int c0 = slice * cols_per_slice; c0 < (slice + 1) * cols_per_slice; c0 += 32, ++n) {
+      uint8_t* tile = mine + (n % T) * 4096;
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = make_float4(c0 + j, lane, warp, n);
+      if (mode <= 1) {
+        if (n >= T) {
+          if (lane == 0 || mode == 1) {
+            if (T == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else if (T == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else if (T == 4) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory");
+          }
+          __syncwarp();
+        }
+        if (do_sts) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t off = mode == 0 ? (uint32_t)((j * 16) ^ ((lane & 7) << 4)) : (uint32_t)(j * 16);
+            *reinterpret_cast<float4*>(tile + lane * 128 + off) = v[j];
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (mode == 0) {
+          if (lane == 0) {
+            if (hint == 0)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap), "r"(smem_u32(tile)),
+                           "r"(c0), "r"(row0 + rb)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(&tmap),
+                           "r"(smem_u32(tile)), "r"(c0), "r"(row0 + rb), "l"(policy)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          float* g = Y + (size_t)(row0 + rb + lane) * N + c0;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(g), "r"(smem_u32(tile + lane * 128)) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else if (mode == 2) {
+        float* g = Y + (size_t)(row0 + rb + lane) * N + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) __stcs(reinterpret_cast<float4*>(g) + j, v[j]);
+      } else {
+        // transpose through shared memory: lane writes its row swizzled, then the warp re-reads row by row
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(tile + lane * 128 + ((j * 16) ^ ((lane & 7) << 4))) = v[j];
+        __syncwarp();
+#pragma unroll
+        for (int r4 = 0; r4 < 32; r4 += 4) {
+          const int r = r4 + (lane >> 3), ch = lane & 7;
+          const float4 o = *reinterpret_cast<const float4*>(tile + r * 128 + ((ch * 16) ^ ((r & 7) << 4)));
+          __stcs(reinterpret_cast<float4*>(Y + (size_t)(row0 + rb + r) * N + c0) + ch, o);
+        }
+        __syncwarp();
+      }
+    }
+  if (mode <= 1 && (lane == 0 || mode == 1)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main() {
+  const int M = 148 * 512;  // 148 CTAs x 512 rows: runs of 100+ us, the launch overhead drops out
+  float *Y, *flush;
+  CK(cudaMalloc(&Y, (size_t)M * 2304 * 4));
+  CK(cudaMalloc(&flush, 256u << 20));
+  void* sym = nullptr; cudaDriverEntryPointQueryResult qr;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr));
+  EncodeTiledFn enc = (EncodeTiledFn)sym;
+  CK(cudaFuncSetAttribute(store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int ctas = 148, rows = 512;
+  for (int N : {768, 2304}) {
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M}; cuuint64_t strides[1] = {(cuuint64_t)N * 4}; cuuint32_t box[2] = {32, 32}; cuuint32_t es[2] = {1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
+    const double bytes = (double)ctas * rows * N * 4;
+    struct Cfg { int mode, E, T, sts, hint; };
+    const Cfg cfgs[] = {{0, 8, 2, 1, 0}, {0, 8, 2, 1, 1}, {0, 8, 2, 1, 2}, {0, 8, 2, 1, 3}, {0, 4, 4, 1, 0}, {0, 4, 4, 1, 1}, {0, 16, 2, 1, 0}, {0, 16, 2, 1, 1}};
+    for (const Cfg& c : cfgs) {
+      if (N % (32 * (c.E / 4)) != 0 || (size_t)c.E * c.T * 4096 > 220 * 1024) continue;
+      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+      float best = 1e9;
+      for (int i = 0; i < 4; ++i) {
+        cudaMemsetAsync(flush, 1, 256u << 20);
+        cudaEventRecord(a);
+        store_kernel<<<ctas, c.E * 32, (size_t)c.E * c.T * 4096>>>(tm, Y, N, rows, c.E, c.T, c.mode, c.sts, c.hint);
+        cudaEventRecord(b);
+        CK(cudaEventSynchronize(b));
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+      }
+      CK(cudaGetLastError());
+      const char* names[] = {"TMA tensor store 32x128B", "cp.async.bulk 128 B per lane", "st.global.v4 thread=row", "smem transpose + st.global.v4 rows"};
+      printf("N=%4d %-36s warps=%2d tiles/warp=%d sts=%d hint=%d : %6.0f GB/s  %5.1f B/clk/SM @1.9GHz  (%.1f us incl. launch)\n", N, names[c.mode], c.E, c.T, c.sts, c.hint,
+             bytes / best / 1e6, bytes / best / 1e6 / 148 / 1.9, best * 1e3);
+    }
+  }
+  return 0;
+}
