@@ -888,19 +888,19 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as_ * p.BN);
       const int row0 = mb * p.rows_per_tile + q * 32;
-      const int cols_per_slice = ((p.BN + 1) >> 1) + 31 & ~31;  // 128 for BN = 256; smaller BN: the second slice may stay idle
-      const int c_lo = slice * cols_per_slice;
-      const int c_end = min(min(c_lo + cols_per_slice, p.BN), p.N - n0);
+      // the two column slices of a lane quarter take alternating 32-column groups, so a row's two 128-byte pieces
+      // leave the SM close together in time (measured +6 % on the store path, scripts/mb/storebench.cu)
+      const int n_cols = min(p.BN, p.N - n0);
       // rows_per_tile is a multiple of 16: the tile's last lane quarter may own only 16 rows, which go out
       // through the 16-row box so that the neighbouring tile's rows are never touched
       const int rows_q = min(32, p.rows_per_tile - q * 32);
       const bool any_rows = (rows_q > 0) && (row0 < p.M);
       const CUtensorMap* ymap = (rows_q == 32) ? &tmap_y : &tmap_y16;
-      for (int c0 = c_lo; c0 < c_end; c0 += 32) {
+      for (int c0 = slice * 32; c0 < n_cols; c0 += 64) {
         uint32_t v[32];
 #ifdef OSQ_ENABLE_TRACE
         const bool probe = (w == 0 && lane == 0 && cacc == 2);
-        const int pslot = 900 + ((c0 - c_lo) >> 5) * 6;
+        const int pslot = 900 + (c0 >> 6) * 6;
         if (probe) OSQ_TRACE(pslot + 0);
 #endif
         tmem_ld32(taddr + c0, v);

@@ -14,7 +14,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 // CTA owns `rows` rows (multiple of 32) x N columns; warp w: quarter = w % 4 (32 rows), column slice = w / 4
 __global__ void __launch_bounds__(1024, 1)
-store_kernel(const __grid_constant__ CUtensorMap tmap, float* Y, int N, int rows, int E, int T, int mode, int do_sts, int hint) {
+store_kernel(const __grid_constant__ CUtensorMap tmap, float* Y, int N, int rows, int E, int T, int mode, int do_sts, int hint, int interleave) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= E) return;
@@ -28,7 +28,8 @@ store_kernel(const __grid_constant__ CUtensorMap tmap, float* Y, int N, int rows
   const int row0 = blockIdx.x * rows + q * 32;
   int n = 0;
   for (int rb = 0; rb < rows; rb += 128)
-    for (int c0 = slice * cols_per_slice; c0 < (slice + 1) * cols_per_slice; c0 += 32, ++n) {
+    for (int g = 0; g < cols_per_slice / 32; ++g, ++n) {
+      const int c0 = interleave ? (g * slices + slice) * 32 : slice * cols_per_slice + g * 32;
       uint8_t* tile = mine + (n % T) * 4096;
       float4 v[8];
 #pragma unroll
@@ -109,8 +110,8 @@ int main() {
     if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
     const double bytes = (double)ctas * rows * N * 4;
-    struct Cfg { int mode, E, T, sts, hint; };
-    const Cfg cfgs[] = {{0, 8, 2, 1, 0}, {0, 8, 2, 1, 1}, {0, 8, 2, 1, 2}, {0, 8, 2, 1, 3}, {0, 4, 4, 1, 0}, {0, 4, 4, 1, 1}, {0, 16, 2, 1, 0}, {0, 16, 2, 1, 1}};
+    struct Cfg { int mode, E, T, sts, hint, il; };
+    const Cfg cfgs[] = {{0, 4, 4, 1, 0, 0}, {0, 8, 2, 1, 0, 0}, {0, 8, 2, 1, 0, 1}, {0, 16, 2, 1, 0, 0}, {0, 16, 2, 1, 0, 1}, {0, 16, 1, 1, 0, 1}, {0, 32, 1, 1, 0, 1}, {3, 8, 1, 1, 0, 1}, {3, 16, 1, 1, 0, 1}};
     for (const Cfg& c : cfgs) {
       if (N % (32 * (c.E / 4)) != 0 || (size_t)c.E * c.T * 4096 > 220 * 1024) continue;
       cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -118,7 +119,7 @@ int main() {
       for (int i = 0; i < 4; ++i) {
         cudaMemsetAsync(flush, 1, 256u << 20);
         cudaEventRecord(a);
-        store_kernel<<<ctas, c.E * 32, (size_t)c.E * c.T * 4096>>>(tm, Y, N, rows, c.E, c.T, c.mode, c.sts, c.hint);
+        store_kernel<<<ctas, c.E * 32, (size_t)c.E * c.T * 4096>>>(tm, Y, N, rows, c.E, c.T, c.mode, c.sts, c.hint, c.il);
         cudaEventRecord(b);
         CK(cudaEventSynchronize(b));
         float ms; cudaEventElapsedTime(&ms, a, b);
@@ -126,7 +127,7 @@ int main() {
       }
       CK(cudaGetLastError());
       const char* names[] = {"TMA tensor store 32x128B", "cp.async.bulk 128 B per lane", "st.global.v4 thread=row", "smem transpose + st.global.v4 rows"};
-      printf("N=%4d %-36s warps=%2d tiles/warp=%d sts=%d hint=%d : %6.0f GB/s  %5.1f B/clk/SM @1.9GHz  (%.1f us incl. launch)\n", N, names[c.mode], c.E, c.T, c.sts, c.hint,
+      printf("N=%4d %-36s warps=%2d tiles/warp=%d sts=%d hint=%d interleaved=%d : %6.0f GB/s  %5.1f B/clk/SM @1.9GHz  (%.1f us incl. launch)\n", N, names[c.mode], c.E, c.T, c.sts, c.hint, c.il,
              bytes / best / 1e6, bytes / best / 1e6 / 148 / 1.9, best * 1e3);
     }
   }
