@@ -14,7 +14,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 // CTA owns `rows` rows (multiple of 32) x N columns; warp w: quarter = w % 4 (32 rows), column slice = w / 4
 __global__ void __launch_bounds__(1024, 1)
-store_kernel(const __grid_constant__ CUtensorMap tmap, float* Y, int N, int rows, int E, int T, int mode, int do_sts, int hint, int interleave) {
+store_kernel(const __grid_constant__ CUtensorMap tmap, float* Y, int N, int rows, int E, int T, int mode, int do_sts, int hint, int interleave, const __grid_constant__ CUtensorMap tmap3, int J) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= E) return;
@@ -34,7 +34,30 @@ store_kernel(const __grid_constant__ CUtensorMap tmap, float* Y, int N, int rows
       float4 v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = make_float4(c0 + j, lane, warp, n);
-      if (mode <= 1) {
+      if (mode == 4) {
+        // one store = 32 rows x J adjacent 32-column groups: shared layout [32 rows][J][128 B], 128B-swizzled per unit
+        if ((g % J) == 0) {
+          if (n / J >= T) {
+            if (lane == 0) { if (T == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+            __syncwarp();
+          }
+        }
+        uint8_t* big = smem + (size_t)warp * T * J * 4096 + (size_t)((n / J) % T) * J * 4096;
+        const int jj = g % J;
+        const uint32_t unit = (uint32_t)(lane * J + jj);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(big + unit * 128 + ((j ^ (unit & 7)) << 4)) = v[j];
+        if (jj == J - 1) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap3), "r"(smem_u32(big)),
+                         "r"(0), "r"((c0 >> 5) - (J - 1)), "r"(row0 + rb)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else if (mode <= 1) {
         if (n >= T) {
           if (lane == 0 || mode == 1) {
             if (T == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -88,7 +111,7 @@ store_kernel(const __grid_constant__ CUtensorMap tmap, float* Y, int N, int rows
         __syncwarp();
       }
     }
-  if (mode <= 1 && (lane == 0 || mode == 1)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if ((mode <= 1 || mode == 4) && (lane == 0 || mode == 1)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -110,24 +133,30 @@ int main() {
     if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
     const double bytes = (double)ctas * rows * N * 4;
-    struct Cfg { int mode, E, T, sts, hint, il; };
-    const Cfg cfgs[] = {{0, 4, 4, 1, 0, 0}, {0, 8, 2, 1, 0, 0}, {0, 8, 2, 1, 0, 1}, {0, 16, 2, 1, 0, 0}, {0, 16, 2, 1, 0, 1}, {0, 16, 1, 1, 0, 1}, {0, 32, 1, 1, 0, 1}, {3, 8, 1, 1, 0, 1}, {3, 16, 1, 1, 0, 1}};
+    struct Cfg { int mode, E, T, sts, hint, il, J; };
+    const Cfg cfgs[] = {{0, 8, 2, 1, 0, 0, 1}, {4, 8, 2, 1, 0, 0, 1}, {4, 8, 1, 1, 0, 0, 2}, {4, 8, 2, 1, 0, 0, 2}, {4, 8, 1, 1, 0, 0, 3}, {4, 8, 2, 1, 0, 0, 3}, {4, 8, 1, 1, 0, 0, 4}, {4, 8, 1, 1, 0, 0, 6}, {4, 4, 2, 1, 0, 0, 6}, {4, 4, 1, 1, 0, 0, 12}, {4, 16, 1, 1, 0, 0, 3}};
     for (const Cfg& c : cfgs) {
-      if (N % (32 * (c.E / 4)) != 0 || (size_t)c.E * c.T * 4096 > 220 * 1024) continue;
+      if (N % (32 * (c.E / 4) * c.J) != 0 || (size_t)c.E * c.T * c.J * 4096 > 220 * 1024) continue;
+      CUtensorMap tm3;
+      {
+        cuuint64_t d3[3] = {32, (cuuint64_t)(N / 32), (cuuint64_t)M}; cuuint64_t s3[2] = {128, (cuuint64_t)N * 4}; cuuint32_t b3[3] = {32, (cuuint32_t)c.J, 32}; cuuint32_t e3[3] = {1, 1, 1};
+        CUresult r3 = enc(&tm3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, Y, d3, s3, b3, e3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r3 != CUDA_SUCCESS) { printf("3D encode failed %d (J=%d)\n", (int)r3, c.J); continue; }
+      }
       cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
       float best = 1e9;
       for (int i = 0; i < 4; ++i) {
         cudaMemsetAsync(flush, 1, 256u << 20);
         cudaEventRecord(a);
-        store_kernel<<<ctas, c.E * 32, (size_t)c.E * c.T * 4096>>>(tm, Y, N, rows, c.E, c.T, c.mode, c.sts, c.hint, c.il);
+        store_kernel<<<ctas, c.E * 32, (size_t)c.E * c.T * c.J * 4096>>>(tm, Y, N, rows, c.E, c.T, c.mode, c.sts, c.hint, c.il, tm3, c.J);
         cudaEventRecord(b);
         CK(cudaEventSynchronize(b));
         float ms; cudaEventElapsedTime(&ms, a, b);
         if (ms < best) best = ms;
       }
       CK(cudaGetLastError());
-      const char* names[] = {"TMA tensor store 32x128B", "cp.async.bulk 128 B per lane", "st.global.v4 thread=row", "smem transpose + st.global.v4 rows"};
-      printf("N=%4d %-36s warps=%2d tiles/warp=%d sts=%d hint=%d interleaved=%d : %6.0f GB/s  %5.1f B/clk/SM @1.9GHz  (%.1f us incl. launch)\n", N, names[c.mode], c.E, c.T, c.sts, c.hint, c.il,
+      const char* names[] = {"TMA tensor store 32x128B", "cp.async.bulk 128 B per lane", "st.global.v4 thread=row", "smem transpose + st.global.v4 rows", "TMA 3D store 32 rows x J x 128B"};
+      printf("N=%4d %-36s warps=%2d tiles/warp=%d sts=%d hint=%d interleaved=%d J=%d : %6.0f GB/s  %5.1f B/clk/SM @1.9GHz  (%.1f us incl. launch)\n", N, names[c.mode], c.E, c.T, c.sts, c.hint, c.il, c.J,
              bytes / best / 1e6, bytes / best / 1e6 / 148 / 1.9, best * 1e3);
     }
   }
