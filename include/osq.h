@@ -180,17 +180,19 @@ int osq_pack_weight_s8(const float* w, int64_t N, int64_t K, const float* scale,
  *   lsq_grad_factor > 0, as in K1).  A [M, K] fp32 row-major (raw, un-quantised, or already
  *   fake-quantised -- fq is idempotent), Y [M, N] fp32 row-major.
  *
- *   One persistent, warp-specialised tcgen05 kernel: converter warps stream fp32 A with 128-bit
- *   loads and turn it into integer bins in the UMMA shared-memory layout, the packed weight bins
- *   arrive by TMA, `tcgen05.mma kind::i8` (u8 x s8 -> s32, exact) accumulates in TMEM, the epilogue
+ *   One persistent, warp-specialised tcgen05 kernel: fp32 A arrives by TMA in per-warp landing slots, converter
+ *   warps turn it into integer bins in the UMMA shared-memory layout, the packed weight bins arrive by TMA,
+ *   `tcgen05.mma kind::i8` (u8 x s8 -> s32, exact for every bit-width <= 8) accumulates in TMEM, the epilogue
  *   applies the zero-point correction, scales and bias and writes fp32 Y with TMA stores.
- *   mma_kind: 0 = auto, 1 = kind::i8, 2 = kind::f16 (bf16 code tiles, exact for a_bit,w_bit <= 7).
+ *   mma_kind: 0 = auto, 1 = kind::i8 (the only kind built; anything else is rejected).
  *
- *   Shape contract: K % 128 == 0, N % 16 == 0, M >= 1.  a_codes (optional uint8 [M, K], 16-byte
- *   aligned): receives the activation bins (bin - a_qmin) the kernel fed to the tensor core (parity
- *   side output).  When K > 1024 the converted block no longer fits in shared memory; if a_codes is
- *   given it doubles as an L2-resident code cache so fp32 A is read and quantised once (otherwise
- *   A is re-read and re-quantised for every 256-column chunk of N).
+ *   Shape contract: K % 128 == 0, K <= 32768 (int32 accumulators), N % 16 == 0, M >= 1; A, Y, w_codes 16-byte
+ *   aligned.  a_codes (optional uint8 [M, K], 16-byte aligned): receives the activation bins (bin - a_qmin) the
+ *   kernel fed to the tensor core (parity side output).  When K > 1024 the converted block no longer fits in
+ *   shared memory; if a_codes is given it doubles as an L2-resident code cache so fp32 A is read and quantised
+ *   once (otherwise A is re-read and re-quantised for every chunk of N).
+ *   Several Linears that consume the same A (BERT query | key | value) may be served by one call over their
+ *   row-concatenated w_codes / w_scale / w_rowsum / bias: every output column is computed independently.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* A;

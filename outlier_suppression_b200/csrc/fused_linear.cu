@@ -35,10 +35,8 @@
 namespace osq {
 
 constexpr int kBM = 128;            // rows of A per CTA tile (UMMA M)
-constexpr int kBNMax = 256;         // widest N chunk (UMMA N); the resident-A mode uses 128
 constexpr int kStageK = 128;        // k elements (= bytes, u8/s8) per smem stage row: one 128B swizzle row
 constexpr int kUmmaK = 32;          // k per tcgen05.mma kind::i8
-constexpr int kAStageBytes = kBM * kStageK;          // 16 KB
 constexpr int kTmemCols = 512;                       // acc stages x BN: 4 x 128 or 2 x 256
 constexpr int kWorkerWarp0 = 4, kNumWorkers = 16;    // warps 4..19 convert A (phase A); warps 4..11 also run the epilogue
 constexpr int kNumEpiWarps = 8;                      // workers 0..7: four TMEM lane quarters x two column halves of a chunk
