@@ -11,20 +11,24 @@
 //
 // Data flow per CTA (one 128-row block of A at a time, all of N for that block):
 //
-//   warps 4-19  (16)  workers, phase A: 128-bit streaming loads of fp32 A straight into registers (8 rows x
-//                     512 B in flight per warp, software pipelined in two halves) -> integer bins -> A ring
-//                     in the UMMA K-major SW128 shared-memory layout               (a_full / a_empty)
+//   warps 4-19  (16)  workers, phase A: fp32 A arrives by TMA in one 4 KB landing slot per warp (its 8 rows x one
+//                     k-block); slot -> registers -> integer bins -> A ring in the UMMA K-major SW128
+//                     shared-memory layout; the slot is re-armed as soon as it is in registers
+//                                                                                  (x_full, a_full / a_empty)
+//                     (variant `_ldg`: 128-bit streaming loads straight into registers instead of the slots)
 //   warp 0  (1 lane)  TMA: s8 weight tiles [BN rows x 128 k], SW128 -> W ring      (w_full / w_empty)
 //   warp 1  (1 lane)  tcgen05.mma  D[tmem] (+)= A[smem] * W[smem]^T, commit -> w_empty/a_empty/acc_full
-//   warp 2            TMEM allocation; (1 lane) TMA re-load of cached bins for N chunks >= 1 when K > 1024
+//   warp 2            TMEM allocation; (1 lane) TMA re-load of cached bins for the later sweeps when K > 1024
+//   warp 3            idle (optional L2 prefetcher of the `_ldg` variant)
 //   warps 4-11 (8)    workers, phase B (epilogue): tcgen05.ld -> zero-point correction, scales, bias ->
-//                     swizzled smem tile -> TMA store (full 128-byte lines) of fp32 Y
+//                     swizzled smem tile (the landing slots, two per warp) -> TMA store of fp32 Y
 //
 // When all of K fits in the A ring (K/128 <= 8: BERT-base 768, BART 1024) the converted A block stays
 // RESIDENT in shared memory and is reused for every N chunk: each activation element is read from HBM
-// once and quantised once.  Otherwise (K = 3072/4096) pass 0 converts A and also spills the bins (1 B per
-// element) to a caller-provided code cache that stays in L2; the remaining N chunks re-load the bins
-// by TMA directly in the UMMA layout -- fp32 A is still read from HBM exactly once.
+// once and quantised once.  Otherwise (K = 3072/4096) the first sweep converts A, feeds every TMEM accumulator
+// stage per k-block and spills the bins (1 B per element) to a caller-provided code cache that stays in L2; the
+// remaining N chunks re-load the bins by TMA directly in the UMMA layout -- fp32 A is still read from HBM once.
+// Variant `_pair` runs two CTAs as one tcgen05 cta_group::2 (M = 256): see DESIGN.md section 5.
 #include <cuda.h>
 #include <type_traits>
 #include <stdlib.h>
