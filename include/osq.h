@@ -59,6 +59,13 @@ int osq_fq_per_tensor_f32(const float* x, float* y, int16_t* codes, int64_t n,
 
 /* K2  per-channel (ch_axis = 0) fake-quantize of a [rows, cols] matrix.
  *     replaces util_quant.py:18-26 (fake_quantize_per_channel_affine), fake_quant.py:119-122. */
+/* K1b the same per-tensor fake-quantize with the bins as a uint8 side output in the operand format of
+ *     osq_fused_fq_linear (bin - qmin, needs qmax - qmin <= 255): a QLinear that consumes y (quantized_module.py:71-72)
+ *     can be fed `bins` instead of re-reading and re-quantising the fp32 tensor (A = NULL, a_codes = bins). */
+int osq_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int64_t n, const float* scale,
+                               const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin,
+                               int qmax, void* stream);
+
 int osq_fq_per_channel_f32(const float* x, float* y, int16_t* codes, int64_t rows, int64_t cols,
                            const float* scale, const int32_t* zero_point, int qmin, int qmax,
                            void* stream);
@@ -191,11 +198,14 @@ int osq_pack_weight_s8(const float* w, int64_t N, int64_t K, const float* scale,
  *   kernel fed to the tensor core (parity side output).  When K > 1024 the converted block no longer fits in
  *   shared memory; if a_codes is given it doubles as an L2-resident code cache so fp32 A is read and quantised
  *   once (otherwise A is re-read and re-quantised for every chunk of N).
+ *   Bins-in: A == NULL and a_codes != NULL -> a_codes already holds the activation bins (osq_fq_per_tensor_bins_f32 of
+ *   the upstream activation quantizer); the kernel TMA-loads them straight into the UMMA layout and converts nothing.
+ *   The result is bit-identical to the fp32-in launch.
  *   Several Linears that consume the same A (BERT query | key | value) may be served by one call over their
  *   row-concatenated w_codes / w_scale / w_rowsum / bias: every output column is computed independently.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
-  const float* A;
+  const float* A;        /* [M, K] fp32, or NULL for a bins-in launch (then a_codes is the input) */
   int64_t M, K;
   const float* a_scale;  /* device [1] */
   const void* a_zp;      /* device [1] */

@@ -9,9 +9,17 @@ namespace osq {
 constexpr int kFqThreads = 256;
 constexpr int kFqUnroll = 4;  // float4s in flight per thread
 
-template <bool kCodes>
+// kCodes: 0 = no side output, 1 = int16 bins q (parity tests), 2 = uint8 bins q - qmin (the operand format of the
+// fused Linear kernel: a downstream QLinear can consume them instead of re-reading and re-quantising the fp32 tensor)
+template <int kCodes>
+__device__ __forceinline__ void put_code(void* codes, int64_t i, float q, float qmin) {
+  if (kCodes == 1) static_cast<int16_t*>(codes)[i] = (int16_t)rintf(q);
+  if (kCodes == 2) static_cast<uint8_t*>(codes)[i] = (uint8_t)(int)(q - qmin);
+}
+
+template <int kCodes>
 __global__ void __launch_bounds__(kFqThreads)
-fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, int16_t* __restrict__ codes,
+fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, void* __restrict__ codes,
                      int64_t n, const float* __restrict__ scale, const void* __restrict__ zp,
                      int zp_is_int32, float g, float qmin, float qmax) {
   const QParam p = load_qparam(scale, zp, zp_is_int32, g, qmin, qmax,
@@ -27,13 +35,14 @@ fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, int16_t
     for (int64_t i = tid; i < n; i += nthreads) {
       float q;
       y[i] = fq_elem(x[i], s, z, qmin, qmax, q);
-      if (kCodes) codes[i] = (int16_t)rintf(q);
+      put_code<kCodes>(codes, i, q, qmin);
     }
     return;
   }
   const int64_t nvec = (n - head) >> 2;
   const float4* xv = reinterpret_cast<const float4*>(x + head);
   float4* yv = reinterpret_cast<float4*>(y + head);
+  const bool word_codes = kCodes == 2 && (((uintptr_t)codes + (uintptr_t)head) & 3) == 0;  // four bins per 32-bit store
   for (int64_t base = tid; base < nvec; base += nthreads * kFqUnroll) {
     float4 v[kFqUnroll];
 #pragma unroll
@@ -52,10 +61,16 @@ fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, int16_t
         o.z = fq_elem(v[u].z, s, z, qmin, qmax, q2);
         o.w = fq_elem(v[u].w, s, z, qmin, qmax, q3);
         __stcs(yv + i, o);
-        if (kCodes) {
-          int16_t* c = codes + head + (i << 2);
-          c[0] = (int16_t)rintf(q0); c[1] = (int16_t)rintf(q1);
-          c[2] = (int16_t)rintf(q2); c[3] = (int16_t)rintf(q3);
+        if (kCodes != 0) {
+          const int64_t e = head + (i << 2);
+          if (word_codes) {
+            const uint32_t w = (uint32_t)(int)(q0 - qmin) | ((uint32_t)(int)(q1 - qmin) << 8) | ((uint32_t)(int)(q2 - qmin) << 16) |
+                               ((uint32_t)(int)(q3 - qmin) << 24);
+            *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(codes) + e) = w;
+          } else {
+            put_code<kCodes>(codes, e, q0, qmin); put_code<kCodes>(codes, e + 1, q1, qmin);
+            put_code<kCodes>(codes, e + 2, q2, qmin); put_code<kCodes>(codes, e + 3, q3, qmin);
+          }
         }
       }
     }
@@ -66,7 +81,7 @@ fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, int16_t
     int64_t j = i < head ? i : tail_start + (i - head);
     float q;
     y[j] = fq_elem(x[j], s, z, qmin, qmax, q);
-    if (kCodes) codes[j] = (int16_t)rintf(q);
+    put_code<kCodes>(codes, j, q, qmin);
   }
 }
 
@@ -198,29 +213,44 @@ int osq_lsqplus_backward_f32(const float* x, const float* dy, float* dx, int64_t
   return OSQ_OK;
 }
 
-int osq_fq_per_tensor_f32(const float* x, float* y, int16_t* codes, int64_t n, const float* scale,
-                          const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin,
-                          int qmax, void* stream) {
+static int launch_fq_per_tensor(const char* who, const float* x, float* y, void* codes, int code_kind, int64_t n, const float* scale,
+                               const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin, int qmax, void* stream) {
   using namespace osq;
-  OSQ_CHECK_ARG(n >= 0, "osq_fq_per_tensor_f32: n < 0");
+  OSQ_CHECK_ARG(n >= 0, "%s: n < 0", who);
   if (n == 0) return OSQ_OK;
-  OSQ_CHECK_ARG(x && y && scale && zero_point, "osq_fq_per_tensor_f32: null pointer");
-  OSQ_CHECK_ARG(qmin < qmax, "osq_fq_per_tensor_f32: qmin >= qmax");
-  OSQ_CHECK_ARG(!(lsq_grad_factor > 0.f && zp_is_int32), "osq_fq_per_tensor_f32: LSQ+ needs a float zero_point");
+  OSQ_CHECK_ARG(x && y && scale && zero_point, "%s: null pointer", who);
+  OSQ_CHECK_ARG(qmin < qmax, "%s: qmin >= qmax", who);
+  OSQ_CHECK_ARG(!(lsq_grad_factor > 0.f && zp_is_int32), "%s: LSQ+ needs a float zero_point", who);
+  OSQ_CHECK_ARG(code_kind != 2 || qmax - qmin <= 255, "%s: uint8 bins need at most 8 bits", who);
   int sms = sm_count();
   if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
   int64_t per_block = (int64_t)kFqThreads * 4 * kFqUnroll;
   int64_t want = (n + per_block - 1) / per_block;
   int grid = (int)(want < (int64_t)sms * 8 ? (want < 1 ? 1 : want) : (int64_t)sms * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (codes)
-    fq_per_tensor_kernel<true><<<grid, kFqThreads, 0, st>>>(x, y, codes, n, scale, zero_point, zp_is_int32,
-                                                            lsq_grad_factor, (float)qmin, (float)qmax);
+  const float fmin_ = (float)qmin, fmax_ = (float)qmax;
+  if (codes == nullptr)
+    fq_per_tensor_kernel<0><<<grid, kFqThreads, 0, st>>>(x, y, nullptr, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_);
+  else if (code_kind == 1)
+    fq_per_tensor_kernel<1><<<grid, kFqThreads, 0, st>>>(x, y, codes, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_);
   else
-    fq_per_tensor_kernel<false><<<grid, kFqThreads, 0, st>>>(x, y, nullptr, n, scale, zero_point, zp_is_int32,
-                                                             lsq_grad_factor, (float)qmin, (float)qmax);
+    fq_per_tensor_kernel<2><<<grid, kFqThreads, 0, st>>>(x, y, codes, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
+}
+
+int osq_fq_per_tensor_f32(const float* x, float* y, int16_t* codes, int64_t n, const float* scale,
+                          const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin,
+                          int qmax, void* stream) {
+  return launch_fq_per_tensor("osq_fq_per_tensor_f32", x, y, codes, 1, n, scale, zero_point, zp_is_int32, lsq_grad_factor, qmin, qmax, stream);
+}
+
+int osq_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int64_t n, const float* scale,
+                               const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin,
+                               int qmax, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(bins != nullptr, "osq_fq_per_tensor_bins_f32: null bins");
+  return launch_fq_per_tensor("osq_fq_per_tensor_bins_f32", x, y, bins, 2, n, scale, zero_point, zp_is_int32, lsq_grad_factor, qmin, qmax, stream);
 }
 
 int osq_fq_per_channel_f32(const float* x, float* y, int16_t* codes, int64_t rows, int64_t cols,

@@ -70,6 +70,8 @@ struct FusedParams {
   int w_stage_bytes;  // BN * 128
   int resident;       // converted A block stays in smem for all N chunks
   int cached;         // streaming mode with a code cache: passes >= 1 TMA-load bins instead of re-converting
+  int codes_in;       // A is NULL: a_codes already holds the activation bins (written by the upstream fake-quant kernel);
+                      // every sweep TMA-loads them, nothing is converted
   const float* A;
   const float* a_scale;
   const void* a_zp;
@@ -444,7 +446,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_y);
     tma_prefetch_desc(&tmap_y16);
-    if (p.cached) tma_prefetch_desc(&tmap_codes);
+    if (p.cached || p.codes_in) tma_prefetch_desc(&tmap_codes);
     if (p.prefetch) tma_prefetch_desc(&tmap_a);
     sm.converted = 0;
   }
@@ -629,13 +631,15 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       }
     }
   } else if (warp == 2) {
-    // ===================== TMA producer: cached bins for N chunks >= 1 (K > 1024 only) =====================
-    if (lane == 0 && p.cached) {
+    // ===================== TMA producer: activation bins =====================
+    // code cache (K > 1024): the sweeps after the first re-load the bins the workers spilled;
+    // bins-in mode: the upstream fake-quant kernel wrote them, every sweep (resident A: the only one) loads them
+    if (lane == 0 && (p.cached || p.codes_in)) {
       if (p.pdl) pdl_wait_prior_grids();
       for (int it = 0; it < n_my_blocks; ++it) {
         const int mb = blockIdx.x + it * gridDim.x;
-        mbar_wait(&sm.codes_ready, it & 1);  // every worker has published this block's bins
-        for (int pass = 1; pass < a_passes; ++pass)
+        if (!p.codes_in) mbar_wait(&sm.codes_ready, it & 1);  // every worker has published this block's bins
+        for (int pass = p.codes_in ? 0 : 1; pass < a_passes; ++pass)
           for (int kb = 0; kb < p.KB; ++kb) {
             const uint32_t pa = (uint32_t)((it * a_passes + pass) * p.KB + kb);
             const int a_st = pa % p.a_stages;
@@ -675,7 +679,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     if constexpr (kXTma) {
       // the first landing-slot fill of the first tile goes out before the quantisation parameters are even read
       const int row0 = (int)blockIdx.x * p.rows_per_tile + w * kRowsPerWorker;
-      if (lane == 0 && w * kRowsPerWorker < p.rows_per_tile && row0 < p.M) {
+      if (lane == 0 && !p.codes_in && w * kRowsPerWorker < p.rows_per_tile && row0 < p.M) {
         const uint32_t bar = smem_u32(&sm.x_full[w]);
         mbar_arrive_expect_tx_u32(bar, (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker) * (uint32_t)(kStageK * 4));
         tma_load_2d_u32(smem_u32(x_ring + (size_t)w * kXSlotBytes), &tmap_a, bar, 0, row0);
@@ -979,14 +983,16 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       const uint32_t pa_block = (uint32_t)it * (uint32_t)(a_passes * p.KB);
       // cached mode: the TMA thread must have issued every re-load pass of the previous block before this
       // warp runs ahead on the same ring (two producers may never be more than one ring cycle apart)
-      if (p.cached && it > 0) mbar_wait(&sm.passes_issued, (it - 1) & 1);
       if (w < kNumEpiWarps) fetch_consts(0);
+      if (!p.codes_in) {
+      if (p.cached && it > 0) mbar_wait(&sm.passes_issued, (it - 1) & 1);
       if (p.alias_xo && it > 0 && w < kNumEpiWarps) {  // this warp's landing slot was its store tile: reads must be done
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
       }
       if constexpr (kXTma) convert_pass_tma(mb, pa_block, it == 0); else convert_pass(mb, pa_block);
-      if (p.cached) {
+      }
+      if (p.cached && !p.codes_in) {
         // bins of this m-block are in the code cache: publish them to the async proxy (TMA) of this CTA
         __threadfence();
         fence_proxy_async_all();
@@ -994,12 +1000,12 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         if (lane == 0) mbar_arrive(&sm.codes_ready);
         skip_ring((uint32_t)(a_passes - 1) * (uint32_t)p.KB);  // N chunks >= 1 are filled by the TMA thread
       }
-      if (p.alias_xo) { obufs = (it == n_my_blocks - 1) ? p.out_bufs : 1; n_stores = 0; }
+      if (p.alias_xo && !p.codes_in) { obufs = (it == n_my_blocks - 1) ? p.out_bufs : 1; n_stores = 0; }
       if (w < kNumEpiWarps && it == 0) tmem_base = tmem_address();
       if (w < kNumEpiWarps) publish_consts();  // chunk 0 constants
       for (int nc = 0; nc < p.NC; ++nc) {
         // no code cache and K too large for residency: re-convert A for the next N chunk first
-        if (!p.resident && !p.cached && nc + 1 < p.NC) {
+        if (!p.resident && !p.cached && !p.codes_in && nc + 1 < p.NC) {
           if constexpr (kXTma) convert_pass_tma(mb, pa_block + (uint32_t)(nc + 1) * p.KB, false); else convert_pass(mb, pa_block + (uint32_t)(nc + 1) * p.KB);
         }
         if (w < kNumEpiWarps) epilogue_chunk(mb, nc);
@@ -1126,7 +1132,7 @@ int osq_pack_weight_s8(const float* w, int64_t N, int64_t K, const float* scale,
 int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   using namespace osq;
   OSQ_CHECK_ARG(a != nullptr, "osq_fused_fq_linear: null args");
-  OSQ_CHECK_ARG(a->A && a->a_scale && a->a_zp && a->w_codes && a->w_scale && a->w_rowsum && a->Y,
+  OSQ_CHECK_ARG((a->A || a->a_codes) && a->a_scale && a->a_zp && a->w_codes && a->w_scale && a->w_rowsum && a->Y,
                 "osq_fused_fq_linear: null pointer");
   OSQ_CHECK_ARG(a->M >= 1 && a->M < (1ll << 31) - 256, "osq_fused_fq_linear: M out of range");
   OSQ_CHECK_ARG(a->K >= kStageK && a->K % kStageK == 0 && a->K <= 32768, "osq_fused_fq_linear: K must be a multiple of 128, at most 32768 (int32 accumulators)");
@@ -1206,7 +1212,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   Plan best; memset(&best, 0, sizeof(best));
   static int max_ctas[64][3] = {{0}};
   int grid = 0;
-  for (int csz = (env_csz == 2 && p.KB <= kMaxAStages) ? 2 : 1; csz >= 1 && !best.ok; --csz) {
+  for (int csz = (env_csz == 2 && p.KB <= kMaxAStages && a->A != nullptr) ? 2 : 1; csz >= 1 && !best.ok; --csz) {
     p.csz = csz;
     attr[0].val.clusterDim.x = (unsigned)csz;
     // how many CTAs can be co-resident (1 CTA / SM)
@@ -1255,7 +1261,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
       const int xo_min = x_tma ? x_bytes : out1;            // aliased X/O region, or one set of store tiles
       pl.resident = (p.KB <= kMaxAStages && p.KB * p.a_stage_bytes + 2 * w_stage + xo_min <= budget) ? 1 : 0;
       if (csz > 1 && !(pl.resident && x_tma)) return pl;
-      pl.cached = (!pl.resident && nc > 1 && a->a_codes != nullptr) ? 1 : 0;
+      pl.cached = (!pl.resident && (nc > 1 || a->A == nullptr) && a->a_codes != nullptr) ? 1 : 0;
       pl.a_stages = pl.resident ? p.KB : 4;
       // X and O can share memory only when conversion and epilogue never interleave inside a tile
       const bool can_alias = pl.resident || pl.cached || nc == 1;
@@ -1280,7 +1286,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
       pl.score = (pl.w_stages >= 3 ? 4 : 0) + (pl.out_bufs >= 2 ? 2 : 0) + (bn == 256 ? 1 : 0);
       return pl;
     };
-    const bool x_ok = env_xtma != 0 && p.K % 4 == 0;
+      const bool x_ok = (env_xtma != 0 && p.K % 4 == 0) || a->A == nullptr;  // bins-in launches use the TMA variant's layout
     const int bn_cands[3] = {256, 192, 128};
     for (int xt = x_ok ? 1 : 0; xt >= 0 && !best.ok; --xt)
       for (int i = 0; i < 3; ++i) {
@@ -1300,6 +1306,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
   p.w_stage_bytes = (p.BN / p.csz * kStageK + 1023) / 1024 * 1024;  // pair: each CTA stages half of the tile's rows
   p.resident = best.resident; p.cached = best.cached;
+  p.codes_in = (a->A == nullptr) ? 1 : 0;
   p.a_stages = best.a_stages; p.w_stages = best.w_stages; p.out_bufs = best.out_bufs;
   p.x_tma = best.x_tma; p.alias_xo = best.alias;
   // streamed A with a code cache: all accumulator stages are fed in one sweep over K (the later sweeps re-load the
@@ -1325,7 +1332,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   if (int rc = make_map_2d(&map_y16, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
                            p.M < 16 ? (uint32_t)p.M : 16u, CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
-  if (p.cached) {
+  if (p.cached || p.codes_in) {
     if (int rc = make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->a_codes, (uint64_t)p.K, (uint64_t)p.M, kStageK,
                              (uint32_t)(p.M < p.rows_per_tile ? p.M : p.rows_per_tile), CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
@@ -1335,8 +1342,8 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   // fp32 activation: [8 rows x 128 floats] boxes (one worker's rows of one k-block) for the landing slots; the
   // same map serves the optional L2 prefetcher (OSQ_FUSED_PREFETCH = distance in k-blocks; measured: 3 is neutral,
   // 6 and 12 are 3-8 % slower -> off by default)
-  p.prefetch = (p.x_tma == 0 && p.K % 4 == 0) ? env_pf : 0;
-  if (p.x_tma || p.prefetch > 0) {
+  p.prefetch = (p.x_tma == 0 && !p.codes_in && p.K % 4 == 0) ? env_pf : 0;
+  if ((p.x_tma && !p.codes_in) || p.prefetch > 0) {
     if (int rc = make_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->A, (uint64_t)p.K, (uint64_t)p.M, kStageK,
                              (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker), CU_TENSOR_MAP_SWIZZLE_NONE))
       return rc;
@@ -1353,7 +1360,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
       seen[n_seen][0] = p.M; seen[n_seen][1] = p.K; seen[n_seen][2] = p.N; ++n_seen;
       fprintf(stderr, "[osq] fused M=%d K=%d N=%d: grid=%d cluster=%d rows/tile=%d tiles/cta=%d BN=%d chunks=%d mode=%s a_stages=%d(%d B) "
                       "w_stages=%d(%d B) acc_stages=%d out_bufs=%d x_tma=%d alias=%d sweeps=%d smem=%zu\n",
-              p.M, p.K, p.N, grid, p.csz, p.rows_per_tile, p.n_iters, p.BN, p.NC, p.resident ? "resident" : (p.cached ? "streamed+cache" : "streamed"),
+              p.M, p.K, p.N, grid, p.csz, p.rows_per_tile, p.n_iters, p.BN, p.NC, p.codes_in ? (p.resident ? "bins-in resident" : "bins-in streamed") : p.resident ? "resident" : (p.cached ? "streamed+cache" : "streamed"),
               p.a_stages, p.a_stage_bytes, p.w_stages, p.w_stage_bytes, p.acc_stages, p.out_bufs, p.x_tma, p.alias_xo, p.a_passes, smem_bytes);
     }
   }

@@ -70,12 +70,22 @@ def _dense_like(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 # K1 / K2
 # ------------------------------------------------------------------------------------------------
 def fq_per_tensor(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int,
-                  lsq_grad_factor: float = 0.0, want_codes: bool = False):
-    """util_quant.py:11-15 / :48-55 with device-resident qparams. Returns y (and int16 bins)."""
+                  lsq_grad_factor: float = 0.0, want_codes: bool = False, want_bins: bool = False):
+    """util_quant.py:11-15 / :48-55 with device-resident qparams. Returns y (and int16 bins with want_codes, or
+    uint8 ``bin - qmin`` in the fused Linear's operand format with want_bins)."""
     _require_cuda(x, scale, zero_point)
     x, y = _dense_like(x)
+    if want_bins and x.numel() > 0:
+        if scale.dtype != torch.float32:
+            raise TypeError("scale must be float32")
+        bins = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        check(_lib.load().osq_fq_per_tensor_bins_f32(x.data_ptr(), y.data_ptr(), bins.data_ptr(), x.numel(), scale.data_ptr(),
+                                                     zero_point.data_ptr(), int(zero_point.dtype == torch.int32),
+                                                     float(lsq_grad_factor), int(qmin), int(qmax), _stream()),
+              "osq_fq_per_tensor_bins_f32")
+        return y, bins
     if x.numel() == 0:
-        return (y, torch.empty_like(x, dtype=torch.int16)) if want_codes else y
+        return (y, torch.empty_like(x, dtype=torch.int16)) if (want_codes or want_bins) else y
     zp_is_int = zero_point.dtype == torch.int32
     if not zp_is_int and zero_point.dtype != torch.float32:
         raise TypeError("zero_point must be int32 or float32")
@@ -318,22 +328,32 @@ def fused_linear_supported(k: int, n: int) -> bool:
 
 
 def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum, bias, lsq_grad_factor=0.0,
-                    mma_kind=0, want_codes=False, out=None, use_code_cache=True, trace=None):
-    """activation fq + weight fq + Linear in one tcgen05 kernel. a: [..., K] fp32 -> [..., N] fp32."""
+                    mma_kind=0, want_codes=False, out=None, use_code_cache=True, trace=None, a_bins=None):
+    """activation fq + weight fq + Linear in one tcgen05 kernel. a: [..., K] fp32 -> [..., N] fp32.
+    a_bins (uint8, same shape as a, contiguous; from fq_per_tensor(want_bins=True) with the same qparams): bins-in launch,
+    the fp32 tensor is not read at all (only its shape is used); the result is bit-identical."""
     _require_cuda(a, a_scale, a_zp, w_codes, w_scale, w_rowsum, bias)
-    if a.dtype != torch.float32:
-        a = a.float()
-    a2 = a.reshape(-1, a.shape[-1])
-    if not a2.is_contiguous():
-        a2 = a2.contiguous()
-    m, k = a2.shape
+    if a_bins is not None:
+        if a_bins.dtype != torch.uint8 or a_bins.numel() != a.numel() or not a_bins.is_contiguous() or not a_bins.is_cuda:
+            raise ValueError("a_bins must be a contiguous CUDA uint8 tensor with as many elements as a")
+        m, k = a.numel() // a.shape[-1], a.shape[-1]
+        a_ptr = None
+    else:
+        if a.dtype != torch.float32:
+            a = a.float()
+        a2 = a.reshape(-1, a.shape[-1])
+        if not a2.is_contiguous():
+            a2 = a2.contiguous()
+        m, k = a2.shape
+        a_ptr = a2.data_ptr()
     n = w_codes.shape[0]
     y = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
     # K > 1024: the bins do not fit in shared memory -> give the kernel an (L2 resident) code cache
     need_cache = use_code_cache and k > 1024 and n > 256
-    dbg = torch.empty((m, k), dtype=torch.uint8, device=a.device) if (want_codes or need_cache) else None
+    dbg = a_bins if a_bins is not None else (
+        torch.empty((m, k), dtype=torch.uint8, device=a.device) if (want_codes or need_cache) else None)
     args = FusedLinearArgs()
-    args.A, args.M, args.K = a2.data_ptr(), m, k
+    args.A, args.M, args.K = a_ptr, m, k
     args.a_scale, args.a_zp = a_scale.data_ptr(), a_zp.data_ptr()
     args.a_zp_is_int32 = int(a_zp.dtype == torch.int32)
     args.lsq_grad_factor = float(lsq_grad_factor)

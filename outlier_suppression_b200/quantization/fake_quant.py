@@ -21,9 +21,20 @@ _TAG = "_osq_producer"
 
 
 def producer_of(t: torch.Tensor):
-    """The live quantizer whose output ``t`` is, or None."""
-    ref = getattr(t, _TAG, None)
-    return ref() if ref is not None else None
+    """The live quantizer whose output ``t`` is, or None.  An in-place edit after the quantizer ran voids the tag
+    (the values are no longer fixed points of the fake-quant, so re-quantising them would change the result)."""
+    tag = getattr(t, _TAG, None)
+    if tag is None or tag[1] != t._version:
+        return None
+    return tag[0]()
+
+
+def bins_of(t: torch.Tensor):
+    """uint8 bins the producing fake-quant launch wrote next to ``t`` (None if absent, stale or ``t`` is strided)."""
+    tag = getattr(t, "_osq_bins", None)
+    if tag is None or tag[1] != t._version or not t.is_contiguous() or tag[0].numel() != t.numel():
+        return None
+    return tag[0]
 
 
 class QuantizeBase(nn.Module):
@@ -95,9 +106,27 @@ class QuantizeBase(nn.Module):
     def _per_channel_qparam_targets(self, rows):
         return None, None
 
+    # set by a QLinear that consumed this quantizer's output through the fused kernel: from then on the fake-quant
+    # launch also writes the uint8 bins (1 extra byte / element) and the Linear reads those instead of the fp32 tensor
+    _emit_bins = False
+
+    def _fq_per_tensor_tagged(self, X, scale, zero_point, g=0.0):
+        """No-grad per-tensor fake-quant (K1) whose output carries the producer tag and, when a fused QLinear is
+        known to consume it, the bins in the fused kernel's operand format."""
+        if (self._emit_bins and X.is_cuda and X.dim() >= 2 and X.shape[-1] % 128 == 0 and X.is_contiguous()
+                and self.quant_max - self.quant_min <= 255 and X.numel() > 0):
+            y, bins = ops.fq_per_tensor(X, scale, zero_point, self.quant_min, self.quant_max, lsq_grad_factor=g, want_bins=True)
+            self._tag(y)
+            try:
+                y._osq_bins = (bins, y._version)
+            except Exception:  # pragma: no cover
+                pass
+            return y
+        return self._tag(ops.fq_per_tensor(X, scale, zero_point, self.quant_min, self.quant_max, lsq_grad_factor=g))
+
     def _tag(self, y: torch.Tensor) -> torch.Tensor:
         try:
-            setattr(y, _TAG, weakref.ref(self))
+            setattr(y, _TAG, (weakref.ref(self), y._version))
         except Exception:  # pragma: no cover  (tensor subclasses that refuse attributes)
             pass
         return y
@@ -143,7 +172,7 @@ class FixedFakeQuantize(QuantizeBase):
             elif _needs_grad(X):
                 X = _SteFixedPerTensor.apply(X, self.scale, self.zero_point, self.quant_min, self.quant_max)
             else:
-                X = self._tag(ops.fq_per_tensor(X, self.scale, self.zero_point, self.quant_min, self.quant_max))
+                X = self._fq_per_tensor_tagged(X, self.scale, self.zero_point)
         return X
 
 
@@ -222,6 +251,9 @@ class LSQPlusFakeQuantize(QuantizeBase):
             if self.ch_axis != -1:
                 X = UQ.fake_quantize_learnableplus_per_channel_affine_training(X, self.scale, self.zero_point, self.ch_axis,
                                                                               self.quant_min, self.quant_max, g)
+            elif X.is_cuda and not (torch.is_grad_enabled() and (X.requires_grad or self.scale.requires_grad
+                                                                   or self.zero_point.requires_grad)):
+                X = self._fq_per_tensor_tagged(X, self.scale.detach(), self.zero_point.detach(), float(g))
             else:
                 X = UQ.fake_quantize_learnableplus_per_tensor_affine_training(X, self.scale, self.zero_point,
                                                                              self.quant_min, self.quant_max, g)

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .fake_quant import FixedFakeQuantize, LSQFakeQuantize, LSQPlusFakeQuantize, producer_of
+from .fake_quant import FixedFakeQuantize, LSQFakeQuantize, LSQPlusFakeQuantize, bins_of, producer_of
 from .observer import (AvgMinMaxObserver, AvgMSEFastObserver, AvgMSEObserver, AvgPruneMinMaxObserver,
                        AvgQuantileObserver, LSQPlusObserver, MinMaxObserver, MSEFastObserver, MSEObserver)
 
@@ -33,7 +33,16 @@ FakeQuantizeDict = {
 }
 
 # statistics for tests / benches: which path QLinear.forward took
-stats = {"fused": 0, "unfused": 0, "grouped_launch": 0, "grouped_hit": 0}
+stats = {"fused": 0, "unfused": 0, "grouped_launch": 0, "grouped_hit": 0, "bins_in": 0}
+
+
+def _take_bins(input, aq):
+    """Bins the producing quantizer left next to ``input`` (and a request for them from now on)."""
+    aq._emit_bins = os.environ.get("OSQ_DISABLE_BINS") != "1"
+    bins = bins_of(input)
+    if bins is not None:
+        stats["bins_in"] += 1
+    return bins
 
 
 class QuantizedModule(nn.Module):
@@ -139,8 +148,9 @@ class QLinear(QuantizedOperator, nn.Linear):
             codes, rowsum, w_scale = self._packed_weight()
             g = aq.grad_factor(input) if isinstance(aq, LSQPlusFakeQuantize) else 0.0
             stats["fused"] += 1
+            bins = _take_bins(input, aq)
             return ops.fused_fq_linear(input, aq.scale.detach(), aq.zero_point.detach(), aq.quant_min, aq.quant_max,
-                                       codes, w_scale, rowsum, self.bias, lsq_grad_factor=g)
+                                       codes, w_scale, rowsum, self.bias, lsq_grad_factor=g, a_bins=bins)
         stats["unfused"] += 1
         w = self._cached_fq_weight() if self._weight_is_static() else self.weight_fake_quant(self.weight)
         return F.linear(input, w, self.bias)
@@ -194,7 +204,7 @@ class QLinearGroup:
         codes, rowsum, w_scale, bias = self._packed_weight()
         g = aq.grad_factor(input) if isinstance(aq, LSQPlusFakeQuantize) else 0.0
         y = ops.fused_fq_linear(input, aq.scale.detach(), aq.zero_point.detach(), aq.quant_min, aq.quant_max,
-                                codes, w_scale, rowsum, bias, lsq_grad_factor=g)
+                                codes, w_scale, rowsum, bias, lsq_grad_factor=g, a_bins=_take_bins(input, aq))
         stats["grouped_launch"] += 1
         stats["fused"] += 1
         outs, col = {}, 0

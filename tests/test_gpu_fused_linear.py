@@ -179,3 +179,37 @@ def test_cta_pair_mode_and_register_path_in_subprocess():
         r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
                            timeout=240)
         assert r.returncode == 0 and "variant ok" in r.stdout, "%s failed:\n%s\n%s" % (env, r.stdout[-2000:], r.stderr[-3000:])
+
+
+@pytest.mark.parametrize("m,k,n", [(300, 768, 768), (16384, 768, 2304), (1000, 3072, 768), (130, 128, 16), (4096, 1024, 1024)])
+@pytest.mark.parametrize("lsq", [False, True])
+def test_bins_in_launch_is_bit_identical(m, k, n, lsq):
+    """The fake-quant kernel's uint8 side output (bin - qmin) equals the bins the fused kernel derives itself, and a
+    bins-in launch (A = NULL, a_codes = bins) reproduces the fp32-in result bit for bit."""
+    from outlier_suppression_b200 import ops
+    g = torch.Generator().manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=g)
+    a[:, :3] *= 20
+    w, bias = O.synth_linear(n, k, seed=5)
+    a_qmin, a_qmax = O.quant_range(6, False)
+    mn, mx = O.global_minmax(a)
+    a_scale, a_zp = O.qparams_from_minmax(mn * 0.7, mx * 0.7, a_qmin, a_qmax, False)
+    if lsq:
+        a_scale_t, a_zp_t = a_scale.reshape(1).cuda(), (a_zp.reshape(1).float() + 0.37).clamp(a_qmin, a_qmax).cuda()
+        gfac = 1.0 / (a.numel() * a_qmax) ** 0.5
+    else:
+        a_scale_t, a_zp_t, gfac = a_scale.reshape(1).cuda(), a_zp.reshape(1).to(torch.int32).cuda(), 0.0
+    w_scale, w_zp, w_qmin, w_qmax = O.weight_qparams_minmax(w, 6, True)
+    codes, rowsum = ops.pack_weight(w.cuda(), w_scale.cuda(), w_zp.cuda(), w_qmin, w_qmax)
+    ag = a.cuda()
+    y_fq, bins = ops.fq_per_tensor(ag, a_scale_t, a_zp_t, a_qmin, a_qmax, lsq_grad_factor=gfac, want_bins=True)
+    y_fq2, q16 = ops.fq_per_tensor(ag, a_scale_t, a_zp_t, a_qmin, a_qmax, lsq_grad_factor=gfac, want_codes=True)
+    np.testing.assert_array_equal(y_fq.cpu().numpy(), y_fq2.cpu().numpy())
+    np.testing.assert_array_equal(bins.cpu().numpy().astype(np.int16), q16.cpu().numpy() - a_qmin)
+    y_ref, own = ops.fused_fq_linear(ag, a_scale_t, a_zp_t, a_qmin, a_qmax, codes, w_scale.cuda(), rowsum, bias.cuda(),
+                                     lsq_grad_factor=gfac, want_codes=True)
+    np.testing.assert_array_equal(own.cpu().numpy(), bins.cpu().numpy())
+    for src in (ag, y_fq):       # raw or already fake-quantised activations: the fp32 tensor is not read in a bins-in launch
+        y = ops.fused_fq_linear(src, a_scale_t, a_zp_t, a_qmin, a_qmax, codes, w_scale.cuda(), rowsum, bias.cuda(),
+                                lsq_grad_factor=gfac, a_bins=bins)
+        np.testing.assert_array_equal(y.cpu().numpy(), y_ref.cpu().numpy())

@@ -210,3 +210,53 @@ def test_host_step_runner_matches_direct_calls():
     with pytest.raises(IndexError):
         runner.result(0)
     assert runner.h2d_bytes == 128 * 64 * 4 and runner.d2h_bytes == 128 * 64 * 4
+
+
+def test_quantizer_hands_bins_to_qlinear():
+    """Second forward on: the activation quantizer's launch also writes uint8 bins and the QLinear (single and
+    grouped) consumes them (stats['bins_in']); outputs stay bit-identical, and an in-place edit of the quantized
+    tensor invalidates the bins (falls back to re-quantising the fp32 values)."""
+    from outlier_suppression_b200 import quantization as Q
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    g = torch.Generator().manual_seed(9)
+    a_cfg = QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1)
+    w_cfg = QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)
+    net = torch.nn.Module()
+    for name in ("query", "key", "value", "dense"):
+        m = torch.nn.Linear(H, H)
+        m.weight.data = torch.randn(H, H, generator=g) * 0.05
+        setattr(net, name, qm.Quantizer(m, w_cfg))
+    net.in_post_act_fake_quantize = qm.Quantizer(None, a_cfg)
+    net.ctx_post_act_fake_quantize = qm.Quantizer(None, QC("FixedFakeQuantize", "AvgMinMaxObserver", 8, False, -1))
+    net.cuda()
+    x = (torch.randn(B, S, H, generator=g) * 2).cuda()
+    Q.enable_calibration_woquantization(net, quantizer_type="fake_quant")
+    net.in_post_act_fake_quantize(x); net.ctx_post_act_fake_quantize(x)
+    for m in (net.query, net.key, net.value, net.dense):
+        m.weight_fake_quant(m.weight)
+    Q.enable_quantization(net)
+
+    @torch.no_grad()
+    def run():
+        xq = net.in_post_act_fake_quantize(x)
+        outs = [net.query(xq), net.key(xq), net.value(xq)]
+        cq = net.ctx_post_act_fake_quantize(x)
+        outs.append(net.dense(cq))
+        return outs
+
+    before = qm.stats["bins_in"]
+    first = run()                                   # nobody asked for bins yet
+    assert qm.stats["bins_in"] == before
+    second = run()                                  # grouped q|k|v launch + the single dense launch take bins
+    assert qm.stats["bins_in"] == before + 2
+    for a, b in zip(first, second):
+        same(a, b)
+    with torch.no_grad():
+        xq = net.in_post_act_fake_quantize(x)
+        assert xq._osq_bins[0].dtype == torch.uint8 and xq._osq_bins[0].shape == xq.shape
+        xq.mul_(0.5)                                # in-place edit: the bins no longer describe the tensor
+        n_before = qm.stats["bins_in"]
+        edited = net.query(xq)
+        assert qm.stats["bins_in"] == n_before
+        ref = net.query(net.in_post_act_fake_quantize(x * 1.0).mul(0.5).clone())  # untagged clone: unfused path on the same values
+    close(edited, ref)
