@@ -16,12 +16,13 @@ for K, N in SHAPES:
     w_scale = (w.abs().amax(1) / 31.5).contiguous(); w_zp = torch.zeros(N, dtype=torch.int32, device="cuda")
     codes, rowsum = ops.pack_weight(w, w_scale, w_zp, -32, 31)
     tr = torch.zeros(2048, dtype=torch.int64, device="cuda")
+    bins = ops.fq_per_tensor(a, a_scale, a_zp, 0, 63, lsq_grad_factor=1e-4, want_bins=True)[1] if os.environ.get('TRACE_BINS') == '1' else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
-        ops.fused_fq_linear(a, a_scale, a_zp, 0, 63, codes, w_scale, rowsum, bias, lsq_grad_factor=1e-4)
+        ops.fused_fq_linear(a, a_scale, a_zp, 0, 63, codes, w_scale, rowsum, bias, lsq_grad_factor=1e-4, a_bins=bins)
     tr.zero_()
     e0.record()
-    ops.fused_fq_linear(a, a_scale, a_zp, 0, 63, codes, w_scale, rowsum, bias, lsq_grad_factor=1e-4, trace=tr)
+    ops.fused_fq_linear(a, a_scale, a_zp, 0, 63, codes, w_scale, rowsum, bias, lsq_grad_factor=1e-4, trace=tr, a_bins=bins)
     e1.record()
     torch.cuda.synchronize()
     t = tr.cpu().tolist()
