@@ -151,8 +151,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {  //
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive on the leader's barrier.  Default semantics (release at CTA scope), as in CUTLASS' 2-SM pipelines: what
+// the arrive orders are this CTA's own shared-memory writes (already made visible to the async proxy by the
+// fence.proxy.async in front of it), which only this SM's tensor core reads.  `.release.cluster` here cost 1.7 K
+// cycles per k-block in the conversion loop (5.0 K instead of 3.3 K) and made the pair slower than two single CTAs.
 __device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster_u32(uint32_t bar, uint32_t parity) {  // acquire at cluster scope: the peer's writes are visible
   asm volatile(
@@ -1168,7 +1172,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
     env_ob = geti("OSQ_FUSED_OUTBUFS", 0);
     env_kb = geti("OSQ_FUSED_SMEM_KB", 227);
     if (env_kb < 100 || env_kb > 227) env_kb = 227;
-    env_csz = geti("OSQ_FUSED_CLUSTER", 1);
+    env_csz = geti("OSQ_FUSED_CLUSTER", 2);  // CTA pair whenever the plan allows it (resident A, >= 2 tiles, fp32-in)
     env_pdl = geti("OSQ_FUSED_PDL", 1);
     env_pf = geti("OSQ_FUSED_PREFETCH", 0);
     env_xtma = geti("OSQ_FUSED_XTMA", 1);

@@ -163,9 +163,10 @@ PAIR_CASES = "[(256, 768, 768), (1000, 768, 2304), (16384, 768, 768), (300, 1024
 
 
 def test_cta_pair_mode_and_register_path_in_subprocess():
-    """The launch plan is read from the environment once per process, so the two non-default kernel variants run in
-    child processes: OSQ_FUSED_CLUSTER=2 (tcgen05 cta_group::2: one W tile copy per CTA pair) and OSQ_FUSED_XTMA=0
-    (fp32 A through 128-bit register loads instead of TMA landing slots).  Same parity bar as every other case."""
+    """The launch plan is read from the environment once per process, so every kernel variant gets a child process of
+    its own whatever the default is: OSQ_FUSED_CLUSTER=2 (tcgen05 cta_group::2: one W tile copy per CTA pair),
+    OSQ_FUSED_CLUSTER=1 (one CTA per tile) and OSQ_FUSED_XTMA=0 (fp32 A through 128-bit register loads instead of TMA
+    landing slots).  Same parity bar as every other case."""
     import os
     import subprocess
     import sys
@@ -175,7 +176,7 @@ def test_cta_pair_mode_and_register_path_in_subprocess():
             "    run_case(m, k, n, 6, 6, True, 100 + i, gamma=bool(i & 1))\n"
             "    run_case(m, k, n, 8, 8, False, 200 + i)\n"
             "print('variant ok')\n" % PAIR_CASES)
-    for env in ({"OSQ_FUSED_CLUSTER": "2"}, {"OSQ_FUSED_XTMA": "0"}):
+    for env in ({"OSQ_FUSED_CLUSTER": "2"}, {"OSQ_FUSED_CLUSTER": "1"}, {"OSQ_FUSED_XTMA": "0"}):
         r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
                            timeout=240)
         assert r.returncode == 0 and "variant ok" in r.stdout, "%s failed:\n%s\n%s" % (env, r.stdout[-2000:], r.stderr[-3000:])
