@@ -158,6 +158,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {  //
 __device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster_u32(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n_cluster_u32(uint32_t cluster_bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(n) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster_u32(uint32_t bar, uint32_t parity) {  // acquire at cluster scope: the peer's writes are visible
   asm volatile(
       "{\n\t"
@@ -604,11 +610,11 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
             for (int j = 0; j < n_c; ++j) {  // the sweep's accumulator stages must have been drained
               uint32_t s = as_ + (uint32_t)j, ph = aph;
               if (s >= n_acc) { s -= n_acc; ph ^= 1; }
-              mbar_wait_u32(acc_empty0 + s * 8, ph ^ 1);
+              if (pair) mbar_wait_cluster_u32(acc_empty0 + s * 8, ph ^ 1); else mbar_wait_u32(acc_empty0 + s * 8, ph ^ 1);
             }
             tc_fence_after();
             for (int kb = 0; kb < p.KB; ++kb) {
-              mbar_wait_u32(a_full0 + st_a * 8, sph_a);
+              if (pair) mbar_wait_cluster_u32(a_full0 + st_a * 8, sph_a); else mbar_wait_u32(a_full0 + st_a * 8, sph_a);
               const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)p.a_stage_bytes) >> 4);
               for (int j = 0; j < n_c; ++j) {
                 mbar_wait_u32(w_full0 + ws * 8, wph);
@@ -617,17 +623,24 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
                 if (s >= n_acc) s -= n_acc;
                 const uint32_t d_tmem = tmem_base + s * (uint32_t)p.BN;
                 const uint64_t db = desc_hi | (uint64_t)((w_base + ws * w_bytes) >> 4);
+                if (!pair) {
 #pragma unroll
-                for (int k = 0; k < kStageK / kUmmaK; ++k)
-                  umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
-                umma_commit_u32(w_empty0 + ws * 8);
+                  for (int k = 0; k < kStageK / kUmmaK; ++k)
+                    umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
+                  umma_commit_u32(w_empty0 + ws * 8);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < kStageK / kUmmaK; ++k)
+                    umma_i8_pair(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), idesc, (kb | k) != 0);
+                  umma_commit_pair_u32(w_empty0 + ws * 8);
+                }
                 if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1; }
               }
-              umma_commit_u32(a_empty0 + st_a * 8);
+              if (pair) umma_commit_pair_u32(a_empty0 + st_a * 8); else umma_commit_u32(a_empty0 + st_a * 8);
               if (++st_a == (uint32_t)p.a_stages) { st_a = 0; sph_a ^= 1; }
             }
             for (int j = 0; j < n_c; ++j) {
-              umma_commit_u32(acc_full0 + as_ * 8);
+              if (pair) umma_commit_pair_u32(acc_full0 + as_ * 8); else umma_commit_u32(acc_full0 + as_ * 8);
               if (++as_ == n_acc) { as_ = 0; aph ^= 1; }
             }
           }
@@ -648,9 +661,17 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
             const uint32_t pa = (uint32_t)((it * a_passes + pass) * p.KB + kb);
             const int a_st = pa % p.a_stages;
             mbar_wait(&sm.a_empty[a_st], ((pa / p.a_stages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&sm.a_full[a_st], p.codes_box_bytes);
-            mbar_arrive_n(&sm.a_full[a_st], kNumWorkers - 1);  // a_full always counts kNumWorkers arrivals
-            tma_load_2d(a_ring + (size_t)a_st * p.a_stage_bytes, &tmap_codes, &sm.a_full[a_st], kb * kStageK, mb * p.rows_per_tile);
+            if (!pair) {
+              mbar_arrive_expect_tx(&sm.a_full[a_st], p.codes_box_bytes);
+              mbar_arrive_n(&sm.a_full[a_st], kNumWorkers - 1);  // a_full always counts kNumWorkers arrivals
+              tma_load_2d(a_ring + (size_t)a_st * p.a_stage_bytes, &tmap_codes, &sm.a_full[a_st], kb * kStageK, mb * p.rows_per_tile);
+            } else {
+              // the leader's a_full counts kNumWorkers arrivals per CTA and the bytes of both CTAs' boxes
+              const uint32_t lbar = mapa_u32(smem_u32(&sm.a_full[a_st]), 0);
+              mbar_arrive_expect_tx_cluster_u32(lbar, p.codes_box_bytes);
+              mbar_arrive_n_cluster_u32(lbar, kNumWorkers - 1);
+              tma_load_2d_pair_u32(smem_u32(a_ring + (size_t)a_st * p.a_stage_bytes), &tmap_codes, lbar, kb * kStageK, mb * p.rows_per_tile);
+            }
           }
         mbar_arrive(&sm.passes_issued);  // workers may start filling the ring for the next m-block
       }
@@ -1216,7 +1237,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   Plan best; memset(&best, 0, sizeof(best));
   static int max_ctas[64][3] = {{0}};
   int grid = 0;
-  for (int csz = (env_csz == 2 && p.KB <= kMaxAStages && a->A != nullptr) ? 2 : 1; csz >= 1 && !best.ok; --csz) {
+  for (int csz = (env_csz == 2 && a->A != nullptr) ? 2 : 1; csz >= 1 && !best.ok; --csz) {
     p.csz = csz;
     attr[0].val.clusterDim.x = (unsigned)csz;
     // how many CTAs can be co-resident (1 CTA / SM)
@@ -1264,8 +1285,9 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
       const int budget = total - 2 * ((bn + 31) & ~31) * (int)sizeof(float);
       const int xo_min = x_tma ? x_bytes : out1;            // aliased X/O region, or one set of store tiles
       pl.resident = (p.KB <= kMaxAStages && p.KB * p.a_stage_bytes + 2 * w_stage + xo_min <= budget) ? 1 : 0;
-      if (csz > 1 && !(pl.resident && x_tma)) return pl;
+      if (csz > 1 && !x_tma) return pl;
       pl.cached = (!pl.resident && (nc > 1 || a->A == nullptr) && a->a_codes != nullptr) ? 1 : 0;
+      if (csz > 1 && !(pl.resident || pl.cached)) return pl;  // the pair needs resident A or the code-cache sweeps
       pl.a_stages = pl.resident ? p.KB : 4;
       // X and O can share memory only when conversion and epilogue never interleave inside a tile
       const bool can_alias = pl.resident || pl.cached || nc == 1;
