@@ -1237,7 +1237,7 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   Plan best; memset(&best, 0, sizeof(best));
   static int max_ctas[64][3] = {{0}};
   int grid = 0;
-  for (int csz = (env_csz == 2 && a->A != nullptr) ? 2 : 1; csz >= 1 && !best.ok; --csz) {
+  for (int csz = env_csz == 2 ? 2 : 1; csz >= 1 && !best.ok; --csz) {
     p.csz = csz;
     attr[0].val.clusterDim.x = (unsigned)csz;
     // how many CTAs can be co-resident (1 CTA / SM)
@@ -1304,6 +1304,11 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
       // the W stream needs ~2.5 stages of 32 KB in flight to cover the L2 latency: a third stage comes first
       if (rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
       if (!pl.alias && pl.out_bufs == 1 && env_ob != 1 && rest >= out1) { pl.out_bufs = 2; rest -= out1; }
+      // beyond that: W to four stages, then (streamed A) the A ring to six, then whatever is left to W and A
+      // (measured on 3072->768: 4 W + 6 A stages beat 6 + 4 and 3 + 8)
+      while (pl.w_stages < 4 && rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
+      if (!pl.resident)
+        while (pl.a_stages < 6 && rest >= p.a_stage_bytes) { ++pl.a_stages; rest -= p.a_stage_bytes; }
       while (pl.w_stages < kMaxWStages && rest >= w_stage) { ++pl.w_stages; rest -= w_stage; }
       if (!pl.resident)
         while (pl.a_stages < kMaxAStages && rest >= p.a_stage_bytes) { ++pl.a_stages; rest -= p.a_stage_bytes; }
