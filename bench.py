@@ -245,6 +245,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=device)
 
     if args.no_group:
