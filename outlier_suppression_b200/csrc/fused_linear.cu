@@ -59,6 +59,8 @@ struct FusedParams {
   int acc_stages;     // TMEM accumulator stages (512 / BN, at most 4)
   int n_mblocks;
   int csz;            // 1, or 2 = CTA pair: tcgen05 cta_group::2 (M = 256 over two SMs, each CTA stages half of every W tile)
+  int mb_count;       // CTAs along M (= grid / nsplit); a CTA's row tiles are mb_lane, mb_lane + mb_count, ...
+  int nsplit, cps;    // N is split over `nsplit` groups of CTAs, `cps` chunks each (few rows: keeps row tiles >= 64 and still fills the SMs)
   int n_iters;        // tiles per CTA (identical for every CTA; out-of-range tiles are phantoms that only keep the W protocol alive)
   int rows_per_tile;  // valid rows per CTA tile (<= 128, multiple of 16): chosen so the tile count fills all SMs
   int a_stages, w_stages, out_bufs;
@@ -501,8 +503,12 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
   if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x] = gtimer();
 
   const int n_my_blocks = p.n_iters;
+  // this CTA's place in the (row tile, column split) grid and its chunk range [nc0, nc0 + ncn)
+  const int mb_lane = (int)blockIdx.x % p.mb_count;
+  const int nc0 = ((int)blockIdx.x / p.mb_count) * p.cps;
+  const int ncn = min(p.cps, p.NC - nc0);
   if (p.pdl && threadIdx.x == 0) pdl_launch_dependents();
-  const int a_passes = p.a_passes;  // how many times the A ring is filled per m-block
+  const int a_passes = p.resident ? 1 : (ncn + p.cpp - 1) / p.cpp;  // how many times the A ring is filled per m-block
 
   if (warp == 0) {
     // ===================== TMA producer: packed weight tiles =====================
@@ -516,9 +522,9 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       const uint32_t leader_full0 = pair ? mapa_u32(full0, 0) : full0;
       uint32_t ws = 0, wph = 0;        // ring stage and its phase parity
       // tile order = the MMA issuer's: resident A: chunk-major; streamed A: per sweep, k-block-major over its chunks
-      const int n_tiles = p.NC * p.KB;
+      const int n_tiles = ncn * p.KB;
       for (int it = 0; it < n_my_blocks; ++it)
-        for (int t = 0, nc = 0, kb = 0, c_lo = 0, j = 0; t < n_tiles; ++t) {
+        for (int t = 0, nc = nc0, kb = 0, c_lo = nc0, j = 0; t < n_tiles; ++t) {
           {
             mbar_wait_u32(empty0 + ws * 8, wph ^ 1);
             if (!pair) {
@@ -537,7 +543,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
           if (p.resident) {
             if (++kb == p.KB) { kb = 0; ++nc; }
           } else {
-            const int n_c = min(p.cpp, p.NC - c_lo);
+            const int n_c = min(p.cpp, nc0 + ncn - c_lo);
             if (++j == n_c) { j = 0; if (++kb == p.KB) { kb = 0; c_lo += n_c; } }
             nc = c_lo + j;
           }
@@ -561,12 +567,12 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       for (int it = 0; it < n_my_blocks; ++it) {
         if (p.resident) {
           // resident A: chunk-major, the converted block is filled once per m-block and released after its last chunk
-          for (int nc = 0; nc < p.NC; ++nc) {
+          for (int nc = 0; nc < ncn; ++nc) {
             if (pair) mbar_wait_cluster_u32(acc_empty0 + as_ * 8, aph ^ 1); else mbar_wait_u32(acc_empty0 + as_ * 8, aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as_ * (uint32_t)p.BN;
             st_a = 0; sph_a = (uint32_t)it & 1;
-            const bool wait_a = nc == 0, free_a = nc == p.NC - 1;
+            const bool wait_a = nc == 0, free_a = nc == ncn - 1;
             for (int kb = 0; kb < p.KB; ++kb) {
               if (wait_a) { if (pair) mbar_wait_cluster_u32(a_full0 + st_a * 8, sph_a); else mbar_wait_u32(a_full0 + st_a * 8, sph_a); }
 #ifdef OSQ_ENABLE_TRACE
@@ -605,8 +611,8 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         } else {
           // streamed A: every sweep over K feeds `cpp` accumulators at once (k-block-major), so the bins pass
           // through the ring ceil(NC / cpp) times instead of NC times
-          for (int c_lo = 0; c_lo < p.NC; c_lo += p.cpp) {
-            const int n_c = min(p.cpp, p.NC - c_lo);
+          for (int c_lo = 0; c_lo < ncn; c_lo += p.cpp) {
+            const int n_c = min(p.cpp, ncn - c_lo);
             for (int j = 0; j < n_c; ++j) {  // the sweep's accumulator stages must have been drained
               uint32_t s = as_ + (uint32_t)j, ph = aph;
               if (s >= n_acc) { s -= n_acc; ph ^= 1; }
@@ -654,7 +660,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     if (lane == 0 && (p.cached || p.codes_in)) {
       if (p.pdl) pdl_wait_prior_grids();
       for (int it = 0; it < n_my_blocks; ++it) {
-        const int mb = blockIdx.x + it * gridDim.x;
+        const int mb = mb_lane + it * p.mb_count;
         if (!p.codes_in) mbar_wait(&sm.codes_ready, it & 1);  // every worker has published this block's bins
         for (int pass = p.codes_in ? 0 : 1; pass < a_passes; ++pass)
           for (int kb = 0; kb < p.KB; ++kb) {
@@ -683,10 +689,10 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     // L2 a bounded distance ahead (in the order the workers consume them), so their loads see L2 latency.
     if (lane == 0 && p.prefetch > 0) {
       if (p.pdl) pdl_wait_prior_grids();
-      const int passes_per_block = (p.resident || p.cached) ? 1 : p.NC;  // fp32 A is re-read per chunk only without a cache
+      const int passes_per_block = (p.resident || p.cached) ? 1 : ncn;  // fp32 A is re-read per chunk only without a cache
       uint32_t done = 0;
       for (int it = 0; it < n_my_blocks; ++it) {
-        const int mb = blockIdx.x + it * gridDim.x;
+        const int mb = mb_lane + it * p.mb_count;
         if (mb >= p.n_mblocks) break;
         for (int pass = 0; pass < passes_per_block; ++pass)
           for (int kb = 0; kb < p.KB; ++kb, ++done) {
@@ -703,7 +709,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     if (p.pdl) pdl_wait_prior_grids();
     if constexpr (kXTma) {
       // the first landing-slot fill of the first tile goes out before the quantisation parameters are even read
-      const int row0 = (int)blockIdx.x * p.rows_per_tile + w * kRowsPerWorker;
+      const int row0 = mb_lane * p.rows_per_tile + w * kRowsPerWorker;
       if (lane == 0 && !p.codes_in && w * kRowsPerWorker < p.rows_per_tile && row0 < p.M) {
         const uint32_t bar = smem_u32(&sm.x_full[w]);
         mbar_arrive_expect_tx_u32(bar, (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker) * (uint32_t)(kStageK * 4));
@@ -913,7 +919,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     auto epilogue_chunk = [&](int mb, int nc) {
       const int as_ = cacc % p.acc_stages;
       const int n0 = nc * p.BN;
-      if (nc + 1 < p.NC) fetch_consts(nc + 1);
+      if (nc + 1 < nc0 + ncn) fetch_consts(nc + 1);
       mbar_wait(&sm.acc_full[as_], (cacc / p.acc_stages) & 1);
       tc_fence_after();
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4);
@@ -999,16 +1005,16 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       ++cacc;
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");  // every reader of this chunk's constants is done
       if (w == 0 && lane == 0 && cacc <= 60) OSQ_TRACE(512 + (cacc - 1) * 4 + 2);
-      if (nc + 1 < p.NC) publish_consts();
+      if (nc + 1 < nc0 + ncn) publish_consts();
       if (w == 0 && lane == 0 && cacc <= 60) OSQ_TRACE(512 + (cacc - 1) * 4 + 3);
     };
 
     for (int it = 0; it < n_my_blocks; ++it) {
-      const int mb = blockIdx.x + it * gridDim.x;
+      const int mb = mb_lane + it * p.mb_count;
       const uint32_t pa_block = (uint32_t)it * (uint32_t)(a_passes * p.KB);
       // cached mode: the TMA thread must have issued every re-load pass of the previous block before this
       // warp runs ahead on the same ring (two producers may never be more than one ring cycle apart)
-      if (w < kNumEpiWarps) fetch_consts(0);
+      if (w < kNumEpiWarps) fetch_consts(nc0);
       if (!p.codes_in) {
       if (p.cached && it > 0) mbar_wait(&sm.passes_issued, (it - 1) & 1);
       if (p.alias_xo && it > 0 && w < kNumEpiWarps) {  // this warp's landing slot was its store tile: reads must be done
@@ -1028,12 +1034,12 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       if (p.alias_xo && !p.codes_in) { obufs = (it == n_my_blocks - 1) ? p.out_bufs : 1; n_stores = 0; }
       if (w < kNumEpiWarps && it == 0) tmem_base = tmem_address();
       if (w < kNumEpiWarps) publish_consts();  // chunk 0 constants
-      for (int nc = 0; nc < p.NC; ++nc) {
+      for (int lc = 0; lc < ncn; ++lc) {
         // no code cache and K too large for residency: re-convert A for the next N chunk first
-        if (!p.resident && !p.cached && !p.codes_in && nc + 1 < p.NC) {
-          if constexpr (kXTma) convert_pass_tma(mb, pa_block + (uint32_t)(nc + 1) * p.KB, false); else convert_pass(mb, pa_block + (uint32_t)(nc + 1) * p.KB);
+        if (!p.resident && !p.cached && !p.codes_in && lc + 1 < ncn) {
+          if constexpr (kXTma) convert_pass_tma(mb, pa_block + (uint32_t)(lc + 1) * p.KB, false); else convert_pass(mb, pa_block + (uint32_t)(lc + 1) * p.KB);
         }
-        if (w < kNumEpiWarps) epilogue_chunk(mb, nc);
+        if (w < kNumEpiWarps) epilogue_chunk(mb, nc0 + lc);
       }
     }
     if (w < kNumEpiWarps && lane == 0) tma_store_wait_all();
@@ -1236,7 +1242,8 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   struct Plan { int ok, bn, resident, cached, a_stages, w_stages, out_bufs, x_tma, alias, score; };
   Plan best; memset(&best, 0, sizeof(best));
   static int max_ctas[64][3] = {{0}};
-  int grid = 0;
+  int grid = 0, nsplit_max = 1;
+  bool split_n = false;
   for (int csz = env_csz == 2 ? 2 : 1; csz >= 1 && !best.ok; --csz) {
     p.csz = csz;
     attr[0].val.clusterDim.x = (unsigned)csz;
@@ -1268,6 +1275,13 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
       rpt = (rpt + 15) / 16 * 16;
       if (rpt > kBM) rpt = kBM;
       if (rpt < 16) rpt = 16;
+      // Few rows (M < 64 x SMs): shrinking the row tile further would leave every CTA streaming all of W for a
+      // handful of rows, with one TMEM lane quarter busy in the epilogue.  Keep 64-row tiles and split N across
+      // groups of CTAs instead (each group converts the same rows, which come from L2 after the first touch).
+      static int env_nsplit = -1;
+      if (env_nsplit < 0) { const char* e = getenv("OSQ_FUSED_NSPLIT"); env_nsplit = e ? atoi(e) : 1; }
+      split_n = env_nsplit != 0 && rpt < 64 && p.M > 64 && p.N > 256;
+      if (split_n) rpt = 64;
       p.rows_per_tile = (int)rpt;
     }
     p.n_mblocks = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
@@ -1275,6 +1289,9 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
     grid = p.n_mblocks < G ? p.n_mblocks : G;
     grid = (grid + csz - 1) / csz * csz;
     p.n_iters = (p.n_mblocks + grid - 1) / grid;
+    p.mb_count = grid;
+    p.nsplit = 1;
+    nsplit_max = split_n ? G / grid : 1;
     p.a_stage_bytes = p.rows_per_tile * kStageK;
 
     auto make_plan = [&](int bn, int x_tma) {
@@ -1344,7 +1361,17 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   // bins by TMA).  Without a cache the workers re-convert per chunk and must keep one stage free for the epilogue
   // they run in between, so they stay at one chunk per sweep.
   p.cpp = p.cached ? p.acc_stages : 1;
-  p.a_passes = p.resident ? 1 : (p.NC + p.cpp - 1) / p.cpp;
+  // column split: `cps` chunks per group of CTAs, a whole number of sweeps each
+  p.cps = p.NC;
+  if (nsplit_max > 1 && p.NC > 1) {
+    int ns = nsplit_max < p.NC ? nsplit_max : p.NC;
+    int cps = (p.NC + ns - 1) / ns;
+    cps = (cps + p.cpp - 1) / p.cpp * p.cpp;
+    p.cps = cps;
+    p.nsplit = (p.NC + cps - 1) / cps;
+    grid = p.mb_count * p.nsplit;
+  }
+  p.a_passes = p.resident ? 1 : (p.cps + p.cpp - 1) / p.cpp;
   const int const_bytes = 2 * ((p.BN + 31) & ~31) * (int)sizeof(float);
   const size_t smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes +
                             (p.x_tma ? (size_t)x_bytes : 0) + (p.alias_xo ? 0 : (size_t)p.out_bufs * out1) +
@@ -1389,9 +1416,9 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
     for (int i = 0; i < n_seen; ++i) known |= (seen[i][0] == p.M && seen[i][1] == p.K && seen[i][2] == p.N);
     if (!known && n_seen < 16) {
       seen[n_seen][0] = p.M; seen[n_seen][1] = p.K; seen[n_seen][2] = p.N; ++n_seen;
-      fprintf(stderr, "[osq] fused M=%d K=%d N=%d: grid=%d cluster=%d rows/tile=%d tiles/cta=%d BN=%d chunks=%d mode=%s a_stages=%d(%d B) "
+      fprintf(stderr, "[osq] fused M=%d K=%d N=%d: grid=%d (n-split %d) cluster=%d rows/tile=%d tiles/cta=%d BN=%d chunks=%d mode=%s a_stages=%d(%d B) "
                       "w_stages=%d(%d B) acc_stages=%d out_bufs=%d x_tma=%d alias=%d sweeps=%d smem=%zu\n",
-              p.M, p.K, p.N, grid, p.csz, p.rows_per_tile, p.n_iters, p.BN, p.NC, p.codes_in ? (p.resident ? "bins-in resident" : "bins-in streamed") : p.resident ? "resident" : (p.cached ? "streamed+cache" : "streamed"),
+              p.M, p.K, p.N, grid, p.nsplit, p.csz, p.rows_per_tile, p.n_iters, p.BN, p.NC, p.codes_in ? (p.resident ? "bins-in resident" : "bins-in streamed") : p.resident ? "resident" : (p.cached ? "streamed+cache" : "streamed"),
               p.a_stages, p.a_stage_bytes, p.w_stages, p.w_stage_bytes, p.acc_stages, p.out_bufs, p.x_tma, p.alias_xo, p.a_passes, smem_bytes);
     }
   }
