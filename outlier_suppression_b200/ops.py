@@ -78,7 +78,7 @@ def fq_per_tensor(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor
     if want_bins and x.numel() > 0:
         if scale.dtype != torch.float32:
             raise TypeError("scale must be float32")
-        bins = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        bins = torch.empty_like(x, dtype=torch.uint8)  # same (dense) strides as x / y: the kernel runs over the flat storage
         check(_lib.load().osq_fq_per_tensor_bins_f32(x.data_ptr(), y.data_ptr(), bins.data_ptr(), x.numel(), scale.data_ptr(),
                                                      zero_point.data_ptr(), int(zero_point.dtype == torch.int32),
                                                      float(lsq_grad_factor), int(qmin), int(qmax), _stream()),
