@@ -144,7 +144,9 @@ __device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // ---- CTA pair (cta_group::2): the leader CTA issues the MMAs for both SMs; barriers the leader waits on collect
-// arrivals from both CTAs, barriers both CTAs wait on are signalled by multicast commits
+// arrivals from both CTAs, barriers both CTAs wait on are signalled by multicast commits.  Waits and remote arrives
+// use the default (CTA-scope) semantics, as CUTLASS' 2-SM pipelines do: the data these barriers guard never leaves
+// the SM that wrote it (each tensor core reads its own CTA's shared memory).
 __device__ __forceinline__ void umma_commit_pair_u32(uint32_t bar) {  // arrives on `bar` at this offset in BOTH CTAs
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
@@ -165,19 +167,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_cluster_u32(uint32_t clust
 }
 __device__ __forceinline__ void mbar_arrive_n_cluster_u32(uint32_t cluster_bar, uint32_t n) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(n) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster_u32(uint32_t bar, uint32_t parity) {  // acquire at cluster scope: the peer's writes are visible
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -568,13 +557,13 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         if (p.resident) {
           // resident A: chunk-major, the converted block is filled once per m-block and released after its last chunk
           for (int nc = 0; nc < ncn; ++nc) {
-            if (pair) mbar_wait_cluster_u32(acc_empty0 + as_ * 8, aph ^ 1); else mbar_wait_u32(acc_empty0 + as_ * 8, aph ^ 1);
+            mbar_wait_u32(acc_empty0 + as_ * 8, aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as_ * (uint32_t)p.BN;
             st_a = 0; sph_a = (uint32_t)it & 1;
             const bool wait_a = nc == 0, free_a = nc == ncn - 1;
             for (int kb = 0; kb < p.KB; ++kb) {
-              if (wait_a) { if (pair) mbar_wait_cluster_u32(a_full0 + st_a * 8, sph_a); else mbar_wait_u32(a_full0 + st_a * 8, sph_a); }
+              if (wait_a) mbar_wait_u32(a_full0 + st_a * 8, sph_a);
 #ifdef OSQ_ENABLE_TRACE
               const int tslot = (it * p.NC + nc) * p.KB + kb;
               if (tslot >= 36 && tslot < 72) OSQ_TRACE(1400 + 3 * (tslot - 36));
@@ -616,11 +605,11 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
             for (int j = 0; j < n_c; ++j) {  // the sweep's accumulator stages must have been drained
               uint32_t s = as_ + (uint32_t)j, ph = aph;
               if (s >= n_acc) { s -= n_acc; ph ^= 1; }
-              if (pair) mbar_wait_cluster_u32(acc_empty0 + s * 8, ph ^ 1); else mbar_wait_u32(acc_empty0 + s * 8, ph ^ 1);
+              mbar_wait_u32(acc_empty0 + s * 8, ph ^ 1);
             }
             tc_fence_after();
             for (int kb = 0; kb < p.KB; ++kb) {
-              if (pair) mbar_wait_cluster_u32(a_full0 + st_a * 8, sph_a); else mbar_wait_u32(a_full0 + st_a * 8, sph_a);
+              mbar_wait_u32(a_full0 + st_a * 8, sph_a);
               const uint64_t da = desc_hi | (uint64_t)((a_base + st_a * (uint32_t)p.a_stage_bytes) >> 4);
               for (int j = 0; j < n_c; ++j) {
                 mbar_wait_u32(w_full0 + ws * 8, wph);
