@@ -60,6 +60,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
+    # the sources changed: a library built from older sources must not survive a failed rebuild (it would be loaded,
+    # shipped to the GPU box and measured as if it were current)
+    for stale in (LIB_PATH, stamp):
+        if os.path.exists(stale):
+            os.remove(stale)
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
