@@ -260,10 +260,6 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrives on `bar` once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -274,15 +270,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -314,19 +301,6 @@ struct ConvParam {
   float s, rinv, mz, lo, hi, zc, span;
 };
 
-__device__ __forceinline__ uint32_t quant_bin(float x, const ConvParam& c) {
-  float u = fmaf(x, c.rinv, c.mz);
-  float nf = __fsub_rn(u, c.mz);
-  float e = fmaf(x, c.rinv, -nf);
-  if (!(fabsf(e) <= 0.4999f)) {  // near a tie, huge, or NaN: exact path
-    float t = __fdiv_rn(x, c.s);
-    float v = __fadd_rn(rintf(t), c.zc);
-    v = fminf(fmaxf(v, 0.f), c.span);
-    u = __fadd_rn(v, kMagic);
-  }
-  u = fminf(fmaxf(u, c.lo), c.hi);
-  return __float_as_uint(u);  // low byte = bin - qmin
-}
 
 __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
@@ -371,31 +345,6 @@ __device__ __forceinline__ uint32_t quant_bin4_fast(const float4 x, const ConvPa
   return pack4(__float_as_uint(u0), __float_as_uint(u1), __float_as_uint(u2), __float_as_uint(u3));
 }
 
-// two rows at once: 8 independent fast-path chains and ONE branch (the conversion loop is bound by
-// fixed-latency dependencies, so instruction-level parallelism is what buys throughput)
-__device__ __forceinline__ void quant_bin4x2(const float4 a, const float4 b, const ConvParam& c, uint32_t& wa, uint32_t& wb) {
-  float u0 = fmaf(a.x, c.rinv, c.mz), u1 = fmaf(a.y, c.rinv, c.mz), u2 = fmaf(a.z, c.rinv, c.mz), u3 = fmaf(a.w, c.rinv, c.mz);
-  float v0 = fmaf(b.x, c.rinv, c.mz), v1 = fmaf(b.y, c.rinv, c.mz), v2 = fmaf(b.z, c.rinv, c.mz), v3 = fmaf(b.w, c.rinv, c.mz);
-  const float e0 = fmaf(a.x, c.rinv, -__fsub_rn(u0, c.mz)), e1 = fmaf(a.y, c.rinv, -__fsub_rn(u1, c.mz));
-  const float e2 = fmaf(a.z, c.rinv, -__fsub_rn(u2, c.mz)), e3 = fmaf(a.w, c.rinv, -__fsub_rn(u3, c.mz));
-  const float f0 = fmaf(b.x, c.rinv, -__fsub_rn(v0, c.mz)), f1 = fmaf(b.y, c.rinv, -__fsub_rn(v1, c.mz));
-  const float f2 = fmaf(b.z, c.rinv, -__fsub_rn(v2, c.mz)), f3 = fmaf(b.w, c.rinv, -__fsub_rn(v3, c.mz));
-  // NaN-safe: !(x <= t) is true for NaN residuals
-  const float worst = fmaxf(fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fmaxf(fabsf(e2), fabsf(e3))),
-                            fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(f2), fabsf(f3))));
-  const float nan_probe = ((e0 + e1) + (e2 + e3)) + ((f0 + f1) + (f2 + f3));  // NaN if any residual is NaN (fmaxf drops NaNs)
-  if (!(worst <= 0.4999f) | (nan_probe != nan_probe)) {
-    wa = quant_bin4_exact(a.x, a.y, a.z, a.w, c.s, c.zc, c.span);
-    wb = quant_bin4_exact(b.x, b.y, b.z, b.w, c.s, c.zc, c.span);
-    return;
-  }
-  u0 = fminf(fmaxf(u0, c.lo), c.hi); u1 = fminf(fmaxf(u1, c.lo), c.hi);
-  u2 = fminf(fmaxf(u2, c.lo), c.hi); u3 = fminf(fmaxf(u3, c.lo), c.hi);
-  v0 = fminf(fmaxf(v0, c.lo), c.hi); v1 = fminf(fmaxf(v1, c.lo), c.hi);
-  v2 = fminf(fmaxf(v2, c.lo), c.hi); v3 = fminf(fmaxf(v3, c.lo), c.hi);
-  wa = pack4(__float_as_uint(u0), __float_as_uint(u1), __float_as_uint(u2), __float_as_uint(u3));
-  wb = pack4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
-}
 
 #ifdef OSQ_ENABLE_TRACE
 #define OSQ_TRACE(slot) do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[(slot)] = clock64(); } while (0)
