@@ -41,7 +41,7 @@ namespace osq {
 constexpr int kBM = 128;            // rows of A per CTA tile (UMMA M)
 constexpr int kStageK = 128;        // k elements (= bytes, u8/s8) per smem stage row: one 128B swizzle row
 constexpr int kUmmaK = 32;          // k per tcgen05.mma kind::i8
-constexpr int kTmemCols = 512;                       // acc stages x BN: 4 x 128 or 2 x 256
+constexpr int kTmemCols = 512;                       // all of TMEM: acc stages x BN (2 x 256, 2 x 192, 4 x 128)
 constexpr int kWorkerWarp0 = 4, kNumWorkers = 16;    // warps 4..19 convert A (phase A); warps 4..11 also run the epilogue
 constexpr int kNumEpiWarps = 8;                      // workers 0..7: four TMEM lane quarters x two column halves of a chunk
 constexpr int kNumThreads = (kWorkerWarp0 + kNumWorkers) * 32;  // 640
@@ -55,7 +55,7 @@ struct FusedParams {
   int M, K, N;
   int KB;             // K / 128
   int NC;             // number of N chunks
-  int BN;             // chunk width: 128 (resident A) or 256 (streamed A), or N when N is smaller
+  int BN;             // chunk width chosen by the host plan: 256 (CTA pairs, streamed A), 192 (single CTAs, resident A), or N when N is smaller
   int acc_stages;     // TMEM accumulator stages (512 / BN, at most 4)
   int n_mblocks;
   int csz;            // 1, or 2 = CTA pair: tcgen05 cta_group::2 (M = 256 over two SMs, each CTA stages half of every W tile)
@@ -69,7 +69,7 @@ struct FusedParams {
   int cpp;            // N chunks accumulated concurrently in TMEM per sweep (streamed A with a code cache: all acc stages)
   int x_tma;          // fp32 A arrives by TMA into per-worker landing slots (else: 128-bit loads into registers)
   int alias_xo;       // the TMA-store staging tiles share the landing slots' memory
-  int w_stage_bytes;  // BN * 128
+  int w_stage_bytes;  // (BN / csz) * 128: a CTA of a pair stages half of the tile's rows
   int resident;       // converted A block stays in smem for all N chunks
   int cached;         // streaming mode with a code cache: passes >= 1 TMA-load bins instead of re-converting
   int codes_in;       // A is NULL: a_codes already holds the activation bins (written by the upstream fake-quant kernel);
