@@ -667,6 +667,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     const int r_base = w * kRowsPerWorker;  // this warp's 8 rows of the 128-row block
     const uint32_t lc16 = ((uint32_t)lane >> 2) << 4, lane_in = ((uint32_t)lane & 3) << 2;
     uint32_t cacc = 0, n_stores = 0;
+    uint32_t acc_st = 0, acc_ph = 0;  // accumulator stage of the next chunk and its phase parity (running: no divisions per chunk)
 
     float4 x[kRowsPerWorker];
     // one conversion pass over all k-blocks of m-block `mb`; ring positions start at pa0.
@@ -855,10 +856,10 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     int obufs = p.out_bufs;  // store tiles this warp may cycle through in the current m-block
     uint32_t tmem_base = 0;   // fetched right before the first epilogue chunk
     auto epilogue_chunk = [&](int mb, int nc) {
-      const int as_ = cacc % p.acc_stages;
+      const int as_ = (int)acc_st;
       const int n0 = nc * p.BN;
       if (nc + 1 < nc0 + ncn) fetch_consts(nc + 1);
-      mbar_wait(&sm.acc_full[as_], (cacc / p.acc_stages) & 1);
+      mbar_wait(&sm.acc_full[as_], acc_ph);
       tc_fence_after();
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as_ * p.BN);
@@ -941,6 +942,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       if (lane == 0) { if (pair) mbar_arrive_cluster_u32(mapa_u32(smem_u32(&sm.acc_empty[as_]), 0)); else mbar_arrive(&sm.acc_empty[as_]); }
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4 + 1);
       ++cacc;
+      if (++acc_st == (uint32_t)p.acc_stages) { acc_st = 0; acc_ph ^= 1; }
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");  // every reader of this chunk's constants is done
       if (w == 0 && lane == 0 && cacc <= 60) OSQ_TRACE(512 + (cacc - 1) * 4 + 2);
       if (nc + 1 < nc0 + ncn) publish_consts();
