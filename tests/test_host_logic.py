@@ -184,3 +184,29 @@ def test_sibling_linear_grouping_discovery():
     Q.enable_quantization(net)                                   # idempotent through the togglers
     assert net.a.query._sibling_group is ga
     assert all("_sibling_group" not in k for k in net.state_dict())
+
+
+def test_ctypes_structures_match_the_header():
+    """Field names and order of the three C structs in include/osq.h vs their ctypes mirrors in _lib.py (an ABI drift
+    here would silently scramble kernel arguments)."""
+    from outlier_suppression_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "osq.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+
+    def fields(struct_name):
+        end = re.search(r"\}\s*%s\s*;" % struct_name, hdr)
+        assert end, struct_name
+        start = hdr.rfind("typedef struct", 0, end.start())
+        body = hdr[hdr.index("{", start) + 1:end.start()]
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", part)[-1])
+        return names
+
+    for cname, cls in (("osq_tokens_t", _lib.Tokens), ("osq_stat_epilogue_t", _lib.StatEpilogue),
+                       ("osq_fused_linear_t", _lib.FusedLinearArgs)):
+        assert fields(cname) == [f[0] for f in cls._fields_], cname
