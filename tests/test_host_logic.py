@@ -210,3 +210,32 @@ def test_ctypes_structures_match_the_header():
     for cname, cls in (("osq_tokens_t", _lib.Tokens), ("osq_stat_epilogue_t", _lib.StatEpilogue),
                        ("osq_fused_linear_t", _lib.FusedLinearArgs)):
         assert fields(cname) == [f[0] for f in cls._fields_], cname
+
+
+def test_ctypes_argument_counts_match_the_header():
+    """Every prototype of include/osq.h has exactly as many parameters as its ctypes argtypes list in _lib.py."""
+    import ctypes as C
+    from outlier_suppression_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "osq.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+
+    class Rec:                                   # records what _declare() assigns, without loading the library
+        def __init__(self):
+            self.fns = {}
+
+        def __getattr__(self, name):
+            return self.fns.setdefault(name, type("F", (), {})())
+
+    rec = Rec()
+    _lib._declare(rec)
+    checked = 0
+    for name in _lib.EXPORTS:
+        m = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, hdr, flags=re.S)
+        assert m, "%s is not declared in osq.h" % name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        argtypes = getattr(rec.fns.get(name), "argtypes", None)
+        if argtypes is not None:
+            assert len(argtypes) == len(params), (name, len(argtypes), len(params))
+            checked += 1
+    assert checked >= 14
+    assert C.sizeof(_lib.Tokens) == 64
