@@ -121,56 +121,115 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path on the host cores (reference is Python and cannot travel)
+# CPU arm: the reference's OWN modules (quantization.Quantizer -> LSQPlusFakeQuantize / QLinear, imported unmodified from
+# /root/reference or the staged oracle/_ref) on the host cores; falls back to the oracle port only if no reference tree
+# travelled.  A step = the FULL 72-site stack (12 layers x 6 sites: act fake-quant -> weight fake-quant -> F.linear)
+# over a bounded sample of the batch (CPU_SAMPLE_SEQS of the 32 sequences), so ms_per_step is what a step really took.
 # ---------------------------------------------------------------------------------------------
-def cpu_layer_time(reps, warmup=1):
-    """seconds for ONE encoder layer's six sites (act LSQ+ fq -> weight fq -> F.linear) on all host threads."""
-    from oracle import osq_oracle as O  # CPU baseline leg only
+CPU_SAMPLE_SEQS = 8  # 8 x 512 = 4096 of the 16384 tokens per step (tokens/s on the CPU is flat in M at this size)
+
+
+def cpu_stack(sample_seqs):
+    """(step_fn, tokens_per_step, kind, description): the 72-site stack on CPU tensors."""
     torch.set_num_threads(os.cpu_count() or 1)
-    a768, a3072 = synth_act(H, 11).reshape(M, H), synth_act(FF, 12).reshape(M, FF)
+    ms = sample_seqs * S
+    a768, a3072 = synth_act(H, 11)[:sample_seqs], synth_act(FF, 12)[:sample_seqs]
+    lens = synth_lens()[:sample_seqs]
+    try:
+        from oracle import ref_shim  # CPU baseline leg only
+        have_ref = ref_shim.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        with ref_shim.cpu_only():
+            R = ref_shim.load()
+            from quant_transformer.quantization.quantized_module import Quantizer as RQuantizer
+            layers = []
+            for layer in range(LAYERS):
+                mods = []
+                for i, (name, k, n, gam) in enumerate(SITES):
+                    w, b = synth_weight(n, k, 1000 * layer + 100 + i, gam)
+                    lin = torch.nn.Linear(k, n)
+                    lin.weight.data, lin.bias.data = w, b
+                    ql = RQuantizer(lin, W_QCFG)
+                    aq = RQuantizer(None, A_QCFG)
+                    aq.observer.set_name("layer.%d.%s" % (layer, name))
+                    aq.observer.set_percentile(0.99)
+                    a = a768 if k == H else a3072
+                    ql.weight_fake_quant.enable_observer(); ql.weight_fake_quant(ql.weight); ql.weight_fake_quant.disable_observer()
+                    aq.enable_observer(); aq(a[:2], lens[:2], 1); aq.disable_observer()
+                    aq.enable_fake_quant(); ql.weight_fake_quant.enable_fake_quant()
+                    mods.append((aq, ql, a))
+                layers.append(mods)
+
+        def step():
+            with ref_shim.cpu_only(), torch.no_grad():
+                for mods in layers:
+                    for aq, ql, a in mods:
+                        ql(aq(a, lens, 1))   # fake_quant.py:178-209 -> quantized_module.py:71-72
+        return step, ms, "reference", ("reference modules (quant_transformer.quantization LSQPlusFakeQuantize -> QLinear), full 72-site "
+                                       "stack per step on %d of 32 sequences (%d tokens)" % (sample_seqs, ms))
+    from oracle import osq_oracle as O  # CPU baseline leg only
     sites = []
-    for i, (_, k, n, gam) in enumerate(SITES):
-        w, b = synth_weight(n, k, 100 + i, gam)
-        ws, wz, wqmin, wqmax = O.weight_qparams_minmax(w, W_BIT, True)
-        a = a768 if k == H else a3072
-        qmin, qmax = O.quant_range(A_BIT, False)
-        st = O.ObserverState()
-        O.observe_avg_prune_minmax(st, a.reshape(B, S, k)[:4], 0.99, "x", None, 1)
-        s, z = O.qparams_from_minmax(st.min_val, st.max_val, qmin, qmax, False)
-        sites.append((a, s.reshape(1), z.reshape(1).float(), qmin, qmax, w, ws, wz, wqmin, wqmax, b))
+    for layer in range(LAYERS):
+        for i, (_, k, n, gam) in enumerate(SITES):
+            w, b = synth_weight(n, k, 1000 * layer + 100 + i, gam)
+            ws, wz, wqmin, wqmax = O.weight_qparams_minmax(w, W_BIT, True)
+            a = (a768 if k == H else a3072).reshape(ms, k)
+            qmin, qmax = O.quant_range(A_BIT, False)
+            st = O.ObserverState()
+            O.observe_avg_prune_minmax(st, a.reshape(sample_seqs, S, k)[:2], 0.99, "x", None, 1)
+            sc, z = O.qparams_from_minmax(st.min_val, st.max_val, qmin, qmax, False)
+            sites.append((a, sc.reshape(1), z.reshape(1).float(), qmin, qmax, w, ws, wz, wqmin, wqmax, b))
+
+    def step():
+        with torch.no_grad():
+            for a, sc, z, qmin, qmax, w, ws, wz, wqmin, wqmax, b in sites:
+                O.qlinear(O.fq_lsqplus_per_tensor(a, sc, z, qmin, qmax), w, ws, wz, wqmin, wqmax, b)
+    return step, ms, "port", "oracle port (no reference tree on this machine), full 72-site stack per step on %d tokens" % ms
+
+
+def cpu_time_steps(step, steps, warmup):
+    for _ in range(warmup):
+        step()
     times = []
-    with torch.no_grad():
-        for r in range(warmup + reps):
-            t0 = time.perf_counter()
-            for a, s, z, qmin, qmax, w, ws, wz, wqmin, wqmax, b in sites:
-                x_fq = O.fq_lsqplus_per_tensor(a, s, z, qmin, qmax)
-                O.qlinear(x_fq, w, ws, wz, wqmin, wqmax, b)
-            if r >= warmup:
-                times.append(time.perf_counter() - t0)
-    return statistics.median(times), times
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return times
 
 
 def cpu_baseline_record(reps):
-    t_layer, _ = cpu_layer_time(reps)
-    return {"value": M / (LAYERS * t_layer), "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": "1 of 12 identical encoder layers (6 QLinear sites, M=16384) x %d reps, median, scaled x12; "
-                      "oracle port of util_quant.py/quantized_module.py on torch CPU threads" % reps}
+    step, ms, kind, what = cpu_stack(CPU_SAMPLE_SEQS)
+    times = cpu_time_steps(step, reps, 1)
+    return {"value": ms / statistics.median(times), "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": kind,
+            "sample": "%s; median of %d steps after 1 warm-up" % (what, reps), "s_per_step": statistics.median(times)}
+
+
+def workload_config(world):
+    """identical in both arms (the driver compares them)"""
+    return {"workload": "BERT-base seq512 6-bit twc_fine_gamma (LSQ+ acts / AvgPruneMinMax p=.99, Fixed per-channel weights, gamma "
+                        "folded), batch 32 per GPU (M=16384), 72 QLinear sites per step",
+            "l2": "inputs/outputs rotate over 4x50MB / 2x151MB / 2x201MB buffers (> 126 MB L2) between launches",
+            "parallelism": "dp%d (independent batches, no collective)" % world}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t_layer, times = cpu_layer_time(max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
-    value = M / (LAYERS * t_layer)
+    step, ms, kind, what = cpu_stack(CPU_SAMPLE_SEQS)
+    t0 = time.perf_counter()
+    times = cpu_time_steps(step, max(1, args.steps), max(0, args.warmup))
+    total = sum(times)
+    value = ms * len(times) / total
     rec = {"impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": LAYERS * t_layer * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "BERT-base seq512 6-bit twc_fine_gamma, batch 32 (M=16384), 72 QLinear sites",
-                      "note": "each step times one encoder layer (1/12 of the stack) and is scaled x12"},
-           "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": "port",
-                            "sample": "1 of 12 identical encoder layers per step, scaled x12"},
-           "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(int(os.environ.get("WORLD_SIZE", "1"))),
+           "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": kind, "sample": what},
+           "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": time.perf_counter() - t0}
     print(json.dumps(rec))
 
 
@@ -438,12 +497,9 @@ def main():
         rec = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8 (u8 x s8 -> s32 bins, fp32 I/O)",
                "data": "synthetic",
-               "config": {"workload": "BERT-base seq512 6-bit twc_fine_gamma (LSQ+ acts / AvgPruneMinMax p=.99, Fixed per-channel weights, gamma folded), "
-                                      "batch 32 per GPU (M=16384), 72 QLinear sites per step in %d fused launches%s" % (
-                                          LAYERS * len(order), "" if args.no_group else " (q|k|v of a layer share one launch)"),
-                          "launch": launch_mode, "host_issue_ms_per_step": host_issue_ms,
-                          "l2": "inputs/outputs rotate over 4x50MB / 2x151MB / 2x201MB buffers (> 126 MB L2) between launches",
-                          "parallelism": "dp%d (independent batches, no collective)" % world},
+               "config": workload_config(world),
+               "launch": {"mode": launch_mode, "host_issue_ms_per_step": host_issue_ms, "fused_launches_per_step": LAYERS * len(order),
+                          "grouping": "none" if args.no_group else "q|k|v of a layer share one launch"},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * LAYERS * len(order),
                "clocks": clocks}
         print(json.dumps(rec))

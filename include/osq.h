@@ -172,7 +172,9 @@ int osq_mse_brent_rows_f32(const float* w, int64_t rows, int64_t cols, int qmin,
  * gamma_migration.py:46-76), scale[N]/zp[N] from the weight quantizer.
  *   codes  [N, K] int8  : q - zp  (the dequantised weight is codes * scale[n])
  *   rowsum [N]    int32 : sum_k codes[n, k]   (zero-point correction of the u8 x s8 contraction)
- * Requires qmin - zp >= -128 and qmax - zp <= 127 for every row (true for every symmetric config).
+ * Requires qmin - zp >= -128 and qmax - zp <= 127 for every row: any zp in [qmin, qmax] qualifies when
+ * qmax - qmin <= 127 (<= 7 bits); an 8-bit range must be the symmetric one, [-128, 127] with zp == 0.
+ * Asymmetric 8-bit weights (range [0, 255]) return OSQ_EINVAL; out-of-range bins saturate (never wrap).
  * ------------------------------------------------------------------------------------------- */
 int osq_pack_weight_s8(const float* w, int64_t N, int64_t K, const float* scale, const int32_t* zp,
                        int qmin, int qmax, int8_t* codes, int32_t* rowsum, void* stream);

@@ -1025,6 +1025,7 @@ pack_weight_s8_kernel(const float* __restrict__ w, int64_t N, int64_t K, const f
       float q;
       fq_elem(w[n * K + k], s, z, qmin, qmax, q);
       int c = (q != q) ? 0 : (int)(q - z);
+      c = c < -128 ? -128 : (c > 127 ? 127 : c);  // contract: zp == 0 for 8-bit ranges; saturate, never wrap
       codes[n * K + k] = (int8_t)c;
       acc += c;
     }
@@ -1092,6 +1093,10 @@ int osq_pack_weight_s8(const float* w, int64_t N, int64_t K, const float* scale,
   OSQ_CHECK_ARG(w && scale && zp && codes && rowsum, "osq_pack_weight_s8: null pointer");
   OSQ_CHECK_ARG(N > 0 && K > 0, "osq_pack_weight_s8: empty weight");
   OSQ_CHECK_ARG(qmax - qmin <= 255 && qmin < qmax, "osq_pack_weight_s8: more than 8 bits");
+  // q - zp must fit the s8 operand: any zp in [qmin, qmax] is safe up to 7 bits; an 8-bit range only with the
+  // symmetric layout [-128, 127] (zp == 0).  Asymmetric 8-bit weights ([0, 255]) are NOT representable.
+  OSQ_CHECK_ARG(qmax - qmin <= 127 || (qmin >= -128 && qmax <= 127),
+                "osq_pack_weight_s8: q - zp does not fit int8 (asymmetric 8-bit weights are not supported by the fused path)");
   int sms = sm_count();
   if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
   int64_t g = N < (int64_t)sms * 8 ? N : (int64_t)sms * 8;

@@ -303,10 +303,13 @@ int osq_mse_brent_rows_f32(const float* w, int64_t rows, int64_t cols, int qmin,
   if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
   const int row_in_smem = cols * 4 <= 160 * 1024;
   const size_t smem = row_in_smem ? (size_t)cols * 4 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in is per device, not per process (one process may drive several GPUs)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OSQ_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
     OSQ_CUDA(cudaFuncSetAttribute(mse_brent_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   int64_t g = rows < (int64_t)sms * 8 ? rows : (int64_t)sms * 8;
   mse_brent_rows_kernel<<<(int)g, kBrentThreads, smem, (cudaStream_t)stream>>>(w, rows, cols, (float)qmin, (float)qmax, symmetric,

@@ -323,8 +323,14 @@ def pack_weight(w, scale, zero_point, qmin, qmax):
     return codes, rowsum
 
 
-def fused_linear_supported(k: int, n: int) -> bool:
-    return k >= 128 and k % 128 == 0 and n >= 16 and n % 16 == 0
+def fused_linear_supported(k: int, n: int, a: Optional[torch.Tensor] = None) -> bool:
+    """The shape / alignment contract of osq_fused_fq_linear (include/osq.h): K % 128 == 0, K <= 32768 (int32
+    accumulators), N % 16 == 0, N <= 2^20, 16-byte aligned operands."""
+    if not (128 <= k <= 32768 and k % 128 == 0 and 16 <= n <= (1 << 20) and n % 16 == 0):
+        return False
+    if a is not None and a.is_contiguous() and a.data_ptr() % 16 != 0:
+        return False
+    return True
 
 
 def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum, bias, lsq_grad_factor=0.0,

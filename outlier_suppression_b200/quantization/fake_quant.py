@@ -26,7 +26,10 @@ def producer_of(t: torch.Tensor):
     tag = getattr(t, _TAG, None)
     if tag is None or tag[1] != t._version:
         return None
-    return tag[0]()
+    q = tag[0]()
+    if q is None or _qparam_stamp(q) != tag[2]:
+        return None  # the quantizer's (scale, zero_point) changed since it produced t: t is no longer its fixed point
+    return q
 
 
 def bins_of(t: torch.Tensor):
@@ -34,7 +37,15 @@ def bins_of(t: torch.Tensor):
     tag = getattr(t, "_osq_bins", None)
     if tag is None or tag[1] != t._version or not t.is_contiguous() or tag[0].numel() != t.numel():
         return None
+    if producer_of(t) is None:  # stale qparams void the bins together with the fusion
+        return None
     return tag[0]
+
+
+def _qparam_stamp(q):
+    """Everything that identifies the (scale, zero_point) a quantizer used: rewritten by an observer pass or
+    load_state_dict (epoch), or edited in place by an optimizer step / the LSQ+ sanitiser (tensor versions)."""
+    return (q.qparam_epoch, q.scale.data_ptr(), q.scale._version, q.zero_point.data_ptr(), q.zero_point._version)
 
 
 class QuantizeBase(nn.Module):
@@ -99,6 +110,20 @@ class QuantizeBase(nn.Module):
         self.qparam_epoch += 1
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
+    def _run_observer(self, X, observation_mask, seq_pos, owner):
+        """One observer step; True when the launch also refreshed (scale, zero_point).  Goes through the observer's
+        ``__call__`` when hooks are registered on it (the reference always does, fake_quant.py:109,180), else
+        straight to the kernel wrapper."""
+        obs = self.observer
+        if obs._forward_hooks or obs._forward_pre_hooks:
+            obs._owner_hint = owner
+            try:
+                obs(X, observation_mask, seq_pos)
+            finally:
+                obs._owner_hint = None
+            return obs._last_fused
+        return obs._observe(X, observation_mask, seq_pos, owner)
+
     # ---- where the observer kernels may write the refreshed qparams ----
     def _per_tensor_qparam_targets(self):
         return None, None
@@ -126,7 +151,7 @@ class QuantizeBase(nn.Module):
 
     def _tag(self, y: torch.Tensor) -> torch.Tensor:
         try:
-            setattr(y, _TAG, (weakref.ref(self), y._version))
+            setattr(y, _TAG, (weakref.ref(self), y._version, _qparam_stamp(self)))
         except Exception:  # pragma: no cover  (tensor subclasses that refuse attributes)
             pass
         return y
@@ -154,7 +179,7 @@ class FixedFakeQuantize(QuantizeBase):
 
     def forward(self, X, observation_mask=None, seq_pos=-1):
         if self.observer_enabled == 1 and X.numel() > 0:
-            fused = self.observer._observe(X.detach(), observation_mask, seq_pos, self)
+            fused = self._run_observer(X.detach(), observation_mask, seq_pos, self)
             if not fused:
                 _scale, _zero_point = self.observer.calculate_qparams(self.observer.min_val, self.observer.max_val)
                 _scale, _zero_point = _scale.to(self.scale.device), _zero_point.to(self.zero_point.device)
@@ -229,7 +254,7 @@ class LSQPlusFakeQuantize(QuantizeBase):
     def forward(self, X, observation_mask=None, seq_pos=-1):
         sanitized_by_kernel = False
         if self.observer_enabled == 1 and X.numel() > 0:
-            fused = self.observer._observe(X.detach(), observation_mask, seq_pos, self)
+            fused = self._run_observer(X.detach(), observation_mask, seq_pos, self)
             if not fused:
                 _scale, _zero_point = self.observer.calculate_qparams(self.observer.min_val, self.observer.max_val)
                 _scale, _zero_point = _scale.to(self.scale.device), _zero_point.to(self.zero_point.device)
@@ -276,7 +301,7 @@ class LSQFakeQuantize(QuantizeBase):
 
     def forward(self, X, observation_mask=None, seq_pos=-1):
         if self.observer_enabled == 1 and X.numel() > 0:
-            self.observer._observe(X.detach(), observation_mask, seq_pos, None)
+            self._run_observer(X.detach(), observation_mask, seq_pos, None)
             _scale, _zero_point = self.observer.calculate_qparams(self.observer.min_val, self.observer.max_val)
             if self.ch_axis != -1:
                 self.scale.data = torch.ones_like(_scale, dtype=torch.float32)

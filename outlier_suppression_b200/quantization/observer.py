@@ -58,6 +58,9 @@ class ObserverBase(nn.Module):
         self.register_buffer("min_val", torch.tensor(float("inf")))
         self.register_buffer("max_val", torch.tensor(float("-inf")))
 
+    _owner_hint = None   # the quantizer on whose behalf __call__ runs (set by QuantizeBase._run_observer)
+    _last_fused = False
+
     # --- attribute pokes used by state.py / token_wise_clipping.py ---
     def set_name(self, name):
         self.name = name
@@ -103,7 +106,7 @@ class ObserverBase(nn.Module):
     def forward(self, x_orig, observation_mask=None, seq_pos=-1):
         if x_orig.numel() == 0:
             return x_orig
-        self._observe(x_orig, observation_mask, seq_pos, None)
+        self._last_fused = self._observe(x_orig, observation_mask, seq_pos, self._owner_hint)
         return x_orig
 
 

@@ -120,10 +120,14 @@ class QLinear(QuantizedOperator, nn.Linear):
         wq = self.weight_fake_quant
         if not self._weight_is_static() or wq.ch_axis != 0 or wq.quant_max - wq.quant_min > 255:
             return None
+        # the packed operand is s8 (q - zp): always representable up to 7 bits, at 8 bits only for the symmetric
+        # range (zp == 0).  Asymmetric 8-bit weights take the unfused path (osq_pack_weight_s8 rejects them too).
+        if wq.quant_max - wq.quant_min > 127 and not (wq.symmetric and wq.quant_min >= -128 and wq.quant_max <= 127):
+            return None
         if torch.is_grad_enabled() and (input.requires_grad or aq.scale.requires_grad or
                                         (self.bias is not None and self.bias.requires_grad)):
             return None  # training / learn_scale stage: reference semantics through autograd
-        if not ops.fused_linear_supported(self.in_features, self.out_features):
+        if not ops.fused_linear_supported(self.in_features, self.out_features, input):
             return None
         return aq
 
@@ -169,6 +173,7 @@ class QLinearGroup:
         self.members = list(members)
         self._packed = None
         self._pending = None  # (input tensor, its version, {id(member): output view})
+        self.misses = 0       # grouped launches whose sibling outputs were never collected
 
     def _packed_weight(self):
         key = tuple((m._weight_key(), None if m.bias is None else (m.bias.data_ptr(), m.bias._version)) for m in self.members)
@@ -193,8 +198,12 @@ class QLinearGroup:
                 self._pending = None
             stats["grouped_hit"] += 1
             return out
+        if pend is not None and pend[2]:
+            # the previous grouped launch computed siblings nobody asked for with that tensor (different inputs per
+            # sibling, or k/v served from a cache): this group's members do not share an input -> stop grouping it
+            self.misses += 1
         self._pending = None
-        if os.environ.get("OSQ_DISABLE_GROUPING") == "1":
+        if os.environ.get("OSQ_DISABLE_GROUPING") == "1" or self.misses >= 2:
             return None
         for m in self.members:  # every sibling must be on the fused path with this very producer
             if m is not member and m._fusable_producer(input) is not aq:
@@ -217,6 +226,9 @@ class QLinearGroup:
 
 
 SIBLING_NAME_SETS = (("query", "key", "value"), ("q_proj", "k_proj", "v_proj"))
+# cross-attention blocks feed q_proj the decoder states and k_proj / v_proj the encoder states (quant_bart.py:166-175):
+# their projections never share an input, so they are never grouped
+CROSS_ATTENTION_MARKERS = ("encoder_attn", "crossattention", "cross_attn")
 
 
 def group_sibling_linears(model):
@@ -224,7 +236,13 @@ def group_sibling_linears(model):
     with the same in_features) and ties them into a QLinearGroup.  Idempotent; returns the number of groups.  Called
     by the state togglers, so a reference driver gets it without any change."""
     n = 0
-    for parent in model.modules():
+    for pname, parent in model.named_modules():
+        leaf = pname.rsplit(".", 1)[-1]
+        if any(mk in leaf for mk in CROSS_ATTENTION_MARKERS) or getattr(parent, "is_cross_attention", False):
+            for kid in parent.children():
+                if isinstance(kid, QLinear):
+                    kid._sibling_group = None
+            continue
         kids = dict(parent.named_children())
         for names in SIBLING_NAME_SETS:
             members = [kids.get(k) for k in names]

@@ -318,6 +318,82 @@ def gen_qlinear():
     save("qlinear", **out)
 
 
+def gen_extra():
+    """Goldens for the restatements no shipped twc/minmax config reaches but the registries expose:
+    AvgQuantileObserver, MSEObserver / AvgMSEObserver, LSQPlusObserver, LSQFakeQuantize, per-channel LSQ+, QEmbedding."""
+    g = torch.Generator().manual_seed(107)
+    out = {}
+    # ---- AvgQuantileObserver (observer.py:240-282): three batches, with and without pad mask ----
+    for cname, shape, seq_pos, lens in (("quant_mask", (4, 24, 96), 1, [24, 9, 1, 17]), ("quant_nomask", (3, 40, 64), -1, None)):
+        xs = [_act(g, shape, len(shape) - 1) for _ in range(3)]
+        mask = None if lens is None else torch.tensor(lens)
+        for thr, bins in ((0.999, 2048), (0.99, 256)):
+            o = R_obs.AvgQuantileObserver(bit=6, symmetric=False, ch_axis=-1, threshold=thr, bins=bins)
+            tr = []
+            for x in xs:
+                o(x, observation_mask=mask, seq_pos=seq_pos)
+                tr.append([float(o.min_val), float(o.max_val)])
+            out["%s_trace_%d" % (cname, bins)] = np.array(tr, dtype=np.float32)
+        for b, x in enumerate(xs):
+            out["%s_x%d" % (cname, b)] = x
+        out["%s_lens" % cname] = np.array(lens if lens is not None else [], dtype=np.int64)
+        out["%s_meta" % cname] = np.array([seq_pos])
+    # ---- MSEObserver / AvgMSEObserver (observer.py:285-409): 1-D (symmetric), 1-D one-sided, 2-D (asymmetric, 4-bit) ----
+    lens = torch.tensor([10, 4])
+    xs = [_act(g, (2, 10, 24), 2) for _ in range(2)]
+    out.update({"mse_x0": xs[0], "mse_x1": xs[1], "mse_lens": lens})
+    for tag, cls, bit, sym in (("mse_sym", R_obs.MSEObserver, 6, True), ("avgmse_sym", R_obs.AvgMSEObserver, 6, True),
+                               ("mse_asym4", R_obs.MSEObserver, 4, False), ("avgmse_asym4", R_obs.AvgMSEObserver, 4, False)):
+        o = cls(bit=bit, symmetric=sym, ch_axis=-1)
+        tr = []
+        for x in xs:
+            o(x, observation_mask=lens, seq_pos=1)
+            tr.append([float(o.min_val), float(o.max_val)])
+        out[tag + "_trace"] = np.array(tr, dtype=np.float32)
+    xp = torch.rand(2, 10, 24, generator=g) * 3
+    o = R_obs.AvgMSEObserver(bit=6, symmetric=False, ch_axis=-1)
+    o(xp)
+    out.update({"mse_pos_x": xp, "mse_pos": np.array([float(o.min_val), float(o.max_val)], dtype=np.float32)})
+    # ---- LSQPlusObserver (observer.py:148-173): per-tensor and per-channel ----
+    w = torch.randn(16, 48, generator=g) * 0.05
+    w[3] *= 6
+    for tag, ch in (("lsqobs_t", -1), ("lsqobs_c", 0)):
+        o = R_obs.LSQPlusObserver(bit=4, symmetric=True, ch_axis=ch)
+        o(w)
+        s, z = o.calculate_qparams(o.min_val, o.max_val)
+        out.update({tag + "_min": o.min_val, tag + "_max": o.max_val, tag + "_scale": s, tag + "_zp": z})
+    out["lsq_w"] = w
+    # ---- LSQFakeQuantize (fake_quant.py:129-167) and per-channel LSQ+ (fake_quant.py:170-209) forward ----
+    x = _act(g, (2, 16, 48), 2)
+    out["lsq_x"] = x
+    for tag, quantizer, obs, ch, inp in (("lsq_t", "LSQFakeQuantize", "MinMaxObserver", -1, x),
+                                         ("lsq_c", "LSQFakeQuantize", "MinMaxObserver", 0, w),
+                                         ("lsqplus_c", "LSQPlusFakeQuantize", "MinMaxObserver", 0, w)):
+        q = R_qm.Quantizer(None, QC(quantizer, obs, 6, True, ch))
+        q.enable_observer()
+        q(inp)
+        q.disable_observer()
+        q.enable_fake_quant()
+        if quantizer == "LSQPlusFakeQuantize":
+            q.zero_point.data += 0.3
+        with torch.no_grad():
+            y = q(inp)
+        out.update({tag + "_y": y, tag + "_scale": q.scale.data.clone(), tag + "_zp": q.zero_point.data.clone().float()})
+    # ---- QEmbedding (quantized_module.py:75-100) ----
+    emb = torch.nn.Embedding(50, 32, padding_idx=0)
+    emb.weight.data = torch.randn(50, 32, generator=g) * 0.1
+    qe = R_qm.Quantizer(emb, QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0))
+    ids = torch.randint(0, 50, (3, 11), generator=g)
+    qe.weight_fake_quant.enable_observer()
+    qe(ids)
+    qe.weight_fake_quant.disable_observer()
+    qe.weight_fake_quant.enable_fake_quant()
+    with torch.no_grad():
+        y = qe(ids)
+    out.update({"emb_w": emb.weight.data, "emb_ids": ids, "emb_y": y, "emb_scale": qe.weight_fake_quant.scale.clone()})
+    save("extra", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # reduction order independent of the thread count
     gen_fq_per_tensor()
@@ -328,3 +404,4 @@ if __name__ == "__main__":
     gen_minmax_per_channel()
     gen_mse()
     gen_qlinear()
+    gen_extra()

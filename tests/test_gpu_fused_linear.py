@@ -214,3 +214,85 @@ def test_bins_in_launch_is_bit_identical(m, k, n, lsq):
         y = ops.fused_fq_linear(src, a_scale_t, a_zp_t, a_qmin, a_qmax, codes, w_scale.cuda(), rowsum, bias.cuda(),
                                 lsq_grad_factor=gfac, a_bins=bins)
         np.testing.assert_array_equal(y.cpu().numpy(), y_ref.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Every shape bench.py times, at the size it times it (M = 32 x 512), and the BART-large sites of BASELINE config 4
+# at the per-GPU eval batch (M = 4 x 1024) and at M = 16384.  Same bar as everywhere: bins bit-exact, Y tolerance.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,n,cache", [(768, 3072, True), (3072, 768, True), (3072, 768, False), (768, 2304, True)])
+def test_fused_benchmarked_shapes_at_full_size(k, n, cache):
+    run_case(16384, k, n, 6, 6, True, seed=k + n, gamma=(k == 768), use_code_cache=cache)
+
+
+@pytest.mark.parametrize("m", [4096, 16384])
+@pytest.mark.parametrize("k,n", [(1024, 1024), (1024, 4096), (4096, 1024)])
+def test_fused_bart_large_sites(m, k, n):
+    run_case(m, k, n, 6, 6, True, seed=m + k + n, gamma=(k == 1024))
+
+
+def test_asymmetric_8bit_weights_take_the_unfused_path():
+    """q - zp of an asymmetric 8-bit weight spans [-255, 255] and does not fit the s8 operand.  The
+    module must fall back to reference semantics (separate launches) and the C ABI must refuse to pack."""
+    from outlier_suppression_b200 import _lib, ops
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(256, 64)
+    lin.weight.data += 0.3  # lopsided rows: zero points far from the middle
+    ql = qm.Quantizer(lin, QC("FixedFakeQuantize", "MinMaxObserver", 8, False, 0)).cuda()
+    aq = qm.Quantizer(None, QC("FixedFakeQuantize", "AvgMinMaxObserver", 8, False, -1)).cuda()
+    x = torch.randn(4, 32, 256, device="cuda")
+    ql.weight_fake_quant.enable_observer(); ql(x); ql.weight_fake_quant.disable_observer()
+    aq.enable_observer(); aq(x); aq.disable_observer()
+    aq.enable_fake_quant(); ql.weight_fake_quant.enable_fake_quant()
+    before = dict(qm.stats)
+    with torch.no_grad():
+        y = ql(aq(x))
+    assert qm.stats["unfused"] == before["unfused"] + 1 and qm.stats["fused"] == before["fused"]
+    w, b = lin.weight.detach(), lin.bias.detach()
+    mn, mx = w.min(1).values, w.max(1).values
+    ws, wz = O.qparams_from_minmax(mn, mx, 0, 255, False)
+    amn, amx = O.global_minmax(x.cpu())
+    s, z = O.qparams_from_minmax(amn, amx, 0, 255, False)
+    ref = O.qlinear(O.fq_per_tensor(x.cpu(), s.item(), int(z.item()), 0, 255), w, ws, wz.to(torch.int32), 0, 255, b)
+    close(y, ref, rel=1e-4)
+    wq = ql.weight_fake_quant
+    with pytest.raises(_lib.OsqError, match="int8"):
+        ops.pack_weight(ql.weight, wq.scale, wq.zero_point, 0, 255)
+    # 7-bit asymmetric weights DO fit (|q - zp| <= 127) and stay on the fused path, bit-exact bins
+    ql7 = qm.Quantizer(lin, QC("FixedFakeQuantize", "MinMaxObserver", 7, False, 0)).cuda()
+    ql7.weight_fake_quant.enable_observer(); ql7(x); ql7.weight_fake_quant.disable_observer()
+    ql7.weight_fake_quant.enable_fake_quant()
+    before = dict(qm.stats)
+    with torch.no_grad():
+        y7 = ql7(aq(x))
+    assert qm.stats["fused"] == before["fused"] + 1
+    ws7, wz7 = O.qparams_from_minmax(mn, mx, 0, 127, False)
+    ref7 = O.qlinear(O.fq_per_tensor(x.cpu(), s.item(), int(z.item()), 0, 255), w, ws7, wz7.to(torch.int32), 0, 127, b)
+    close(y7, ref7)
+
+
+def test_stale_qparams_void_the_producer_tag():
+    """a tensor produced under OLD (scale, zero_point) must not be re-quantised by the fused kernel with the
+    NEW ones (optimizer step, another observer pass, load_state_dict)."""
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    from outlier_suppression_b200.quantization.fake_quant import bins_of, producer_of
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(128, 32)
+    ql = qm.Quantizer(lin, QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)).cuda()
+    aq = qm.Quantizer(None, QC("LSQPlusFakeQuantize", "AvgMinMaxObserver", 6, False, -1)).cuda()
+    x = torch.randn(2, 64, 128, device="cuda")
+    ql.weight_fake_quant.enable_observer(); ql(x); ql.weight_fake_quant.disable_observer()
+    aq.enable_observer(); aq(x); aq.disable_observer()
+    aq.enable_fake_quant(); ql.weight_fake_quant.enable_fake_quant()
+    with torch.no_grad():
+        ql(aq(x))            # first fused call: from now on the quantizer emits bins
+        x_fq = aq(x)
+        assert producer_of(x_fq) is aq and bins_of(x_fq) is not None
+        y_good = ql(x_fq)
+        aq.scale.mul_(1.5)   # what an optimizer step does
+        assert producer_of(x_fq) is None and bins_of(x_fq) is None
+        before = dict(qm.stats)
+        y = ql(x_fq)
+        assert qm.stats["unfused"] == before["unfused"] + 1
+    close(y, y_good, rel=1e-5)  # reference semantics: Linear over the tensor as it is, NOT re-quantised with the new scale

@@ -239,3 +239,44 @@ def test_ctypes_argument_counts_match_the_header():
             checked += 1
     assert checked >= 14
     assert C.sizeof(_lib.Tokens) == 64
+
+
+def test_cross_attention_projections_are_not_grouped():
+    """BART encoder_attn feeds q_proj the decoder states and k_proj / v_proj the encoder states
+    (quant_bart.py:166-175); only self-attention siblings share an input and may share a launch."""
+    from outlier_suppression_b200.quantization import quantized_module as qm
+
+    def attn():
+        m = torch.nn.Module()
+        for nme in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            setattr(m, nme, qm.Quantizer(torch.nn.Linear(128, 128), QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)))
+        return m
+
+    layer = torch.nn.Module()
+    layer.self_attn, layer.encoder_attn = attn(), attn()
+    bert = torch.nn.Module()
+    bert.self = torch.nn.Module()
+    for nme in ("query", "key", "value"):
+        setattr(bert.self, nme, qm.Quantizer(torch.nn.Linear(128, 128), QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)))
+    net = torch.nn.ModuleList([layer, bert])
+    assert qm.group_sibling_linears(net) == 2
+    assert layer.self_attn.q_proj._sibling_group is layer.self_attn.v_proj._sibling_group is not None
+    assert layer.self_attn.out_proj._sibling_group is None
+    assert all(getattr(layer.encoder_attn, n)._sibling_group is None for n in ("q_proj", "k_proj", "v_proj"))
+    assert bert.self.query._sibling_group.members == [bert.self.query, bert.self.key, bert.self.value]
+
+
+def test_pack_weight_rejects_ranges_that_do_not_fit_int8():
+    from outlier_suppression_b200 import _lib
+    lib = _lib.load()
+    fake = 4096  # never dereferenced: argument validation precedes any launch
+    assert lib.osq_pack_weight_s8(fake, 8, 128, fake, fake, 0, 255, fake, fake, None) == -1
+    assert b"int8" in lib.osq_last_error()
+    assert lib.osq_pack_weight_s8(fake, 8, 128, fake, fake, -256, 255, fake, fake, None) == -1
+
+
+def test_fused_linear_supported_mirrors_the_kernel_contract():
+    from outlier_suppression_b200 import ops
+    assert ops.fused_linear_supported(768, 768) and ops.fused_linear_supported(32768, 16)
+    for k, n in ((100, 768), (768, 100), (65536, 768), (768, 8), (768, (1 << 20) + 16)):
+        assert not ops.fused_linear_supported(k, n)

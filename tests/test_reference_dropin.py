@@ -10,8 +10,10 @@ import types
 import pytest
 import torch
 
-REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "quant_transformer")), reason="reference tree not present")
+from oracle import make_ref
+
+REF = make_ref.root() or "/root/reference"
+pytestmark = pytest.mark.skipif(make_ref.root() is None, reason="reference tree not present (neither /root/reference nor oracle/_ref)")
 
 
 class QC:
@@ -51,10 +53,11 @@ def test_reference_quant_bert_runs_on_this_backend():
         sys.modules.setdefault(m, types.ModuleType(m))
     if REF not in sys.path:
         sys.path.insert(0, REF)
+    from oracle import ref_shim
+    ref_shim.purge()
     import outlier_suppression_b200
     backend = outlier_suppression_b200.install_as_reference_backend()
     _compat_shims()
-    sys.modules.pop("quant_transformer.model.quant_bert", None)
     from quant_transformer.model import quant_bert  # the reference's file, unmodified
     assert quant_bert.Quantizer is backend.Quantizer
 
@@ -83,3 +86,43 @@ def test_reference_quant_bert_runs_on_this_backend():
     sd = model.state_dict()
     for n in quantizers:
         assert n + ".scale" in sd and n + ".zero_point" in sd and n + ".observer.min_val" in sd
+
+
+def test_staged_reference_tree_is_verbatim():
+    """oracle/make_ref.py stages a byte-identical copy of the reference package for the GPU box (git-ignored)."""
+    root = make_ref.build()
+    assert root is not None and make_ref.staged() and make_ref.verify()
+    if make_ref.source_available():
+        import json
+        assert json.load(open(make_ref.MANIFEST))["files"] == make_ref._tree(make_ref.SRC_ROOT)
+    tracked = os.popen("git -C %s ls-files oracle/_ref 2>/dev/null" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))).read()
+    assert tracked.strip() == "", "reference sources must never be committed"
+
+
+def test_fp_forward_of_unmodified_quant_bert_on_this_backend_cpu():
+    """With every quantizer disabled the model is plain torch: the reference's model file, bound to this backend's
+    Quantizer / QLinear / QEmbedding classes, must reproduce the FP HuggingFace model (no CUDA needed)."""
+    from oracle import ref_model as RM
+    ns = RM.load_stack("b200")
+    qcfg = RM.quant_config()
+    fp = RM.fp_bert()
+    model = RM.build_model(ns, fp, qcfg, "cpu")
+    ns.quantization.disable_all(model)
+    batch = RM.synth_batches(1, 4, 32, 100, "cpu")[0]
+    with torch.no_grad():
+        got = model(**batch)
+        want = fp(**batch).logits
+    got = got[0] if isinstance(got, tuple) else got.logits
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (got, want)
+
+
+def test_lockstep_harness_self_check_reference_vs_reference():
+    """tests/lockstep.py (used by the -m gpu model-level test) replays our calls into the reference's modules; run with
+    the reference on BOTH sides it must find zero differences and must have visited every quantizer / operator."""
+    from oracle import ref_model as RM
+    from tests import lockstep
+    r = lockstep.run("reference", "cpu", RM.quant_config())
+    assert r["n_act"] == 18 and r["checked"]["q"] == 18 * 7 and r["checked"]["op"] == 17 * 7
+    assert r["scale_drift"] == 0.0
+    for a, b in zip(r["logits"], r["ref_logits"]):
+        assert torch.equal(a, b)
