@@ -275,6 +275,126 @@ def build_stack(device):
     return layers, acts, outs, ops
 
 
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 5: observer-only sweep, AvgPruneMinMax over synthetic [256, 2048, 4096] fp32 activations processed as 8
+# calibration batches of [32, 2048, 4096] (1 GiB each), p = 0.99, pad mask in-kernel.  Batch i belongs to rank i mod N;
+# ONE all-reduce of the slot table, ONE replay launch (dist.py).  The state after the pass must be bit-identical for any N.
+# ---------------------------------------------------------------------------------------------
+def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
+    from outlier_suppression_b200 import ops
+    from outlier_suppression_b200.dist import my_batches, sharded_calibration
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer
+    OB, OS, OF, NB = 32, 2048, 4096, 8
+    mine = my_batches(NB, rank, world)
+    slabs = {}
+    for i in mine:  # deterministic per batch index, so every N sees the same 8 batches (1 GiB each: far beyond L2)
+        g = torch.Generator(device=device).manual_seed(500 + i)
+        x = torch.randn(OB, OS, OF, generator=g, device=device)
+        x[..., :6] *= 30.0
+        slabs[i] = x
+    lens = torch.randint(OS // 4, OS + 1, (OB,), generator=torch.Generator().manual_seed(77))
+    lens[0] = OS
+    valid_tokens = int(lens.sum())
+    lens = lens.to(device)
+    net = torch.nn.Module()
+    net.x_act_fake_quant = Quantizer(None, A_QCFG).to(device)
+    q = net.x_act_fake_quant
+    q.observer.set_name("x"); q.observer.set_percentile(0.99); q.enable_observer()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def one_pass(timed=False):
+        q.observer.cnt = 0
+        q.observer.min_val.fill_(float("inf")); q.observer.max_val.fill_(float("-inf"))
+        if timed:
+            e[0].record()
+        with sharded_calibration(net, NB) as ctl:
+            for i in mine:
+                ctl.set_batch(i)
+                q(slabs[i], lens, 1)
+            if timed:
+                e[1].record()
+        if timed:
+            e[2].record()
+
+    for _ in range(3):
+        one_pass()
+    torch.cuda.synchronize()
+    t_pass, t_tail = [], []
+    for _ in range(reps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        one_pass(timed=True)
+        torch.cuda.synchronize()
+        t_pass.append(e[0].elapsed_time(e[2])); t_tail.append(e[1].elapsed_time(e[2]))
+    ms, tail = statistics.median(t_pass), statistics.median(t_tail)
+    if dist is not None:
+        t = torch.tensor([ms, tail], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, tail = float(t[0]), float(t[1])
+    state = [float(q.observer.min_val), float(q.observer.max_val), float(q.scale.data), float(q.zero_point.data)]
+    same_on_all_ranks = True
+    if dist is not None:
+        st = torch.tensor(state, dtype=torch.float64, device=device)
+        lo, hi = st.clone(), st.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same_on_all_ranks = bool(torch.equal(lo, hi))
+    # the HBM-bound kernel alone (per-token pass over one slab), CUDA events around single launches
+    evs = []
+    for r in range(6):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.token_minmax(slabs[mine[r % len(mine)]], lens, 1); b_.record(); evs.append((a, b_))
+    torch.cuda.synchronize()
+    k_ms = statistics.median(x.elapsed_time(y) for x, y in evs[2:])
+    valid_bytes = 4.0 * valid_tokens * OF                        # algorithmic: one read of every valid token (pad rows are skipped)
+    gbs_pass = NB * valid_bytes / (ms * 1e-3) / 1e9 / world      # per-GPU rate: each GPU reads NB / world slabs
+    return {"workload": "AvgPruneMinMax p=.99 over [256,2048,4096] fp32 as 8 batches of [32,2048,4096], batch i on rank i mod N",
+            "n_gpus": world, "ms_per_pass": ms, "ms_collective_and_replay": tail,
+            "value": NB * valid_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s of valid-token bytes, whole job",
+            "per_gpu_gbs": gbs_pass, "frac_of_hbm_peak": gbs_pass / peak, "peak": peak, "peak_source": peak_src,
+            "valid_token_fraction": valid_tokens / (OB * OS),
+            "token_minmax_kernel": {"ms_per_slab": k_ms, "gbs_valid": valid_bytes / (k_ms * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": valid_bytes / (k_ms * 1e-3) / 1e9 / peak},
+            "launches_per_batch": 2, "collective": "one all_reduce(SUM) of the [n_obs, 8, 2] slot table + one replay launch",
+            "state": state, "state_identical_on_all_ranks": same_on_all_ranks}
+
+
+def bart_large_sites(device, ops, peak, m_tokens=4096):
+    """BASELINE config 4 (BART-large XSum, eval batch 4 x 1024 source tokens per GPU, 6-bit): the encoder layer's fused sites
+    (q|k|v 1024->3072 grouped, out 1024->1024, fc1 1024->4096, fc2 4096->1024) at the per-GPU eval size."""
+    out = {}
+    g = torch.Generator(device=device).manual_seed(3)
+    for name, k, n in (("qkv", 1024, 3072), ("out", 1024, 1024), ("fc1", 1024, 4096), ("fc2", 4096, 1024)):
+        acts = [torch.randn(m_tokens, k, generator=g, device=device) for _ in range(max(2, int(160e6 // (m_tokens * k * 4)) + 1))]
+        ys = [torch.empty(m_tokens, n, device=device) for _ in range(len(acts))]
+        w = torch.randn(n, k, generator=g, device=device) * 0.05
+        ws = (w.abs().amax(1) / 31.5).clamp_min(1e-8)
+        codes, rowsum = ops.pack_weight(w, ws, torch.zeros(n, dtype=torch.int32, device=device), -32, 31)
+        bias = torch.zeros(n, device=device)
+        sc, zp = torch.tensor([0.12], device=device), torch.tensor([31.0], device=device)
+        def chain():
+            for a, y in zip(acts, ys):
+                ops.fused_fq_linear(a, sc, zp, 0, 63, codes, ws, rowsum, bias, lsq_grad_factor=1e-3, out=y)
+        chain(); torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(4):
+                chain()
+        gr.replay()
+        evs = []
+        for _ in range(5):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(); gr.replay(); b_.record(); evs.append((a_, b_))
+        torch.cuda.synchronize()
+        us = statistics.median(x.elapsed_time(y) for x, y in evs) / (4 * len(acts)) * 1e3
+        by = 4 * m_tokens * k + 4 * m_tokens * n + n * k + 12 * n
+        out[name] = {"K": k, "N": n, "us": us, "bytes": by, "frac_of_hbm_peak": by / (us * 1e-6) / 1e9 / peak}
+    layer_us = sum(v["us"] for v in out.values())
+    return {"workload": "BART-large encoder layer sites at the per-GPU eval batch of config 4 (M = 4 x 1024 tokens), 6-bit",
+            "M": m_tokens, "sites": out, "us_per_layer": layer_us, "tokens_per_s_12_layers": m_tokens / (12 * layer_us * 1e-6)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,6 +405,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python launch loop instead of CUDA graph replay")
     ap.add_argument("--no-group", action="store_true", help="launch q, k and v separately (72 launches per step)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 observer sweep and the config-4 site timings")
     ap.add_argument("--only-value", action="store_true", help="profiling runs: timed stack only, no roofline/e2e/cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -489,6 +610,14 @@ def main():
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "error": repr(ex)}
 
+    sweep_rec = bart_rec = None
+    if not args.no_sweep:
+        try:
+            bart_rec = bart_large_sites(device, ops, peak) if rank == 0 else None
+            sweep_rec = observer_sweep(device, rank, world, dist, peak, peak_src)
+        except Exception as ex:  # pragma: no cover
+            sweep_rec = {"error": repr(ex)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_record(args.cpu_reps)
@@ -501,7 +630,7 @@ def main():
                "launch": {"mode": launch_mode, "host_issue_ms_per_step": host_issue_ms, "fused_launches_per_step": LAYERS * len(order),
                           "grouping": "none" if args.no_group else "q|k|v of a layer share one launch"},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * LAYERS * len(order),
-               "clocks": clocks}
+               "clocks": clocks, "observer_sweep": sweep_rec, "config4_bart_large": bart_rec}
         print(json.dumps(rec))
     if dist is not None:
         dist.destroy_process_group()

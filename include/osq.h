@@ -135,6 +135,41 @@ int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t 
                                   const int32_t* n_valid, float percentile, float* cur_minmax,
                                   const osq_stat_epilogue_t* epi, void* workspace, void* stream);
 
+
+/* K4c the whole AvgPruneMinMaxObserver step (observer.py:50-70,214-237) as two back-to-back launches: the per-token
+ *     pass of K4a, then -- by programmatic dependent launch -- ONE thread-block cluster that keeps the [T] vectors in
+ *     (distributed) shared memory and runs the exact radix select for rank lo and lo+1 of |tmax| and |tmin|, the clip /
+ *     aminmax and the running-statistics epilogue from there.  Bit-identical to K4a + K4b'.  tmin / tmax ([B*S] fp32)
+ *     and n_valid (int32[1]) are caller-owned scratch.  Up to 8 x 24576 tokens per call; longer vectors take K4b'. */
+int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float percentile,
+                          float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
+                          const osq_stat_epilogue_t* epi, void* workspace, void* stream);
+
+/* AvgQuantileObserver.forward (observer.py:253-282) in two launches: K3 (masked min/max -> cur_minmax), then a histogram
+ * of |x| over the valid tokens in `bins` equal bins of [0, R], R = max(-min, max) (ATen CPU histc binning, fp32), the
+ * reference's sequential cumulative scan (`cur_total + cnt >= threshold * numel`, compared in fp32), the clip of
+ * (min, max) to +-(i + 0.5) * R / bins and the running average / qparams of `epi`.  hist: caller-owned uint32[bins],
+ * zero-initialised once (the kernel re-arms it).  bins <= 8192. */
+int osq_quantile_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, int bins,
+                             double threshold, uint32_t* hist, float* cur_minmax, const osq_stat_epilogue_t* epi,
+                             void* workspace, void* stream);
+
+/* Rank-sharded calibration (no counterpart in the reference, which is single-GPU): replays the running average of
+ * observer.py:194-202 over a slot table [n_obs, n_batches, 2] (per-batch (min, max) of every observer, summed across ranks
+ * by ONE all-reduce) in batch order, one thread per observer, and rewrites every observer's state and its quantizer's
+ * (scale, zero_point) (observer.py:100-119) through `targets` (device array) -- no host round trip. */
+typedef struct {
+  float* state_min;   /* [1] device: observer.min_val (updated in place; +-inf = no batch seen yet) */
+  float* state_max;   /* [1] device: observer.max_val */
+  float* scale_out;   /* [1] device or NULL */
+  void* zp_out;       /* [1] device or NULL */
+  int zp_out_is_int32;
+  int qmin, qmax, symmetric;
+} osq_replay_target_t;
+
+int osq_replay_average_f32(const float* table, int n_obs, int n_batches, int cnt0, const osq_replay_target_t* targets,
+                           void* stream);
+
 /* per-row min/max of a [rows, cols] matrix with the running-extrema update of
  * MinMaxObserver(ch_axis=0) (observer.py:141-144) and per-row calculate_qparams.
  * state_min/state_max [rows] are updated in place (first = 1 overwrites them). */

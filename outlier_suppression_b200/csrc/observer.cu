@@ -574,6 +574,327 @@ prune_apply_kernel(const float* __restrict__ tmin, const float* __restrict__ tma
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K4c: the whole token-pruning tail as ONE thread-block cluster with the [T] vectors resident in (distributed) shared
+// memory -- the path AvgPruneMinMaxObserver takes (observer.py:50-70 run ~94 k times by token-wise clipping).
+//
+// Launched right behind token_minmax_kernel with programmatic dependent launch, so its CTAs are already resident and
+// parked on griddepcontrol.wait when the per-token pass drains.  Every CTA of the cluster copies its slice of
+// tmin / tmax (<= kSliceMax tokens, two fp32 vectors) from L2 into shared memory ONCE; the exact radix select then
+// sweeps shared memory only: three digit passes (11 + 11 + 9 bits of the fp32 pattern of |v|) that track FOUR order
+// statistics at once -- rank lo and rank lo+1 (the pair torch.quantile's lerp needs) of |tmax| and of |tmin| --
+// followed by one clip / aminmax sweep and the running-statistics epilogue.  Histograms of the CTAs are merged in CTA
+// 0's shared memory with DSMEM atomics (only non-empty bins travel) between hardware cluster barriers.
+// With one CTA (T <= 24576: every BERT-base / RoBERTa-base shape up to 48 x 512 tokens) there is no inter-CTA traffic.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 1024;
+constexpr int kSelBins = 2048;
+constexpr int kSliceMax = 24576;       // tokens per CTA: 2 x 96 KB of shared memory
+constexpr int kSelMaxCluster = 8;      // portable cluster size -> up to 196608 tokens per observer call
+
+struct SelTarget {          // one order statistic being selected
+  unsigned int prefix;      // bits fixed so far
+  unsigned int krem;        // rank inside the candidates that match the prefix
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_atomic_add(uint32_t cluster_addr, unsigned int v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int dsmem_ld_u32(uint32_t cluster_addr) {
+  unsigned int v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsmem_st_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+// first bin b of hist[0..kSelBins) with (sum of bins below b) + hist[b] > krem; executed by one full warp
+__device__ __forceinline__ void warp_pick_bin_wide(const unsigned int* hist, unsigned int krem, unsigned int& bin, unsigned int& below) {
+  const int lane = threadIdx.x & 31;
+  constexpr int kPer = kSelBins / 32;  // 64 consecutive bins per lane
+  unsigned int sum = 0;
+  for (int j = 0; j < kPer; ++j) sum += hist[lane * kPer + j];
+  unsigned int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned int vote = __ballot_sync(0xffffffffu, incl > krem);
+  const int src = vote ? __ffs(vote) - 1 : 31;
+  unsigned int acc = incl - sum, pick = lane * kPer + kPer - 1, run = incl - sum;
+  bool found = false;
+  for (int j = 0; j < kPer; ++j) {
+    const unsigned int h = hist[lane * kPer + j];
+    if (!found && run + h > krem) { pick = lane * kPer + j; acc = run; found = true; }
+    run += h;
+  }
+  bin = __shfl_sync(0xffffffffu, pick, src);
+  below = __shfl_sync(0xffffffffu, acc, src);
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+prune_select_cluster_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
+                            const int32_t* __restrict__ n_valid, float percentile, float* __restrict__ cur,
+                            osq_stat_epilogue_t epi) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  __shared__ SelTarget tg[4];        // [side * 2 + which]: side 0 = |tmax|, 1 = |tmin|; which 0 = rank lo, 1 = rank lo + 1
+  __shared__ float part[2][kSelMaxCluster];
+  __shared__ float red[2][32];
+  const uint32_t rank = cluster_ctarank(), nct = cluster_nctarank();
+  const int64_t per = (n_slots + nct - 1) / nct;
+  const int64_t begin = (int64_t)rank * per;
+  const int cnt = (int)max((int64_t)0, min(per, n_slots - begin));
+  float* vmax = reinterpret_cast<float*>(sel_smem);
+  float* vmin = vmax + kSliceMax;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(vmin + kSliceMax);  // [4][kSelBins]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // token_minmax_kernel's tmin / tmax / n_valid are complete and visible
+  const int T = *n_valid;
+  // ---- slice -> shared memory (the only global read of the [T] vectors); invalid tokens keep (+inf, -inf) ----
+  for (int i = tid; i < cnt; i += kSelThreads) {
+    vmax[i] = __ldcg(tmax + begin + i);
+    vmin[i] = __ldcg(tmin + begin + i);
+  }
+  const float frank = __fmul_rn(percentile, (float)(T > 0 ? T - 1 : 0));   // torch.quantile: rank = p * (T - 1) in fp32
+  const int lo = (int)frank;
+  const bool need_pair = (int)ceilf(frank) != lo;
+  const unsigned int k1 = (unsigned int)((lo + 1 < T) ? lo + 1 : lo);
+  if (tid < 4) { tg[tid].prefix = 0u; tg[tid].krem = (tid & 1) ? k1 : (unsigned int)lo; }
+  __syncthreads();
+  float thr_up = INFINITY, thr_lo = -INFINITY;
+  if (T > 0) {
+    const int shifts[3] = {20, 9, 0};
+    const unsigned int widths[3] = {11, 11, 9};
+    unsigned int mask = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+      const int sh = shifts[pass];
+      const unsigned int dm = (1u << widths[pass]) - 1u;
+      for (int i = tid; i < 4 * kSelBins; i += kSelThreads) hist[i] = 0;
+      __syncthreads();
+      const SelTarget t0 = tg[0], t1 = tg[1], t2 = tg[2], t3 = tg[3];
+      const bool same_mx = t0.prefix == t1.prefix, same_mn = t2.prefix == t3.prefix;
+      for (int i = tid; i < cnt; i += kSelThreads) {
+        const float a = vmin[i], b = vmax[i];
+        const bool ok = a <= b;
+        const unsigned int ub = __float_as_uint(fabsf(b)), ua = __float_as_uint(fabsf(a));
+        const unsigned int db = (ub >> sh) & dm, da = (ua >> sh) & dm;
+        if (pass == 0) {  // leading digits are almost constant: aggregate equal digits inside the warp first
+          const unsigned int kb = ok ? db : 0xFFFFFFFFu, ka = ok ? da : 0xFFFFFFFFu;
+          const unsigned int pb = __match_any_sync(__activemask(), kb);
+          if (ok && lane == __ffs(pb) - 1) atomicAdd(&hist[db], (unsigned int)__popc(pb));
+          const unsigned int pa = __match_any_sync(__activemask(), ka);
+          if (ok && lane == __ffs(pa) - 1) atomicAdd(&hist[2 * kSelBins + da], (unsigned int)__popc(pa));
+        } else if (ok) {
+          if ((ub & mask) == t0.prefix) atomicAdd(&hist[db], 1u);
+          if (!same_mx && (ub & mask) == t1.prefix) atomicAdd(&hist[kSelBins + db], 1u);
+          if ((ua & mask) == t2.prefix) atomicAdd(&hist[2 * kSelBins + da], 1u);
+          if (!same_mn && (ua & mask) == t3.prefix) atomicAdd(&hist[3 * kSelBins + da], 1u);
+        }
+      }
+      __syncthreads();
+      if (nct > 1) {
+        // merge into CTA 0: the other CTAs add their non-empty bins into its histograms through DSMEM
+        cluster_sync_all();                      // CTA 0 has finished its own sweep (its counts are in place)
+        if (rank != 0) {
+          const uint32_t base = map_to_cta(smem_addr(hist), 0);
+          for (int i = tid; i < 4 * kSelBins; i += kSelThreads) {
+            const unsigned int c = hist[i];
+            if (c) dsmem_atomic_add(base + 4u * i, c);
+          }
+        }
+        cluster_sync_all();
+      }
+      if (rank == 0 && warp < 4) {
+        const int side = warp >> 1;
+        const bool same = side ? same_mn : same_mx;
+        const unsigned int* h = hist + ((same ? (warp & ~1) : warp) * kSelBins);
+        unsigned int bin, below;
+        warp_pick_bin_wide(h, tg[warp].krem, bin, below);
+        __syncwarp();
+        if (lane == 0) { tg[warp].prefix |= bin << sh; tg[warp].krem -= below; }
+      }
+      __syncthreads();
+      if (nct > 1) {
+        cluster_sync_all();                      // CTA 0's targets are final for this pass
+        if (rank != 0 && tid < 8) {
+          const uint32_t src = map_to_cta(smem_addr(&tg[0]), 0);
+          reinterpret_cast<unsigned int*>(&tg[0])[tid] = dsmem_ld_u32(src + 4u * tid);
+        }
+        __syncthreads();
+        cluster_sync_all();                      // everyone has read them before CTA 0 may change them again
+      }
+      mask |= dm << sh;
+    }
+    const float a_mx = __uint_as_float(tg[0].prefix), b_mx = __uint_as_float(tg[1].prefix);
+    const float a_mn = __uint_as_float(tg[2].prefix), b_mn = __uint_as_float(tg[3].prefix);
+    thr_up = quantile_from_pair(a_mx, need_pair ? b_mx : a_mx, frank, lo);
+    thr_lo = -quantile_from_pair(a_mn, need_pair ? b_mn : a_mn, frank, lo);
+  }
+  // ---- clip + aminmax over the kept tokens (observer.py:66-69, 227) ----
+  float lower = INFINITY, upper = -INFINITY;
+  if (T > 0)
+    for (int i = tid; i < cnt; i += kSelThreads) {
+      const float a = vmin[i], b = vmax[i];
+      if (a <= b) {
+        if (b <= thr_up) upper = fmaxf(upper, b);
+        if (a >= thr_lo) lower = fminf(lower, a);
+      }
+    }
+  lower = warp_min(lower);
+  upper = warp_max(upper);
+  if (lane == 0) { red[0][warp] = lower; red[1][warp] = upper; }
+  __syncthreads();
+  if (warp == 0) {
+    lower = warp_min(red[0][lane]);
+    upper = warp_max(red[1][lane]);
+    if (lane == 0) {
+      if (nct > 1) {
+        dsmem_st_f32(map_to_cta(smem_addr(&part[0][rank]), 0), lower);
+        dsmem_st_f32(map_to_cta(smem_addr(&part[1][rank]), 0), upper);
+      } else {
+        part[0][0] = lower;
+        part[1][0] = upper;
+      }
+    }
+  }
+  if (nct > 1) cluster_sync_all(); else __syncthreads();
+  if (rank == 0 && tid == 0) {
+    lower = INFINITY; upper = -INFINITY;
+    for (uint32_t c = 0; c < nct; ++c) { lower = fminf(lower, part[0][c]); upper = fmaxf(upper, part[1][c]); }
+    cur[0] = lower;
+    cur[1] = upper;
+    stat_epilogue(epi, lower, upper);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// AvgQuantileObserver (observer.py:253-282): histogram of |x| over the valid tokens in `bins` equal bins of [0, R],
+// R = max(-min, max); first bin whose cumulative count reaches threshold * numel; clip; running average.
+// Second launch of the observer (the first is K3, which leaves (min, max) in cur[]).  Binning follows ATen's CPU histc
+// (probed on torch 2.11: pos = int((|x| * bins) / R) in fp32, the right edge falls into the last bin); the cumulative
+// scan and its comparison run in fp32 like the reference's Python loop over an fp32 histogram.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxQuantileBins = 8192;
+
+__device__ __forceinline__ void hist_abs_run(const float* __restrict__ p, int64_t len, int64_t stride, int lane, float fb, float R,
+                                             int bins, unsigned int* hist) {
+  for (int64_t j = lane; j < len; j += 32) {
+    const float a = fabsf(__ldg(p + j * stride));
+    if (!(a <= R)) continue;  // NaN (histc skips it)
+    int pos = (int)__fdiv_rn(__fmul_rn(a, fb), R);
+    if (pos >= bins) pos = bins - 1;
+    atomicAdd(&hist[pos], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(kObsThreads)
+abs_hist_kernel(const float* __restrict__ x, osq_tokens_t tk, const int64_t* __restrict__ lens, int n_lens, int bins,
+                double threshold, unsigned int* __restrict__ ghist, float* __restrict__ cur, osq_stat_epilogue_t epi,
+                void* wsp) {
+  extern __shared__ unsigned int shist[];
+  const int lane = threadIdx.x & 31;
+  const float mn0 = cur[0], mx0 = cur[1];
+  const float R = fmaxf(-mn0, mx0);
+  const float fb = (float)bins;
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) shist[i] = 0;
+  __syncthreads();
+  const int64_t warp_global = (int64_t)blockIdx.x * kObsWarps + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * kObsWarps;
+  const int64_t n_seg = tk.B * tk.S * tk.F1;
+  for (int64_t seg = warp_global; seg < n_seg; seg += n_warps) {
+    const int64_t f1 = seg % tk.F1;
+    const int64_t bs = seg / tk.F1;
+    const int64_t s_ = bs % tk.S, b = bs / tk.S;
+    if (!token_valid(lens, n_lens, b, s_)) continue;
+    hist_abs_run(x + b * tk.sb + s_ * tk.ss + f1 * tk.sf1, tk.F2, tk.sf2, lane, fb, R, bins, shist);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+    const unsigned int c = shist[i];
+    if (c) atomicAdd(&ghist[i], c);
+  }
+  Partials ws = carve(wsp);
+  if (!last_cta(ws.ticket)) return;
+  // ---- last CTA: the reference's sequential scan, then clip + running average + qparams ----
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) { shist[i] = __ldcg(&ghist[i]); ghist[i] = 0; }  // read + re-arm
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *ws.ticket = 0;
+    int64_t tokens = 0;
+    if (lens == nullptr) tokens = tk.B * tk.S;
+    else
+      for (int64_t b = 0; b < tk.B && b < n_lens; ++b) {
+        const int64_t l = lens[b];
+        tokens += l < 0 ? 0 : (l > tk.S ? tk.S : l);
+      }
+    const double numel = (double)(tokens * tk.F1 * tk.F2);
+    const float need = (float)(threshold * numel);   // a fp32 tensor compared with a Python float compares in fp32
+    float total = 0.f, clip = R;
+    for (int i = 0; i < bins; ++i) {
+      const float c = (float)shist[i];
+      if (__fadd_rn(total, c) >= need) {
+        clip = __fmul_rn((float)i + 0.5f, __fdiv_rn(R, fb));
+        break;
+      }
+      total = __fadd_rn(total, c);
+    }
+    const float lo = (-clip > mn0) ? -clip : mn0;   // Python max(min_val_cur, -clip_value)
+    const float hi = (clip < mx0) ? clip : mx0;     // Python min(max_val_cur, clip_value)
+    cur[0] = lo;
+    cur[1] = hi;
+    stat_epilogue(epi, lo, hi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rank-sharded calibration (dist.py): after the one all-reduce of the slot table [n_obs, n_batches, 2] every rank
+// replays observer.py:194-202  m <- (m*cnt + cur)/(cnt+1)  in batch order for ALL observers in one launch (one thread per
+// observer) and refreshes every owning quantizer's (scale, zero_point) through a pointer table -- no host round trip.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+replay_average_kernel(const float* __restrict__ table, int n_obs, int n_batches, int cnt0, const osq_replay_target_t* __restrict__ tgt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_obs) return;
+  osq_replay_target_t t = tgt[i];
+  osq_stat_epilogue_t e;
+  e.mode = 1;
+  e.state_min = t.state_min;
+  e.state_max = t.state_max;
+  e.scale_out = nullptr;   // qparams once, after the last batch
+  e.zp_out = nullptr;
+  e.zp_out_is_int32 = t.zp_out_is_int32;
+  e.qmin = t.qmin; e.qmax = t.qmax; e.symmetric = t.symmetric;
+  for (int b = 0; b < n_batches; ++b) {
+    e.cnt = cnt0 + b;
+    if (b == n_batches - 1) { e.scale_out = t.scale_out; e.zp_out = t.zp_out; }
+    stat_epilogue(e, table[((int64_t)i * n_batches + b) * 2], table[((int64_t)i * n_batches + b) * 2 + 1]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-row min/max + running extrema + per-row qparams (weights, MinMaxObserver ch_axis=0)
 // ---------------------------------------------------------------------------------------------
@@ -704,6 +1025,80 @@ int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t 
   int64_t g2 = (n_slots + kObsThreads * 4 - 1) / (kObsThreads * 4);
   if (g2 > sms) g2 = sms;
   prune_apply_kernel<<<(int)g2, kObsThreads, 0, st>>>(tmin, tmax, n_slots, n_valid, sw, cur_minmax, *epi, workspace);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+
+int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float percentile,
+                          float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
+                          const osq_stat_epilogue_t* epi, void* workspace, void* stream) {
+  using namespace osq;
+  if (int rc = check_tokens(tok, "osq_prune_observe_f32")) return rc;
+  OSQ_CHECK_ARG(x && tmin && tmax && n_valid && cur_minmax && epi && workspace, "osq_prune_observe_f32: null pointer");
+  OSQ_CHECK_ARG(percentile >= 0.f && percentile <= 1.f, "osq_prune_observe_f32: percentile outside [0,1]");
+  const int64_t n_slots = tok->B * tok->S;
+  OSQ_CHECK_ARG(n_slots > 0 && n_slots < (int64_t)INT32_MAX, "osq_prune_observe_f32: token count out of range");
+  int grid = reduction_grid(n_slots);
+  if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  token_minmax_kernel<<<grid, kObsThreads, 0, st>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid);
+  OSQ_LAUNCH_CHECK();
+  const int64_t nct = (n_slots + kSliceMax - 1) / kSliceMax;
+  if (nct > kSelMaxCluster)  // longer than a cluster's shared memory: the multi-launch radix select over L2
+    return osq_prune_select_unsorted_f32(tmin, tmax, n_slots, n_valid, percentile, cur_minmax, epi, workspace, stream);
+  const size_t smem = (size_t)2 * kSliceMax * 4 + (size_t)4 * kSelBins * 4;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OSQ_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    OSQ_CUDA(cudaFuncSetAttribute(prune_select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev & 63] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)nct, 1, 1);
+  cfg.blockDim = dim3(kSelThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)nct;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // park behind the per-token pass (griddepcontrol.wait)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  OSQ_CUDA(cudaLaunchKernelEx(&cfg, prune_select_cluster_kernel, (const float*)tmin, (const float*)tmax, n_slots,
+                              (const int32_t*)n_valid, percentile, cur_minmax, *epi));
+  return OSQ_OK;
+}
+
+int osq_quantile_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, int bins,
+                             double threshold, uint32_t* hist, float* cur_minmax, const osq_stat_epilogue_t* epi,
+                             void* workspace, void* stream) {
+  using namespace osq;
+  if (int rc = check_tokens(tok, "osq_quantile_observe_f32")) return rc;
+  OSQ_CHECK_ARG(x && hist && cur_minmax && epi && workspace, "osq_quantile_observe_f32: null pointer");
+  OSQ_CHECK_ARG(bins >= 1 && bins <= kMaxQuantileBins, "osq_quantile_observe_f32: bins must be in [1, 8192]");
+  OSQ_CHECK_ARG(threshold >= 0.0 && threshold <= 1.0, "osq_quantile_observe_f32: threshold outside [0,1]");
+  int grid = reduction_grid(tok->B * tok->S * tok->F1);
+  if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  osq_stat_epilogue_t none = *epi;
+  none.mode = 0;
+  minmax_masked_kernel<<<grid, kObsThreads, 0, st>>>(x, *tok, lens, n_lens, cur_minmax, none, workspace);
+  abs_hist_kernel<<<grid, kObsThreads, (size_t)bins * 4, st>>>(x, *tok, lens, n_lens, bins, threshold, hist, cur_minmax, *epi,
+                                                              workspace);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_replay_average_f32(const float* table, int n_obs, int n_batches, int cnt0, const osq_replay_target_t* targets,
+                           void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(table && targets && n_obs > 0 && n_batches > 0 && cnt0 >= 0, "osq_replay_average_f32: bad argument");
+  replay_average_kernel<<<(n_obs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(table, n_obs, n_batches, cnt0, targets);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

@@ -102,16 +102,29 @@ def sharded_calibration(model, n_batches: int, group=None):
     if not observers:
         return
     table.all_reduce(group)
+    cnt0 = observers[0].cnt
+    if table.buf.is_cuda:
+        # ONE launch replays the recurrence for every observer and rewrites every quantizer's (scale, zero_point)
+        # through a pointer table: no .cpu(), no per-observer launches, no synchronisation
+        entries = []
+        for o, q in zip(observers, owners):
+            o._ensure_scalar_state(device)
+            s_out, z_out = q._per_tensor_qparam_targets()
+            entries.append((o.min_val, o.max_val, s_out, z_out, o.quant_min, o.quant_max, o.symmetric))
+        ops.replay_average(table.buf, cnt0, ops.replay_targets(entries, device))
+        for o, q in zip(observers, owners):
+            o.cnt = cnt0 + n_batches
+            q.qparam_epoch += 1
+        return
+    # host tensors (gloo world, CPU-side tests of the sharding logic): same recurrence in torch ops
     state_min = torch.stack([o.min_val.detach().float().reshape(()) for o in observers])
     state_max = torch.stack([o.max_val.detach().float().reshape(()) for o in observers])
-    cnt0 = observers[0].cnt
     mn, mx, cnt = table.replay(cnt0, state_min, state_max)
-    mn, mx = mn.to(device), mx.to(device)
     for i, (o, q) in enumerate(zip(observers, owners)):
         o.min_val = mn[i].clone()
         o.max_val = mx[i].clone()
         o.cnt = cnt
-        scale, zp = ops.calc_qparams(o.min_val, o.max_val, o.quant_min, o.quant_max, o.symmetric)
+        scale, zp = o.calculate_qparams(o.min_val, o.max_val)
         s_out, z_out = q._per_tensor_qparam_targets()
         s_out.copy_(scale.reshape(s_out.shape))
         z_out.copy_(zp.reshape(z_out.shape).to(z_out.dtype))

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import FusedLinearArgs, StatEpilogue, Tokens, check
+from ._lib import FusedLinearArgs, ReplayTarget, StatEpilogue, Tokens, check
 
 _workspaces = {}
 
@@ -214,11 +214,39 @@ def token_minmax(x, lens, seq_pos):
     return tmin, tmax, n_valid
 
 
+_token_scratch = {}
+
+
+def _token_vectors(device, n: int):
+    """per-(device, stream) scratch for the per-token extrema of one observer call: (tmin[n], tmax[n], n_valid[1]).
+    Grown, never shrunk: the observer runs ~100 k times per calibration and must not hit the allocator."""
+    key = (torch.device(device).index, _stream())
+    buf = _token_scratch.get(key)
+    if buf is None or buf[0].numel() < 2 * n:
+        cap = max(2 * n, 1 << 16)
+        buf = (torch.empty(cap, dtype=torch.float32, device=device), torch.empty(1, dtype=torch.int32, device=device))
+        _token_scratch[key] = buf
+    return buf[0][:n], buf[0][n:2 * n], buf[1]
+
+
 def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
-                         scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None, use_sort=False) -> torch.Tensor:
+                         scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None, use_sort=False,
+                         legacy_select=False) -> torch.Tensor:
     """AvgPruneMinMaxObserver's token pruning (observer.py:50-70,214-237): one pass over the activation (per-token
-    extrema), then the exact radix select + clip selection + running statistics on the [T] vectors (one launch up
-    to 32768 tokens, six small multi-CTA launches above)."""
+    extrema) and, parked behind it by programmatic dependent launch, one thread-block cluster that keeps the [T]
+    vectors in shared memory for the exact radix select + clip selection + running statistics
+    (osq_prune_observe_f32).  ``legacy_select`` / ``use_sort`` run the earlier L2-resident select paths (cross-checks)."""
+    if not (use_sort or legacy_select):
+        x = _prep_act(x)
+        tok = token_geometry(x, seq_pos)
+        tmin, tmax, n_valid = _token_vectors(x.device, tok.B * tok.S)
+        cur = _cur_out(out, x.device)
+        epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
+        lens_t, n_lens = _lens_arg(lens, x.device)
+        check(_lib.load().osq_prune_observe_f32(x.data_ptr(), C.byref(tok), _ptr(lens_t), n_lens, float(percentile),
+                                                tmin.data_ptr(), tmax.data_ptr(), n_valid.data_ptr(), cur.data_ptr(),
+                                                C.byref(epi), workspace(x.device).data_ptr(), _stream()), "osq_prune_observe_f32")
+        return cur
     tmin, tmax, n_valid = token_minmax(x, lens, seq_pos)
     cur = _cur_out(out, tmin.device)
     epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
@@ -236,6 +264,54 @@ def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0,
                                                         workspace(tmin.device).data_ptr(), _stream()),
               "osq_prune_select_unsorted_f32")
     return cur
+
+
+_hist_scratch = {}
+
+
+def observe_quantile(x, lens, seq_pos, bins, threshold, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
+                     scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None) -> torch.Tensor:
+    """AvgQuantileObserver.forward (observer.py:253-282): masked min/max, |x| histogram, cumulative-threshold clip and
+    the running average in two launches (osq_quantile_observe_f32)."""
+    x = _prep_act(x)
+    if x.dim() >= 3 and seq_pos != -1:
+        tok = token_geometry(x, seq_pos)
+    else:
+        x = x if x.is_contiguous() else x.contiguous()
+        tok = Tokens(1, 1, 1, x.numel(), 0, 0, 0, 1)
+        lens = None
+    key = (x.device.index, _stream(), int(bins))
+    hist = _hist_scratch.get(key)
+    if hist is None:
+        hist = _hist_scratch[key] = torch.zeros(int(bins), dtype=torch.int32, device=x.device)
+    cur = _cur_out(out, x.device)
+    epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
+    lens_t, n_lens = _lens_arg(lens, x.device)
+    check(_lib.load().osq_quantile_observe_f32(x.data_ptr(), C.byref(tok), _ptr(lens_t), n_lens, int(bins), float(threshold),
+                                               hist.data_ptr(), cur.data_ptr(), C.byref(epi), workspace(x.device).data_ptr(),
+                                               _stream()), "osq_quantile_observe_f32")
+    return cur
+
+
+def replay_targets(entries, device) -> torch.Tensor:
+    """Device copy of an osq_replay_target_t array.  entries: (state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
+    per observer (tensors; scale_out / zp_out may be None)."""
+    arr = (ReplayTarget * len(entries))()
+    for t, (mn, mx, s_out, z_out, qmin, qmax, sym) in zip(arr, entries):
+        t.state_min, t.state_max, t.scale_out, t.zp_out = _ptr(mn), _ptr(mx), _ptr(s_out), _ptr(z_out)
+        t.zp_out_is_int32 = int(z_out is not None and z_out.dtype == torch.int32)
+        t.qmin, t.qmax, t.symmetric = int(qmin), int(qmax), int(bool(sym))
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return raw.to(device)
+
+
+def replay_average(table: torch.Tensor, cnt0: int, targets: torch.Tensor) -> None:
+    """observer.py:194-202 replayed over the all-reduced slot table [n_obs, n_batches, 2] for every observer in one launch."""
+    _require_cuda(table, targets)
+    n_obs, n_batches = table.shape[0], table.shape[1]
+    assert table.is_contiguous() and table.dtype == torch.float32
+    check(_lib.load().osq_replay_average_f32(table.data_ptr(), n_obs, n_batches, int(cnt0), targets.data_ptr(), _stream()),
+          "osq_replay_average_f32")
 
 
 def rowwise_minmax_qparams(w, first, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric):

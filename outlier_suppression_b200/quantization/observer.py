@@ -341,7 +341,8 @@ class LSQPlusObserver(ObserverBase):
 
 
 class AvgQuantileObserver(ObserverBase):
-    """Histogram-quantile clipping averaged over batches (observer.py:240-282)."""
+    """Histogram-quantile clipping averaged over batches (observer.py:240-282): masked min/max, the |x| histogram, the
+    cumulative-threshold clip and the running average run on the device in two launches (osq_quantile_observe_f32)."""
 
     def __init__(self, bit=8, symmetric=False, ch_axis=-1, ema_ratio=0.9, threshold=0.99999, bins=2048):
         super().__init__(bit=bit, symmetric=symmetric, ch_axis=ch_axis)
@@ -350,22 +351,12 @@ class AvgQuantileObserver(ObserverBase):
 
     def _observe(self, x, observation_mask, seq_pos, quantizer=None):
         self._ensure_scalar_state(x.device)
-        v = _valid_tokens(x.detach().float(), observation_mask, seq_pos)
-        mn, mx = torch.aminmax(v)
-        top = torch.max(-mn, mx)
-        hist = torch.histc(v.abs(), bins=self.bins, min=0.0, max=float(top))
-        over = torch.nonzero(torch.cumsum(hist, 0) >= self.threshold * v.numel())
-        clip = (over[0, 0].float() + 0.5) * (top / self.bins) if over.numel() else top
-        mn, mx = torch.max(mn, -clip), torch.min(mx, clip)
-        if bool(self.max_val.isinf()):
-            self.min_val, self.max_val = mn, mx
-        else:
-            self.min_val = self.min_val * self.cnt + mn
-            self.max_val = self.max_val * self.cnt + mx
+        s_out, z_out = self._fused_targets(quantizer)
+        ops.observe_quantile(x.detach(), observation_mask, seq_pos, self.bins, self.threshold, mode=ops.STAT_AVERAGE,
+                             cnt=self.cnt, state_min=self.min_val, state_max=self.max_val, scale_out=s_out, zp_out=z_out,
+                             qmin=self.quant_min, qmax=self.quant_max, symmetric=self.symmetric)
         self.cnt += 1
-        self.min_val = self.min_val / self.cnt
-        self.max_val = self.max_val / self.cnt
-        return False
+        return s_out is not None
 
 
 class MSEObserver(ObserverBase):

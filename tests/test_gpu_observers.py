@@ -107,9 +107,98 @@ def test_long_token_vectors_multi_cta_select():
                 same(first, torch.stack([lo, hi]))
                 same(ops.observe_prune_minmax(xg, lg, 1, p), first)
                 same(ops.observe_prune_minmax(xg, lg, 1, p, use_sort=True), first)
+                same(ops.observe_prune_minmax(xg, lg, 1, p, legacy_select=True), first)   # six-launch select over L2
     # all tokens masked out on the long path
     z = ops.observe_prune_minmax(xg, torch.zeros(300, dtype=torch.int64, device="cuda"), 1, 0.99)
     assert float(z[0]) == float("inf") and float(z[1]) == float("-inf")
+
+
+def test_cluster_select_sizes_and_fallback():
+    """The shared-memory cluster select (osq_prune_observe_f32) at every cluster size 1..8, at slice boundaries, and the
+    fall-back to the multi-launch select beyond 8 x 24576 tokens -- all bit-identical to torch.quantile on the CPU."""
+    from outlier_suppression_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    for n_tok in (1, 2, 31, 1000, 24576, 24577, 49152, 60000, 100000, 196608, 196609, 250000):
+        x = torch.randn(1, n_tok, 8, generator=g) * torch.rand(1, n_tok, 1, generator=g).mul(5).exp()
+        if n_tok % 2 == 0:
+            x = (x * 4).round() / 4          # duplicates around the selected ranks
+        tok = O.token_matrix(x, None, 1)
+        tmin, tmax = O.token_minmax(tok)
+        xg = x.cuda()
+        for p in (0.99, 0.5, 1.0, 0.0, 0.999):
+            lo, hi = O.prune_bounds(tmin, tmax, p)
+            same(ops.observe_prune_minmax(xg, None, 1, p), torch.stack([lo, hi]))
+    # ragged mask whose valid tokens all sit in the LAST cluster slice
+    x = torch.randn(6, 10000, 8, generator=g)
+    lens = torch.tensor([0, 0, 0, 0, 0, 7777])
+    lo, hi = O.prune_minmax(O.token_matrix(x, lens.tolist(), 1), 0.9)
+    same(ops.observe_prune_minmax(x.cuda(), lens.cuda(), 1, 0.9), torch.stack([lo, hi]))
+
+
+def test_config5_slab_bit_exact():
+    """BASELINE config 5: one [32, 2048, 4096] fp32 slab (1 GiB, 65536 tokens -> a cluster of 3 CTAs) of the observer
+    sweep, AvgPruneMinMax p = 0.99 with the pad mask, against the CPU oracle -- the size bench.py's observer_sweep times."""
+    from outlier_suppression_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(32, 2048, 4096, generator=g, device="cuda")
+    x[..., :6] *= 30.0
+    lens = torch.randint(512, 2049, (32,), generator=torch.Generator().manual_seed(1))
+    lens[0] = 2048
+    cur = ops.observe_prune_minmax(x, lens.cuda(), 1, 0.99).cpu()
+    gmin, gmax, nv = ops.token_minmax(x, lens.cuda(), 1)
+    assert int(nv) == int(lens.sum())
+    # oracle in 4 chunks of 8 sequences (token order is batch-major, so concatenating the chunks' vectors is exact)
+    tmins, tmaxs = [], []
+    for c in range(4):
+        tok = O.token_matrix(x[8 * c:8 * c + 8].cpu(), lens[8 * c:8 * c + 8].tolist(), 1)
+        a, b = O.token_minmax(tok)
+        tmins.append(a); tmaxs.append(b)
+    tmin, tmax = torch.cat(tmins), torch.cat(tmaxs)
+    valid = (gmin <= gmax).cpu()
+    same(gmin.cpu()[valid], tmin); same(gmax.cpu()[valid], tmax)
+    lo, hi = O.prune_bounds(tmin, tmax, 0.99)
+    same(cur, torch.stack([lo, hi]))
+
+
+def test_sharded_calibration_device_replay_matches_sequential():
+    """dist.sharded_calibration on CUDA tensors: slot table -> (all-reduce) -> ONE replay launch that rewrites every
+    observer's state and every quantizer's (scale, zero_point).  Must be bit-identical to plain sequential calibration."""
+    from outlier_suppression_b200.dist import sharded_calibration
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(4, 64, 96, generator=g) * (1 + b) for b in range(5)]
+    lens = torch.tensor([64, 10, 33, 1]).cuda()
+
+    def make():
+        net = torch.nn.Module()
+        net.a_act_fake_quant = Quantizer(None, QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1))
+        net.b_act_fake_quant = Quantizer(None, QC("FixedFakeQuantize", "AvgMinMaxObserver", 8, False, -1))
+        net.c_act_fake_quant = Quantizer(None, QC("FixedFakeQuantize", "AvgMinMaxObserver", 6, True, -1))
+        net.cuda()
+        for i, q in enumerate((net.a_act_fake_quant, net.b_act_fake_quant, net.c_act_fake_quant)):
+            q.observer.set_name("x%d" % i); q.observer.set_percentile(0.9); q.enable_observer()
+        return net
+
+    def run(net, x):
+        for i, q in enumerate((net.a_act_fake_quant, net.b_act_fake_quant, net.c_act_fake_quant)):
+            q(x.cuda() * (i + 1), lens, 1)
+
+    seq = make()
+    for x in xs:
+        run(seq, x)
+    shd = make()
+    with sharded_calibration(shd, len(xs[:3])) as ctl:      # first pass: 3 batches
+        for i, x in enumerate(xs[:3]):
+            ctl.set_batch(i); run(shd, x)
+    with sharded_calibration(shd, len(xs[3:])) as ctl:      # second pass continues the running average (cnt0 = 3)
+        for i, x in enumerate(xs[3:]):
+            ctl.set_batch(i); run(shd, x)
+    for name in ("a_act_fake_quant", "b_act_fake_quant", "c_act_fake_quant"):
+        a, b = getattr(seq, name), getattr(shd, name)
+        same(a.observer.min_val, b.observer.min_val); same(a.observer.max_val, b.observer.max_val)
+        same(a.scale.detach().reshape(-1), b.scale.detach().reshape(-1))
+        same(a.zero_point.detach().reshape(-1).float(), b.zero_point.detach().reshape(-1).float())
+        assert a.observer.cnt == b.observer.cnt == 5 and a.zero_point.dtype == b.zero_point.dtype
 
 
 def test_fp16_input_and_empty():

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "osq.h")).read()
     declared = set(re.findall(r"\b(osq_[a-z0-9_]+)\s*\(", header))
-    declared -= {"osq_tokens_t", "osq_stat_epilogue_t", "osq_fused_linear_t"}
+    declared -= {"osq_tokens_t", "osq_stat_epilogue_t", "osq_fused_linear_t", "osq_replay_target_t"}
     assert declared, "no declarations parsed"
     for name in sorted(declared):
         assert hasattr(lib, name), "libosq_b200.so does not export %s" % name
@@ -208,7 +208,7 @@ def test_ctypes_structures_match_the_header():
         return names
 
     for cname, cls in (("osq_tokens_t", _lib.Tokens), ("osq_stat_epilogue_t", _lib.StatEpilogue),
-                       ("osq_fused_linear_t", _lib.FusedLinearArgs)):
+                       ("osq_fused_linear_t", _lib.FusedLinearArgs), ("osq_replay_target_t", _lib.ReplayTarget)):
         assert fields(cname) == [f[0] for f in cls._fields_], cname
 
 
