@@ -137,10 +137,11 @@ int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t 
 
 
 /* K4c the whole AvgPruneMinMaxObserver step (observer.py:50-70,214-237) as two back-to-back launches: the per-token
- *     pass of K4a, then -- by programmatic dependent launch -- ONE thread-block cluster that keeps the [T] vectors in
- *     (distributed) shared memory and runs the exact radix select for rank lo and lo+1 of |tmax| and |tmin|, the clip /
- *     aminmax and the running-statistics epilogue from there.  Bit-identical to K4a + K4b'.  tmin / tmax ([B*S] fp32)
- *     and n_valid (int32[1]) are caller-owned scratch.  Up to 8 x 24576 tokens per call; longer vectors take K4b'. */
+ *     pass of K4a -- which also histograms the first radix digit of |tmax| / |tmin| into the workspace with fire-and-forget
+ *     L2 reductions -- then, by programmatic dependent launch, ONE small CTA that picks the first-digit bins of rank lo and
+ *     lo+1 on both sides, compacts their members into shared memory in one sweep of the [T] vectors, finishes the exact
+ *     select there, and runs the clip / aminmax sweep and the running-statistics epilogue.  Bit-identical to K4a + K4b'.
+ *     tmin / tmax ([B*S] fp32) and n_valid (int32[1]) are caller-owned scratch; workspace: osq_workspace_bytes(), zeroed once. */
 int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float percentile,
                           float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
                           const osq_stat_epilogue_t* epi, void* workspace, void* stream);

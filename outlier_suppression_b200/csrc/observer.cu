@@ -6,9 +6,14 @@
 // then the last CTA to finish (ticket counter) folds the partials and runs the running-statistics
 // epilogue (running average / extrema + calculate_qparams) so a whole observer.forward() is ONE
 // launch with no host synchronisation.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace osq {
+
+__device__ __forceinline__ long long obs_gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define OBS_STAMP(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) trace[(slot)] = obs_gtimer(); } while (0)
 
 constexpr int kObsThreads = 512;
 constexpr int kObsWarps = kObsThreads / 32;
@@ -178,11 +183,24 @@ minmax_flat_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ c
 __global__ void __launch_bounds__(kObsThreads)
 token_minmax_kernel(const float* __restrict__ x, osq_tokens_t tk, const int64_t* __restrict__ lens,
                     int n_lens, float* __restrict__ tmin, float* __restrict__ tmax,
-                    int32_t* __restrict__ n_valid) {
+                    int32_t* __restrict__ n_valid, unsigned int* __restrict__ hist0) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kObsWarps + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * kObsWarps;
   const int64_t n_tok = tk.B * tk.S;
+  // a dependent launch (the cluster select of osq_prune_observe_f32) may be scheduled as soon as SMs free up; it parks
+  // on griddepcontrol.wait until this grid has completed and flushed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // first radix digit of the select that follows: counted per CTA in shared memory (one atomic per token and side, by
+  // lane 0 of the token's warp), flushed as a handful of L2 reductions at the end -- same-address L2 atomics serialise,
+  // and the leading digits of per-token extrema are nearly constant
+  __shared__ unsigned int sh0[2 * 2048];
+  long long* trace = reinterpret_cast<long long*>(hist0 + 2 * 2048);   // workspace: the stamps follow the table
+  if (hist0 != nullptr) {
+    OBS_STAMP(0);
+    for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) sh0[i] = 0;
+    __syncthreads();
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     int64_t t = 0;
     if (lens == nullptr) t = n_tok;
@@ -208,7 +226,19 @@ token_minmax_kernel(const float* __restrict__ x, osq_tokens_t tk, const int64_t*
     if (lane == 0) {
       tmin[t] = mn;
       tmax[t] = mx;
+      if (hist0 != nullptr && mn <= mx) {
+        atomicAdd(&sh0[__float_as_uint(fabsf(mx)) >> 20], 1u);
+        atomicAdd(&sh0[2048 + (__float_as_uint(fabsf(mn)) >> 20)], 1u);
+      }
     }
+  }
+  if (hist0 != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) {
+      const unsigned int c = sh0[i];
+      if (c) atomicAdd(hist0 + i, c);   // fire-and-forget reduction in L2
+    }
+    OBS_STAMP(1);
   }
 }
 
@@ -576,65 +606,42 @@ prune_apply_kernel(const float* __restrict__ tmin, const float* __restrict__ tma
 
 
 // ---------------------------------------------------------------------------------------------
-// K4c: the whole token-pruning tail as ONE thread-block cluster with the [T] vectors resident in (distributed) shared
-// memory -- the path AvgPruneMinMaxObserver takes (observer.py:50-70 run ~94 k times by token-wise clipping).
+// K4c: the token-pruning tail of AvgPruneMinMaxObserver (observer.py:50-70; run ~94 k times by token-wise clipping) as ONE
+// small CTA parked behind the per-token pass by programmatic dependent launch -- with no shared-memory atomics on the
+// hot path (they cost ~2 cycles per lane: a histogram over all T tokens on one SM is what made the earlier single-CTA
+// selects take 25-50 us at T = 16384).
 //
-// Launched right behind token_minmax_kernel with programmatic dependent launch, so its CTAs are already resident and
-// parked on griddepcontrol.wait when the per-token pass drains.  Every CTA of the cluster copies its slice of
-// tmin / tmax (<= kSliceMax tokens, two fp32 vectors) from L2 into shared memory ONCE; the exact radix select then
-// sweeps shared memory only: three digit passes (11 + 11 + 9 bits of the fp32 pattern of |v|) that track FOUR order
-// statistics at once -- rank lo and rank lo+1 (the pair torch.quantile's lerp needs) of |tmax| and of |tmin| --
-// followed by one clip / aminmax sweep and the running-statistics epilogue.  Histograms of the CTAs are merged in CTA
-// 0's shared memory with DSMEM atomics (only non-empty bins travel) between hardware cluster barriers.
-// With one CTA (T <= 24576: every BERT-base / RoBERTa-base shape up to 48 x 512 tokens) there is no inter-CTA traffic.
+//  (0) the FIRST radix digit (top 11 bits of the fp32 pattern of |tmax| / |tmin|) is histogrammed by the per-token pass
+//      itself, per CTA in shared memory and flushed as a few L2 reductions -- spread over all SMs, hidden under the HBM stream;
+//  (a) the tail reads that 2 x 2048-bin table, re-arms it, and picks the first-digit bin of rank lo on both sides;
+//  (b) ONE sweep of the [T] vectors (L2, 128-bit loads) compacts the members of the two bins into shared-memory lists
+//      (warp-aggregated appends: one atomic per warp) and records the smallest magnitude above each bin;
+//  (c) the remaining 20 bits are resolved 4 at a time over the lists only: every thread counts its members' digits in
+//      packed 16-bit register fields, warps combine them with shuffles, one warp per side picks the digit -- 5 passes of
+//      two barriers each, both sides at once;
+//  (c') one more pass over each list yields rank lo + 1 (the second value torch.quantile's lerp interpolates): the
+//      selected value again if it has a duplicate, else the smallest member above it, else the smallest magnitude above
+//      the bin;
+//  (d) a second sweep of the vectors does the clip + aminmax; thread 0 runs the running-statistics epilogue.
+// A bin with more members than a list holds is processed straight from L2 with a membership test (same code, different
+// source), so any T < 2^21 and any value distribution works.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSelThreads = 1024;
-constexpr int kSelBins = 2048;
-constexpr int kSliceMax = 24576;       // tokens per CTA: 2 x 96 KB of shared memory
-constexpr int kSelMaxCluster = 8;      // portable cluster size -> up to 196608 tokens per observer call
+constexpr int kSelBins0 = 2048;        // first digit: bits [30:20]
+constexpr int kSelCap = 8192;          // entries per candidate list (one per side)
+constexpr int64_t kSelMaxTokens = (int64_t)1 << 21;
 
-struct SelTarget {          // one order statistic being selected
-  unsigned int prefix;      // bits fixed so far
-  unsigned int krem;        // rank inside the candidates that match the prefix
-};
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void dsmem_atomic_add(uint32_t cluster_addr, unsigned int v) {
-  asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int dsmem_ld_u32(uint32_t cluster_addr) {
-  unsigned int v;
-  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void dsmem_st_f32(uint32_t cluster_addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-
-// first bin b of hist[0..kSelBins) with (sum of bins below b) + hist[b] > krem; executed by one full warp
+// first bin b of hist[0..BINS) with (sum of bins below b) + hist[b] > krem; executed by one full warp.
+// Lane l owns bins [P l, P l + P), P = BINS / 32: it sums them in a rotated order (conflict free), a warp scan finds the
+// owning lane, then the whole warp scans that lane's P bins, P / 32 per lane.
+template <int BINS>
 __device__ __forceinline__ void warp_pick_bin_wide(const unsigned int* hist, unsigned int krem, unsigned int& bin, unsigned int& below) {
   const int lane = threadIdx.x & 31;
-  constexpr int kPer = kSelBins / 32;  // 64 consecutive bins per lane
+  constexpr int kPer = BINS / 32, kPer2 = kPer / 32;
+  static_assert(kPer % 32 == 0 && kPer2 >= 1 && kPer2 <= 2, "BINS must be 1024 or 2048");
   unsigned int sum = 0;
-  for (int j = 0; j < kPer; ++j) sum += hist[lane * kPer + j];
+#pragma unroll 8
+  for (int j = 0; j < kPer; ++j) sum += hist[lane * kPer + ((j + lane) & (kPer - 1))];
   unsigned int incl = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -643,126 +650,244 @@ __device__ __forceinline__ void warp_pick_bin_wide(const unsigned int* hist, uns
   }
   const unsigned int vote = __ballot_sync(0xffffffffu, incl > krem);
   const int src = vote ? __ffs(vote) - 1 : 31;
-  unsigned int acc = incl - sum, pick = lane * kPer + kPer - 1, run = incl - sum;
-  bool found = false;
-  for (int j = 0; j < kPer; ++j) {
-    const unsigned int h = hist[lane * kPer + j];
-    if (!found && run + h > krem) { pick = lane * kPer + j; acc = run; found = true; }
-    run += h;
+  const unsigned int base = __shfl_sync(0xffffffffu, incl - sum, src);   // count of all bins below lane src's range
+  const unsigned int h0 = hist[src * kPer + kPer2 * lane];
+  const unsigned int h1 = kPer2 == 2 ? hist[src * kPer + kPer2 * lane + 1] : 0u;
+  unsigned int inc2 = h0 + h1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, inc2, o);
+    if (lane >= o) inc2 += t;
   }
-  bin = __shfl_sync(0xffffffffu, pick, src);
-  below = __shfl_sync(0xffffffffu, acc, src);
+  const unsigned int v2 = __ballot_sync(0xffffffffu, base + inc2 > krem);
+  const int l2 = v2 ? __ffs(v2) - 1 : 31;
+  const unsigned int before = base + inc2 - (h0 + h1);                   // count below this lane's bins
+  const bool first = (kPer2 == 1) || (before + h0 > krem);
+  const unsigned int my_bin = (unsigned int)(src * kPer + kPer2 * lane + (first ? 0 : 1));
+  const unsigned int my_below = first ? before : before + h0;
+  bin = __shfl_sync(0xffffffffu, my_bin, l2);
+  below = __shfl_sync(0xffffffffu, my_below, l2);
 }
 
+// calls f(tmin[i], tmax[i]) for every slot, 8 slots per thread in flight (two 128-bit loads per vector) when aligned.
+// Every lane of a warp calls f the same number of times (f may use warp votes); slots past the end are presented as
+// (+inf, -inf), i.e. as invalid tokens, which every f ignores.
+template <class F>
+__device__ __forceinline__ void sweep_pairs(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n, F&& f) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float4 inv_a = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), inv_b = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (((((uintptr_t)tmin) | ((uintptr_t)tmax)) & 15) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(tmin);
+    const float4* b4 = reinterpret_cast<const float4*>(tmax);
+    const int64_t nv = n >> 2;
+    for (int64_t base = tid - lane; base < nv; base += 2 * kSelThreads) {   // warp-uniform trip count
+      const int64_t i = base + lane;
+      const bool one = i < nv, two = i + kSelThreads < nv;
+      const float4 a0 = one ? __ldcg(a4 + i) : inv_a, b0 = one ? __ldcg(b4 + i) : inv_b;
+      const float4 a1 = two ? __ldcg(a4 + i + kSelThreads) : inv_a, b1 = two ? __ldcg(b4 + i + kSelThreads) : inv_b;
+      f(a0.x, b0.x); f(a0.y, b0.y); f(a0.z, b0.z); f(a0.w, b0.w);
+      f(a1.x, b1.x); f(a1.y, b1.y); f(a1.z, b1.z); f(a1.w, b1.w);
+    }
+    if (tid < 32 && (n & 3)) {                                              // up to three trailing slots: warp 0
+      const int64_t i = (nv << 2) + lane;
+      f(i < n ? __ldcg(tmin + i) : INFINITY, i < n ? __ldcg(tmax + i) : -INFINITY);
+    }
+  } else {
+    for (int64_t base = tid - lane; base < n; base += kSelThreads) {
+      const int64_t i = base + lane;
+      f(i < n ? __ldcg(tmin + i) : INFINITY, i < n ? __ldcg(tmax + i) : -INFINITY);
+    }
+  }
+}
+
+// sixteen 16-bit counters in eight 32-bit registers.  Combined across the warp with the REDUX unit (__reduce_add_sync:
+// one instruction per word) -- a shuffle tree would cost 80 SHFL per warp, side and pass, and SHFL issues at one warp
+// instruction per clock per SM: with 32 warps that alone was 13 us.
+struct Packed16 {
+  unsigned int q[8];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = 0u;
+  }
+  __device__ __forceinline__ void add(unsigned int digit, bool pred) {  // no dynamic register indexing
+    const unsigned int inc = pred ? (1u << ((digit & 1u) << 4)) : 0u;
+    const unsigned int w = digit >> 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] += (w == (unsigned int)i) ? inc : 0u;
+  }
+  __device__ __forceinline__ void warp_sum() {   // fields never overflow (<= 65535 members per warp and pass)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = __reduce_add_sync(0xffffffffu, q[i]);
+  }
+  __device__ __forceinline__ unsigned int get(int j) const { return (q[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu; }
+};
+
 __global__ void __launch_bounds__(kSelThreads, 1)
-prune_select_cluster_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
-                            const int32_t* __restrict__ n_valid, float percentile, float* __restrict__ cur,
-                            osq_stat_epilogue_t epi) {
-  extern __shared__ __align__(16) unsigned char sel_smem[];
-  __shared__ SelTarget tg[4];        // [side * 2 + which]: side 0 = |tmax|, 1 = |tmin|; which 0 = rank lo, 1 = rank lo + 1
-  __shared__ float part[2][kSelMaxCluster];
+prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
+                         const int32_t* __restrict__ n_valid, float percentile, unsigned int* __restrict__ ghist0,
+                         float* __restrict__ cur, osq_stat_epilogue_t epi) {
+  extern __shared__ __align__(16) unsigned int sel_smem[];
+  unsigned int* h0 = sel_smem;                                                              // [2][kSelBins0]
+  unsigned int (*list)[kSelCap] = reinterpret_cast<unsigned int (*)[kSelCap]>(h0 + 2 * kSelBins0);  // [2][kSelCap]
+  __shared__ unsigned int part[2][32][16];     // per-warp digit counts of the current pass
+  __shared__ unsigned int s_prefix[2], s_krem[2], s_nbin[2], s_nlist[2], s_minabove[2], s_cntle[2], s_next[2];
   __shared__ float red[2][32];
-  const uint32_t rank = cluster_ctarank(), nct = cluster_nctarank();
-  const int64_t per = (n_slots + nct - 1) / nct;
-  const int64_t begin = (int64_t)rank * per;
-  const int cnt = (int)max((int64_t)0, min(per, n_slots - begin));
-  float* vmax = reinterpret_cast<float*>(sel_smem);
-  float* vmin = vmax + kSliceMax;
-  unsigned int* hist = reinterpret_cast<unsigned int*>(vmin + kSliceMax);  // [4][kSelBins]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // token_minmax_kernel's tmin / tmax / n_valid are complete and visible
+  long long* trace = reinterpret_cast<long long*>(ghist0 + 2 * kSelBins0);
+  OBS_STAMP(2);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // token_minmax_kernel's vectors, n_valid and first-digit table are complete
+  OBS_STAMP(3);
   const int T = *n_valid;
-  // ---- slice -> shared memory (the only global read of the [T] vectors); invalid tokens keep (+inf, -inf) ----
-  for (int i = tid; i < cnt; i += kSelThreads) {
-    vmax[i] = __ldcg(tmax + begin + i);
-    vmin[i] = __ldcg(tmin + begin + i);
-  }
   const float frank = __fmul_rn(percentile, (float)(T > 0 ? T - 1 : 0));   // torch.quantile: rank = p * (T - 1) in fp32
   const int lo = (int)frank;
   const bool need_pair = (int)ceilf(frank) != lo;
-  const unsigned int k1 = (unsigned int)((lo + 1 < T) ? lo + 1 : lo);
-  if (tid < 4) { tg[tid].prefix = 0u; tg[tid].krem = (tid & 1) ? k1 : (unsigned int)lo; }
-  __syncthreads();
   float thr_up = INFINITY, thr_lo = -INFINITY;
+
+  // ---- (a) first digit: read the table (and re-arm it for the next call on this stream), pick the two bins ----
+  for (int i = tid; i < 2 * kSelBins0; i += kSelThreads) {
+    const unsigned int c = __ldcg(ghist0 + i);
+    h0[i] = c;
+    if (c) ghist0[i] = 0;
+  }
+  if (tid < 2) { s_nlist[tid] = 0; s_minabove[tid] = 0xFFFFFFFFu; s_cntle[tid] = 0; s_next[tid] = 0xFFFFFFFFu; }
+  __syncthreads();
   if (T > 0) {
-    const int shifts[3] = {20, 9, 0};
-    const unsigned int widths[3] = {11, 11, 9};
-    unsigned int mask = 0;
-    for (int pass = 0; pass < 3; ++pass) {
-      const int sh = shifts[pass];
-      const unsigned int dm = (1u << widths[pass]) - 1u;
-      for (int i = tid; i < 4 * kSelBins; i += kSelThreads) hist[i] = 0;
-      __syncthreads();
-      const SelTarget t0 = tg[0], t1 = tg[1], t2 = tg[2], t3 = tg[3];
-      const bool same_mx = t0.prefix == t1.prefix, same_mn = t2.prefix == t3.prefix;
-      for (int i = tid; i < cnt; i += kSelThreads) {
-        const float a = vmin[i], b = vmax[i];
-        const bool ok = a <= b;
-        const unsigned int ub = __float_as_uint(fabsf(b)), ua = __float_as_uint(fabsf(a));
-        const unsigned int db = (ub >> sh) & dm, da = (ua >> sh) & dm;
-        if (pass == 0) {  // leading digits are almost constant: aggregate equal digits inside the warp first
-          const unsigned int kb = ok ? db : 0xFFFFFFFFu, ka = ok ? da : 0xFFFFFFFFu;
-          const unsigned int pb = __match_any_sync(__activemask(), kb);
-          if (ok && lane == __ffs(pb) - 1) atomicAdd(&hist[db], (unsigned int)__popc(pb));
-          const unsigned int pa = __match_any_sync(__activemask(), ka);
-          if (ok && lane == __ffs(pa) - 1) atomicAdd(&hist[2 * kSelBins + da], (unsigned int)__popc(pa));
-        } else if (ok) {
-          if ((ub & mask) == t0.prefix) atomicAdd(&hist[db], 1u);
-          if (!same_mx && (ub & mask) == t1.prefix) atomicAdd(&hist[kSelBins + db], 1u);
-          if ((ua & mask) == t2.prefix) atomicAdd(&hist[2 * kSelBins + da], 1u);
-          if (!same_mn && (ua & mask) == t3.prefix) atomicAdd(&hist[3 * kSelBins + da], 1u);
-        }
-      }
-      __syncthreads();
-      if (nct > 1) {
-        // merge into CTA 0: the other CTAs add their non-empty bins into its histograms through DSMEM
-        cluster_sync_all();                      // CTA 0 has finished its own sweep (its counts are in place)
-        if (rank != 0) {
-          const uint32_t base = map_to_cta(smem_addr(hist), 0);
-          for (int i = tid; i < 4 * kSelBins; i += kSelThreads) {
-            const unsigned int c = hist[i];
-            if (c) dsmem_atomic_add(base + 4u * i, c);
-          }
-        }
-        cluster_sync_all();
-      }
-      if (rank == 0 && warp < 4) {
-        const int side = warp >> 1;
-        const bool same = side ? same_mn : same_mx;
-        const unsigned int* h = hist + ((same ? (warp & ~1) : warp) * kSelBins);
-        unsigned int bin, below;
-        warp_pick_bin_wide(h, tg[warp].krem, bin, below);
-        __syncwarp();
-        if (lane == 0) { tg[warp].prefix |= bin << sh; tg[warp].krem -= below; }
-      }
-      __syncthreads();
-      if (nct > 1) {
-        cluster_sync_all();                      // CTA 0's targets are final for this pass
-        if (rank != 0 && tid < 8) {
-          const uint32_t src = map_to_cta(smem_addr(&tg[0]), 0);
-          reinterpret_cast<unsigned int*>(&tg[0])[tid] = dsmem_ld_u32(src + 4u * tid);
-        }
-        __syncthreads();
-        cluster_sync_all();                      // everyone has read them before CTA 0 may change them again
-      }
-      mask |= dm << sh;
+    if (warp < 2) {   // side 0 = |tmax|, side 1 = |tmin|
+      unsigned int bin, below;
+      warp_pick_bin_wide<kSelBins0>(h0 + warp * kSelBins0, (unsigned int)lo, bin, below);
+      if (lane == 0) { s_prefix[warp] = bin << 20; s_krem[warp] = (unsigned int)lo - below; s_nbin[warp] = h0[warp * kSelBins0 + bin]; }
     }
-    const float a_mx = __uint_as_float(tg[0].prefix), b_mx = __uint_as_float(tg[1].prefix);
-    const float a_mn = __uint_as_float(tg[2].prefix), b_mn = __uint_as_float(tg[3].prefix);
+    __syncthreads();
+    OBS_STAMP(4);
+    // ---- (b) one sweep over the vectors: compact the members of the chosen bins, smallest magnitude above each bin ----
+    const unsigned int bin_mx = s_prefix[0] >> 20, bin_mn = s_prefix[1] >> 20;
+    const bool listed_mx = s_nbin[0] <= kSelCap, listed_mn = s_nbin[1] <= kSelCap;
+    unsigned int above_mx = 0xFFFFFFFFu, above_mn = 0xFFFFFFFFu;
+    auto append = [&](int side, bool pred, unsigned int u) {   // warp-aggregated: one shared atomic per warp and call
+      const unsigned int m = __ballot_sync(0xffffffffu, pred);
+      if (m == 0) return;
+      const int leader = __ffs(m) - 1;
+      unsigned int base = 0;
+      if (lane == leader) base = atomicAdd(&s_nlist[side], (unsigned int)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (pred) list[side][base + __popc(m & ((1u << lane) - 1u))] = u;
+    };
+    sweep_pairs(tmin, tmax, n_slots, [&](float a, float b) {
+      const bool ok = a <= b;
+      const unsigned int ub = __float_as_uint(fabsf(b)), ua = __float_as_uint(fabsf(a));
+      const unsigned int db = ub >> 20, da = ua >> 20;
+      if (listed_mx) append(0, ok && db == bin_mx, ub);
+      if (listed_mn) append(1, ok && da == bin_mn, ua);
+      if (ok && db > bin_mx) above_mx = min(above_mx, ub);
+      if (ok && da > bin_mn) above_mn = min(above_mn, ua);
+    });
+    above_mx = __reduce_min_sync(0xffffffffu, above_mx);
+    above_mn = __reduce_min_sync(0xffffffffu, above_mn);
+    if (lane == 0) {
+      if (above_mx != 0xFFFFFFFFu) atomicMin(&s_minabove[0], above_mx);
+      if (above_mn != 0xFFFFFFFFu) atomicMin(&s_minabove[1], above_mn);
+    }
+    __syncthreads();
+    // members of side sd: from its list, or (crowded bin) straight from L2 with the membership test
+    auto for_members = [&](int sd, auto&& g) {
+      if (sd == 0 ? listed_mx : listed_mn) {
+        const unsigned int n = s_nlist[sd];
+        for (unsigned int i = tid; i < n; i += kSelThreads) g(list[sd][i]);
+      } else {
+        const unsigned int bin = sd == 0 ? bin_mx : bin_mn;
+        sweep_pairs(tmin, tmax, n_slots, [&](float a, float b) {
+          const unsigned int u = __float_as_uint(fabsf(sd == 0 ? b : a));
+          if (a <= b && (u >> 20) == bin) g(u);
+        });
+      }
+    };
+    OBS_STAMP(5);
+    // ---- (c) the remaining 20 bits, 4 per pass, counted in registers ----
+    unsigned int mask = 0xFFFu << 20;
+#pragma unroll 1
+    for (int sh = 16; sh >= 0; sh -= 4) {
+#pragma unroll
+      for (int sd = 0; sd < 2; ++sd) {
+        Packed16 cc;
+        cc.clear();
+        const unsigned int prefix = s_prefix[sd];
+        for_members(sd, [&](unsigned int u) { cc.add((u >> sh) & 15u, (u & mask) == prefix); });
+        cc.warp_sum();
+        unsigned int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mine = (lane == j) ? cc.get(j) : mine;
+        if (lane < 16) part[sd][warp][lane] = mine;
+      }
+      __syncthreads();
+      if (warp < 2) {  // one warp per side: lanes 0..15 own one digit each
+        unsigned int cnt = 0;
+        if (lane < 16) {
+#pragma unroll 8
+          for (int w = 0; w < 32; ++w) cnt += part[warp][(w + lane) & 31][lane];
+        }
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const unsigned int krem = s_krem[warp];
+        const unsigned int vote = __ballot_sync(0xffffffffu, lane < 16 && incl > krem);
+        const int d = vote ? __ffs(vote) - 1 : 15;
+        const unsigned int below = __shfl_sync(0xffffffffu, incl - cnt, d);
+        __syncwarp();
+        if (lane == 0) { s_prefix[warp] |= (unsigned int)d << sh; s_krem[warp] = krem - below; }
+      }
+      __syncthreads();
+      mask |= 0xFu << sh;
+    }
+    OBS_STAMP(6);
+    // ---- (c') rank lo + 1 ----
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+      const unsigned int a = s_prefix[sd];
+      unsigned int cle = 0, nxt = 0xFFFFFFFFu;
+      for_members(sd, [&](unsigned int u) { if (u <= a) ++cle; else nxt = min(nxt, u); });
+      cle = __reduce_add_sync(0xffffffffu, cle);
+      nxt = __reduce_min_sync(0xffffffffu, nxt);
+      if (lane == 0) {
+        if (cle) atomicAdd(&s_cntle[sd], cle);
+        if (nxt != 0xFFFFFFFFu) atomicMin(&s_next[sd], nxt);
+      }
+    }
+    __syncthreads();
+    // the number of ALL valid tokens <= a is (tokens in lower first-digit bins) + (members <= a); rank lo + 1 equals a
+    // iff that count reaches lo + 2, else it is the next larger magnitude
+    if (warp < 2) {
+      unsigned int below = 0;
+      const unsigned int bin = s_prefix[warp] >> 20;
+      for (unsigned int i = lane; i < bin; i += 32) below += h0[warp * kSelBins0 + i];
+      below = __reduce_add_sync(0xffffffffu, below);
+      if (lane == 0) {
+        const unsigned int a = s_prefix[warp];
+        unsigned int b = a;
+        if ((unsigned int)lo + 1u < (unsigned int)T && below + s_cntle[warp] < (unsigned int)lo + 2u)
+          b = (s_next[warp] != 0xFFFFFFFFu) ? s_next[warp] : ((s_minabove[warp] != 0xFFFFFFFFu) ? s_minabove[warp] : a);
+        s_next[warp] = b;   // reuse: the value of rank lo + 1
+      }
+    }
+    __syncthreads();
+    const float a_mx = __uint_as_float(s_prefix[0]), b_mx = __uint_as_float(s_next[0]);
+    const float a_mn = __uint_as_float(s_prefix[1]), b_mn = __uint_as_float(s_next[1]);
     thr_up = quantile_from_pair(a_mx, need_pair ? b_mx : a_mx, frank, lo);
     thr_lo = -quantile_from_pair(a_mn, need_pair ? b_mn : a_mn, frank, lo);
   }
-  // ---- clip + aminmax over the kept tokens (observer.py:66-69, 227) ----
+  // ---- (d) clip + aminmax over the kept tokens (observer.py:66-69, 227) ----
+  OBS_STAMP(7);
   float lower = INFINITY, upper = -INFINITY;
   if (T > 0)
-    for (int i = tid; i < cnt; i += kSelThreads) {
-      const float a = vmin[i], b = vmax[i];
+    sweep_pairs(tmin, tmax, n_slots, [&](float a, float b) {
       if (a <= b) {
         if (b <= thr_up) upper = fmaxf(upper, b);
         if (a >= thr_lo) lower = fminf(lower, a);
       }
-    }
+    });
   lower = warp_min(lower);
   upper = warp_max(upper);
   if (lane == 0) { red[0][warp] = lower; red[1][warp] = upper; }
@@ -771,25 +896,13 @@ prune_select_cluster_kernel(const float* __restrict__ tmin, const float* __restr
     lower = warp_min(red[0][lane]);
     upper = warp_max(red[1][lane]);
     if (lane == 0) {
-      if (nct > 1) {
-        dsmem_st_f32(map_to_cta(smem_addr(&part[0][rank]), 0), lower);
-        dsmem_st_f32(map_to_cta(smem_addr(&part[1][rank]), 0), upper);
-      } else {
-        part[0][0] = lower;
-        part[1][0] = upper;
-      }
+      cur[0] = lower;
+      cur[1] = upper;
+      stat_epilogue(epi, lower, upper);
+      OBS_STAMP(8);
     }
   }
-  if (nct > 1) cluster_sync_all(); else __syncthreads();
-  if (rank == 0 && tid == 0) {
-    lower = INFINITY; upper = -INFINITY;
-    for (uint32_t c = 0; c < nct; ++c) { lower = fminf(lower, part[0][c]); upper = fmaxf(upper, part[1][c]); }
-    cur[0] = lower;
-    cur[1] = upper;
-    stat_epilogue(epi, lower, upper);
-  }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // AvgQuantileObserver (observer.py:253-282): histogram of |x| over the valid tokens in `bins` equal bins of [0, R],
@@ -931,7 +1044,9 @@ static int reduction_grid(int64_t units_of_work) {
   int sms = sm_count();
   if (sms <= 0) return -1;
   int64_t g = (units_of_work + kObsWarps - 1) / kObsWarps;
-  int64_t cap = (int64_t)sms * 4;  // 4 CTAs of 512 threads = 64 warps / SM
+  static int per_sm = -1;          // experiment knob; default 4 CTAs of 512 threads = 64 warps / SM
+  if (per_sm < 0) { const char* e = getenv("OSQ_OBS_CTAS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1 || per_sm > 4) per_sm = 4; }
+  int64_t cap = (int64_t)sms * per_sm;
   if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
@@ -980,7 +1095,7 @@ int osq_token_minmax_f32(const float* x, const osq_tokens_t* tok, const int64_t*
   OSQ_CHECK_ARG(tok->B * tok->S < (int64_t)INT32_MAX, "osq_token_minmax_f32: too many tokens");
   int grid = reduction_grid(tok->B * tok->S);
   if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
-  token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid);
+  token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, nullptr);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }
@@ -1039,38 +1154,44 @@ int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t
   OSQ_CHECK_ARG(percentile >= 0.f && percentile <= 1.f, "osq_prune_observe_f32: percentile outside [0,1]");
   const int64_t n_slots = tok->B * tok->S;
   OSQ_CHECK_ARG(n_slots > 0 && n_slots < (int64_t)INT32_MAX, "osq_prune_observe_f32: token count out of range");
+  if (n_slots >= kSelMaxTokens) {  // beyond the packed 16-bit counters of the tail: the multi-launch select over L2
+    if (int rc = osq_token_minmax_f32(x, tok, lens, n_lens, tmin, tmax, n_valid, stream)) return rc;
+    return osq_prune_select_unsorted_f32(tmin, tmax, n_slots, n_valid, percentile, cur_minmax, epi, workspace, stream);
+  }
   int grid = reduction_grid(n_slots);
   if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
   cudaStream_t st = (cudaStream_t)stream;
-  token_minmax_kernel<<<grid, kObsThreads, 0, st>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid);
-  OSQ_LAUNCH_CHECK();
-  const int64_t nct = (n_slots + kSliceMax - 1) / kSliceMax;
-  if (nct > kSelMaxCluster)  // longer than a cluster's shared memory: the multi-launch radix select over L2
-    return osq_prune_select_unsorted_f32(tmin, tmax, n_slots, n_valid, percentile, cur_minmax, epi, workspace, stream);
-  const size_t smem = (size_t)2 * kSliceMax * 4 + (size_t)4 * kSelBins * 4;
+  constexpr size_t kSelSmem = (size_t)(2 * kSelBins0 + 2 * kSelCap) * 4;
   static bool attr_set[64] = {false};
   int dev = 0;
   OSQ_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    OSQ_CUDA(cudaFuncSetAttribute(prune_select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OSQ_CUDA(cudaFuncSetAttribute(prune_select_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmem));
+    // both kernels of the pair ask for the same shared-memory carve-out: an SM whose L1 / shared split has to change
+    // between two kernels drains first, which costs more than the tail kernel itself
+    static int carve = -2;
+    if (carve == -2) { const char* e = getenv("OSQ_OBS_CARVEOUT"); carve = e ? atoi(e) : 50; }
+    if (carve >= 0) {
+      OSQ_CUDA(cudaFuncSetAttribute(prune_select_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      OSQ_CUDA(cudaFuncSetAttribute(token_minmax_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    }
     attr_set[dev & 63] = true;
   }
+  unsigned int* hist0 = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + kSelectHist0Offset);
+  token_minmax_kernel<<<grid, kObsThreads, 0, st>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, hist0);
+  OSQ_LAUNCH_CHECK();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)nct, 1, 1);
+  cfg.gridDim = dim3(1, 1, 1);
   cfg.blockDim = dim3(kSelThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = kSelSmem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)nct;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // park behind the per-token pass (griddepcontrol.wait)
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // park behind the per-token pass (griddepcontrol.wait)
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  OSQ_CUDA(cudaLaunchKernelEx(&cfg, prune_select_cluster_kernel, (const float*)tmin, (const float*)tmax, n_slots,
-                              (const int32_t*)n_valid, percentile, cur_minmax, *epi));
+  cfg.numAttrs = 1;
+  OSQ_CUDA(cudaLaunchKernelEx(&cfg, prune_select_tail_kernel, (const float*)tmin, (const float*)tmax, n_slots,
+                              (const int32_t*)n_valid, percentile, hist0, cur_minmax, *epi));
   return OSQ_OK;
 }
 

@@ -78,7 +78,7 @@ def _avg_observers(model):
 
 
 @contextmanager
-def sharded_calibration(model, n_batches: int, group=None):
+def sharded_calibration(model, n_batches: int, group=None, table: Optional[SlotTable] = None):
     """Usage (every rank):
 
         with sharded_calibration(model, n_batches) as ctl:
@@ -86,11 +86,17 @@ def sharded_calibration(model, n_batches: int, group=None):
                 ctl.set_batch(i); model(**batch[i])
 
     On exit the slot table is all-reduced once and every enabled Avg* observer (and its quantizer's
-    scale / zero_point) holds exactly what a sequential pass over all batches would have produced."""
+    scale / zero_point) holds exactly what a sequential pass over all batches would have produced.
+    ``table``: an existing SlotTable of the right shape to reuse (zeroed in place) -- keeps the slot addresses stable,
+    so the per-batch launches of a pass can be captured once in a CUDA graph and replayed."""
     from . import ops
     observers, owners = _avg_observers(model)
     device = next((o.min_val.device for o in observers), torch.device("cpu"))
-    table = SlotTable(len(observers), n_batches, device)
+    if table is None:
+        table = SlotTable(len(observers), n_batches, device)
+    else:
+        assert table.n_obs == len(observers) and table.n_batches == n_batches and table.buf.device == torch.device(device)
+        table.buf.zero_()
     ctl = _Controller(table, observers, owners)
     for i, o in enumerate(observers):
         o._shard = (ctl, i)

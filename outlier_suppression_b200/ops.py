@@ -222,11 +222,12 @@ def _token_vectors(device, n: int):
     Grown, never shrunk: the observer runs ~100 k times per calibration and must not hit the allocator."""
     key = (torch.device(device).index, _stream())
     buf = _token_scratch.get(key)
-    if buf is None or buf[0].numel() < 2 * n:
-        cap = max(2 * n, 1 << 16)
+    n4 = (n + 3) & ~3   # both vectors 16-byte aligned (the select tail reads them with 128-bit loads)
+    if buf is None or buf[0].numel() < 2 * n4:
+        cap = max(2 * n4, 1 << 16)
         buf = (torch.empty(cap, dtype=torch.float32, device=device), torch.empty(1, dtype=torch.int32, device=device))
         _token_scratch[key] = buf
-    return buf[0][:n], buf[0][n:2 * n], buf[1]
+    return buf[0][:n], buf[0][n4:n4 + n], buf[1]
 
 
 def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
