@@ -429,6 +429,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python launch loop instead of CUDA graph replay")
     ap.add_argument("--no-group", action="store_true", help="launch q, k and v separately (72 launches per step)")
+    ap.add_argument("--multi", action="store_true", help="hand each layer's site list to osq_fused_fq_linear_multi (with OSQ_FUSED_MULTI=1: one "
+                    "persistent launch per layer; measured 10 %% slower than one launch per site, see DESIGN.md)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 observer sweep and the config-4 site timings")
     ap.add_argument("--only-value", action="store_true", help="profiling runs: timed stack only, no roofline/e2e/cpu legs")
     args = ap.parse_args()
@@ -473,10 +475,30 @@ def main():
     plan = [[next(s for s in mods if s["name"] == n) for n in order] for mods in layers]
     shape_of = {s["name"]: (s["k"], s["n"]) for s in layers[0]}
 
+    def site_args(site):
+        k, n = site["k"], site["n"]
+        a = acts[k][counters[k] % len(acts[k])]
+        counters[k] += 1
+        out = outs[n][counters[n] % len(outs[n])]
+        counters[n] += 1
+        aq = site["aq"]
+        cache = site.get("cache")
+        if cache is None and k > 1024 and n > 256:
+            cache = site["cache"] = torch.empty((M, k), dtype=torch.uint8, device=device)
+        return dict(a=a, a_scale=aq.scale.data, a_zp=aq.zero_point.data, a_qmin=aq.quant_min, a_qmax=aq.quant_max,
+                    w_codes=site["codes"], w_scale=site["w_scale"], w_rowsum=site["rowsum"], bias=site["bias"],
+                    lsq_grad_factor=site["g"], out=out, cache=cache)
+
     def step():
-        for sites in plan:
-            for site in sites:
-                launch(site)
+        if not args.multi:
+            for sites in plan:
+                for site in sites:
+                    launch(site)
+        else:
+            # the step's sites read and write independent buffers: each layer's launches go to the library as ONE list
+            # (osq_fused_fq_linear_multi: one persistent grid per run of compatible sites)
+            for sites in plan:
+                ops.fused_fq_linear_multi([site_args(site) for site in sites])
 
     def barrier():
         torch.cuda.synchronize()
@@ -503,7 +525,7 @@ def main():
     run_step, launch_mode = step, "eager loop"
     if not args.no_graph:
         step_graph = make_graph(step)
-        run_step, launch_mode = step_graph.replay, "one CUDA graph per step (%d kernel nodes, PDL edges)" % (LAYERS * len(order))
+        run_step, launch_mode = step_graph.replay, "one CUDA graph per step (%d kernel nodes, PDL edges)" % (LAYERS * len(order) if not args.multi else LAYERS)
     for _ in range(args.warmup):
         run_step()
     barrier()
@@ -651,9 +673,11 @@ def main():
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8 (u8 x s8 -> s32 bins, fp32 I/O)",
                "data": "synthetic",
                "config": workload_config(world),
-               "launch": {"mode": launch_mode, "host_issue_ms_per_step": host_issue_ms, "fused_launches_per_step": LAYERS * len(order),
+               "launch": {"mode": launch_mode, "host_issue_ms_per_step": host_issue_ms, "fused_sites_per_step": LAYERS * len(order),
+                          "kernel_launches_per_step": LAYERS * len(order) if not args.multi else LAYERS,
+                          "multi_site": "off" if not args.multi else "a layer's %d independent sites per persistent launch (osq_fused_fq_linear_multi)" % len(order),
                           "grouping": "none" if args.no_group else "q|k|v of a layer share one launch"},
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * LAYERS * len(order),
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * (LAYERS * len(order) if not args.multi else LAYERS),
                "clocks": clocks, "observer_sweep": sweep_rec, "config4_bart_large": bart_rec}
         print(json.dumps(rec))
     if dist is not None:

@@ -263,6 +263,14 @@ typedef struct {
 
 int osq_fused_fq_linear(const osq_fused_linear_t* args, void* stream);
 
+/* K6 for a list of INDEPENDENT sites (no site reads what another site of the list writes): runs of compatible sites --
+ * up to 4, same grid and launch plan family -- execute as ONE persistent launch in which every CTA walks the list, so the
+ * launch gap, the wait for the slowest CTA and the first-load latency are paid once per run instead of once per site;
+ * incompatible sites fall back to individual launches, in list order.  Results are bit-identical to n_sites calls of
+ * osq_fused_fq_linear.  Typical use: the Linears of several layers fed from independent buffers (BASELINE config 2's
+ * synthetic site stack), or sibling projections that cannot share one weight concatenation. */
+int osq_fused_fq_linear_multi(const osq_fused_linear_t* sites, int n_sites, void* stream);
+
 /* LSQ+ backward (fine stage `learn_scale`, token_wise_clipping.py:72-108; gradients of
  * util_quant.py:48-55):  dx = dy * 1[qmin <= q <= qmax];
  *   dscale += g * sum dy * (inside ? rint(x/s) - x/s : q_clamped - z);  dzp += g * sum dy * (inside ? 0 : -s)

@@ -11,7 +11,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libosq_b200.so")
+LIB_PATH = os.environ.get("OSQ_LIB_PATH") or os.path.join(_PKG, "libosq_b200.so")  # OSQ_LIB_PATH: A/B builds of the same ABI
 
 EXPORTS = [
     "osq_version", "osq_last_error", "osq_sm_count", "osq_workspace_bytes",
@@ -20,7 +20,7 @@ EXPORTS = [
     "osq_prune_observe_f32", "osq_quantile_observe_f32", "osq_replay_average_f32",
     "osq_rowwise_minmax_qparams_f32", "osq_calc_qparams_f32",
     "osq_mse_multi_f32", "osq_mse_brent_rows_f32",
-    "osq_pack_weight_s8", "osq_fused_fq_linear", "osq_lsqplus_backward_f32",
+    "osq_pack_weight_s8", "osq_fused_fq_linear", "osq_fused_fq_linear_multi", "osq_lsqplus_backward_f32",
 ]
 
 
@@ -82,6 +82,7 @@ def _declare(lib):
         "osq_mse_brent_rows_f32": [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp],
         "osq_pack_weight_s8": [vp, i64, i64, vp, vp, i32, i32, vp, vp, vp],
         "osq_fused_fq_linear": [C.POINTER(FusedLinearArgs), vp],
+        "osq_fused_fq_linear_multi": [C.POINTER(FusedLinearArgs), i32, vp],
         "osq_lsqplus_backward_f32": [vp, vp, vp, i64, vp, vp, f32, i32, i32, vp, vp],
     }
     for name, argtypes in sig.items():

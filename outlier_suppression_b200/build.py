@@ -27,7 +27,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     # no --use_fast_math: bins must be bit-exact with IEEE division + rint
     "-I" + INCLUDE, "-I" + CSRC,
-] + (["-DOSQ_ENABLE_TRACE"] if os.environ.get("OSQ_BUILD_TRACE") == "1" else [])
+] + (["-DOSQ_ENABLE_TRACE"] if os.environ.get("OSQ_BUILD_TRACE") == "1" else []) + \
+    [f for f in os.environ.get("OSQ_BUILD_DEFINES", "").split() if f.startswith("-D")]   # experiment builds (A/B variants)
 
 
 def _nvcc() -> str:

@@ -87,6 +87,10 @@ struct FusedParams {
   uint32_t codes_box_bytes;  // bytes one code-cache TMA box delivers
   int pdl;                   // launched with programmatic stream serialization
   int prefetch;              // L2 prefetch distance of the fp32 activation in k-blocks (0 = off)
+  int store3d;               // epilogue: the two column slices of a lane quarter share one 8 KB staging tile and leave as ONE 3-D tensor store
+                             // of 32 rows x 2 x 128 B (256 contiguous bytes per row); tmap_y / tmap_y16 are then 3-D maps [M][N/32][32]
+  int more_sites;            // multi-site launch: another site follows in this kernel (barriers are invalidated at teardown, TMEM is kept)
+  int first_site;            // this site allocates TMEM (always 1 for a single-site launch)
   int dbg;                   // profiling experiments (OSQ_FUSED_DBG): 1 = W tile pinned, 2 = no Y stores, 4 = A rows pinned
   long long* trace;          // optional debug timeline: CTA 0 clock64 stamps [0,1024), per-CTA globaltimer start/end [1024, 1024+2*grid)
 };
@@ -98,6 +102,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
@@ -174,6 +181,24 @@ __device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtenso
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same load with an L2 eviction-priority hint (createpolicy): fp32 A is touched once, it should not displace the code cache
+__device__ __forceinline__ void tma_load_2d_hint_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ bool hint_a_any(const FusedParams& p) { return !(p.dbg & 512); }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
 // pair mode: lands in this CTA's shared memory, completes transaction bytes on the LEADER's barrier (cluster address)
 __device__ __forceinline__ void tma_load_2d_pair_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
@@ -207,6 +232,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// named barrier of the two epilogue warps (64 threads) of lane quarter q; immediate ids keep ptxas from reserving all 16
+__device__ __forceinline__ void pair_barrier(int q) {
+  switch (q) {
+    case 0: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+  }
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -371,9 +410,12 @@ static_assert(sizeof(Smem) % 16 == 0, "constants must stay 16-byte aligned");
 // One body, three entry points (below): <registers path>, <TMA landing slots>, <TMA landing slots + CTA pair>.
 // Only the pair variant contains cta_group::2 instructions: the driver refuses to launch a kernel that uses them
 // without a cluster of two.
-template <bool kXTma, bool kPair>
+template <bool kXTma, bool kPair, bool kS3d>
 __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, const CUtensorMap& tmap_y, const CUtensorMap& tmap_y16,
-                                                     const CUtensorMap& tmap_codes, const CUtensorMap& tmap_a, const FusedParams& p) {
+                                                     const CUtensorMap& tmap_codes, const CUtensorMap& tmap_a, const FusedParams& p,
+                                                     uint32_t& tmem_keep) {
+  // multi-site launches allocate TMEM once (the allocation permit is relinquished right after) and carry the address from
+  // site to site in `tmem_keep`; p.first_site / p.more_sites say where this site sits in the list
   // dynamic shared memory, 1024B aligned by the attribute (SWIZZLE_128B tiles need it):
   // [A ring][W ring][fp32 landing slots][TMA-store staging tiles (may alias the slots)][Smem bookkeeping]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -413,7 +455,10 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     fence_barrier_init();
   }
   if constexpr (pair) {
-    if (warp == 2) tmem_alloc_pair(&sm.tmem_base, kTmemCols);
+    if (warp == 2) {
+      if (p.first_site) tmem_alloc_pair(&sm.tmem_base, kTmemCols);
+      else if (lane == 0) sm.tmem_base = tmem_keep;
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit
@@ -423,7 +468,8 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     // through its own mbarrier to the two consumers of the address (MMA issuer, epilogue warps)
     __syncthreads();
     if (warp == 2) {
-      tmem_alloc(&sm.tmem_base, kTmemCols);
+      if (p.first_site) tmem_alloc(&sm.tmem_base, kTmemCols);
+      else if (lane == 0) sm.tmem_base = tmem_keep;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.tmem_ready);
@@ -453,7 +499,10 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     if (lane == 0) {
       // the packed weights may have been written by the kernel right before this one (first call after a
       // re-pack): like every other global access they are ordered after the previous grid
-      if (p.pdl) pdl_wait_prior_grids();
+      // Only a kernel that calls griddepcontrol.launch_dependents early can still be running here, and no such kernel
+      // writes packed weights (osq_pack_weight_s8 never triggers early, so this grid starts after it has completed and
+      // flushed): the weight stream does not wait for the previous grid.  OSQ_FUSED_DBG=256 restores the wait.
+      if (p.pdl && (p.dbg & 256)) pdl_wait_prior_grids();
       const uint32_t w_bytes = (uint32_t)p.w_stage_bytes;
       const uint32_t w_base = smem_u32(w_ring), full0 = smem_u32(&sm.w_full[0]), empty0 = smem_u32(&sm.w_empty[0]);
       const int slice = p.BN / p.csz;  // rows of the tile this CTA stages (pair: half, the MMA reads both halves)
@@ -654,6 +703,14 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         tma_load_2d_u32(smem_u32(x_ring + (size_t)w * kXSlotBytes), &tmap_a, bar, 0, row0);
       }
     }
+    // streamed A with a code cache: the bins must survive in L2 until the later sweeps re-load them, so everything that is
+    // touched once (fp32 A in, Y out) is marked evict-first.  OSQ_FUSED_DBG=512 turns the hints off.
+    const bool hint = ((p.cached && !p.codes_in) || (p.dbg & 1024)) && !(p.dbg & 512);
+    // fp32 A is read exactly once in every plan: its loads are evict-first everywhere (+0.5 % on the resident sites; marking Y
+    // evict-first as well made single sites 1-4 % faster but the interleaved step and the module chain, whose next kernel
+    // reads Y, slower -- so Y keeps the default policy unless the code cache needs the room)
+    const bool hint_a = !(p.dbg & 512);
+    const uint64_t pol_once = hint_a_any(p) ? l2_policy_evict_first() : 0ull;
     const QParam qp = load_qparam(p.a_scale, p.a_zp, p.a_zp_is_int32, p.g, p.qmin, p.qmax,
                                   blockIdx.x == 0 && w == 0 && lane == 0);
     ConvParam cp;
@@ -781,7 +838,8 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
             __syncwarp();
             if (lane == 0) {
               mbar_arrive_expect_tx_u32(x_bar, x_box_bytes);
-              tma_load_2d_u32(smem_u32(x_slot), &tmap_a, x_bar, (kb + 1) * kStageK, row_first);
+              if (hint_a) tma_load_2d_hint_u32(smem_u32(x_slot), &tmap_a, x_bar, (kb + 1) * kStageK, row_first, pol_once);
+              else tma_load_2d_u32(smem_u32(x_slot), &tmap_a, x_bar, (kb + 1) * kStageK, row_first);
             }
           }
           uint32_t risky_mask = 0;
@@ -872,6 +930,103 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       const int rows_q = min(32, p.rows_per_tile - q * 32);
       const bool any_rows = (rows_q > 0) && (row0 < p.M);
       const CUtensorMap* ymap = (rows_q == 32) ? &tmap_y : &tmap_y16;
+      if constexpr (kS3d) {
+        // Pair store: at every step the two slices of this lane quarter cover 64 adjacent columns.  Both write their 32 x 128 B
+        // half into ONE 8 KB staging tile laid out [32 rows][2][128 B] (the box of the 3-D map [M][N/32][32]); slice 0 then
+        // issues a single tensor store that writes 256 contiguous bytes per row (measured +10-12 % over 128-byte rows,
+        // profiles/r01_storebench_3d.txt).  Two tiles per quarter (the landing slots of both warps): store i overlaps step
+        // i + 1.  One 64-thread named barrier per step couples the two warps.
+        const uint32_t unit = (uint32_t)lane * 2u + (uint32_t)slice;      // 128-byte unit of this thread's row half
+        const uint32_t usw = unit & 7u;                                  // SWIZZLE_128B phase of that unit
+        const uint32_t bit = ((uint32_t)lane >> 2) & 1u;                 // lanes l and l + 4 share usw: they swap even / odd chunks
+        const bool issuer = slice == 0;
+        for (int cb = 0; cb < n_cols; cb += 64) {
+          const int c0 = cb + slice * 32;
+          const bool active = c0 < n_cols;                               // last chunk of an N that is an odd multiple of 32
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);   // (an inactive slice reads columns of the stage nobody stores: harmless)
+          tmem_ld_wait();
+          if (!any_rows) continue;  // uniform over both warps of the quarter
+          const uint32_t kbuf = n_stores & (uint32_t)(obufs - 1);
+          uint8_t* tile = p.alias_xo ? x_ring + (size_t)(kbuf * kNumEpiWarps + 2u * (uint32_t)q) * kXSlotBytes
+                                     : o_ring + (size_t)(kbuf * kNumEpiWarps + 2u * (uint32_t)q) * kOutTileBytes;
+          if (obufs == 1) {  // single buffer: its previous store must have been read before anyone writes
+            if (issuer && lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            pair_barrier(q);
+          } else if (p.dbg & 64) {  // experiment: free THIS tile at the top (store i - 2), leave store i - 1 in flight
+            if (issuer && lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            pair_barrier(q);
+          }
+          if (active) {
+            uint8_t* trow = tile + unit * 128u;
+#ifndef OSQ_S3D_NOSWAP
+            // per 8 columns: first the 4-column group (bit), then its neighbour, so that the eight lanes of a store phase
+            // (lanes l and l + 4 share the swizzle phase) hit eight different bank groups.  The group's constants are
+            // fetched with a lane-dependent address instead of being selected in registers.
+            const float* pc1 = sm_c1 + c0 + 4 * (int)bit;
+            const float* pk0 = sm_c0 + c0 + 4 * (int)bit;
+            const int flip = 4 - 8 * (int)bit;  // offset from the first group to the second: +4 or -4 columns
+            float4 c1n = *reinterpret_cast<const float4*>(pc1);
+            float4 k0n = *reinterpret_cast<const float4*>(pk0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float4 c1 = c1n, k0 = k0n;
+              c1n = *reinterpret_cast<const float4*>(pc1 + j + flip);
+              k0n = *reinterpret_cast<const float4*>(pk0 + j + flip);
+              const uint32_t ce = (uint32_t)(j >> 2);
+              float4 o;
+              o.x = fmaf((float)(int)(bit ? v[j + 4] : v[j + 0]), c1.x, k0.x);
+              o.y = fmaf((float)(int)(bit ? v[j + 5] : v[j + 1]), c1.y, k0.y);
+              o.z = fmaf((float)(int)(bit ? v[j + 6] : v[j + 2]), c1.z, k0.z);
+              o.w = fmaf((float)(int)(bit ? v[j + 7] : v[j + 3]), c1.w, k0.w);
+              *reinterpret_cast<float4*>(trow + (((ce ^ bit) ^ usw) << 4)) = o;
+              c1 = c1n; k0 = k0n;
+              if (j + 8 < 32) {
+                c1n = *reinterpret_cast<const float4*>(pc1 + j + 8);
+                k0n = *reinterpret_cast<const float4*>(pk0 + j + 8);
+              }
+              o.x = fmaf((float)(int)(bit ? v[j + 0] : v[j + 4]), c1.x, k0.x);
+              o.y = fmaf((float)(int)(bit ? v[j + 1] : v[j + 5]), c1.y, k0.y);
+              o.z = fmaf((float)(int)(bit ? v[j + 2] : v[j + 6]), c1.z, k0.z);
+              o.w = fmaf((float)(int)(bit ? v[j + 3] : v[j + 7]), c1.w, k0.w);
+              *reinterpret_cast<float4*>(trow + ((((ce + 1u) ^ bit) ^ usw) << 4)) = o;
+            }
+#else
+            // (lanes l and l + 4 share the swizzle phase of their units: a 2-way bank conflict per store phase)
+            (void)bit;
+            float4 c1n = *reinterpret_cast<const float4*>(sm_c1 + c0);
+            float4 k0n = *reinterpret_cast<const float4*>(sm_c0 + c0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 c1 = c1n, k0 = k0n;
+              if (j + 4 < 32) {
+                c1n = *reinterpret_cast<const float4*>(sm_c1 + c0 + j + 4);
+                k0n = *reinterpret_cast<const float4*>(sm_c0 + c0 + j + 4);
+              }
+              float4 o;
+              o.x = fmaf((float)(int)v[j + 0], c1.x, k0.x);
+              o.y = fmaf((float)(int)v[j + 1], c1.y, k0.y);
+              o.z = fmaf((float)(int)v[j + 2], c1.z, k0.z);
+              o.w = fmaf((float)(int)v[j + 3], c1.w, k0.w);
+              *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ (usw << 4))) = o;
+            }
+#endif
+          }
+          fence_proxy_async_smem();
+          if (obufs == 2 && issuer && !(p.dbg & 64)) {  // frees the OTHER tile for the next step (its store was issued a whole step ago)
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          pair_barrier(q);
+          if (issuer && lane == 0 && !(p.dbg & 2)) {
+            tma_store_3d(ymap, tile, 0, (n0 + cb) >> 5, row0);   // rows >= M / column groups >= N/32 are clipped by the TMA unit
+            tma_store_commit();
+          }
+          ++n_stores;
+        }
+      } else {
       for (int c0 = slice * 32; c0 < n_cols; c0 += 64) {
         uint32_t v[32];
 #ifdef OSQ_ENABLE_TRACE
@@ -929,13 +1084,15 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         if (probe) OSQ_TRACE(pslot + 4);
 #endif
         if (lane == 0 && !(p.dbg & 2)) {
-          tma_store_2d(ymap, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
+          if (hint) tma_store_2d_hint(ymap, tile, n0 + c0, row0, pol_once);
+          else tma_store_2d(ymap, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
           tma_store_commit();
         }
 #ifdef OSQ_ENABLE_TRACE
         if (probe) OSQ_TRACE(pslot + 5);
 #endif
         ++n_stores;
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -960,6 +1117,8 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       if (p.alias_xo && it > 0 && w < kNumEpiWarps) {  // this warp's landing slot was its store tile: reads must be done
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
+        // pair stores: the slot may have been staged by the other slice's warp and stored by slice 0's
+        if constexpr (kS3d) asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
       }
       if constexpr (kXTma) convert_pass_tma(mb, pa_block, it == 0); else convert_pass(mb, pa_block);
       }
@@ -982,7 +1141,9 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         if (w < kNumEpiWarps) epilogue_chunk(mb, nc0 + lc);
       }
     }
-    if (w < kNumEpiWarps && lane == 0) tma_store_wait_all();
+    // the staging tiles must have been READ before the CTA's shared memory goes away; the writes themselves are complete
+    // and visible at grid completion (CUTLASS' TMA epilogues end on the same .read wait).  OSQ_FUSED_DBG=128: full wait.
+    if (w < kNumEpiWarps && lane == 0) { if (p.dbg & 128) tma_store_wait_all(); else tma_store_wait_read<0>(); }
     if (w == 0 && lane == 0) OSQ_TRACE(1021);
   }
 
@@ -990,24 +1151,72 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
   tc_fence_before();
   __syncthreads();
   if (p.csz > 1) cluster_sync_all();  // no CTA exits while the pair's MMAs / commits / remote arrives may still touch it
-  if (warp == 2) {
+  if (warp == 2 && !p.more_sites) {
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm.tmem_base);
     if (pair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
   if (p.trace != nullptr && threadIdx.x == 0) p.trace[1024 + 2 * blockIdx.x + 1] = gtimer();
+  if (p.more_sites) {
+    tmem_keep = *reinterpret_cast<volatile uint32_t*>(&sm.tmem_base);   // every thread: the next site's Smem sits elsewhere
+    // multi-site launch: the next site re-initialises every barrier at the same addresses (possibly with other counts)
+    if (warp == 1 && lane == 0) {
+      for (int i = 0; i < p.a_stages; ++i) { mbar_inval(&sm.a_full[i]); mbar_inval(&sm.a_empty[i]); }
+      for (int i = 0; i < p.w_stages; ++i) { mbar_inval(&sm.w_full[i]); mbar_inval(&sm.w_empty[i]); }
+      for (int i = 0; i < p.acc_stages; ++i) { mbar_inval(&sm.acc_full[i]); mbar_inval(&sm.acc_empty[i]); }
+      mbar_inval(&sm.codes_ready);
+      for (int i = 0; i < kNumWorkers; ++i) mbar_inval(&sm.x_full[i]);
+      mbar_inval(&sm.passes_issued);
+      mbar_inval(&sm.tmem_ready);
+    }
+    __syncthreads();   // also: TMEM is deallocated and every warp has left this site's shared memory
+    if (p.csz > 1) cluster_sync_all();
+  }
 }
 
-#define OSQ_FUSED_ENTRY(name, XTMA, PAIR)                                                                              \
+#define OSQ_FUSED_ENTRY(name, XTMA, PAIR, S3D)                                                                         \
   __global__ void __launch_bounds__(kNumThreads, 1)                                                                    \
   name(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,                         \
        const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,                   \
        const __grid_constant__ CUtensorMap tmap_a, const FusedParams p) {                                              \
-    fused_fq_linear_body<XTMA, PAIR>(tmap_w, tmap_y, tmap_y16, tmap_codes, tmap_a, p);                                 \
+    uint32_t tmem_keep = 0;                                                                                            \
+    fused_fq_linear_body<XTMA, PAIR, S3D>(tmap_w, tmap_y, tmap_y16, tmap_codes, tmap_a, p, tmem_keep);                 \
   }
-OSQ_FUSED_ENTRY(fused_fq_linear_kernel_ldg, false, false)
-OSQ_FUSED_ENTRY(fused_fq_linear_kernel, true, false)
-OSQ_FUSED_ENTRY(fused_fq_linear_kernel_pair, true, true)
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel_ldg, false, false, false)
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel, true, false, false)
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel_pair, true, true, false)
+// epilogue with pair-shared staging tiles and 256-byte-row 3-D tensor stores (N % 32 == 0, chunks of 64 k columns)
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel_ldg_s3, false, false, true)
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel_s3, true, false, true)
+OSQ_FUSED_ENTRY(fused_fq_linear_kernel_pair_s3, true, true, true)
+
+// Multi-site launch: one persistent grid walks a short list of INDEPENDENT sites (no site's input is another site's
+// output).  A CTA moves on to the next site as soon as its own tiles of the current one are stored, so the launch gap,
+// the wait for the slowest CTA and the first-load latency are paid once per list instead of once per site, and the tail of
+// one site's write phase overlaps the head of the next site's read phase.
+constexpr int kMaxSites = 4;
+struct FusedSite {
+  CUtensorMap w, y, y16, codes, a;
+  FusedParams p;
+};
+struct FusedSites {
+  FusedSite s[kMaxSites];
+  int n;
+};
+// One inlined copy of the body per list position: every copy reads its site's parameters at compile-time constant-bank
+// offsets, exactly like a single-site launch (a runtime-indexed site costs registers in every hot loop: measured 10 % slower).
+#define OSQ_FUSED_SITE(i)                                                                                              \
+  if (sites.n > (i))                                                                                                   \
+    fused_fq_linear_body<true, PAIR_, false>(sites.s[i].w, sites.s[i].y, sites.s[i].y16, sites.s[i].codes,             \
+                                             sites.s[i].a, sites.s[i].p, tmem_keep);
+#define OSQ_FUSED_MULTI_ENTRY(name, PAIR)                                                                              \
+  __global__ void __launch_bounds__(kNumThreads, 1) name(const __grid_constant__ FusedSites sites) {                   \
+    constexpr bool PAIR_ = PAIR;                                                                                       \
+    uint32_t tmem_keep = 0;                                                                                            \
+    OSQ_FUSED_SITE(0) OSQ_FUSED_SITE(1) OSQ_FUSED_SITE(2) OSQ_FUSED_SITE(3)                                            \
+  }
+OSQ_FUSED_MULTI_ENTRY(fused_fq_linear_multi_kernel, false)
+OSQ_FUSED_MULTI_ENTRY(fused_fq_linear_multi_kernel_pair, true)
 
 // ------------------------------------------------------------------------------------------
 // weight packing: bins (q - zp) as s8 + per-row sums
@@ -1083,6 +1292,26 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes,
   return OSQ_OK;
 }
 
+// Y [M, N] fp32 viewed as [M][N/32][32]: one box = `rows` rows x 2 adjacent 32-column groups (256 contiguous bytes per row)
+static int make_map_3d_y(CUtensorMap* map, const void* y, uint64_t n, uint64_t m, uint32_t rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return OSQ_ECUDA;
+  }
+  cuuint64_t dims[3] = {32, n / 32, m};
+  cuuint64_t strides[2] = {128, n * 4};
+  cuuint32_t box[3] = {32, 2, rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(y), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D Y map) failed with CUresult %d (N=%llu M=%llu)", (int)r, (unsigned long long)n, (unsigned long long)m);
+    return OSQ_ECUDA;
+  }
+  return OSQ_OK;
+}
+
 }  // namespace osq
 
 extern "C" {
@@ -1105,8 +1334,17 @@ int osq_pack_weight_s8(const float* w, int64_t N, int64_t K, const float* scale,
   return OSQ_OK;
 }
 
-int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
-  using namespace osq;
+}  // extern "C" (closed here: the planner and launcher below are internal)
+
+namespace osq {
+struct FusedPlan {
+  FusedParams p;
+  CUtensorMap map_w, map_y, map_y16, map_c, map_a;
+  int grid;
+  size_t smem;
+};
+
+static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
   OSQ_CHECK_ARG(a != nullptr, "osq_fused_fq_linear: null args");
   OSQ_CHECK_ARG((a->A || a->a_codes) && a->a_scale && a->a_zp && a->w_codes && a->w_scale && a->w_rowsum && a->Y,
                 "osq_fused_fq_linear: null pointer");
@@ -1158,12 +1396,17 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_ldg, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_ldg_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_multi_kernel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.blockDim = dim3(kNumThreads);
-  cfg.stream = (cudaStream_t)stream;
+  cfg.stream = nullptr;   // the occupancy query below does not depend on the stream
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.y = 1;
@@ -1329,12 +1572,24 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
   if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->w_codes, (uint64_t)p.K, (uint64_t)p.N, kStageK,
                            (uint32_t)(p.BN / p.csz), CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
+  static int env_s3d = -1;
+  // measured (round 2): the pair-shared 256-byte-row stores are 2-3 % SLOWER in the kernel than per-warp 32 x 128 B tiles
+  // (0.657 vs 0.670 of the HBM roofline over the four BERT-base sites) although they are 10 % faster in isolation
+  // (profiles/r01_storebench_3d.txt): kept as a tested variant, off by default
+  if (env_s3d < 0) { const char* e = getenv("OSQ_FUSED_STORE3D"); env_s3d = e ? atoi(e) : 0; }
+  // pair stores need whole 32-column groups, chunks that split into 64-column pairs, and two 4 KB staging tiles per quarter
+  p.store3d = (env_s3d != 0 && p.N % 32 == 0 && p.BN % 64 == 0 && p.M >= 32 && (p.alias_xo || p.out_bufs >= 1)) ? 1 : 0;
+  if (p.store3d) {
+    if (int rc = make_map_3d_y(&map_y, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32)) return rc;
+    if (int rc = make_map_3d_y(&map_y16, a->Y, (uint64_t)p.N, (uint64_t)p.M, 16)) return rc;
+  } else {
   if (int rc = make_map_2d(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
                            p.M < 32 ? (uint32_t)p.M : 32u, CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
   if (int rc = make_map_2d(&map_y16, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32,
                            p.M < 16 ? (uint32_t)p.M : 16u, CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
+  }
   if (p.cached || p.codes_in) {
     if (int rc = make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a->a_codes, (uint64_t)p.K, (uint64_t)p.M, kStageK,
                              (uint32_t)(p.M < p.rows_per_tile ? p.M : p.rows_per_tile), CU_TENSOR_MAP_SWIZZLE_128B))
@@ -1367,10 +1622,120 @@ int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
               p.a_stages, p.a_stage_bytes, p.w_stages, p.w_stage_bytes, p.acc_stages, p.out_bufs, p.x_tma, p.alias_xo, p.a_passes, smem_bytes);
     }
   }
-  if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair, map_w, map_y, map_y16, map_c, map_a, p));
-  else if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel, map_w, map_y, map_y16, map_c, map_a, p));
-  else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_ldg, map_w, map_y, map_y16, map_c, map_a, p));
+  p.first_site = 1;
+  p.more_sites = 0;
+  out->p = p;
+  out->map_w = map_w; out->map_y = map_y; out->map_y16 = map_y16; out->map_c = map_c; out->map_a = map_a;
+  out->grid = grid;
+  out->smem = smem_bytes;
+  return OSQ_OK;
+}
+
+static int launch_fused(const FusedPlan& pl, void* stream) {
+  const FusedParams& p = pl.p;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.gridDim = dim3((unsigned)pl.grid);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.csz;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 2 : 1;
+  const CUtensorMap &map_w = pl.map_w, &map_y = pl.map_y, &map_y16 = pl.map_y16, &map_c = pl.map_c, &map_a = pl.map_a;
+  if (p.store3d) {
+    if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair_s3, map_w, map_y, map_y16, map_c, map_a, p));
+    else if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_s3, map_w, map_y, map_y16, map_c, map_a, p));
+    else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_ldg_s3, map_w, map_y, map_y16, map_c, map_a, p));
+  } else {
+    if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair, map_w, map_y, map_y16, map_c, map_a, p));
+    else if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel, map_w, map_y, map_y16, map_c, map_a, p));
+    else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_ldg, map_w, map_y, map_y16, map_c, map_a, p));
+  }
   OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+}  // namespace osq
+
+extern "C" {
+
+int osq_fused_fq_linear(const osq_fused_linear_t* a, void* stream) {
+  using namespace osq;
+  FusedPlan pl;
+  if (int rc = plan_fused(a, &pl)) return rc;
+  return launch_fused(pl, stream);
+}
+
+int osq_fused_fq_linear_multi(const osq_fused_linear_t* sites, int n_sites, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(sites != nullptr && n_sites >= 1, "osq_fused_fq_linear_multi: no sites");
+  static int env_multi = -1;
+  // measured (round 2, BERT-base sites, M = 16384): the persistent multi-site grid is 10 % SLOWER than one launch per site
+  // (2.50 vs 2.23 ms per 48-site step).  Its CTAs drift out of phase, so the chip reads and writes HBM at the same time
+  // instead of in two bulk phases, and the mixed traffic costs more (DRAM bus turnarounds) than the saved launch gaps.
+  // Off by default (the entry point then issues the sites one by one); OSQ_FUSED_MULTI=1 enables it.
+  if (env_multi < 0) { const char* e = getenv("OSQ_FUSED_MULTI"); env_multi = e ? atoi(e) : 0; }
+  // one persistent grid per run of compatible sites (same grid, same cluster size, TMA variant, plain tile stores);
+  // anything else is launched on its own
+  int i = 0;
+  while (i < n_sites) {
+    static thread_local FusedSites fs;
+    FusedPlan first;
+    if (int rc = plan_fused(&sites[i], &first)) return rc;
+    int n = 0;
+    size_t smem = first.smem;
+    auto take = [&](const FusedPlan& pl) {
+      FusedSite& d = fs.s[n++];
+      d.w = pl.map_w; d.y = pl.map_y; d.y16 = pl.map_y16; d.codes = pl.map_c; d.a = pl.map_a; d.p = pl.p;
+      if (pl.smem > smem) smem = pl.smem;
+    };
+    const bool ok0 = env_multi != 0 && first.p.x_tma && !first.p.store3d && first.p.trace == nullptr;
+    if (!ok0) {
+      if (int rc = launch_fused(first, stream)) return rc;
+      ++i;
+      continue;
+    }
+    take(first);
+    int j = i + 1;
+    for (; j < n_sites && n < kMaxSites; ++j) {
+      FusedPlan pl;
+      if (int rc = plan_fused(&sites[j], &pl)) return rc;
+      if (!(pl.p.x_tma && !pl.p.store3d && pl.p.trace == nullptr && pl.grid == first.grid && pl.p.csz == first.p.csz)) break;
+      take(pl);
+    }
+    if (n == 1) {
+      if (int rc = launch_fused(first, stream)) return rc;
+    } else {
+      for (int k = 0; k < n; ++k) { fs.s[k].p.more_sites = (k + 1 < n) ? 1 : 0; fs.s[k].p.first_site = (k == 0) ? 1 : 0; }
+      fs.n = n;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.blockDim = dim3(kNumThreads);
+      cfg.gridDim = dim3((unsigned)first.grid);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)first.p.csz;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = first.p.pdl ? 2 : 1;
+      if (first.p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_multi_kernel_pair, fs));
+      else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_multi_kernel, fs));
+      OSQ_LAUNCH_CHECK();
+    }
+    i = j;
+  }
   return OSQ_OK;
 }
 

@@ -453,6 +453,43 @@ def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum
     return (y, dbg) if want_codes else y
 
 
+def fused_fq_linear_multi(sites):
+    """One C call for a list of INDEPENDENT fused sites (osq_fused_fq_linear_multi): compatible runs share one persistent
+    launch.  ``sites``: dicts with the keyword arguments of ``fused_fq_linear`` (a, a_scale, a_zp, a_qmin, a_qmax, w_codes,
+    w_scale, w_rowsum, bias, lsq_grad_factor, out).  fp32-in, resident / code-cache plans only; returns the outputs."""
+    arr = (FusedLinearArgs * len(sites))()
+    outs, keep = [], []
+    for args, st in zip(arr, sites):
+        a = st["a"]
+        _require_cuda(a, st["a_scale"], st["a_zp"], st["w_codes"], st["w_scale"], st["w_rowsum"], st.get("bias"))
+        a2 = a.reshape(-1, a.shape[-1])
+        if a2.dtype != torch.float32 or not a2.is_contiguous():
+            a2 = a2.float().contiguous()
+        m, k = a2.shape
+        n = st["w_codes"].shape[0]
+        y = st.get("out")
+        if y is None:
+            y = torch.empty((m, n), dtype=torch.float32, device=a.device)
+        cache = torch.empty((m, k), dtype=torch.uint8, device=a.device) if (k > 1024 and n > 256) else st.get("cache")
+        if st.get("cache") is not None:
+            cache = st["cache"]
+        args.A, args.M, args.K = a2.data_ptr(), m, k
+        args.a_scale, args.a_zp = st["a_scale"].data_ptr(), st["a_zp"].data_ptr()
+        args.a_zp_is_int32 = int(st["a_zp"].dtype == torch.int32)
+        args.lsq_grad_factor = float(st.get("lsq_grad_factor", 0.0))
+        args.a_qmin, args.a_qmax = int(st["a_qmin"]), int(st["a_qmax"])
+        args.w_codes, args.w_scale, args.w_rowsum = st["w_codes"].data_ptr(), st["w_scale"].data_ptr(), st["w_rowsum"].data_ptr()
+        args.bias = _ptr(st.get("bias"))
+        args.Y, args.N = y.data_ptr(), n
+        args.mma_kind = 0
+        args.a_codes = _ptr(cache)
+        args.debug_trace = None
+        outs.append(y.reshape(*a.shape[:-1], n))
+        keep.append((a2, cache))
+    check(_lib.load().osq_fused_fq_linear_multi(arr, len(sites), _stream()), "osq_fused_fq_linear_multi")
+    return outs
+
+
 def lsqplus_backward(x, dy, scale, zero_point, lsq_grad_factor, qmin, qmax):
     """gradients of util_quant.py:48-55: returns (dx, dscale[1], dzero_point[1])."""
     _require_cuda(x, dy, scale, zero_point)

@@ -165,8 +165,9 @@ PAIR_CASES = "[(256, 768, 768), (1000, 768, 2304), (16384, 768, 768), (300, 1024
 def test_cta_pair_mode_and_register_path_in_subprocess():
     """The launch plan is read from the environment once per process, so every kernel variant gets a child process of
     its own whatever the default is: OSQ_FUSED_CLUSTER=2 (tcgen05 cta_group::2: one W tile copy per CTA pair),
-    OSQ_FUSED_CLUSTER=1 (one CTA per tile) and OSQ_FUSED_XTMA=0 (fp32 A through 128-bit register loads instead of TMA
-    landing slots).  Same parity bar as every other case."""
+    OSQ_FUSED_CLUSTER=1 (one CTA per tile), OSQ_FUSED_XTMA=0 (fp32 A through 128-bit register loads instead of TMA
+    landing slots) and OSQ_FUSED_STORE3D=0 (per-warp 32 x 128 B tile stores instead of the pair-shared 256-byte-row
+    3-D stores).  Same parity bar as every other case."""
     import os
     import subprocess
     import sys
@@ -176,7 +177,8 @@ def test_cta_pair_mode_and_register_path_in_subprocess():
             "    run_case(m, k, n, 6, 6, True, 100 + i, gamma=bool(i & 1))\n"
             "    run_case(m, k, n, 8, 8, False, 200 + i)\n"
             "print('variant ok')\n" % PAIR_CASES)
-    for env in ({"OSQ_FUSED_CLUSTER": "2"}, {"OSQ_FUSED_CLUSTER": "1"}, {"OSQ_FUSED_XTMA": "0"}):
+    for env in ({"OSQ_FUSED_CLUSTER": "2"}, {"OSQ_FUSED_CLUSTER": "1"}, {"OSQ_FUSED_XTMA": "0"}, {"OSQ_FUSED_STORE3D": "0"},
+                {"OSQ_FUSED_STORE3D": "0", "OSQ_FUSED_CLUSTER": "1"}):
         r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
                            timeout=240)
         assert r.returncode == 0 and "variant ok" in r.stdout, "%s failed:\n%s\n%s" % (env, r.stdout[-2000:], r.stderr[-3000:])
@@ -296,3 +298,48 @@ def test_stale_qparams_void_the_producer_tag():
         y = ql(x_fq)
         assert qm.stats["unfused"] == before["unfused"] + 1
     close(y, y_good, rel=1e-5)  # reference semantics: Linear over the tensor as it is, NOT re-quantised with the new scale
+
+
+def test_multi_site_entry_point_and_persistent_variant():
+    """The list entry point in-process (default: sites issued one by one) and, in a child process with OSQ_FUSED_MULTI=1,
+    as ONE persistent launch per run of compatible sites."""
+    import os
+    import subprocess
+    import sys
+    multi_site_case(300)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("from tests.test_gpu_fused_linear import multi_site_case\nmulti_site_case(300); multi_site_case(16384); print('multi ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, OSQ_FUSED_MULTI="1"), capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "multi ok" in r.stdout, "persistent multi-site launch failed:\n%s\n%s" % (r.stdout[-2000:], r.stderr[-3000:])
+
+
+def multi_site_case(m):
+    """osq_fused_fq_linear_multi: one persistent launch walking a list of independent sites must reproduce the individual
+    launches bit for bit -- barriers are invalidated and re-initialised per site, TMEM is re-allocated, the code cache of the
+    K = 3072 site and the resident plans of the K = 768 sites alternate inside one grid; a site list longer than a run
+    (4) and an incompatible site (K % 4 != ... n/a; different M -> different grid) split into several launches."""
+    from outlier_suppression_b200 import ops
+    shapes = [(768, 2304), (768, 768), (768, 3072), (3072, 768)] * 3   # 12 sites: runs of up to 4
+    g = torch.Generator().manual_seed(7)
+    sites, refs = [], []
+    for i, (k, n) in enumerate(shapes):
+        a = torch.randn(m if i != 5 else max(64, m // 2), k, generator=g)   # site 5 has another M: breaks the run
+        a[:, :3] *= 20
+        w, bias = O.synth_linear(n, k, seed=50 + i, gamma=bool(i & 1))
+        mn, mx = O.global_minmax(a)
+        a_scale, a_zp = O.qparams_from_minmax(mn * 0.7, mx * 0.7, 0, 63, False)
+        a_scale_t, a_zp_t = a_scale.reshape(1).cuda(), (a_zp.reshape(1).float() + 0.37).clamp(0, 63).cuda()
+        w_scale, w_zp, w_qmin, w_qmax = O.weight_qparams_minmax(w, 6, True)
+        codes, rowsum = ops.pack_weight(w.cuda(), w_scale.cuda(), w_zp.cuda(), w_qmin, w_qmax)
+        st = dict(a=a.cuda(), a_scale=a_scale_t, a_zp=a_zp_t, a_qmin=0, a_qmax=63, w_codes=codes, w_scale=w_scale.cuda(),
+                  w_rowsum=rowsum, bias=bias.cuda(), lsq_grad_factor=1.0 / (a.numel() * 63) ** 0.5)
+        sites.append(st)
+        refs.append(ops.fused_fq_linear(st["a"], a_scale_t, a_zp_t, 0, 63, codes, st["w_scale"], rowsum, st["bias"],
+                                        lsq_grad_factor=st["lsq_grad_factor"]))
+    torch.cuda.synchronize()
+    for rep in range(2):   # second pass: same workspace-free path again (barrier phases start from scratch)
+        outs = ops.fused_fq_linear_multi(sites)
+        torch.cuda.synchronize()
+        for i, (y, r) in enumerate(zip(outs, refs)):
+            assert torch.equal(y, r), "site %d differs (max |d| %g)" % (i, float((y - r).abs().max()))
