@@ -259,6 +259,18 @@ typedef struct {
   int mma_kind;
   uint8_t* a_codes;      /* optional [M, K] u8: bins side output AND the kernel's code cache (see above) */
   void* debug_trace;     /* optional device int64[2048]: clock64 timeline of CTA 0 + per-CTA globaltimer start/end (profiling aid), else NULL */
+  /* ---- optional output stage: the NEXT activation quantizer fused into the epilogue (quant_bert.py:277-280: dense ->
+   * intermediate_act_fn -> intermediate_act_fn_post_act_fake_quantize).  With out_scale != NULL the kernel writes
+   * Y = fq(act(Linear)) instead of the Linear's output -- bit-identical to K1 applied to act(Linear) -- and, if out_bins is
+   * given, that quantizer's bins (bin - out_qmin, u8 [M, N], 16-byte aligned) in the operand format of a bins-in launch,
+   * so Linear -> activation -> quantizer -> Linear is two launches with a 1 B / element hand-off. */
+  int out_act;             /* 0 = none, 1 = GELU (erf form; op order of ATen's CUDA kernel) */
+  const float* out_scale;  /* device [1] or NULL (no output stage) */
+  const void* out_zp;      /* device [1] */
+  int out_zp_is_int32;
+  float out_lsq_grad_factor; /* 0 for FixedFakeQuantize; LSQ+: 1 / sqrt(M * N * out_qmax) */
+  int out_qmin, out_qmax;
+  uint8_t* out_bins;       /* optional */
 } osq_fused_linear_t;
 
 int osq_fused_fq_linear(const osq_fused_linear_t* args, void* stream);

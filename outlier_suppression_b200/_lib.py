@@ -47,7 +47,9 @@ class FusedLinearArgs(C.Structure):
     _fields_ = [("A", C.c_void_p), ("M", C.c_int64), ("K", C.c_int64), ("a_scale", C.c_void_p), ("a_zp", C.c_void_p),
                 ("a_zp_is_int32", C.c_int), ("lsq_grad_factor", C.c_float), ("a_qmin", C.c_int), ("a_qmax", C.c_int),
                 ("w_codes", C.c_void_p), ("w_scale", C.c_void_p), ("w_rowsum", C.c_void_p), ("bias", C.c_void_p),
-                ("Y", C.c_void_p), ("N", C.c_int64), ("mma_kind", C.c_int), ("a_codes", C.c_void_p), ("debug_trace", C.c_void_p)]
+                ("Y", C.c_void_p), ("N", C.c_int64), ("mma_kind", C.c_int), ("a_codes", C.c_void_p), ("debug_trace", C.c_void_p),
+                ("out_act", C.c_int), ("out_scale", C.c_void_p), ("out_zp", C.c_void_p), ("out_zp_is_int32", C.c_int),
+                ("out_lsq_grad_factor", C.c_float), ("out_qmin", C.c_int), ("out_qmax", C.c_int), ("out_bins", C.c_void_p)]
 
 
 _lock = threading.Lock()

@@ -89,6 +89,14 @@ struct FusedParams {
   int prefetch;              // L2 prefetch distance of the fp32 activation in k-blocks (0 = off)
   int store3d;               // epilogue: the two column slices of a lane quarter share one 8 KB staging tile and leave as ONE 3-D tensor store
                              // of 32 rows x 2 x 128 B (256 contiguous bytes per row); tmap_y / tmap_y16 are then 3-D maps [M][N/32][32]
+  // output stage (kEpi variants): Y is replaced by fq(act(Y)) of the NEXT activation quantizer, whose bins also leave as u8
+  int out_act;               // 0 = none, 1 = GELU (erf form, the op order of ATen's CUDA kernel)
+  const float* out_scale;    // device [1]
+  const void* out_zp;        // device [1]
+  int out_zp_is_int32;
+  float out_g;               // LSQ+ grad factor of the output quantizer (0: FixedFakeQuantize)
+  float out_qmin, out_qmax;
+  uint8_t* out_bins;         // [M, N] u8 (bin - out_qmin) or NULL
   int more_sites;            // multi-site launch: another site follows in this kernel (barriers are invalidated at teardown, TMEM is kept)
   int first_site;            // this site allocates TMEM (always 1 for a single-site launch)
   int dbg;                   // profiling experiments (OSQ_FUSED_DBG): 1 = W tile pinned, 2 = no Y stores, 4 = A rows pinned
@@ -410,7 +418,27 @@ static_assert(sizeof(Smem) % 16 == 0, "constants must stay 16-byte aligned");
 // One body, three entry points (below): <registers path>, <TMA landing slots>, <TMA landing slots + CTA pair>.
 // Only the pair variant contains cta_group::2 instructions: the driver refuses to launch a kernel that uses them
 // without a cluster of two.
-template <bool kXTma, bool kPair, bool kS3d>
+// GELU(x) = (x * 0.5) * (1 + erf(x / sqrt(2))) with the operation order of ATen's CUDA kernel (ActivationGeluKernel.cu,
+// approximate = 'none'): bit-identical to torch.nn.functional.gelu on the same device
+__device__ __forceinline__ float gelu_erf(float x) {
+  return __fmul_rn(__fmul_rn(x, 0.5f), __fadd_rn(1.0f, erff(__fmul_rn(x, 0.70710678118654752440f))));
+}
+// output stage on four adjacent columns: optional activation, then the next quantizer's fake-quant (util_quant.py:11-15 /
+// :48-55 exactly as K1 computes it); returns the dequantised values and the four bins (q - qmin) packed in one word
+__device__ __forceinline__ float4 out_stage4(float4 o, const QParam& oq, float qmin, float qmax, int act, uint32_t& bins) {
+  if (act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+  float q0, q1, q2, q3;
+  float4 r;
+  r.x = fq_elem(o.x, oq.s, oq.z, qmin, qmax, q0);
+  r.y = fq_elem(o.y, oq.s, oq.z, qmin, qmax, q1);
+  r.z = fq_elem(o.z, oq.s, oq.z, qmin, qmax, q2);
+  r.w = fq_elem(o.w, oq.s, oq.z, qmin, qmax, q3);
+  bins = (uint32_t)(int)(q0 - qmin) | ((uint32_t)(int)(q1 - qmin) << 8) | ((uint32_t)(int)(q2 - qmin) << 16) |
+         ((uint32_t)(int)(q3 - qmin) << 24);
+  return r;
+}
+
+template <bool kXTma, bool kPair, bool kS3d, bool kEpi = false>
 __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, const CUtensorMap& tmap_y, const CUtensorMap& tmap_y16,
                                                      const CUtensorMap& tmap_codes, const CUtensorMap& tmap_a, const FusedParams& p,
                                                      uint32_t& tmem_keep) {
@@ -884,6 +912,12 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     const int slice = w >> 2;            // column slice of the chunk (epilogue warps: 0 or 1)
     const float s_a = qp.s;
     const float zcf = cp.zc;
+    QParam oq = QParam{1.f, 0.f};
+    if constexpr (kEpi) {
+      if (w < kNumEpiWarps)
+        oq = load_qparam(p.out_scale, p.out_zp, p.out_zp_is_int32, p.out_g, p.out_qmin, p.out_qmax,
+                         blockIdx.x == 0 && w == 0 && lane == 0);
+    }
     uint8_t* my_tiles = o_ring + (size_t)w * p.out_bufs * kOutTileBytes;
     const uint32_t sw = ((uint32_t)lane & 7) << 4;  // 128B swizzle phase of this thread's staging row
     const int et = threadIdx.x - kWorkerWarp0 * 32;  // 0..255 among the epilogue threads
@@ -1072,7 +1106,21 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
             o.y = fmaf((float)(int)v[j + 1], c1.y, k0.y);
             o.z = fmaf((float)(int)v[j + 2], c1.z, k0.z);
             o.w = fmaf((float)(int)v[j + 3], c1.w, k0.w);
+            if constexpr (kEpi) {
+              uint32_t bw;
+              o = out_stage4(o, oq, p.out_qmin, p.out_qmax, p.out_act, bw);
+              v[j >> 2] = bw;   // v[j .. j + 3] are consumed: the accumulator registers double as the bins' staging
+            }
             *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ sw)) = o;  // 16B chunk (j/4) ^ (row & 7): conflict free
+          }
+          if constexpr (kEpi) {
+            // this thread's row, 32 bins = 32 contiguous bytes = one full sector: straight from registers
+            const int row = row0 + lane;
+            if (p.out_bins != nullptr && lane < rows_q && row < p.M) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out_bins + (size_t)row * (size_t)p.N + (size_t)(n0 + c0));
+              dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+              if (n0 + c0 + 32 <= p.N) dst[1] = make_uint4(v[4], v[5], v[6], v[7]);   // N % 32 == 16: the last group is half
+            }
           }
         }
 #ifdef OSQ_ENABLE_TRACE
@@ -1189,6 +1237,17 @@ OSQ_FUSED_ENTRY(fused_fq_linear_kernel_pair, true, true, false)
 OSQ_FUSED_ENTRY(fused_fq_linear_kernel_ldg_s3, false, false, true)
 OSQ_FUSED_ENTRY(fused_fq_linear_kernel_s3, true, false, true)
 OSQ_FUSED_ENTRY(fused_fq_linear_kernel_pair_s3, true, true, true)
+// output stage: Y leaves as fq(act(Y)) of the next activation quantizer, plus its u8 bins
+#define OSQ_FUSED_ENTRY_EPI(name, PAIR)                                                                                \
+  __global__ void __launch_bounds__(kNumThreads, 1)                                                                    \
+  name(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,                         \
+       const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,                   \
+       const __grid_constant__ CUtensorMap tmap_a, const FusedParams p) {                                              \
+    uint32_t tmem_keep = 0;                                                                                            \
+    fused_fq_linear_body<true, PAIR, false, true>(tmap_w, tmap_y, tmap_y16, tmap_codes, tmap_a, p, tmem_keep);         \
+  }
+OSQ_FUSED_ENTRY_EPI(fused_fq_linear_kernel_epi, false)
+OSQ_FUSED_ENTRY_EPI(fused_fq_linear_kernel_pair_epi, true)
 
 // Multi-site launch: one persistent grid walks a short list of INDEPENDENT sites (no site's input is another site's
 // output).  A CTA moves on to the next site as soon as its own tiles of the current one are stored, so the launch gap,
@@ -1357,6 +1416,14 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
                 "osq_fused_fq_linear: A, Y and w_codes must be 16-byte aligned");
   OSQ_CHECK_ARG(!(a->lsq_grad_factor > 0.f && a->a_zp_is_int32), "osq_fused_fq_linear: LSQ+ needs a float zero_point");
   OSQ_CHECK_ARG(a->a_codes == nullptr || (((uintptr_t)a->a_codes) & 15) == 0, "osq_fused_fq_linear: a_codes must be 16-byte aligned");
+  if (a->out_scale != nullptr) {
+    OSQ_CHECK_ARG(a->out_zp != nullptr && a->out_qmin < a->out_qmax && a->out_qmax - a->out_qmin <= 255, "osq_fused_fq_linear: bad output quantizer");
+    OSQ_CHECK_ARG(a->out_act == 0 || a->out_act == 1, "osq_fused_fq_linear: out_act must be 0 (none) or 1 (GELU)");
+    OSQ_CHECK_ARG(!(a->out_lsq_grad_factor > 0.f && a->out_zp_is_int32), "osq_fused_fq_linear: an LSQ+ output quantizer needs a float zero_point");
+    OSQ_CHECK_ARG(a->out_bins == nullptr || (((uintptr_t)a->out_bins) & 15) == 0, "osq_fused_fq_linear: out_bins must be 16-byte aligned");
+  } else {
+    OSQ_CHECK_ARG(a->out_act == 0 && a->out_bins == nullptr, "osq_fused_fq_linear: out_act / out_bins need an output quantizer (out_scale)");
+  }
 
   int dev = 0, cc_major = 0, sms = sm_count();
   OSQ_CUDA(cudaGetDevice(&dev));
@@ -1375,6 +1442,8 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
   p.qmin = (float)a->a_qmin; p.qmax = (float)a->a_qmax;
   p.w_scale = a->w_scale; p.w_rowsum = a->w_rowsum; p.bias = a->bias; p.a_codes = a->a_codes;
   p.trace = (long long*)a->debug_trace;
+  p.out_act = a->out_act; p.out_scale = a->out_scale; p.out_zp = a->out_zp; p.out_zp_is_int32 = a->out_zp_is_int32;
+  p.out_g = a->out_lsq_grad_factor; p.out_qmin = (float)a->out_qmin; p.out_qmax = (float)a->out_qmax; p.out_bins = a->out_bins;
   static int env_dbg = -1, env_ob = -1, env_kb = -1, env_csz = -1, env_pdl = -1, env_pf = -1, env_xtma = -1, env_bn = -1;
   if (env_dbg < 0) {
     auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
@@ -1399,6 +1468,8 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_ldg_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_multi_kernel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
@@ -1578,7 +1649,11 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
   // (profiles/r01_storebench_3d.txt): kept as a tested variant, off by default
   if (env_s3d < 0) { const char* e = getenv("OSQ_FUSED_STORE3D"); env_s3d = e ? atoi(e) : 0; }
   // pair stores need whole 32-column groups, chunks that split into 64-column pairs, and two 4 KB staging tiles per quarter
-  p.store3d = (env_s3d != 0 && p.N % 32 == 0 && p.BN % 64 == 0 && p.M >= 32 && (p.alias_xo || p.out_bufs >= 1)) ? 1 : 0;
+  if (a->out_scale != nullptr && !p.x_tma) {
+    set_error("osq_fused_fq_linear: the output stage is built for the TMA landing-slot plans only (OSQ_FUSED_XTMA=0 is set?)");
+    return OSQ_EINVAL;
+  }
+  p.store3d = (a->out_scale == nullptr && env_s3d != 0 && p.N % 32 == 0 && p.BN % 64 == 0 && p.M >= 32 && (p.alias_xo || p.out_bufs >= 1)) ? 1 : 0;
   if (p.store3d) {
     if (int rc = make_map_3d_y(&map_y, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32)) return rc;
     if (int rc = make_map_3d_y(&map_y16, a->Y, (uint64_t)p.N, (uint64_t)p.M, 16)) return rc;
@@ -1649,7 +1724,10 @@ static int launch_fused(const FusedPlan& pl, void* stream) {
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 2 : 1;
   const CUtensorMap &map_w = pl.map_w, &map_y = pl.map_y, &map_y16 = pl.map_y16, &map_c = pl.map_c, &map_a = pl.map_a;
-  if (p.store3d) {
+  if (p.out_scale != nullptr) {
+    if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair_epi, map_w, map_y, map_y16, map_c, map_a, p));
+    else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_epi, map_w, map_y, map_y16, map_c, map_a, p));
+  } else if (p.store3d) {
     if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair_s3, map_w, map_y, map_y16, map_c, map_a, p));
     else if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_s3, map_w, map_y, map_y16, map_c, map_a, p));
     else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_ldg_s3, map_w, map_y, map_y16, map_c, map_a, p));
@@ -1696,7 +1774,7 @@ int osq_fused_fq_linear_multi(const osq_fused_linear_t* sites, int n_sites, void
       d.w = pl.map_w; d.y = pl.map_y; d.y16 = pl.map_y16; d.codes = pl.map_c; d.a = pl.map_a; d.p = pl.p;
       if (pl.smem > smem) smem = pl.smem;
     };
-    const bool ok0 = env_multi != 0 && first.p.x_tma && !first.p.store3d && first.p.trace == nullptr;
+    const bool ok0 = env_multi != 0 && first.p.x_tma && !first.p.store3d && first.p.trace == nullptr && first.p.out_scale == nullptr;
     if (!ok0) {
       if (int rc = launch_fused(first, stream)) return rc;
       ++i;
@@ -1707,7 +1785,8 @@ int osq_fused_fq_linear_multi(const osq_fused_linear_t* sites, int n_sites, void
     for (; j < n_sites && n < kMaxSites; ++j) {
       FusedPlan pl;
       if (int rc = plan_fused(&sites[j], &pl)) return rc;
-      if (!(pl.p.x_tma && !pl.p.store3d && pl.p.trace == nullptr && pl.grid == first.grid && pl.p.csz == first.p.csz)) break;
+      if (!(pl.p.x_tma && !pl.p.store3d && pl.p.trace == nullptr && pl.p.out_scale == nullptr && pl.grid == first.grid &&
+            pl.p.csz == first.p.csz)) break;
       take(pl);
     }
     if (n == 1) {

@@ -411,10 +411,12 @@ def fused_linear_supported(k: int, n: int, a: Optional[torch.Tensor] = None) -> 
 
 
 def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum, bias, lsq_grad_factor=0.0,
-                    mma_kind=0, want_codes=False, out=None, use_code_cache=True, trace=None, a_bins=None):
+                    mma_kind=0, want_codes=False, out=None, use_code_cache=True, trace=None, a_bins=None, out_q=None):
     """activation fq + weight fq + Linear in one tcgen05 kernel. a: [..., K] fp32 -> [..., N] fp32.
     a_bins (uint8, same shape as a, contiguous; from fq_per_tensor(want_bins=True) with the same qparams): bins-in launch,
-    the fp32 tensor is not read at all (only its shape is used); the result is bit-identical."""
+    the fp32 tensor is not read at all (only its shape is used); the result is bit-identical.
+    out_q (dict: scale, zp, qmin, qmax, g, act in {None, "gelu"}, bins: bool): fuse the NEXT activation quantizer into the
+    epilogue -- the call returns (fq(act(Linear)), uint8 bins or None) instead of the Linear's output."""
     _require_cuda(a, a_scale, a_zp, w_codes, w_scale, w_rowsum, bias)
     if a_bins is not None:
         if a_bins.dtype != torch.uint8 or a_bins.numel() != a.numel() or not a_bins.is_contiguous() or not a_bins.is_cuda:
@@ -447,9 +449,24 @@ def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum
     args.mma_kind = int(mma_kind)
     args.a_codes = _ptr(dbg)
     args.debug_trace = _ptr(trace)
+    out_bins = None
+    if out_q is not None:
+        _require_cuda(out_q["scale"], out_q["zp"])
+        if out_q["scale"].dtype != torch.float32 or out_q["zp"].dtype not in (torch.float32, torch.int32):
+            raise TypeError("output quantizer: scale must be float32, zero_point float32 or int32")
+        args.out_act = {None: 0, "none": 0, "gelu": 1}[out_q.get("act")]
+        args.out_scale, args.out_zp = out_q["scale"].data_ptr(), out_q["zp"].data_ptr()
+        args.out_zp_is_int32 = int(out_q["zp"].dtype == torch.int32)
+        args.out_lsq_grad_factor = float(out_q.get("g", 0.0))
+        args.out_qmin, args.out_qmax = int(out_q["qmin"]), int(out_q["qmax"])
+        if out_q.get("bins", True):
+            out_bins = torch.empty((m, n), dtype=torch.uint8, device=a.device)
+            args.out_bins = out_bins.data_ptr()
     if m > 0:
         check(_lib.load().osq_fused_fq_linear(C.byref(args), _stream()), "osq_fused_fq_linear")
     y = y.reshape(*a.shape[:-1], n)
+    if out_q is not None:
+        return y, (None if out_bins is None else out_bins.reshape(*a.shape[:-1], n))
     return (y, dbg) if want_codes else y
 
 

@@ -1,0 +1,102 @@
+"""Model-level fusion hooks: the NEXT activation quantizer -- and the GELU in front of it -- fused into
+the epilogue of the producing QLinear, behind unchanged module calls.
+
+The reference wires the feed-forward block as three module calls (model/quant_bert.py:277-280, quant_roberta.py likewise):
+
+    hidden_states = self.dense(hidden_states)                                            # QLinear
+    hidden_states = self.intermediate_act_fn(hidden_states)                              # GELU
+    hidden_states = self.intermediate_act_fn_post_act_fake_quantize(hidden_states, observation_mask, 1)
+
+A Linear cannot know what will consume its output, so the fusion is attached to the ONE module that owns all three steps:
+``fuse_ffn_activation(model)`` finds every module with exactly that attribute triple (duck typing: no import of the
+reference's classes) and wraps its ``forward``.  In the quantized inference state (weight and activation fake-quant on,
+observers off, no autograd) the wrapper makes ONE fused launch whose epilogue applies GELU and the output quantizer
+(osq_fused_fq_linear with an output stage) and returns the quantizer's tensor, tagged and with its uint8 bins, so the
+following QLinear (``output.dense``) runs bins-in: Linear -> GELU -> quantizer -> Linear is two launches with a
+1 B / element hand-off.  In every other state the original forward runs unchanged (calibration, learn_scale, CPU).
+
+The state togglers call this (like ``group_sibling_linears``), so an unmodified reference driver gets it for free;
+``OSQ_DISABLE_EPILOGUE_FUSION=1`` turns it off.
+"""
+from __future__ import annotations
+
+import os
+import types
+
+import torch
+
+from .. import ops
+from .fake_quant import LSQPlusFakeQuantize, QuantizeBase, _qparam_stamp  # noqa: F401
+from .quantized_module import QLinear, _take_bins, stats
+
+_ACT_ATTR = "intermediate_act_fn"
+_Q_ATTR = "intermediate_act_fn_post_act_fake_quantize"
+
+
+def _is_erf_gelu(fn) -> bool:
+    """transformers' ACT2FN["gelu"] (GELUActivation -> nn.functional.gelu) or torch's own gelu, exact (erf) form only."""
+    if fn is torch.nn.functional.gelu:
+        return True
+    if isinstance(fn, torch.nn.GELU):
+        return getattr(fn, "approximate", "none") == "none"
+    name = type(fn).__name__
+    if name == "GELUActivation":
+        return getattr(fn, "act", None) in (torch.nn.functional.gelu, None) or getattr(fn, "act").__name__ == "gelu"
+    return False
+
+
+def _fusable(mod, x):
+    if os.environ.get("OSQ_DISABLE_EPILOGUE_FUSION") == "1" or torch.is_grad_enabled() and x.requires_grad:
+        return None
+    dense, q = mod.dense, getattr(mod, _Q_ATTR, None)
+    if not isinstance(dense, QLinear) or not isinstance(q, QuantizeBase) or not getattr(mod, "qoutput", True):
+        return None
+    if q.fake_quant_enabled != 1 or q.observer_enabled != 0 or q.ch_axis != -1 or q.quant_max - q.quant_min > 255:
+        return None
+    if torch.is_grad_enabled() and (q.scale.requires_grad or dense.weight.requires_grad):
+        return None
+    if not _is_erf_gelu(getattr(mod, _ACT_ATTR, None)):
+        return None
+    aq = dense._fusable_producer(x)
+    if aq is None or not x.is_contiguous():
+        return None
+    return aq, q
+
+
+def _fused_forward(self, hidden_states, observation_mask=None):
+    pair = _fusable(self, hidden_states)
+    if pair is None:
+        return self._osq_unfused_forward(hidden_states, observation_mask=observation_mask)
+    aq, q = pair
+    dense = self.dense
+    codes, rowsum, w_scale = dense._packed_weight()
+    g_in = aq.grad_factor(hidden_states) if isinstance(aq, LSQPlusFakeQuantize) else 0.0
+    n_out = hidden_states.numel() // hidden_states.shape[-1] * dense.out_features
+    g_out = (1.0 / (n_out * q.quant_max) ** 0.5 if q.use_grad_scaling else 1.0) if isinstance(q, LSQPlusFakeQuantize) else 0.0
+    y, bins = ops.fused_fq_linear(hidden_states, aq.scale.detach(), aq.zero_point.detach(), aq.quant_min, aq.quant_max, codes,
+                                  w_scale, rowsum, dense.bias, lsq_grad_factor=g_in, a_bins=_take_bins(hidden_states, aq),
+                                  out_q=dict(scale=q.scale.detach(), zp=q.zero_point.detach(), qmin=q.quant_min, qmax=q.quant_max,
+                                             g=g_out, act="gelu", bins=True))
+    stats["fused"] += 1
+    stats["epilogue_fused"] = stats.get("epilogue_fused", 0) + 1
+    q._tag(y)
+    try:
+        y._osq_bins = (bins, y._version)
+    except Exception:  # pragma: no cover
+        pass
+    return y
+
+
+def fuse_ffn_activation(model) -> int:
+    """Wraps the forward of every ``dense -> intermediate_act_fn -> ..._post_act_fake_quantize`` module.  Idempotent;
+    returns the number of wrapped modules."""
+    n = 0
+    for mod in model.modules():
+        if not (hasattr(mod, "dense") and hasattr(mod, _ACT_ATTR) and hasattr(mod, _Q_ATTR)):
+            continue
+        n += 1
+        if getattr(mod, "_osq_unfused_forward", None) is not None:
+            continue
+        mod._osq_unfused_forward = mod.forward
+        mod.forward = types.MethodType(_fused_forward, mod)
+    return n

@@ -33,7 +33,7 @@ FakeQuantizeDict = {
 }
 
 # statistics for tests / benches: which path QLinear.forward took
-stats = {"fused": 0, "unfused": 0, "grouped_launch": 0, "grouped_hit": 0, "bins_in": 0}
+stats = {"fused": 0, "unfused": 0, "grouped_launch": 0, "grouped_hit": 0, "bins_in": 0, "epilogue_fused": 0}
 
 
 def _take_bins(input, aq):

@@ -17,6 +17,9 @@ def _drop_weight_caches(model):
     # query | key | value style siblings share one fused launch from here on (quantized_module.QLinearGroup)
     from .quantized_module import group_sibling_linears
     group_sibling_linears(model)
+    # dense -> GELU -> quantizer blocks get the fused output stage in the quantized state (quantization/fusion.py)
+    from .fusion import fuse_ffn_activation
+    fuse_ffn_activation(model)
 
 
 def _apply(model, quantizer_type, except_quantizer, observer_on, fq_on, lsq_observer_off=False):

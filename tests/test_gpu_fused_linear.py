@@ -343,3 +343,76 @@ def multi_site_case(m):
         torch.cuda.synchronize()
         for i, (y, r) in enumerate(zip(outs, refs)):
             assert torch.equal(y, r), "site %d differs (max |d| %g)" % (i, float((y - r).abs().max()))
+
+
+@pytest.mark.parametrize("m,k,n", [(300, 768, 3072), (16384, 768, 3072), (515, 3072, 768), (129, 256, 48), (1000, 1024, 4096)])
+@pytest.mark.parametrize("act,lsq_out", [("gelu", True), ("gelu", False), (None, True)])
+def test_output_stage_matches_the_unfused_chain_bit_for_bit(m, k, n, act, lsq_out):
+    """f3: the NEXT activation quantizer (and the GELU in front of it, quant_bert.py:277-280) fused into the Linear's
+    epilogue.  Reference chain on the same device: fused Linear -> torch gelu (erf) -> K1 with bins.  The fused launch
+    must reproduce the chain's dequantised tensor AND its uint8 bins bit for bit, and a bins-in launch of the next Linear
+    fed with those bins must equal the fp32-in launch on the chain's tensor."""
+    from outlier_suppression_b200 import ops
+    g = torch.Generator().manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=g)
+    a[:, :3] *= 20
+    w, bias = O.synth_linear(n, k, seed=9, gamma=True)
+    mn, mx = O.global_minmax(a)
+    a_scale, a_zp = O.qparams_from_minmax(mn * 0.7, mx * 0.7, 0, 63, False)
+    a_scale_t, a_zp_t = a_scale.reshape(1).cuda(), (a_zp.reshape(1).float() + 0.37).clamp(0, 63).cuda()
+    g_in = 1.0 / (a.numel() * 63) ** 0.5
+    w_scale, w_zp, w_qmin, w_qmax = O.weight_qparams_minmax(w, 6, True)
+    codes, rowsum = ops.pack_weight(w.cuda(), w_scale.cuda(), w_zp.cuda(), w_qmin, w_qmax)
+    ag = a.cuda()
+    y = ops.fused_fq_linear(ag, a_scale_t, a_zp_t, 0, 63, codes, w_scale.cuda(), rowsum, bias.cuda(), lsq_grad_factor=g_in)
+    z = torch.nn.functional.gelu(y) if act == "gelu" else y
+    zmin, zmax = float(z.min()), float(z.max())
+    o_scale, o_zp = O.qparams_from_minmax(torch.tensor(zmin * 0.8), torch.tensor(zmax * 0.8), 0, 63, False)
+    if lsq_out:
+        os_t, oz_t, g_out = o_scale.reshape(1).cuda(), (o_zp.reshape(1).float() + 0.21).clamp(0, 63).cuda(), 1.0 / (z.numel() * 63) ** 0.5
+    else:
+        os_t, oz_t, g_out = o_scale.reshape(1).cuda(), o_zp.reshape(1).to(torch.int32).cuda(), 0.0
+    ref_fq, ref_bins = ops.fq_per_tensor(z.contiguous(), os_t, oz_t, 0, 63, lsq_grad_factor=g_out, want_bins=True)
+    got_fq, got_bins = ops.fused_fq_linear(ag, a_scale_t, a_zp_t, 0, 63, codes, w_scale.cuda(), rowsum, bias.cuda(), lsq_grad_factor=g_in,
+                                           out_q=dict(scale=os_t, zp=oz_t, qmin=0, qmax=63, g=g_out, act=act, bins=True))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(got_bins.cpu().numpy(), ref_bins.cpu().numpy())
+    np.testing.assert_array_equal(got_fq.cpu().numpy(), ref_fq.cpu().numpy())
+    assert len(torch.unique(got_bins)) > 8   # the quantizer is really exercised (not saturated)
+    if n % 128 == 0 and n >= 128:
+        # hand-off: the next Linear (n -> 64) bins-in on the fused bins == fp32-in on the chain's tensor
+        w2, b2 = O.synth_linear(64, n, seed=10)
+        ws2, wz2, q2min, q2max = O.weight_qparams_minmax(w2, 6, True)
+        c2, r2 = ops.pack_weight(w2.cuda(), ws2.cuda(), wz2.cuda(), q2min, q2max)
+        y_a = ops.fused_fq_linear(ref_fq, os_t, oz_t, 0, 63, c2, ws2.cuda(), r2, b2.cuda(), lsq_grad_factor=g_out)
+        y_b = ops.fused_fq_linear(got_fq, os_t, oz_t, 0, 63, c2, ws2.cuda(), r2, b2.cuda(), lsq_grad_factor=g_out, a_bins=got_bins)
+        np.testing.assert_array_equal(y_a.cpu().numpy(), y_b.cpu().numpy())
+
+
+def test_output_stage_against_the_cpu_oracle():
+    """The same output stage against the CPU oracle chain (F.linear -> erf GELU -> fake-quant).  CPU and GPU differ in the
+    last ulp of the Linear (fp32 F.linear vs exact integer contraction) and of erf, so a value within an ulp of a rounding
+    tie may land in the neighbouring bin: bins equal for >= 99.9 % of the elements and never more than one bin apart;
+    dequantised values within one quantisation step."""
+    from outlier_suppression_b200 import ops
+    m, k, n = 512, 768, 3072
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(m, k, generator=g)
+    a[:, :3] *= 20
+    w, bias = O.synth_linear(n, k, seed=4, gamma=True)
+    mn, mx = O.global_minmax(a)
+    a_scale, a_zp = O.qparams_from_minmax(mn * 0.7, mx * 0.7, 0, 63, False)
+    w_scale, w_zp, w_qmin, w_qmax = O.weight_qparams_minmax(w, 6, True)
+    y_ref, _, _ = O.fused_fq_linear(a, a_scale.reshape(1), a_zp.reshape(1).to(torch.int32), 0, 63, False, w, w_scale, w_zp, w_qmin, w_qmax, bias)
+    z = torch.nn.functional.gelu(y_ref)
+    o_scale, o_zp = O.qparams_from_minmax(z.min() * 0.8, z.max() * 0.8, 0, 63, False)
+    bins_ref = O.fq_bins(z, o_scale.item(), int(o_zp.item()), 0, 63)
+    fq_ref = O.fq_per_tensor(z, o_scale.item(), int(o_zp.item()), 0, 63)
+    codes, rowsum = ops.pack_weight(w.cuda(), w_scale.cuda(), w_zp.cuda(), w_qmin, w_qmax)
+    got_fq, got_bins = ops.fused_fq_linear(a.cuda(), a_scale.reshape(1).cuda(), a_zp.reshape(1).to(torch.int32).cuda(), 0, 63, codes,
+                                           w_scale.cuda(), rowsum, bias.cuda(),
+                                           out_q=dict(scale=o_scale.reshape(1).cuda(), zp=o_zp.reshape(1).to(torch.int32).cuda(), qmin=0,
+                                                      qmax=63, g=0.0, act="gelu", bins=True))
+    d = (got_bins.cpu().to(torch.int32) - bins_ref.to(torch.int32)).abs()
+    assert int(d.max()) <= 1 and float((d == 0).float().mean()) >= 0.999, (int(d.max()), float((d == 0).float().mean()))
+    assert float((got_fq.cpu() - fq_ref).abs().max()) <= float(o_scale) * 1.0001

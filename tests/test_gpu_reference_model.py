@@ -29,8 +29,11 @@ CONFIGS = {
 
 
 @pytest.mark.parametrize("cfg_name", list(CONFIGS))
-def test_unmodified_quant_bert_runs_the_ptq_schedule_on_cuda(cfg_name):
+def test_unmodified_quant_bert_runs_the_ptq_schedule_on_cuda(cfg_name, monkeypatch):
     from outlier_suppression_b200.quantization import quantized_module as qm
+    # module-level teacher forcing needs every quantizer / QLinear call to happen: the fused output stage (which never
+    # materialises the tensors in between) is checked separately below
+    monkeypatch.setenv("OSQ_DISABLE_EPILOGUE_FUSION", "1")
     stats0 = dict(qm.stats)
     r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
     layers = r["layers"]
@@ -50,3 +53,30 @@ def test_unmodified_quant_bert_runs_the_ptq_schedule_on_cuda(cfg_name):
         assert d <= 2e-2 * float(want.abs().max()) + 1e-3, (d, got, want)
     print("%s: %d quantizer and %d operator calls replayed into reference modules (bit-exact / 1e-3); scale drift vs the "
           "independent CPU run %.2e; max |dlogit| %.2e" % (cfg_name, r["checked"]["q"], r["checked"]["op"], r["scale_drift"], worst))
+
+
+@pytest.mark.parametrize("cfg_name", list(CONFIGS))
+def test_fused_ffn_output_stage_inside_the_unmodified_model(cfg_name, monkeypatch):
+    """The state togglers wrap every dense -> GELU -> quantizer block of the reference's model (quant_bert.py:277-280) with the
+    fused output stage.  Same model, same calibration, fusion on vs off on the same device: the logits must be bit-identical
+    (the fused epilogue reproduces torch's CUDA GELU and K1 exactly), and the fused path must really have been taken."""
+    import torch
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    monkeypatch.setenv("OSQ_DISABLE_EPILOGUE_FUSION", "1")
+    r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
+    model = r["model"]
+    batches = [{k: v.cuda() for k, v in b.items()} for b in RM.synth_batches(3, 4, 32, 100, "cpu", seed=5)]
+
+    def logits():
+        with torch.no_grad():
+            return [(lambda o: o[0] if isinstance(o, tuple) else o.logits)(model(**b)).clone() for b in batches]
+
+    off = logits()
+    for a, b in zip(off, r["logits"]):
+        assert torch.equal(a.cpu(), b)
+    monkeypatch.delenv("OSQ_DISABLE_EPILOGUE_FUSION")
+    before = qm.stats["epilogue_fused"]
+    on = logits()
+    assert qm.stats["epilogue_fused"] - before == 3 * r["layers"], qm.stats
+    for a, b in zip(on, off):
+        assert torch.equal(a, b), float((a - b).abs().max())
