@@ -649,9 +649,38 @@ def main():
             t = torch.tensor([ms_e2e], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t)
+        # what the end-to-end step is made of: the module stack alone (device-resident input, same graph), and the two copies alone
+        parts = {}
+        try:
+            ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+            if runner.graphs[0] is not None:
+                a_, b_ = ev(), ev()
+                a_.record()
+                for _ in range(5):
+                    runner.graphs[0].replay()
+                b_.record(); torch.cuda.synchronize()
+                parts["module_stack_ms_device_only"] = a_.elapsed_time(b_) / 5
+            a_, b_ = ev(), ev()
+            a_.record()
+            for _ in range(5):
+                runner.dev_in[0].copy_(host_in, non_blocking=True)
+            b_.record(); torch.cuda.synchronize()
+            parts["h2d_ms"] = a_.elapsed_time(b_) / 5
+            parts["h2d_gbs"] = host_in.numel() * 4 / (parts["h2d_ms"] * 1e-3) / 1e9
+            a_, b_ = ev(), ev()
+            a_.record()
+            for _ in range(5):
+                runner.host_out[0].copy_(runner.dev_in[0].reshape(runner.host_out[0].shape), non_blocking=True)
+            b_.record(); torch.cuda.synchronize()
+            parts["d2h_ms"] = a_.elapsed_time(b_) / 5
+            parts["d2h_gbs"] = runner.d2h_bytes / (parts["d2h_ms"] * 1e-3) / 1e9
+        except Exception as ex:  # pragma: no cover
+            parts["error"] = repr(ex)
         e2e = {"value": world * M / (ms_e2e / n_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": host_in.numel() * 4,
-               "d2h_bytes_per_step": runner.d2h_bytes, "steps": n_e2e, "host_issue_ms_per_step": e2e_issue_ms,
-               "api": "hostio.HostStepRunner over quantization.Quantizer modules: 4 activation quantizers + 6 QLinear per layer, x12; "
+               "d2h_bytes_per_step": runner.d2h_bytes, "steps": n_e2e, "host_issue_ms_per_step": e2e_issue_ms, "parts": parts,
+               "ms_per_step": ms_e2e / n_e2e,
+               "api": "hostio.HostStepRunner over quantization.Quantizer modules: 4 activation quantizers + 6 QLinear per layer, x12 "
+                      "(the same 72 sites the reference arm runs on the CPU); "
                       "pinned H2D / D2H on side streams, double-buffered, module stack %s; CUDA-event time up to the last download" % ("eager" if args.no_graph else "replayed as a CUDA graph") + ""}
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "error": repr(ex)}

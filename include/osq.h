@@ -66,6 +66,14 @@ int osq_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int64_t 
                                const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin,
                                int qmax, void* stream);
 
+/* K1c an activation and the quantizer behind it as ONE pass: y = fq(act(x)), bins optional (NULL: none).  replaces
+ *     model/quant_bert.py:278-280 (intermediate_act_fn followed by intermediate_act_fn_post_act_fake_quantize): act = 1 is GELU
+ *     in its erf form with the operation order of ATen's CUDA kernel (bit-identical to torch.nn.functional.gelu on the
+ *     same device followed by K1 / K1b); act = 0 is K1b.  9 bytes per element (8 without bins) instead of 8 + 9. */
+int osq_act_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int64_t n, int act, const float* scale,
+                                   const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin,
+                                   int qmax, void* stream);
+
 int osq_fq_per_channel_f32(const float* x, float* y, int16_t* codes, int64_t rows, int64_t cols,
                            const float* scale, const int32_t* zero_point, int qmin, int qmax,
                            void* stream);

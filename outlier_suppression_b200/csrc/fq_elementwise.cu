@@ -17,7 +17,30 @@ __device__ __forceinline__ void put_code(void* codes, int64_t i, float q, float 
   if (kCodes == 2) static_cast<uint8_t*>(codes)[i] = (uint8_t)(int)(q - qmin);
 }
 
-template <int kCodes>
+// GELU(x) = (x * 0.5) * (1 + erf(x / sqrt(2))) with the operation order of ATen's CUDA kernel (approximate = 'none'):
+// bit-identical to torch.nn.functional.gelu on the same device
+__device__ __forceinline__ float gelu_erf_k1(float x) {
+  return __fmul_rn(__fmul_rn(x, 0.5f), __fadd_rn(1.0f, erff(__fmul_rn(x, 0.70710678118654752440f))));
+}
+template <int kAct>
+__device__ __forceinline__ float act_in(float x) { return kAct == 1 ? gelu_erf_k1(x) : x; }
+
+// Division-free fast path of fq_elem.  t' = x * (1/s) differs from the true quotient by a few ulps; when t' is farther than
+// 1e-4 from a rounding tie and small enough for that bound to hold (|t'| < 300), rint(x / s) == rint(t') and the rest of
+// util_quant.py:12-14 is evaluated exactly as fq_elem does.  `risky` (near a tie, huge, inf, NaN: ~2e-4 of the elements)
+// sends the caller to the exact division.  The IEEE division is 40 % of K1's instructions, and K1 is ALU-bound.
+__device__ __forceinline__ float fq_elem_fast(float x, float s, float rinv, float z, float qmin, float qmax, float& q, bool& risky) {
+  const float t = __fmul_rn(x, rinv);
+  const float r = rintf(t);
+  risky = !(fabsf(__fsub_rn(t, r)) < 0.4999f) || !(fabsf(t) < 300.f);
+  const float v = __fadd_rn(r, z);
+  q = fminf(fmaxf(v, qmin), qmax);
+  return __fmul_rn(__fsub_rn(q, z), s);
+}
+
+// kAct: 0 = none, 1 = GELU applied to x before the fake-quant (quant_bert.py:278-280: intermediate_act_fn followed by its
+// quantizer as ONE pass over the tensor)
+template <int kCodes, int kAct = 0>
 __global__ void __launch_bounds__(kFqThreads)
 fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, void* __restrict__ codes,
                      int64_t n, const float* __restrict__ scale, const void* __restrict__ zp,
@@ -25,6 +48,7 @@ fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, void* _
   const QParam p = load_qparam(scale, zp, zp_is_int32, g, qmin, qmax,
                                blockIdx.x == 0 && threadIdx.x == 0);
   const float s = p.s, z = p.z;
+  const float rinv = __frcp_rn(s);
   // head: elements before the first 16-byte boundary, tail: after the last full float4
   int64_t head = (int64_t)((16 - ((uintptr_t)x & 15)) & 15) >> 2;
   if (head > n) head = n;
@@ -34,7 +58,7 @@ fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, void* _
   if (!vec_ok) {
     for (int64_t i = tid; i < n; i += nthreads) {
       float q;
-      y[i] = fq_elem(x[i], s, z, qmin, qmax, q);
+      y[i] = fq_elem(act_in<kAct>(x[i]), s, z, qmin, qmax, q);
       put_code<kCodes>(codes, i, q, qmin);
     }
     return;
@@ -56,10 +80,18 @@ fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, void* _
       if (i < nvec) {
         float4 o;
         float q0, q1, q2, q3;
-        o.x = fq_elem(v[u].x, s, z, qmin, qmax, q0);
-        o.y = fq_elem(v[u].y, s, z, qmin, qmax, q1);
-        o.z = fq_elem(v[u].z, s, z, qmin, qmax, q2);
-        o.w = fq_elem(v[u].w, s, z, qmin, qmax, q3);
+        bool k0, k1, k2, k3;
+        const float a0 = act_in<kAct>(v[u].x), a1 = act_in<kAct>(v[u].y), a2 = act_in<kAct>(v[u].z), a3 = act_in<kAct>(v[u].w);
+        o.x = fq_elem_fast(a0, s, rinv, z, qmin, qmax, q0, k0);
+        o.y = fq_elem_fast(a1, s, rinv, z, qmin, qmax, q1, k1);
+        o.z = fq_elem_fast(a2, s, rinv, z, qmin, qmax, q2, k2);
+        o.w = fq_elem_fast(a3, s, rinv, z, qmin, qmax, q3, k3);
+        if (k0 | k1 | k2 | k3) {  // rare: the whole group through the exact division
+          o.x = fq_elem(a0, s, z, qmin, qmax, q0);
+          o.y = fq_elem(a1, s, z, qmin, qmax, q1);
+          o.z = fq_elem(a2, s, z, qmin, qmax, q2);
+          o.w = fq_elem(a3, s, z, qmin, qmax, q3);
+        }
         __stcs(yv + i, o);
         if (kCodes != 0) {
           const int64_t e = head + (i << 2);
@@ -80,7 +112,7 @@ fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, void* _
   for (int64_t i = tid; i < head + (n - tail_start); i += nthreads) {
     int64_t j = i < head ? i : tail_start + (i - head);
     float q;
-    y[j] = fq_elem(x[j], s, z, qmin, qmax, q);
+    y[j] = fq_elem(act_in<kAct>(x[j]), s, z, qmin, qmax, q);
     put_code<kCodes>(codes, j, q, qmin);
   }
 }
@@ -251,6 +283,33 @@ int osq_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int64_t 
   using namespace osq;
   OSQ_CHECK_ARG(bins != nullptr, "osq_fq_per_tensor_bins_f32: null bins");
   return launch_fq_per_tensor("osq_fq_per_tensor_bins_f32", x, y, bins, 2, n, scale, zero_point, zp_is_int32, lsq_grad_factor, qmin, qmax, stream);
+}
+
+int osq_act_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int64_t n, int act, const float* scale,
+                                   const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin,
+                                   int qmax, void* stream) {
+  using namespace osq;
+  if (act == 0) return launch_fq_per_tensor("osq_act_fq_per_tensor_bins_f32", x, y, bins, 2, n, scale, zero_point, zp_is_int32,
+                                            lsq_grad_factor, qmin, qmax, stream);
+  OSQ_CHECK_ARG(act == 1, "osq_act_fq_per_tensor_bins_f32: act must be 0 (none) or 1 (GELU, erf form)");
+  OSQ_CHECK_ARG(n >= 0, "osq_act_fq_per_tensor_bins_f32: n < 0");
+  if (n == 0) return OSQ_OK;
+  OSQ_CHECK_ARG(x && y && scale && zero_point, "osq_act_fq_per_tensor_bins_f32: null pointer");
+  OSQ_CHECK_ARG(qmin < qmax, "osq_act_fq_per_tensor_bins_f32: qmin >= qmax");
+  OSQ_CHECK_ARG(!(lsq_grad_factor > 0.f && zp_is_int32), "osq_act_fq_per_tensor_bins_f32: LSQ+ needs a float zero_point");
+  OSQ_CHECK_ARG(bins == nullptr || qmax - qmin <= 255, "osq_act_fq_per_tensor_bins_f32: uint8 bins need at most 8 bits");
+  int sms = sm_count();
+  if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  int64_t per_block = (int64_t)kFqThreads * 4 * kFqUnroll;
+  int64_t want = (n + per_block - 1) / per_block;
+  int grid = (int)(want < (int64_t)sms * 8 ? (want < 1 ? 1 : want) : (int64_t)sms * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bins != nullptr)
+    fq_per_tensor_kernel<2, 1><<<grid, kFqThreads, 0, st>>>(x, y, bins, n, scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax);
+  else
+    fq_per_tensor_kernel<0, 1><<<grid, kFqThreads, 0, st>>>(x, y, nullptr, n, scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
 }
 
 int osq_fq_per_channel_f32(const float* x, float* y, int16_t* codes, int64_t rows, int64_t cols,

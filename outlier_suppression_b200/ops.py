@@ -70,11 +70,24 @@ def _dense_like(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 # K1 / K2
 # ------------------------------------------------------------------------------------------------
 def fq_per_tensor(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int,
-                  lsq_grad_factor: float = 0.0, want_codes: bool = False, want_bins: bool = False):
+                  lsq_grad_factor: float = 0.0, want_codes: bool = False, want_bins: bool = False, act: Optional[str] = None):
     """util_quant.py:11-15 / :48-55 with device-resident qparams. Returns y (and int16 bins with want_codes, or
     uint8 ``bin - qmin`` in the fused Linear's operand format with want_bins)."""
     _require_cuda(x, scale, zero_point)
     x, y = _dense_like(x)
+    if act not in (None, "none"):
+        # activation + quantizer as one pass (quant_bert.py:278-280); GELU bit-identical to torch's CUDA kernel
+        if act != "gelu" or want_codes:
+            raise ValueError("act must be None or 'gelu' (and is incompatible with want_codes)")
+        if scale.dtype != torch.float32 or zero_point.dtype not in (torch.float32, torch.int32):
+            raise TypeError("scale must be float32, zero_point float32 or int32")
+        bins = torch.empty_like(x, dtype=torch.uint8) if want_bins else None
+        if x.numel() > 0:
+            check(_lib.load().osq_act_fq_per_tensor_bins_f32(x.data_ptr(), y.data_ptr(), _ptr(bins), x.numel(), 1, scale.data_ptr(),
+                                                             zero_point.data_ptr(), int(zero_point.dtype == torch.int32),
+                                                             float(lsq_grad_factor), int(qmin), int(qmax), _stream()),
+                  "osq_act_fq_per_tensor_bins_f32")
+        return (y, bins) if want_bins else y
     if want_bins and x.numel() > 0:
         if scale.dtype != torch.float32:
             raise TypeError("scale must be float32")

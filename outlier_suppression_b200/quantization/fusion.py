@@ -10,10 +10,16 @@ The reference wires the feed-forward block as three module calls (model/quant_be
 A Linear cannot know what will consume its output, so the fusion is attached to the ONE module that owns all three steps:
 ``fuse_ffn_activation(model)`` finds every module with exactly that attribute triple (duck typing: no import of the
 reference's classes) and wraps its ``forward``.  In the quantized inference state (weight and activation fake-quant on,
-observers off, no autograd) the wrapper makes ONE fused launch whose epilogue applies GELU and the output quantizer
-(osq_fused_fq_linear with an output stage) and returns the quantizer's tensor, tagged and with its uint8 bins, so the
-following QLinear (``output.dense``) runs bins-in: Linear -> GELU -> quantizer -> Linear is two launches with a
-1 B / element hand-off.  In every other state the original forward runs unchanged (calibration, learn_scale, CPU).
+observers off, no autograd) the wrapper runs the block as TWO launches instead of three: the fused Linear, then ONE
+elementwise pass that applies GELU and the quantizer and writes the quantizer's uint8 bins (osq_act_fq_per_tensor_bins_f32:
+9 B / element instead of 8 + 9), so the following QLinear (``output.dense``) runs bins-in.  The returned tensor carries the
+quantizer's tag exactly as if the three modules had been called.  In every other state the original forward runs unchanged
+(calibration, learn_scale, CPU).
+
+``OSQ_EPILOGUE_STAGE=1`` selects the one-launch form instead (GELU and the quantizer inside the Linear's epilogue,
+osq_fused_fq_linear's output stage): bit-identical, but measured 3-4x SLOWER at BERT-base size (768 -> 3072, M = 16384:
+366 us against 55 + 62 + 122 us for the three separate launches) -- erf and the exact division run on the 8 epilogue
+warps of a 1-CTA-per-SM kernel, far from the ALU rate a full-occupancy elementwise kernel reaches.
 
 The state togglers call this (like ``group_sibling_linears``), so an unmodified reference driver gets it for free;
 ``OSQ_DISABLE_EPILOGUE_FUSION=1`` turns it off.
@@ -69,6 +75,22 @@ def _fused_forward(self, hidden_states, observation_mask=None):
         return self._osq_unfused_forward(hidden_states, observation_mask=observation_mask)
     aq, q = pair
     dense = self.dense
+    if os.environ.get("OSQ_EPILOGUE_STAGE") != "1":
+        y = dense(hidden_states)                                   # fused fake-quant + Linear (tcgen05), plain fp32 output
+        n_out = y.numel()
+        g_out = (1.0 / (n_out * q.quant_max) ** 0.5 if q.use_grad_scaling else 1.0) if isinstance(q, LSQPlusFakeQuantize) else 0.0
+        want_bins = q._emit_bins and y.shape[-1] % 128 == 0
+        r = ops.fq_per_tensor(y, q.scale.detach(), q.zero_point.detach(), q.quant_min, q.quant_max, lsq_grad_factor=g_out,
+                              want_bins=want_bins, act="gelu")
+        stats["epilogue_fused"] = stats.get("epilogue_fused", 0) + 1
+        out = r[0] if want_bins else r
+        q._tag(out)
+        if want_bins:
+            try:
+                out._osq_bins = (r[1], out._version)
+            except Exception:  # pragma: no cover
+                pass
+        return out
     codes, rowsum, w_scale = dense._packed_weight()
     g_in = aq.grad_factor(hidden_states) if isinstance(aq, LSQPlusFakeQuantize) else 0.0
     n_out = hidden_states.numel() // hidden_states.shape[-1] * dense.out_features

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+cd "${GRAFT_REPO_ROOT:-.}"
+run() {
+  echo "== bench $*"; timeout 400 python bench.py --steps 20 --warmup 3 --no-cpu --no-sweep "$@" > gpurun_out/bench_ab.json 2> gpurun_out/bench.err; echo "rc=$?"
+  python - <<PY
+import json
+r=json.load(open("gpurun_out/bench_ab.json"))
+print("value %.0f ms %.4f frac %.4f e2e %.0f host_issue %.2f" % (r["value"], r["ms_per_step"], r["roofline"]["frac"], r["e2e"]["value"], r["e2e"]["host_issue_ms_per_step"]))
+PY
+  tail -3 gpurun_out/bench.err
+}
+run
+run --no-epilogue-fusion

@@ -122,3 +122,25 @@ def test_calc_qparams_kernel_golden(golden):
             s, z = ops.calc_qparams(T(g["mins"]).cuda(), T(g["maxs"]).cuda(), qmin, qmax, sym)
             same(s, g["s_%d_%d" % (bit, sym)])
             same(z, g["z_%d_%d" % (bit, sym)])
+
+
+@pytest.mark.parametrize("lsq", [False, True])
+@pytest.mark.parametrize("shape", [(4, 128, 3072), (3, 77, 130), (5,)])
+def test_gelu_then_quantizer_as_one_pass(shape, lsq):
+    """K1c (osq_act_fq_per_tensor_bins_f32): intermediate_act_fn + its quantizer (quant_bert.py:278-280) in one elementwise launch
+    must equal torch's CUDA GELU followed by K1b bit for bit -- tensor and bins."""
+    from outlier_suppression_b200 import ops
+    g = torch.Generator().manual_seed(len(shape) * 7 + int(lsq))
+    x = (torch.randn(*shape, generator=g) * 3).cuda()
+    z = torch.nn.functional.gelu(x)
+    scale = torch.tensor([float(z.max() - z.min()) / 63 * 0.8], device="cuda")
+    if lsq:
+        zp, gf = torch.tensor([3.3], device="cuda"), 1.0 / (x.numel() * 63) ** 0.5
+    else:
+        zp, gf = torch.tensor([3], dtype=torch.int32, device="cuda"), 0.0
+    ref_y, ref_b = ops.fq_per_tensor(z, scale.clone(), zp.clone(), 0, 63, lsq_grad_factor=gf, want_bins=True)
+    got_y, got_b = ops.fq_per_tensor(x, scale.clone(), zp.clone(), 0, 63, lsq_grad_factor=gf, want_bins=True, act="gelu")
+    np.testing.assert_array_equal(got_y.cpu().numpy(), ref_y.cpu().numpy())
+    np.testing.assert_array_equal(got_b.cpu().numpy(), ref_b.cpu().numpy())
+    only_y = ops.fq_per_tensor(x, scale.clone(), zp.clone(), 0, 63, lsq_grad_factor=gf, act="gelu")
+    np.testing.assert_array_equal(only_y.cpu().numpy(), ref_y.cpu().numpy())

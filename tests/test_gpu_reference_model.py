@@ -55,8 +55,9 @@ def test_unmodified_quant_bert_runs_the_ptq_schedule_on_cuda(cfg_name, monkeypat
           "independent CPU run %.2e; max |dlogit| %.2e" % (cfg_name, r["checked"]["q"], r["checked"]["op"], r["scale_drift"], worst))
 
 
+@pytest.mark.parametrize("mode", ["two_launches", "epilogue_stage"])
 @pytest.mark.parametrize("cfg_name", list(CONFIGS))
-def test_fused_ffn_output_stage_inside_the_unmodified_model(cfg_name, monkeypatch):
+def test_fused_ffn_output_stage_inside_the_unmodified_model(cfg_name, mode, monkeypatch):
     """The state togglers wrap every dense -> GELU -> quantizer block of the reference's model (quant_bert.py:277-280) with the
     fused output stage.  Same model, same calibration, fusion on vs off on the same device: the logits must be bit-identical
     (the fused epilogue reproduces torch's CUDA GELU and K1 exactly), and the fused path must really have been taken."""
@@ -75,6 +76,8 @@ def test_fused_ffn_output_stage_inside_the_unmodified_model(cfg_name, monkeypatc
     for a, b in zip(off, r["logits"]):
         assert torch.equal(a.cpu(), b)
     monkeypatch.delenv("OSQ_DISABLE_EPILOGUE_FUSION")
+    if mode == "epilogue_stage":   # GELU + quantizer inside the Linear's epilogue instead of one elementwise pass behind it
+        monkeypatch.setenv("OSQ_EPILOGUE_STAGE", "1")
     before = qm.stats["epilogue_fused"]
     on = logits()
     assert qm.stats["epilogue_fused"] - before == 3 * r["layers"], qm.stats
