@@ -431,6 +431,7 @@ def main():
     ap.add_argument("--no-group", action="store_true", help="launch q, k and v separately (72 launches per step)")
     ap.add_argument("--multi", action="store_true", help="hand each layer's site list to osq_fused_fq_linear_multi (with OSQ_FUSED_MULTI=1: one "
                     "persistent launch per layer; measured 10 %% slower than one launch per site, see DESIGN.md)")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="pipeline depth of the e2e leg (device / host buffer sets in flight)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 observer sweep and the config-4 site timings")
     ap.add_argument("--only-value", action="store_true", help="profiling runs: timed stack only, no roofline/e2e/cpu legs")
     args = ap.parse_args()
@@ -446,6 +447,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    from outlier_suppression_b200.hostio import bind_to_gpu_numa
+    numa = None if os.environ.get("OSQ_BENCH_NO_NUMA_BIND") == "1" else bind_to_gpu_numa(local_rank)
     torch.set_grad_enabled(False)  # inference / calibration path (HF Trainer.evaluate runs under no_grad)
     device = torch.device("cuda", local_rank)
     dist = None
@@ -622,14 +625,14 @@ def main():
     # every step uploads its batch from pinned host memory and downloads its result (both inside the timed region);
     # the copies run on side streams, double-buffered, so they overlap the previous / next step's kernels
     from outlier_suppression_b200.hostio import HostStepRunner
-    runner = HostStepRunner(layer_stack, (B, S, H), (M, H), device, graph=not args.no_graph)
+    runner = HostStepRunner(layer_stack, (B, S, H), (M, H), device, graph=not args.no_graph, depth=args.e2e_depth)
 
     def e2e_step():
         return runner.submit(host_in)
 
     e2e = None
     try:
-        for _ in range(2):
+        for _ in range(runner.depth + 2):   # every buffer set's graph is captured before the timed region
             e2e_step()
         barrier()
         e0.record()
@@ -677,7 +680,7 @@ def main():
         except Exception as ex:  # pragma: no cover
             parts["error"] = repr(ex)
         e2e = {"value": world * M / (ms_e2e / n_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": host_in.numel() * 4,
-               "d2h_bytes_per_step": runner.d2h_bytes, "steps": n_e2e, "host_issue_ms_per_step": e2e_issue_ms, "parts": parts,
+               "d2h_bytes_per_step": runner.d2h_bytes, "steps": n_e2e, "host_issue_ms_per_step": e2e_issue_ms, "parts": parts, "pipeline_depth": args.e2e_depth, "numa_binding": numa,
                "ms_per_step": ms_e2e / n_e2e,
                "api": "hostio.HostStepRunner over quantization.Quantizer modules: 4 activation quantizers + 6 QLinear per layer, x12 "
                       "(the same 72 sites the reference arm runs on the CPU); "
