@@ -203,6 +203,17 @@ int osq_mse_multi_f32(const float* x, const osq_tokens_t* tok, const int64_t* le
                       const float* cand_scale, const float* cand_zp, int n_cand, int qmin, int qmax,
                       double* loss_sum, int64_t* n_valid, void* stream);
 
+/* K5c the whole per-TENSOR search of MSEFastObserver / AvgMSEFastObserver (observer.py:434-494,496-533) as ONE cooperative
+ *     launch: masked min / max, the one_side_dist decision (*one_side_state: -1 undecided, 0 no, 1 pos, 2 neg; decided on
+ *     the first call and kept, observer.py:528-529), then the 1-D bounded Brent (symmetric or one-sided) or the nested
+ *     2-D search (outer Brent over the range, inner Brent over the shift per evaluation, a final inner search) with SciPy's
+ *     _minimize_scalar_bounded restated in fp64; every loss evaluation is a grid-wide reduction behind one grid barrier.
+ *     out4 (device double[4]): best_min, best_max, x_min, x_max.  evals (device int32, optional): loss evaluations.
+ *     scratch: osq_mse_tensor_scratch_bytes() of device memory.  Same tolerance as K5b (tests). */
+int osq_mse_brent_tensor_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, int qmin, int qmax,
+                             int symmetric, int32_t* one_side_state, double* out4, int32_t* evals, void* scratch, void* stream);
+int64_t osq_mse_tensor_scratch_bytes(void);
+
 /* K5b per-row bounded-Brent search of MSEFastObserver(ch_axis=0, symmetric) -- observer.py:483-517
  *     with scipy.optimize.minimize_scalar(method='Bounded') restated on-chip (one CTA per row, row
  *     resident in shared memory).  out_min/out_max [rows]; evals [rows] (int32) optional. */

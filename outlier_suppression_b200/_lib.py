@@ -19,7 +19,7 @@ EXPORTS = [
     "osq_minmax_masked_f32", "osq_minmax_flat_f32", "osq_token_minmax_f32", "osq_prune_select_f32", "osq_prune_select_unsorted_f32",
     "osq_prune_observe_f32", "osq_quantile_observe_f32", "osq_replay_average_f32",
     "osq_rowwise_minmax_qparams_f32", "osq_calc_qparams_f32",
-    "osq_mse_multi_f32", "osq_mse_brent_rows_f32",
+    "osq_mse_multi_f32", "osq_mse_brent_rows_f32", "osq_mse_brent_tensor_f32", "osq_mse_tensor_scratch_bytes",
     "osq_pack_weight_s8", "osq_fused_fq_linear", "osq_fused_fq_linear_multi", "osq_lsqplus_backward_f32",
 ]
 
@@ -66,6 +66,7 @@ def _declare(lib):
     lib.osq_last_error.restype = C.c_char_p
     lib.osq_sm_count.restype = i32
     lib.osq_workspace_bytes.restype = i64
+    lib.osq_mse_tensor_scratch_bytes.restype = i64
     sig = {
         "osq_fq_per_tensor_f32": [vp, vp, vp, i64, vp, vp, i32, f32, i32, i32, vp],
         "osq_fq_per_tensor_bins_f32": [vp, vp, vp, i64, vp, vp, i32, f32, i32, i32, vp],
@@ -83,6 +84,7 @@ def _declare(lib):
         "osq_calc_qparams_f32": [vp, vp, i64, i32, i32, i32, vp, vp, vp, vp],
         "osq_mse_multi_f32": [vp, C.POINTER(Tokens), vp, i32, vp, vp, i32, i32, i32, vp, vp, vp],
         "osq_mse_brent_rows_f32": [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp],
+        "osq_mse_brent_tensor_f32": [vp, C.POINTER(Tokens), vp, i32, i32, i32, i32, vp, vp, vp, vp, vp],
         "osq_pack_weight_s8": [vp, i64, i64, vp, vp, i32, i32, vp, vp, vp],
         "osq_fused_fq_linear": [C.POINTER(FusedLinearArgs), vp],
         "osq_fused_fq_linear_multi": [C.POINTER(FusedLinearArgs), i32, vp],

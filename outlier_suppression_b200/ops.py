@@ -381,6 +381,33 @@ def mse_multi(x, lens, seq_pos, cand_scale, cand_zp, qmin, qmax):
     return loss, n_valid
 
 
+_mse_scratch = {}
+
+
+def mse_brent_tensor(x, lens, seq_pos, qmin, qmax, symmetric, one_side_state):
+    """(Avg)MSEFastObserver per-tensor search (observer.py:434-494) in ONE cooperative launch, no host round trip.
+    one_side_state: device int32[1] (-1 undecided / 0 no / 1 pos / 2 neg), decided on the first call and kept.
+    Returns (out4: device float64[4] = best_min, best_max, x_min, x_max; evals: device int32[1])."""
+    x = _prep_act(x)
+    if x.dim() >= 3 and seq_pos != -1:
+        tok = token_geometry(x, seq_pos)
+    else:
+        x = x if x.is_contiguous() else x.contiguous()
+        tok = Tokens(1, 1, 1, x.numel(), 0, 0, 0, 1)
+        lens = None
+    lens_t, n_lens = _lens_arg(lens, x.device)
+    key = (x.device.index, _stream())
+    scratch = _mse_scratch.get(key)
+    if scratch is None:
+        scratch = _mse_scratch[key] = torch.zeros(int(_lib.load().osq_mse_tensor_scratch_bytes()), dtype=torch.uint8, device=x.device)
+    out4 = torch.empty(4, dtype=torch.float64, device=x.device)
+    evals = torch.empty(1, dtype=torch.int32, device=x.device)
+    check(_lib.load().osq_mse_brent_tensor_f32(x.data_ptr(), C.byref(tok), _ptr(lens_t), n_lens, int(qmin), int(qmax),
+                                               int(bool(symmetric)), one_side_state.data_ptr(), out4.data_ptr(), evals.data_ptr(),
+                                               scratch.data_ptr(), _stream()), "osq_mse_brent_tensor_f32")
+    return out4, evals
+
+
 def mse_brent_rows(w, qmin, qmax, one_side: str, want_evals=False):
     """MSEFastObserver per-channel 1-D search (observer.py:483-517) entirely on-chip."""
     _require_cuda(w)

@@ -196,8 +196,39 @@ class MSEFastObserver(ObserverBase):
         super().__init__(bit=bit, symmetric=symmetric, ch_axis=ch_axis)
         self.p = 2.0
         self.num = 100
-        self.one_side_dist = None  # 'pos', 'neg', 'no'
-        self.loss_evals = 0
+        self._one_side = None      # 'pos', 'neg', 'no' once known on the host
+        self._one_side_dev = None  # device int32[1]: -1 undecided / 0 no / 1 pos / 2 neg (decided by the search kernel)
+        self._evals_dev = []       # device counters of the per-tensor searches (summed lazily by `loss_evals`)
+        self._evals_host = 0
+
+    # one_side_dist is decided on the first batch (observer.py:528-529).  The per-tensor search decides it on the device;
+    # reading the attribute synchronises once and caches the answer.
+    @property
+    def one_side_dist(self):
+        if self._one_side is None and self._one_side_dev is not None:
+            v = int(self._one_side_dev.item())
+            if v >= 0:
+                self._one_side = ("no", "pos", "neg")[v]
+        return self._one_side
+
+    @one_side_dist.setter
+    def one_side_dist(self, value):
+        self._one_side = value
+        if self._one_side_dev is not None:
+            self._one_side_dev.fill_({None: -1, "no": 0, "pos": 1, "neg": 2}[value])
+
+    @property
+    def loss_evals(self):
+        if self._evals_dev:
+            self._evals_host += int(torch.stack(self._evals_dev).sum().item())
+            self._evals_dev = []
+        return self._evals_host
+
+    @loss_evals.setter
+    def loss_evals(self, value):
+        self._evals_host, self._evals_dev = int(value), []
+
+    host_search = False  # True: SciPy on the host drives the per-tensor search (round-1 path, kept as a cross-check)
 
     # ---- loss on the GPU (observer.py:420-432) ----
     def _loss(self, x, mask, seq_pos, new_min, new_max):
@@ -207,8 +238,9 @@ class MSEFastObserver(ObserverBase):
         s = torch.tensor([float(scale)], dtype=torch.float32)       # `x / scale.item()` rounds the scalar to fp32
         z = torch.tensor([float(int(zero_point))], dtype=torch.float32)
         loss_sum, n_valid = ops.mse_multi(x, mask, seq_pos, s, z, self.quant_min, self.quant_max)
-        self.loss_evals += 1
-        return np.float32(loss_sum.item() / max(int(n_valid.item()), 1))
+        self._evals_host += 1
+        both = torch.stack([loss_sum[0], n_valid[0].double()]).tolist()   # one synchronisation per evaluation, not two
+        return np.float32(both[0] / max(int(both[1]), 1))
 
     def _search_1d(self, x, mask, seq_pos, x_min, x_max):
         from scipy.optimize import minimize_scalar
@@ -248,8 +280,17 @@ class MSEFastObserver(ObserverBase):
         """(best_min, best_max) device tensors for this batch (observer.py:496-533)."""
         x = x.detach()
         dev = x.device
-        if self.ch_axis == -1:
-            cur = ops.observe_minmax(x, observation_mask, seq_pos).tolist()  # one sync; the search is host driven anyway
+        if self.ch_axis == -1 and not self.host_search:
+            # the whole (1-D or nested 2-D) bounded-Brent search in ONE cooperative launch, nothing read back
+            if self._one_side_dev is None or self._one_side_dev.device != dev:
+                init = {None: -1, "no": 0, "pos": 1, "neg": 2}[self._one_side]
+                self._one_side_dev = torch.full((1,), init, dtype=torch.int32, device=dev)
+            out4, evals = ops.mse_brent_tensor(x, observation_mask, seq_pos, self.quant_min, self.quant_max, self.symmetric,
+                                               self._one_side_dev)
+            self._evals_dev.append(evals)
+            return out4[0], out4[1]
+        if self.ch_axis == -1:  # first version (host-driven SciPy, one GPU pass + sync per evaluation): cross-check
+            cur = ops.observe_minmax(x, observation_mask, seq_pos).tolist()
             x_min, x_max = cur
             if self.one_side_dist is None:
                 self.one_side_dist = "pos" if x_min >= 0.0 else "neg" if x_max <= 0.0 else "no"
@@ -293,14 +334,13 @@ class AvgMSEFastObserver(MSEFastObserver):
 
     def _observe(self, x, observation_mask, seq_pos, quantizer=None):
         best_min, best_max = self._best_minmax(x, observation_mask, seq_pos)
-        if self.max_val.numel() <= 1 and bool(self.max_val.isinf()):
-            self.min_val, self.max_val = best_min, best_max
-        else:
-            self.min_val = self.min_val * self.cnt + best_min
-            self.max_val = self.max_val * self.cnt + best_max
+        # observer.py:556-566 without reading the state back: `first batch` (max_val still -inf) selected on the device
+        first = torch.isinf(self.max_val.to(best_max.device)).reshape(())
+        mn = torch.where(first, best_min, self.min_val.to(best_min.device) * self.cnt + best_min)
+        mx = torch.where(first, best_max, self.max_val.to(best_max.device) * self.cnt + best_max)
         self.cnt += 1
-        self.min_val = self.min_val / self.cnt
-        self.max_val = self.max_val / self.cnt
+        self.min_val = mn / self.cnt
+        self.max_val = mx / self.cnt
         return False
 
 
