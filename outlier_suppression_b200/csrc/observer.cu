@@ -805,22 +805,9 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
     OBS_STAMP(5);
     // ---- (c) the remaining 20 bits, 4 per pass, counted in registers ----
     unsigned int mask = 0xFFFu << 20;
-#pragma unroll 1
-    for (int sh = 16; sh >= 0; sh -= 4) {
-#pragma unroll
-      for (int sd = 0; sd < 2; ++sd) {
-        Packed16 cc;
-        cc.clear();
-        const unsigned int prefix = s_prefix[sd];
-        for_members(sd, [&](unsigned int u) { cc.add((u >> sh) & 15u, (u & mask) == prefix); });
-        cc.warp_sum();
-        unsigned int mine = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) mine = (lane == j) ? cc.get(j) : mine;
-        if (lane < 16) part[sd][warp][lane] = mine;
-      }
+    auto pick_digit = [&](int sh) {   // after the per-warp digit counts are in part[][][]: one warp per side picks
       __syncthreads();
-      if (warp < 2) {  // one warp per side: lanes 0..15 own one digit each
+      if (warp < 2) {  // lanes 0..15 own one digit each
         unsigned int cnt = 0;
         if (lane < 16) {
 #pragma unroll 8
@@ -840,10 +827,85 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
         if (lane == 0) { s_prefix[warp] |= (unsigned int)d << sh; s_krem[warp] = krem - below; }
       }
       __syncthreads();
+    };
+    constexpr int kRegElems = 4;   // list entries per thread and side on the register path
+    const bool reg_path = listed_mx && listed_mn && s_nlist[0] <= kRegElems * kSelThreads && s_nlist[1] <= kRegElems * kSelThreads;
+    unsigned int em[kRegElems], en[kRegElems];
+    if (reg_path) {
+      // Both lists fit four entries per thread: they move into registers once, both sides are counted in the same pass
+      // with sixteen 8-bit fields per side (<= 128 members per warp, so no field overflows) -- four REDUX per side and pass
+      // instead of eight, no shared-memory traffic in the counting loop.
+#pragma unroll
+      for (int e = 0; e < kRegElems; ++e) {
+        const unsigned int i = (unsigned int)tid + (unsigned int)e * kSelThreads;
+        em[e] = i < s_nlist[0] ? list[0][i] : 0xFFFFFFFFu;   // bit 31 set: never matches a prefix
+        en[e] = i < s_nlist[1] ? list[1][i] : 0xFFFFFFFFu;
+      }
+#pragma unroll 1
+      for (int sh = 16; sh >= 0; sh -= 4) {
+        const unsigned int pm = s_prefix[0], pn = s_prefix[1];
+        unsigned int qm[4] = {0u, 0u, 0u, 0u}, qn[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int e = 0; e < kRegElems; ++e) {
+          const unsigned int dm = (em[e] >> sh) & 15u, dn = (en[e] >> sh) & 15u;
+          const unsigned int im = ((em[e] & mask) == pm) ? (1u << ((dm & 3u) * 8u)) : 0u;
+          const unsigned int in_ = ((en[e] & mask) == pn) ? (1u << ((dn & 3u) * 8u)) : 0u;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            qm[w] += ((dm >> 2) == (unsigned int)w) ? im : 0u;
+            qn[w] += ((dn >> 2) == (unsigned int)w) ? in_ : 0u;
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { qm[w] = __reduce_add_sync(0xffffffffu, qm[w]); qn[w] = __reduce_add_sync(0xffffffffu, qn[w]); }
+        unsigned int wm = 0, wn = 0;   // lane j < 16 keeps digit j's count
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { wm = ((lane >> 2) == w) ? qm[w] : wm; wn = ((lane >> 2) == w) ? qn[w] : wn; }
+        if (lane < 16) {
+          part[0][warp][lane] = (wm >> ((lane & 3) * 8)) & 0xFFu;
+          part[1][warp][lane] = (wn >> ((lane & 3) * 8)) & 0xFFu;
+        }
+        pick_digit(sh);
+        mask |= 0xFu << sh;
+      }
+    } else {
+#pragma unroll 1
+    for (int sh = 16; sh >= 0; sh -= 4) {
+#pragma unroll
+      for (int sd = 0; sd < 2; ++sd) {
+        Packed16 cc;
+        cc.clear();
+        const unsigned int prefix = s_prefix[sd];
+        for_members(sd, [&](unsigned int u) { cc.add((u >> sh) & 15u, (u & mask) == prefix); });
+        cc.warp_sum();
+        unsigned int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mine = (lane == j) ? cc.get(j) : mine;
+        if (lane < 16) part[sd][warp][lane] = mine;
+      }
+      pick_digit(sh);
       mask |= 0xFu << sh;
+    }
     }
     OBS_STAMP(6);
     // ---- (c') rank lo + 1 ----
+    if (reg_path) {
+      const unsigned int am = s_prefix[0], an = s_prefix[1];
+      unsigned int cm = 0, cn = 0, xm = 0xFFFFFFFFu, xn = 0xFFFFFFFFu;
+#pragma unroll
+      for (int e = 0; e < kRegElems; ++e) {
+        if (em[e] <= am) ++cm; else if (em[e] != 0xFFFFFFFFu) xm = min(xm, em[e]);
+        if (en[e] <= an) ++cn; else if (en[e] != 0xFFFFFFFFu) xn = min(xn, en[e]);
+      }
+      cm = __reduce_add_sync(0xffffffffu, cm); cn = __reduce_add_sync(0xffffffffu, cn);
+      xm = __reduce_min_sync(0xffffffffu, xm); xn = __reduce_min_sync(0xffffffffu, xn);
+      if (lane == 0) {
+        if (cm) atomicAdd(&s_cntle[0], cm);
+        if (cn) atomicAdd(&s_cntle[1], cn);
+        if (xm != 0xFFFFFFFFu) atomicMin(&s_next[0], xm);
+        if (xn != 0xFFFFFFFFu) atomicMin(&s_next[1], xn);
+      }
+    } else {
 #pragma unroll
     for (int sd = 0; sd < 2; ++sd) {
       const unsigned int a = s_prefix[sd];
@@ -855,6 +917,7 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
         if (cle) atomicAdd(&s_cntle[sd], cle);
         if (nxt != 0xFFFFFFFFu) atomicMin(&s_next[sd], nxt);
       }
+    }
     }
     __syncthreads();
     // the number of ALL valid tokens <= a is (tokens in lower first-digit bins) + (members <= a); rank lo + 1 equals a
