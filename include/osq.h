@@ -149,9 +149,11 @@ int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t 
  *     L2 reductions -- then, by programmatic dependent launch, ONE small CTA that picks the first-digit bins of rank lo and
  *     lo+1 on both sides, compacts their members into shared memory in one sweep of the [T] vectors, finishes the exact
  *     select there, and runs the clip / aminmax sweep and the running-statistics epilogue.  Bit-identical to K4a + K4b'.
- *     tmin / tmax ([B*S] fp32) and n_valid (int32[1]) are caller-owned scratch; workspace: osq_workspace_bytes(), zeroed once. */
+ *     tmin / tmax ([B*S] fp32) and n_valid (int32[1]) are caller-owned scratch; workspace: osq_workspace_bytes(), zeroed once.
+ *     percentile_dev (optional device float[1]): when given it overrides `percentile` at run time, so a calibration forward
+ *     captured once in a CUDA graph can be replayed for every ratio of token_wise_clipping.find_ratio (:50-66). */
 int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float percentile,
-                          float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
+                          const float* percentile_dev, float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
                           const osq_stat_epilogue_t* epi, void* workspace, void* stream);
 
 /* AvgQuantileObserver.forward (observer.py:253-282) in two launches: K3 (masked min/max -> cur_minmax), then a histogram

@@ -77,7 +77,7 @@ def _declare(lib):
         "osq_token_minmax_f32": [vp, C.POINTER(Tokens), vp, i32, vp, vp, vp, vp],
         "osq_prune_select_f32": [vp, vp, vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_prune_select_unsorted_f32": [vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp, vp],
-        "osq_prune_observe_f32": [vp, C.POINTER(Tokens), vp, i32, f32, vp, vp, vp, vp, C.POINTER(StatEpilogue), vp, vp],
+        "osq_prune_observe_f32": [vp, C.POINTER(Tokens), vp, i32, f32, vp, vp, vp, vp, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_quantile_observe_f32": [vp, C.POINTER(Tokens), vp, i32, i32, C.c_double, vp, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_replay_average_f32": [vp, i32, i32, i32, vp, vp],
         "osq_rowwise_minmax_qparams_f32": [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp],

@@ -724,8 +724,8 @@ struct Packed16 {
 
 __global__ void __launch_bounds__(kSelThreads, 1)
 prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
-                         const int32_t* __restrict__ n_valid, float percentile, unsigned int* __restrict__ ghist0,
-                         float* __restrict__ cur, osq_stat_epilogue_t epi) {
+                         const int32_t* __restrict__ n_valid, float percentile, const float* __restrict__ percentile_dev,
+                         unsigned int* __restrict__ ghist0, float* __restrict__ cur, osq_stat_epilogue_t epi) {
   extern __shared__ __align__(16) unsigned int sel_smem[];
   unsigned int* h0 = sel_smem;                                                              // [2][kSelBins0]
   unsigned int (*list)[kSelCap] = reinterpret_cast<unsigned int (*)[kSelCap]>(h0 + 2 * kSelBins0);  // [2][kSelCap]
@@ -739,6 +739,7 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
   asm volatile("griddepcontrol.wait;" ::: "memory");  // token_minmax_kernel's vectors, n_valid and first-digit table are complete
   OBS_STAMP(3);
   const int T = *n_valid;
+  if (percentile_dev != nullptr) percentile = fminf(fmaxf(*percentile_dev, 0.f), 1.f);   // CUDA-graph replays: the ratio is data
   const float frank = __fmul_rn(percentile, (float)(T > 0 ? T - 1 : 0));   // torch.quantile: rank = p * (T - 1) in fp32
   const int lo = (int)frank;
   const bool need_pair = (int)ceilf(frank) != lo;
@@ -1209,7 +1210,7 @@ int osq_prune_select_unsorted_f32(const float* tmin, const float* tmax, int64_t 
 
 
 int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float percentile,
-                          float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
+                          const float* percentile_dev, float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
                           const osq_stat_epilogue_t* epi, void* workspace, void* stream) {
   using namespace osq;
   if (int rc = check_tokens(tok, "osq_prune_observe_f32")) return rc;
@@ -1218,6 +1219,7 @@ int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t
   const int64_t n_slots = tok->B * tok->S;
   OSQ_CHECK_ARG(n_slots > 0 && n_slots < (int64_t)INT32_MAX, "osq_prune_observe_f32: token count out of range");
   if (n_slots >= kSelMaxTokens) {  // beyond the packed 16-bit counters of the tail: the multi-launch select over L2
+    OSQ_CHECK_ARG(percentile_dev == nullptr, "osq_prune_observe_f32: a device-resident percentile needs fewer than 2^21 tokens");
     if (int rc = osq_token_minmax_f32(x, tok, lens, n_lens, tmin, tmax, n_valid, stream)) return rc;
     return osq_prune_select_unsorted_f32(tmin, tmax, n_slots, n_valid, percentile, cur_minmax, epi, workspace, stream);
   }
@@ -1254,7 +1256,7 @@ int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OSQ_CUDA(cudaLaunchKernelEx(&cfg, prune_select_tail_kernel, (const float*)tmin, (const float*)tmax, n_slots,
-                              (const int32_t*)n_valid, percentile, hist0, cur_minmax, *epi));
+                              (const int32_t*)n_valid, percentile, percentile_dev, hist0, cur_minmax, *epi));
   return OSQ_OK;
 }
 

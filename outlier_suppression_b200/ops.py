@@ -245,11 +245,12 @@ def _token_vectors(device, n: int):
 
 def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
                          scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None, use_sort=False,
-                         legacy_select=False) -> torch.Tensor:
+                         legacy_select=False, percentile_dev=None) -> torch.Tensor:
     """AvgPruneMinMaxObserver's token pruning (observer.py:50-70,214-237): one pass over the activation (per-token
     extrema) and, parked behind it by programmatic dependent launch, one thread-block cluster that keeps the [T]
     vectors in shared memory for the exact radix select + clip selection + running statistics
-    (osq_prune_observe_f32).  ``legacy_select`` / ``use_sort`` run the earlier L2-resident select paths (cross-checks)."""
+    (osq_prune_observe_f32).  ``legacy_select`` / ``use_sort`` run the earlier L2-resident select paths (cross-checks).
+    ``percentile_dev`` (device fp32[1]) overrides ``percentile`` at run time (CUDA-graph replays of a calibration forward)."""
     if not (use_sort or legacy_select):
         x = _prep_act(x)
         tok = token_geometry(x, seq_pos)
@@ -258,7 +259,7 @@ def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0,
         epi = _epilogue(mode, cnt, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric)
         lens_t, n_lens = _lens_arg(lens, x.device)
         check(_lib.load().osq_prune_observe_f32(x.data_ptr(), C.byref(tok), _ptr(lens_t), n_lens, float(percentile),
-                                                tmin.data_ptr(), tmax.data_ptr(), n_valid.data_ptr(), cur.data_ptr(),
+                                                _ptr(percentile_dev), tmin.data_ptr(), tmax.data_ptr(), n_valid.data_ptr(), cur.data_ptr(),
                                                 C.byref(epi), workspace(x.device).data_ptr(), _stream()), "osq_prune_observe_f32")
         return cur
     tmin, tmax, n_valid = token_minmax(x, lens, seq_pos)

@@ -68,8 +68,12 @@ class ObserverBase(nn.Module):
     def set_batch(self, batch):
         self.batch = batch
 
+    _percentile_dev = None  # device fp32[1] mirror of `percentile` (twc.GraphedFindRatio: the ratio of a replayed graph is data)
+
     def set_percentile(self, percentile):
         self.percentile = percentile
+        if self._percentile_dev is not None:
+            self._percentile_dev.fill_(float(percentile))
 
     @torch.jit.export
     def calculate_qparams(self, min_val, max_val):
@@ -177,7 +181,7 @@ class AvgPruneMinMaxObserver(ObserverBase):
             kw = dict(out=shard[0].table.slot(shard[1], shard[0].batch))
         tokenwise = observation_mask is not None or seq_pos != -1
         if tokenwise and "attention_probs" not in self.name:  # observer.py:62-63
-            ops.observe_prune_minmax(x, observation_mask, seq_pos, self.percentile, **kw)
+            ops.observe_prune_minmax(x, observation_mask, seq_pos, self.percentile, percentile_dev=self._percentile_dev, **kw)
         else:
             ops.observe_minmax(x, observation_mask, seq_pos, **kw)
         if shard is not None:
