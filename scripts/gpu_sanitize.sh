@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+cd "${GRAFT_REPO_ROOT:-.}"
+S=/usr/local/cuda/bin/compute-sanitizer
+for tool in memcheck synccheck; do
+  for part in observers mse fq fused; do
+    echo "== $tool $part"; timeout 900 $S --tool $tool --error-exitcode 9 python scripts/sanitize_round2.py $part > gpurun_out/san_${tool}_${part}.log 2>&1; echo "rc=$?"
+    grep -E "ERROR SUMMARY|ok |Error|error:" gpurun_out/san_${tool}_${part}.log | tail -6
+  done
+done
+echo "== racecheck observers"; timeout 900 $S --tool racecheck --error-exitcode 9 python scripts/sanitize_round2.py observers > gpurun_out/san_racecheck_observers.log 2>&1; echo "rc=$?"
+grep -E "RACECHECK SUMMARY|ok |hazard" gpurun_out/san_racecheck_observers.log | tail -8
