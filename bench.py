@@ -303,7 +303,7 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
     q.observer.set_name("x"); q.observer.set_percentile(0.99); q.enable_observer()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     from outlier_suppression_b200.dist import SlotTable
-    table = SlotTable(1, NB, device)
+    table = SlotTable(1, NB, device, peer=(dist is not None and os.environ.get("OSQ_BENCH_PEER") == "1"))
     graph = [None]
 
     def my_batches_eager(ctl):
@@ -312,8 +312,9 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
             q(slabs[i], lens, 1)
 
     def one_pass(timed=False):
+        # restart the running average: with cnt = 0 the recurrence (m * 0 + cur) / 1 returns the first batch exactly, whatever
+        # finite state the previous pass left (no reset launches in the timed pass)
         q.observer.cnt = 0
-        q.observer.min_val.fill_(float("inf")); q.observer.max_val.fill_(float("-inf"))
         if timed:
             e[0].record()
         with sharded_calibration(net, NB, table=table) as ctl:
@@ -379,7 +380,9 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
             "valid_token_fraction": valid_tokens / (OB * OS),
             "token_minmax_kernel": {"ms_per_slab": k_ms, "gbs_valid": valid_bytes / (k_ms * 1e-3) / 1e9,
                                     "frac_of_hbm_peak": valid_bytes / (k_ms * 1e-3) / 1e9 / peak},
-            "launches_per_batch": 2, "issue": "eager" if graph[0] is None else "per-batch launches replayed as one CUDA graph",
+            "launches_per_batch": 2, "exchange": ("cross-rank barrier + peer loads over NVLink inside the replay launch (CUDA symmetric memory, no collective library)"
+                                                if table.hdl is not None else ("one NCCL all_reduce(SUM) of the slot table" if dist is not None else "none (1 GPU)")),
+            "issue": "eager" if graph[0] is None else "per-batch launches replayed as one CUDA graph",
             "collective": "one all_reduce(SUM) of the [n_obs, 8, 2] slot table + one replay launch",
             "state": state, "state_identical_on_all_ranks": same_on_all_ranks}
 

@@ -180,6 +180,12 @@ typedef struct {
 
 int osq_replay_average_f32(const float* table, int n_obs, int n_batches, int cnt0, const osq_replay_target_t* targets,
                            void* stream);
+/* The same replay with NO collective: peer_tables (device array of `world` device pointers) are the slot tables of all ranks,
+ * mapped into this process (NVLink peer memory / CUDA symmetric memory); slot (observer, batch b) is loaded from the table of
+ * rank b mod world, the rank that processed batch b.  The caller orders the launch after every rank's writes (a cross-rank
+ * barrier on the stream) and keeps the tables untouched until every rank has replayed. */
+int osq_replay_average_peer_f32(const float* const* peer_tables, int world, int n_obs, int n_batches, int cnt0,
+                                const osq_replay_target_t* targets, void* stream);
 
 /* per-row min/max of a [rows, cols] matrix with the running-extrema update of
  * MinMaxObserver(ch_axis=0) (observer.py:141-144) and per-row calculate_qparams.

@@ -1052,8 +1052,11 @@ abs_hist_kernel(const float* __restrict__ x, osq_tokens_t tk, const int64_t* __r
 // replays observer.py:194-202  m <- (m*cnt + cur)/(cnt+1)  in batch order for ALL observers in one launch (one thread per
 // observer) and refreshes every owning quantizer's (scale, zero_point) through a pointer table -- no host round trip.
 // ---------------------------------------------------------------------------------------------
+// `peers` != nullptr: slot (observer, batch b) is read from the table of the rank that processed batch b (b mod world) through
+// its peer-mapped pointer -- plain loads over NVLink, no collective library in the path (dist.py: symmetric-memory slot table)
 __global__ void __launch_bounds__(128)
-replay_average_kernel(const float* __restrict__ table, int n_obs, int n_batches, int cnt0, const osq_replay_target_t* __restrict__ tgt) {
+replay_average_kernel(const float* __restrict__ table, const float* const* __restrict__ peers, int world, int n_obs, int n_batches,
+                      int cnt0, const osq_replay_target_t* __restrict__ tgt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_obs) return;
   osq_replay_target_t t = tgt[i];
@@ -1068,7 +1071,9 @@ replay_average_kernel(const float* __restrict__ table, int n_obs, int n_batches,
   for (int b = 0; b < n_batches; ++b) {
     e.cnt = cnt0 + b;
     if (b == n_batches - 1) { e.scale_out = t.scale_out; e.zp_out = t.zp_out; }
-    stat_epilogue(e, table[((int64_t)i * n_batches + b) * 2], table[((int64_t)i * n_batches + b) * 2 + 1]);
+    const float* src = peers != nullptr ? peers[b % world] : table;
+    const float2 v = __ldcv(reinterpret_cast<const float2*>(src + ((int64_t)i * n_batches + b) * 2));   // never a cached copy
+    stat_epilogue(e, v.x, v.y);
   }
 }
 
@@ -1284,7 +1289,16 @@ int osq_replay_average_f32(const float* table, int n_obs, int n_batches, int cnt
                            void* stream) {
   using namespace osq;
   OSQ_CHECK_ARG(table && targets && n_obs > 0 && n_batches > 0 && cnt0 >= 0, "osq_replay_average_f32: bad argument");
-  replay_average_kernel<<<(n_obs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(table, n_obs, n_batches, cnt0, targets);
+  replay_average_kernel<<<(n_obs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(table, nullptr, 1, n_obs, n_batches, cnt0, targets);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_replay_average_peer_f32(const float* const* peer_tables, int world, int n_obs, int n_batches, int cnt0,
+                                const osq_replay_target_t* targets, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(peer_tables && targets && world >= 1 && n_obs > 0 && n_batches > 0 && cnt0 >= 0, "osq_replay_average_peer_f32: bad argument");
+  replay_average_kernel<<<(n_obs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nullptr, peer_tables, world, n_obs, n_batches, cnt0, targets);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

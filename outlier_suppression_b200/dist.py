@@ -20,8 +20,27 @@ import torch.distributed as tdist
 class SlotTable:
     """[n_obs, n_batches, 2] fp32 per-batch statistics + the packed collective + the replay."""
 
-    def __init__(self, n_obs: int, n_batches: int, device="cpu"):
+    def __init__(self, n_obs: int, n_batches: int, device="cpu", peer: bool = False, group=None):
+        """peer=True (CUDA, NCCL world > 1): the table lives in CUDA symmetric memory, every rank maps every other rank's
+        table over NVLink, and the exchange is a cross-rank barrier + peer loads inside the replay kernel instead of an
+        all-reduce (falls back to the all-reduce if symmetric memory cannot be set up)."""
         self.n_obs, self.n_batches = n_obs, n_batches
+        self.hdl = self.peer_ptrs = None
+        self.world = 1
+        dev = torch.device(device)
+        if peer and dev.type == "cuda" and tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                flat = symm.empty(n_obs * n_batches * 2, dtype=torch.float32, device=dev)
+                flat.zero_()
+                self.hdl = symm.rendezvous(flat, group if group is not None else tdist.group.WORLD)
+                self.buf = flat.view(n_obs, n_batches, 2)
+                self.world = tdist.get_world_size(group)
+                self.peer_ptrs = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+                return
+            except Exception as ex:  # pragma: no cover  (no P2P / fabric support: the collective path is always there)
+                self.hdl = self.peer_ptrs = None
+                self.peer_error = repr(ex)
         self.buf = torch.zeros(n_obs, n_batches, 2, dtype=torch.float32, device=device)
 
     def slot(self, obs: int, batch: int) -> torch.Tensor:
@@ -77,6 +96,17 @@ def _avg_observers(model):
     return obs, owners
 
 
+def _targets(table, entries, device):
+    """device copy of the replay pointer table, rebuilt only when a pointer changed (one small upload per model, not per pass)"""
+    from . import ops
+    key = tuple((None if t is None else t.data_ptr()) for e in entries for t in e[:4]) + tuple(e[4:] for e in entries)
+    cached = getattr(table, "_targets_cache", None)
+    if cached is None or cached[0] != key:
+        cached = (key, ops.replay_targets(entries, device))
+        table._targets_cache = cached
+    return cached[1]
+
+
 @contextmanager
 def sharded_calibration(model, n_batches: int, group=None, table: Optional[SlotTable] = None):
     """Usage (every rank):
@@ -96,7 +126,8 @@ def sharded_calibration(model, n_batches: int, group=None, table: Optional[SlotT
         table = SlotTable(len(observers), n_batches, device)
     else:
         assert table.n_obs == len(observers) and table.n_batches == n_batches and table.buf.device == torch.device(device)
-        table.buf.zero_()
+        if table.hdl is None:   # the all-reduce sums: slots of other ranks must be zero.  Peer tables are read slot by slot.
+            table.buf.zero_()
     ctl = _Controller(table, observers, owners)
     for i, o in enumerate(observers):
         o._shard = (ctl, i)
@@ -107,8 +138,23 @@ def sharded_calibration(model, n_batches: int, group=None, table: Optional[SlotT
             o._shard = None
     if not observers:
         return
-    table.all_reduce(group)
     cnt0 = observers[0].cnt
+    if table.hdl is not None:
+        # no collective: a cross-rank barrier on the stream (every rank's slots are written), one replay launch that loads
+        # each slot from its owner's table over NVLink, a second barrier before anybody may rewrite its table
+        entries = []
+        for o, q in zip(observers, owners):
+            o._ensure_scalar_state(device)
+            s_out, z_out = q._per_tensor_qparam_targets()
+            entries.append((o.min_val, o.max_val, s_out, z_out, o.quant_min, o.quant_max, o.symmetric))
+        table.hdl.barrier(channel=0)
+        ops.replay_average_peer(table.peer_ptrs, table.world, table.n_obs, table.n_batches, cnt0, _targets(table, entries, device))
+        table.hdl.barrier(channel=1)
+        for o, q in zip(observers, owners):
+            o.cnt = cnt0 + n_batches
+            q.qparam_epoch += 1
+        return
+    table.all_reduce(group)
     if table.buf.is_cuda:
         # ONE launch replays the recurrence for every observer and rewrites every quantizer's (scale, zero_point)
         # through a pointer table: no .cpu(), no per-observer launches, no synchronisation
@@ -117,7 +163,7 @@ def sharded_calibration(model, n_batches: int, group=None, table: Optional[SlotT
             o._ensure_scalar_state(device)
             s_out, z_out = q._per_tensor_qparam_targets()
             entries.append((o.min_val, o.max_val, s_out, z_out, o.quant_min, o.quant_max, o.symmetric))
-        ops.replay_average(table.buf, cnt0, ops.replay_targets(entries, device))
+        ops.replay_average(table.buf, cnt0, _targets(table, entries, device))
         for o, q in zip(observers, owners):
             o.cnt = cnt0 + n_batches
             q.qparam_epoch += 1

@@ -329,6 +329,14 @@ def replay_average(table: torch.Tensor, cnt0: int, targets: torch.Tensor) -> Non
           "osq_replay_average_f32")
 
 
+def replay_average_peer(peer_ptrs: torch.Tensor, world: int, n_obs: int, n_batches: int, cnt0: int, targets: torch.Tensor) -> None:
+    """The replay with every slot loaded from the table of the rank that owns it (peer-mapped pointers, no collective)."""
+    _require_cuda(peer_ptrs, targets)
+    assert peer_ptrs.dtype == torch.int64 and peer_ptrs.numel() == world
+    check(_lib.load().osq_replay_average_peer_f32(peer_ptrs.data_ptr(), int(world), int(n_obs), int(n_batches), int(cnt0),
+                                                  targets.data_ptr(), _stream()), "osq_replay_average_peer_f32")
+
+
 def rowwise_minmax_qparams(w, first, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric):
     """MinMaxObserver(ch_axis=0) + calculate_qparams on a [N, K] weight in one launch."""
     _require_cuda(w, state_min, state_max)
