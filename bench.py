@@ -591,18 +591,20 @@ def main():
         mult = LAYERS
         tot_bytes += by * mult; tot_ms += ms * mult; n_launch += mult
     # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/*_traffic.json), launch-weighted
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         import glob
         tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
         if tf:
             t = json.load(open(tf[-1]))
             traffic = sum(t[name] for name in order) / len(order)
+            traffic_src = "profiles/%s: dram__bytes_read + write per launch of one `ncu --set full` capture of the same command (not re-measured in this run)" % os.path.basename(tf[-1])
     except Exception:
         traffic = None
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "fused_fq_linear_kernel (kind::i8)", "bytes_per_launch_avg": tot_bytes / n_launch,
+                "traffic": traffic, "traffic_source": traffic_src, "frac_from_ms_per_step": (LAYERS * sum(site_bytes(*shape_of[n]) for n in order)) / (ms_step * 1e-3) / 1e9 / peak,
+                "kernel": "fused_fq_linear_kernel (kind::i8)", "bytes_per_launch_avg": tot_bytes / n_launch,
                 "us_per_launch_avg": tot_ms * 1e3 / n_launch, "sites": per_site}
 
     # ---- e2e: module-level API, batch from pinned host memory, result read back to the host ----
