@@ -829,45 +829,51 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
       }
       __syncthreads();
     };
-    constexpr int kRegElems = 4;   // list entries per thread and side on the register path
-    const bool reg_path = listed_mx && listed_mn && s_nlist[0] <= kRegElems * kSelThreads && s_nlist[1] <= kRegElems * kSelThreads;
-    unsigned int em[kRegElems], en[kRegElems];
+    // Listed sides (the normal case): ONE warp per side resolves the remaining 20 bits and rank lo + 1 on its own -- list in
+    // shared memory, digit counts in packed 16-bit register fields, warp-wide REDUX, the pick in registers -- with no block
+    // barrier at all.  Thirty-two warps taking turns at two barriers, a cross-lane reduction and a one-warp pick per pass
+    // cost 2.2 us per pass whatever the list length; the cross-lane units of one SM are the bottleneck, not the ALUs.
+    const bool reg_path = listed_mx && listed_mn;
     if (reg_path) {
-      // Both lists fit four entries per thread: they move into registers once, both sides are counted in the same pass
-      // with sixteen 8-bit fields per side (<= 128 members per warp, so no field overflows) -- four REDUX per side and pass
-      // instead of eight, no shared-memory traffic in the counting loop.
-#pragma unroll
-      for (int e = 0; e < kRegElems; ++e) {
-        const unsigned int i = (unsigned int)tid + (unsigned int)e * kSelThreads;
-        em[e] = i < s_nlist[0] ? list[0][i] : 0xFFFFFFFFu;   // bit 31 set: never matches a prefix
-        en[e] = i < s_nlist[1] ? list[1][i] : 0xFFFFFFFFu;
-      }
+      if (warp < 2) {
+        const int sd = warp;
+        const unsigned int n = s_nlist[sd];
+        const unsigned int* lst = list[sd];
+        unsigned int prefix = s_prefix[sd], krem = s_krem[sd];
 #pragma unroll 1
-      for (int sh = 16; sh >= 0; sh -= 4) {
-        const unsigned int pm = s_prefix[0], pn = s_prefix[1];
-        unsigned int qm[4] = {0u, 0u, 0u, 0u}, qn[4] = {0u, 0u, 0u, 0u};
+        for (int sh = 16; sh >= 0; sh -= 4) {
+          unsigned int q[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          for (unsigned int i = lane; i < n; i += 32) {
+            const unsigned int u = lst[i];
+            const unsigned int d = (u >> sh) & 15u;
+            const unsigned int inc = ((u & mask) == prefix) ? (1u << ((d & 1u) << 4)) : 0u;
 #pragma unroll
-        for (int e = 0; e < kRegElems; ++e) {
-          const unsigned int dm = (em[e] >> sh) & 15u, dn = (en[e] >> sh) & 15u;
-          const unsigned int im = ((em[e] & mask) == pm) ? (1u << ((dm & 3u) * 8u)) : 0u;
-          const unsigned int in_ = ((en[e] & mask) == pn) ? (1u << ((dn & 3u) * 8u)) : 0u;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            qm[w] += ((dm >> 2) == (unsigned int)w) ? im : 0u;
-            qn[w] += ((dn >> 2) == (unsigned int)w) ? in_ : 0u;
+            for (int w = 0; w < 8; ++w) q[w] += ((d >> 1) == (unsigned int)w) ? inc : 0u;
           }
-        }
 #pragma unroll
-        for (int w = 0; w < 4; ++w) { qm[w] = __reduce_add_sync(0xffffffffu, qm[w]); qn[w] = __reduce_add_sync(0xffffffffu, qn[w]); }
-        unsigned int wm = 0, wn = 0;   // lane j < 16 keeps digit j's count
+          for (int w = 0; w < 8; ++w) q[w] = __reduce_add_sync(0xffffffffu, q[w]);   // <= 8192 members: no field overflows
+          unsigned int below = 0, dsel = 15, done = 0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) { wm = ((lane >> 2) == w) ? qm[w] : wm; wn = ((lane >> 2) == w) ? qn[w] : wn; }
-        if (lane < 16) {
-          part[0][warp][lane] = (wm >> ((lane & 3) * 8)) & 0xFFu;
-          part[1][warp][lane] = (wn >> ((lane & 3) * 8)) & 0xFFu;
+          for (int j = 0; j < 16; ++j) {
+            const unsigned int c = (q[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+            const unsigned int hit = (!done && below + c > krem) ? 1u : 0u;
+            dsel = hit ? (unsigned int)j : dsel;
+            done |= hit;
+            below += done ? 0u : c;
+          }
+          prefix |= dsel << sh;
+          krem -= below;
+          mask |= 0xFu << sh;
         }
-        pick_digit(sh);
-        mask |= 0xFu << sh;
+        // rank lo + 1 inside the list: members <= a, smallest member above a
+        unsigned int cle = 0, nxt = 0xFFFFFFFFu;
+        for (unsigned int i = lane; i < n; i += 32) {
+          const unsigned int u = lst[i];
+          if (u <= prefix) ++cle; else nxt = min(nxt, u);
+        }
+        cle = __reduce_add_sync(0xffffffffu, cle);
+        nxt = __reduce_min_sync(0xffffffffu, nxt);
+        if (lane == 0) { s_prefix[sd] = prefix; s_krem[sd] = krem; s_cntle[sd] = cle; s_next[sd] = nxt; }
       }
     } else {
 #pragma unroll 1
@@ -891,21 +897,7 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
     OBS_STAMP(6);
     // ---- (c') rank lo + 1 ----
     if (reg_path) {
-      const unsigned int am = s_prefix[0], an = s_prefix[1];
-      unsigned int cm = 0, cn = 0, xm = 0xFFFFFFFFu, xn = 0xFFFFFFFFu;
-#pragma unroll
-      for (int e = 0; e < kRegElems; ++e) {
-        if (em[e] <= am) ++cm; else if (em[e] != 0xFFFFFFFFu) xm = min(xm, em[e]);
-        if (en[e] <= an) ++cn; else if (en[e] != 0xFFFFFFFFu) xn = min(xn, en[e]);
-      }
-      cm = __reduce_add_sync(0xffffffffu, cm); cn = __reduce_add_sync(0xffffffffu, cn);
-      xm = __reduce_min_sync(0xffffffffu, xm); xn = __reduce_min_sync(0xffffffffu, xn);
-      if (lane == 0) {
-        if (cm) atomicAdd(&s_cntle[0], cm);
-        if (cn) atomicAdd(&s_cntle[1], cn);
-        if (xm != 0xFFFFFFFFu) atomicMin(&s_next[0], xm);
-        if (xn != 0xFFFFFFFFu) atomicMin(&s_next[1], xn);
-      }
+      // done by the side's warp above
     } else {
 #pragma unroll
     for (int sd = 0; sd < 2; ++sd) {
