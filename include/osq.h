@@ -57,6 +57,20 @@ int osq_fq_per_tensor_f32(const float* x, float* y, int16_t* codes, int64_t n,
                           const float* scale, const void* zero_point, int zp_is_int32,
                           float lsq_grad_factor, int qmin, int qmax, void* stream);
 
+/* K7  GammaResidual + LayerNorm + the LayerNorm's output quantizer as ONE pass (13 B / element instead of 12 + 8 + 9):
+ *       u = res * res_gamma + h            (res, res_gamma optional)     model/util_layernorm.py:41-52 (GammaResidual.forward)
+ *       ln = (u - mean) * rsqrt(var + eps) [* ln_weight] [+ ln_bias]     model/util_layernorm.py:14-15 (QuantizedLayerNorm) and
+ *                                                                        :34-36 (QuantizedSplitLayerNorm: no weight, bias = beta / gamma)
+ *       y = fq(ln), bins = q - qmin (optional)                           util_layernorm.py:16-17 -> util_quant.py:11-15 / :48-55
+ *     replaces quant_bert.py:211-217 / :296-303 (dense -> dropout -> before_LayerNorm_residual -> LayerNorm) behind the dense.
+ *     `ln_out` (optional) receives the un-quantised LayerNorm output.  The quantizer part is bit-identical to K1 applied to
+ *     ln_out; the LayerNorm part is plain fp32 (two-pass mean / variance), within 2e-6 of torch's kernels.
+ *     hidden % 4 == 0; all fp32 pointers 16-byte aligned. */
+int osq_residual_layernorm_fq_f32(const float* h, const float* res, const float* res_gamma, const float* ln_weight,
+                                  const float* ln_bias, float eps, int64_t rows, int64_t hidden, const float* scale,
+                                  const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin, int qmax, float* y,
+                                  uint8_t* bins, float* ln_out, void* stream);
+
 /* K2  per-channel (ch_axis = 0) fake-quantize of a [rows, cols] matrix.
  *     replaces util_quant.py:18-26 (fake_quantize_per_channel_affine), fake_quant.py:119-122. */
 /* K1b the same per-tensor fake-quantize with the bins as a uint8 side output in the operand format of

@@ -88,6 +88,20 @@ __device__ __forceinline__ float fq_elem(float x, float s, float z, float qmin, 
   return __fmul_rn(__fsub_rn(q, z), s);
 }
 
+// Division-free fast path of fq_elem.  t' = x * (1/s) differs from the true quotient by a few ulps; when t' is farther than
+// 1e-4 from a rounding tie and small enough for that bound to hold (|t'| < 300), rint(x / s) == rint(t') and the rest of
+// util_quant.py:12-14 is evaluated exactly as fq_elem does.  `risky` (near a tie, huge, inf, NaN: ~2e-4 of the elements)
+// sends the caller to the exact division.  The IEEE division is 40 % of K1's instructions, and K1 is ALU-bound.
+__device__ __forceinline__ float fq_elem_fast(float x, float s, float rinv, float z, float qmin, float qmax, float& q, bool& risky) {
+  const float t = __fmul_rn(x, rinv);
+  const float r = rintf(t);
+  risky = !(fabsf(__fsub_rn(t, r)) < 0.4999f) || !(fabsf(t) < 300.f);
+  const float v = __fadd_rn(r, z);
+  q = fminf(fmaxf(v, qmin), qmax);
+  return __fmul_rn(__fsub_rn(q, z), s);
+}
+
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -25,19 +25,6 @@ __device__ __forceinline__ float gelu_erf_k1(float x) {
 template <int kAct>
 __device__ __forceinline__ float act_in(float x) { return kAct == 1 ? gelu_erf_k1(x) : x; }
 
-// Division-free fast path of fq_elem.  t' = x * (1/s) differs from the true quotient by a few ulps; when t' is farther than
-// 1e-4 from a rounding tie and small enough for that bound to hold (|t'| < 300), rint(x / s) == rint(t') and the rest of
-// util_quant.py:12-14 is evaluated exactly as fq_elem does.  `risky` (near a tie, huge, inf, NaN: ~2e-4 of the elements)
-// sends the caller to the exact division.  The IEEE division is 40 % of K1's instructions, and K1 is ALU-bound.
-__device__ __forceinline__ float fq_elem_fast(float x, float s, float rinv, float z, float qmin, float qmax, float& q, bool& risky) {
-  const float t = __fmul_rn(x, rinv);
-  const float r = rintf(t);
-  risky = !(fabsf(__fsub_rn(t, r)) < 0.4999f) || !(fabsf(t) < 300.f);
-  const float v = __fadd_rn(r, z);
-  q = fminf(fmaxf(v, qmin), qmax);
-  return __fmul_rn(__fsub_rn(q, z), s);
-}
-
 // kAct: 0 = none, 1 = GELU applied to x before the fake-quant (quant_bert.py:278-280: intermediate_act_fn followed by its
 // quantizer as ONE pass over the tensor)
 template <int kCodes, int kAct = 0>

@@ -43,7 +43,7 @@ constexpr int kStageK = 128;        // k elements (= bytes, u8/s8) per smem stag
 constexpr int kUmmaK = 32;          // k per tcgen05.mma kind::i8
 constexpr int kTmemCols = 512;                       // all of TMEM: acc stages x BN (2 x 256, 2 x 192, 4 x 128)
 constexpr int kWorkerWarp0 = 4, kNumWorkers = 16;    // warps 4..19 convert A (phase A); warps 4..11 also run the epilogue
-constexpr int kNumEpiWarps = 8;                      // workers 0..7: four TMEM lane quarters x two column halves of a chunk
+constexpr int kNumEpiWarps = 8;                      // workers 0..7: four TMEM lane quarters x two column slices of a chunk (kEW = 16: all workers, four slices)
 constexpr int kNumThreads = (kWorkerWarp0 + kNumWorkers) * 32;  // 640
 constexpr int kRowsPerWorker = kBM / kNumWorkers;    // 8
 constexpr int kOutTileBytes = 32 * 128;              // TMA-store staging tile: 32 rows x 32 fp32 columns, SW128
@@ -84,6 +84,10 @@ struct FusedParams {
   const int32_t* w_rowsum;
   const float* bias;
   uint8_t* a_codes;  // optional [M, K]: bins side output / code cache
+  float* Y;          // [M, N] output (the drain epilogue writes it with plain stores; the other variants go through tmap_y)
+  int lsu_mod;       // plain tile stores: every lsu_mod-th step of a warp is written by the LSU instead of the TMA unit (0 = never)
+  int epi16;         // epilogue variant: all sixteen workers (four column slices), single staging tile per warp
+  int drain;         // epilogue variant: staged tiles drained by workers 8..15 with 128-bit stores instead of TMA tensor stores
   uint32_t codes_box_bytes;  // bytes one code-cache TMA box delivers
   int pdl;                   // launched with programmatic stream serialization
   int prefetch;              // L2 prefetch distance of the fp32 activation in k-blocks (0 = off)
@@ -206,6 +210,9 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const 
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
                : "memory");
+}
+__device__ __forceinline__ void stg_hint(float4* dst, const float4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
 }
 // pair mode: lands in this CTA's shared memory, completes transaction bytes on the LEADER's barrier (cluster address)
 __device__ __forceinline__ void tma_load_2d_pair_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
@@ -405,6 +412,7 @@ struct Smem {
   uint64_t acc_full[kMaxAccStages], acc_empty[kMaxAccStages];
   uint64_t codes_ready, passes_issued, tmem_ready;
   uint64_t x_full[kNumWorkers];  // per-worker fp32 landing slot filled (TMA complete_tx)
+  uint64_t d_full[8], d_empty[8];  // drain epilogue: staging tile (lane quarter q, buffer b) staged by both column slices / drained by both drainers
   uint32_t tmem_base;
   volatile uint32_t converted;  // k-blocks worker 0 has converted so far (paces the L2 prefetcher)
 };
@@ -425,20 +433,28 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 // output stage on four adjacent columns: optional activation, then the next quantizer's fake-quant (util_quant.py:11-15 /
 // :48-55 exactly as K1 computes it); returns the dequantised values and the four bins (q - qmin) packed in one word
-__device__ __forceinline__ float4 out_stage4(float4 o, const QParam& oq, float qmin, float qmax, int act, uint32_t& bins) {
+__device__ __forceinline__ float4 out_stage4(float4 o, const QParam& oq, float rinv, float qmin, float qmax, int act, uint32_t& bins) {
   if (act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
   float q0, q1, q2, q3;
+  bool k0, k1, k2, k3;
   float4 r;
-  r.x = fq_elem(o.x, oq.s, oq.z, qmin, qmax, q0);
-  r.y = fq_elem(o.y, oq.s, oq.z, qmin, qmax, q1);
-  r.z = fq_elem(o.z, oq.s, oq.z, qmin, qmax, q2);
-  r.w = fq_elem(o.w, oq.s, oq.z, qmin, qmax, q3);
+  // division-free fast path (exactly K1's): the group is redone with the IEEE division when any element is near a rounding tie
+  r.x = fq_elem_fast(o.x, oq.s, rinv, oq.z, qmin, qmax, q0, k0);
+  r.y = fq_elem_fast(o.y, oq.s, rinv, oq.z, qmin, qmax, q1, k1);
+  r.z = fq_elem_fast(o.z, oq.s, rinv, oq.z, qmin, qmax, q2, k2);
+  r.w = fq_elem_fast(o.w, oq.s, rinv, oq.z, qmin, qmax, q3, k3);
+  if (k0 | k1 | k2 | k3) {
+    r.x = fq_elem(o.x, oq.s, oq.z, qmin, qmax, q0);
+    r.y = fq_elem(o.y, oq.s, oq.z, qmin, qmax, q1);
+    r.z = fq_elem(o.z, oq.s, oq.z, qmin, qmax, q2);
+    r.w = fq_elem(o.w, oq.s, oq.z, qmin, qmax, q3);
+  }
   bins = (uint32_t)(int)(q0 - qmin) | ((uint32_t)(int)(q1 - qmin) << 8) | ((uint32_t)(int)(q2 - qmin) << 16) |
          ((uint32_t)(int)(q3 - qmin) << 24);
   return r;
 }
 
-template <bool kXTma, bool kPair, bool kS3d, bool kEpi = false>
+template <bool kXTma, bool kPair, bool kS3d, bool kEpi = false, bool kDrain = false, int kEW = kNumEpiWarps>
 __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, const CUtensorMap& tmap_y, const CUtensorMap& tmap_y16,
                                                      const CUtensorMap& tmap_codes, const CUtensorMap& tmap_a, const FusedParams& p,
                                                      uint32_t& tmem_keep) {
@@ -446,13 +462,14 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
   // site to site in `tmem_keep`; p.first_site / p.more_sites say where this site sits in the list
   // dynamic shared memory, 1024B aligned by the attribute (SWIZZLE_128B tiles need it):
   // [A ring][W ring][fp32 landing slots][TMA-store staging tiles (may alias the slots)][Smem bookkeeping]
+  static_assert(kEW == 8 || (kEW == 16 && !kS3d && !kDrain), "sixteen epilogue warps: plain 32 x 128 B tile stores only");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* a_ring = smem_raw;
   uint8_t* w_ring = a_ring + (size_t)p.a_stages * p.a_stage_bytes;
   uint8_t* x_ring = w_ring + (size_t)p.w_stages * p.w_stage_bytes;  // 16 fp32 landing slots of 4 KB (x_tma only)
   uint8_t* o_ring = p.alias_xo ? x_ring : x_ring + (kXTma ? kNumWorkers * kXSlotBytes : 0);
   Smem& sm = *reinterpret_cast<Smem*>(p.alias_xo ? x_ring + kNumWorkers * kXSlotBytes
-                                                 : o_ring + (size_t)kNumEpiWarps * p.out_bufs * kOutTileBytes);
+                                                 : o_ring + (size_t)kEW * p.out_bufs * kOutTileBytes);
   // per-column constants; the arrays are padded to a multiple of 32 columns (the epilogue reads 32-column groups)
   const int bn_pad = (p.BN + 31) & ~31;
   float* sm_c1 = reinterpret_cast<float*>(&sm + 1);  // s_a * w_scale[n]
@@ -475,11 +492,12 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     // a_empty / w_empty / acc_full of each CTA receive the leader's multicast commits
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&sm.a_full[i], kNumWorkers * p.csz); mbar_init(&sm.a_empty[i], 1); }
     for (int i = 0; i < p.w_stages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
-    for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps * p.csz); }
+    for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kEW * p.csz); }
     mbar_init(&sm.codes_ready, kNumWorkers);
     for (int i = 0; i < kNumWorkers; ++i) mbar_init(&sm.x_full[i], 1);
     mbar_init(&sm.passes_issued, 1);
     mbar_init(&sm.tmem_ready, 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&sm.d_full[i], 2); mbar_init(&sm.d_empty[i], 2); }
     fence_barrier_init();
   }
   if constexpr (pair) {
@@ -914,10 +932,11 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     const float zcf = cp.zc;
     QParam oq = QParam{1.f, 0.f};
     if constexpr (kEpi) {
-      if (w < kNumEpiWarps)
+      if (w < kEW)
         oq = load_qparam(p.out_scale, p.out_zp, p.out_zp_is_int32, p.out_g, p.out_qmin, p.out_qmax,
                          blockIdx.x == 0 && w == 0 && lane == 0);
     }
+    const float oq_rinv = __frcp_rn(oq.s);
     uint8_t* my_tiles = o_ring + (size_t)w * p.out_bufs * kOutTileBytes;
     const uint32_t sw = ((uint32_t)lane & 7) << 4;  // 128B swizzle phase of this thread's staging row
     const int et = threadIdx.x - kWorkerWarp0 * 32;  // 0..255 among the epilogue threads
@@ -943,7 +962,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         sm_c1[et] = pc1;
         sm_c0[et] = fmaf(-zcf * (float)raw_rs, pc1, raw_b);
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEW * 32) : "memory");
     };
     int obufs = p.out_bufs;  // store tiles this warp may cycle through in the current m-block
     uint32_t tmem_base = 0;   // fetched right before the first epilogue chunk
@@ -964,6 +983,41 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       const int rows_q = min(32, p.rows_per_tile - q * 32);
       const bool any_rows = (rows_q > 0) && (row0 < p.M);
       const CUtensorMap* ymap = (rows_q == 32) ? &tmap_y : &tmap_y16;
+      if constexpr (kDrain) {
+        // Drain epilogue: the store engine is the SM's own LSU.  The two column slices of lane quarter q stage the two 128-byte
+        // halves of a [32 rows][256 B] tile (two tiles per quarter, the landing slots); the two drainer warps of the quarter
+        // (workers 8..15, idle since the conversion ended) re-read it two rows at a time and write 256 contiguous bytes per row
+        // with plain 128-bit stores.  Measured in isolation (scripts/mb/storebench.cu): 21.3 B/clk/SM against 17.8-18.9 for
+        // the 32 x 128 B tensor stores.
+        for (int c0 = slice * 32; c0 < n_cols; c0 += 64) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (!any_rows) continue;  // uniform over the quarter's producers and drainers
+          const uint32_t tb = (uint32_t)q * 2u + (n_stores & 1u);
+          if (n_stores >= 2u) mbar_wait(&sm.d_empty[tb], ((n_stores >> 1) - 1u) & 1u);
+          uint8_t* trow = x_ring + (size_t)tb * (2 * kXSlotBytes) + lane * 256 + slice * 128;
+          float4 c1n = *reinterpret_cast<const float4*>(sm_c1 + c0);
+          float4 k0n = *reinterpret_cast<const float4*>(sm_c0 + c0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 c1 = c1n, k0 = k0n;
+            if (j + 4 < 32) {
+              c1n = *reinterpret_cast<const float4*>(sm_c1 + c0 + j + 4);
+              k0n = *reinterpret_cast<const float4*>(sm_c0 + c0 + j + 4);
+            }
+            float4 o;
+            o.x = fmaf((float)(int)v[j + 0], c1.x, k0.x);
+            o.y = fmaf((float)(int)v[j + 1], c1.y, k0.y);
+            o.z = fmaf((float)(int)v[j + 2], c1.z, k0.z);
+            o.w = fmaf((float)(int)v[j + 3], c1.w, k0.w);
+            *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ sw)) = o;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.d_full[tb]);
+          ++n_stores;
+        }
+      } else
       if constexpr (kS3d) {
         // Pair store: at every step the two slices of this lane quarter cover 64 adjacent columns.  Both write their 32 x 128 B
         // half into ONE 8 KB staging tile laid out [32 rows][2][128 B] (the box of the 3-D map [M][N/32][32]); slice 0 then
@@ -982,8 +1036,8 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
           tmem_ld_wait();
           if (!any_rows) continue;  // uniform over both warps of the quarter
           const uint32_t kbuf = n_stores & (uint32_t)(obufs - 1);
-          uint8_t* tile = p.alias_xo ? x_ring + (size_t)(kbuf * kNumEpiWarps + 2u * (uint32_t)q) * kXSlotBytes
-                                     : o_ring + (size_t)(kbuf * kNumEpiWarps + 2u * (uint32_t)q) * kOutTileBytes;
+          uint8_t* tile = p.alias_xo ? x_ring + (size_t)(kbuf * kEW + 2u * (uint32_t)q) * kXSlotBytes
+                                     : o_ring + (size_t)(kbuf * kEW + 2u * (uint32_t)q) * kOutTileBytes;
           if (obufs == 1) {  // single buffer: its previous store must have been read before anyone writes
             if (issuer && lane == 0) tma_store_wait_read<0>();
             __syncwarp();
@@ -1061,7 +1115,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
           ++n_stores;
         }
       } else {
-      for (int c0 = slice * 32; c0 < n_cols; c0 += 64) {
+      for (int c0 = slice * 32; c0 < n_cols; c0 += (kEW / 4) * 32) {
         uint32_t v[32];
 #ifdef OSQ_ENABLE_TRACE
         const bool probe = (w == 0 && lane == 0 && cacc == 2);
@@ -1075,7 +1129,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
 #endif
         if (!any_rows) continue;  // warp uniform: phantom tile / quarter past the tile's rows
         if (n_stores >= (uint32_t)obufs) {  // the staging tile must have been read out by its previous TMA store
-          if (lane == 0) { if (obufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          if (lane == 0) { if (obufs == 2 && p.lsu_mod == 0) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }  // (mixed engines: bulk groups no longer map to tiles)
           __syncwarp();
         }
 #ifdef OSQ_ENABLE_TRACE
@@ -1083,7 +1137,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
 #endif
         // aliased mode: this warp's own landing slot, plus (last tile only) the slot of worker w + 8, whose owner is
         // through with it once the tile's last MMA has been committed
-        uint8_t* tile = p.alias_xo ? x_ring + (size_t)(((n_stores & 1u) & (uint32_t)(obufs - 1)) * kNumEpiWarps + w) * kXSlotBytes
+        uint8_t* tile = p.alias_xo ? x_ring + (size_t)((kEW == 16 ? 0u : ((n_stores & 1u) & (uint32_t)(obufs - 1)) * 8u) + (uint32_t)w) * kXSlotBytes
                                    : my_tiles + (size_t)(n_stores % (uint32_t)obufs) * kOutTileBytes;
         uint8_t* trow = tile + lane * 128;
         // The constants of the NEXT four columns are loaded before the current four are stored: the compiler
@@ -1108,7 +1162,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
             o.w = fmaf((float)(int)v[j + 3], c1.w, k0.w);
             if constexpr (kEpi) {
               uint32_t bw;
-              o = out_stage4(o, oq, p.out_qmin, p.out_qmax, p.out_act, bw);
+              o = out_stage4(o, oq, oq_rinv, p.out_qmin, p.out_qmax, p.out_act, bw);
               v[j >> 2] = bw;   // v[j .. j + 3] are consumed: the accumulator registers double as the bins' staging
             }
             *reinterpret_cast<float4*>(trow + ((uint32_t)(j << 2) ^ sw)) = o;  // 16B chunk (j/4) ^ (row & 7): conflict free
@@ -1126,6 +1180,27 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
 #ifdef OSQ_ENABLE_TRACE
         if (probe) OSQ_TRACE(pslot + 3);
 #endif
+        // Two store engines: the TMA unit sustains ~18 B/clk/SM on these 32 x 128 B boxes, less than the chip can write.  Every
+        // `lsu_mod`-th step of a warp therefore leaves through the LSU instead: the warp re-reads its tile four rows at a time and
+        // writes 4 x 128 contiguous bytes per 128-bit store instruction.  (kEpi keeps the TMA path: its registers hold the bins.)
+        const bool via_lsu = !kEpi && p.lsu_mod > 0 && (n_stores % (uint32_t)p.lsu_mod) == (uint32_t)p.lsu_mod - 1u;
+        if (via_lsu) {
+          __syncwarp();
+          const int cvalid = min(32, n_cols - c0);         // N % 32 == 16: the last group is half
+          const int ch = lane & 7;
+          float* yrow = p.Y + (size_t)(row0 + (lane >> 3)) * (size_t)p.N + (size_t)(n0 + c0 + ch * 4);
+          const int r_lim = min(rows_q, p.M - row0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const float4 o = *reinterpret_cast<const float4*>(tile + r * 128 + (((uint32_t)ch ^ ((uint32_t)r & 7u)) << 4));
+            if (r < r_lim && ch * 4 < cvalid && !(p.dbg & 2)) {
+              float4* dst = reinterpret_cast<float4*>(yrow + (size_t)(4 * i) * (size_t)p.N);
+              if (hint) stg_hint(dst, o, pol_once); else *dst = o;
+            }
+          }
+          __syncwarp();   // the tile is in registers: the next step may overwrite it
+        } else {
         fence_proxy_async_smem();
         __syncwarp();
 #ifdef OSQ_ENABLE_TRACE
@@ -1135,6 +1210,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
           if (hint) tma_store_2d_hint(ymap, tile, n0 + c0, row0, pol_once);
           else tma_store_2d(ymap, tile, n0 + c0, row0);  // rows >= M / columns >= N are clipped by the TMA unit
           tma_store_commit();
+        }
         }
 #ifdef OSQ_ENABLE_TRACE
         if (probe) OSQ_TRACE(pslot + 5);
@@ -1148,10 +1224,46 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       if (w == 0 && lane == 0 && cacc < 60) OSQ_TRACE(512 + cacc * 4 + 1);
       ++cacc;
       if (++acc_st == (uint32_t)p.acc_stages) { acc_st = 0; acc_ph ^= 1; }
-      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");  // every reader of this chunk's constants is done
+      asm volatile("bar.sync 1, %0;" ::"n"(kEW * 32) : "memory");  // every reader of this chunk's constants is done
       if (w == 0 && lane == 0 && cacc <= 60) OSQ_TRACE(512 + (cacc - 1) * 4 + 2);
       if (nc + 1 < nc0 + ncn) publish_consts();
       if (w == 0 && lane == 0 && cacc <= 60) OSQ_TRACE(512 + (cacc - 1) * 4 + 3);
+    };
+
+    // ---- drain epilogue, consumer side (workers 8..15): quarter dq, row half dh of every staged tile
+    auto drain_chunk = [&](int mb, int nc) {
+      const int dq = (w - kEW) & 3, dh = (w - kEW) >> 2;
+      const int n0 = nc * p.BN;
+      const int n_cols = min(p.BN, p.N - n0);
+      const int row0 = mb * p.rows_per_tile + dq * 32;
+      const int rows_q = min(min(32, p.rows_per_tile - dq * 32), p.M - row0);   // rows of this quarter that exist
+      if (rows_q <= 0) return;                                                  // the producers skip it as well
+      const int ch = lane & 15;
+      const int r_first = dh * 16 + (lane >> 4);
+      float* ybase = p.Y + (size_t)(row0 + r_first) * (size_t)p.N + (size_t)n0 + (size_t)(ch * 4);
+      const uint32_t toff = (uint32_t)(ch >> 3) * 128u;
+      for (int cb = 0; cb < n_cols; cb += 64) {
+        const uint32_t tb = (uint32_t)dq * 2u + (n_stores & 1u);
+        mbar_wait(&sm.d_full[tb], (n_stores >> 1) & 1u);
+        const uint8_t* tile = x_ring + (size_t)tb * (2 * kXSlotBytes);
+        float4 o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r_first + 2 * i;
+          o[i] = *reinterpret_cast<const float4*>(tile + r * 256 + toff + ((((uint32_t)ch & 7u) ^ ((uint32_t)r & 7u)) << 4));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.d_empty[tb]);   // the tile is in registers: the producers may refill it
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r_first + 2 * i;
+          if (r < rows_q && !(p.dbg & 2)) {
+            float4* dst = reinterpret_cast<float4*>(ybase + (size_t)(2 * i) * (size_t)p.N + cb);
+            if (hint) stg_hint(dst, o[i], pol_once); else *dst = o[i];
+          }
+        }
+        ++n_stores;
+      }
     };
 
     for (int it = 0; it < n_my_blocks; ++it) {
@@ -1159,14 +1271,14 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       const uint32_t pa_block = (uint32_t)it * (uint32_t)(a_passes * p.KB);
       // cached mode: the TMA thread must have issued every re-load pass of the previous block before this
       // warp runs ahead on the same ring (two producers may never be more than one ring cycle apart)
-      if (w < kNumEpiWarps) fetch_consts(nc0);
+      if (w < kEW) fetch_consts(nc0);
       if (!p.codes_in) {
       if (p.cached && it > 0) mbar_wait(&sm.passes_issued, (it - 1) & 1);
-      if (p.alias_xo && it > 0 && w < kNumEpiWarps) {  // this warp's landing slot was its store tile: reads must be done
+      if (!kDrain && p.alias_xo && it > 0 && w < kEW) {  // this warp's landing slot was its store tile: reads must be done
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         // pair stores: the slot may have been staged by the other slice's warp and stored by slice 0's
-        if constexpr (kS3d) asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+        if constexpr (kS3d) asm volatile("bar.sync 1, %0;" ::"n"(kEW * 32) : "memory");
       }
       if constexpr (kXTma) convert_pass_tma(mb, pa_block, it == 0); else convert_pass(mb, pa_block);
       }
@@ -1178,20 +1290,24 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         if (lane == 0) mbar_arrive(&sm.codes_ready);
         skip_ring((uint32_t)(a_passes - 1) * (uint32_t)p.KB);  // N chunks >= 1 are filled by the TMA thread
       }
-      if (p.alias_xo && !p.codes_in) { obufs = (it == n_my_blocks - 1) ? p.out_bufs : 1; n_stores = 0; }
-      if (w < kNumEpiWarps && it == 0) tmem_base = tmem_address();
-      if (w < kNumEpiWarps) publish_consts();  // chunk 0 constants
+      if (!kDrain && p.alias_xo && !p.codes_in) { obufs = (it == n_my_blocks - 1 && kEW == 8) ? p.out_bufs : 1; n_stores = 0; }
+      if (kEW == 16) obufs = 1;   // every worker stages in its own landing slot
+      if (w < kEW && it == 0) tmem_base = tmem_address();
+      if (w < kEW) publish_consts();  // chunk 0 constants
       for (int lc = 0; lc < ncn; ++lc) {
         // no code cache and K too large for residency: re-convert A for the next N chunk first
         if (!p.resident && !p.cached && !p.codes_in && lc + 1 < ncn) {
           if constexpr (kXTma) convert_pass_tma(mb, pa_block + (uint32_t)(lc + 1) * p.KB, false); else convert_pass(mb, pa_block + (uint32_t)(lc + 1) * p.KB);
         }
-        if (w < kNumEpiWarps) epilogue_chunk(mb, nc0 + lc);
+        if (w < kEW) epilogue_chunk(mb, nc0 + lc);
+        else if constexpr (kDrain) drain_chunk(mb, nc0 + lc);
       }
+      // drain epilogue: the staging tiles are the landing slots of ALL workers; the next tile's fills wait for the last drain
+      if constexpr (kDrain) { if (it + 1 < n_my_blocks) asm volatile("bar.sync 6, %0;" ::"n"(kNumWorkers * 32) : "memory"); }
     }
     // the staging tiles must have been READ before the CTA's shared memory goes away; the writes themselves are complete
     // and visible at grid completion (CUTLASS' TMA epilogues end on the same .read wait).  OSQ_FUSED_DBG=128: full wait.
-    if (w < kNumEpiWarps && lane == 0) { if (p.dbg & 128) tma_store_wait_all(); else tma_store_wait_read<0>(); }
+    if (!kDrain && w < kEW && lane == 0) { if (p.dbg & 128) tma_store_wait_all(); else tma_store_wait_read<0>(); }
     if (w == 0 && lane == 0) OSQ_TRACE(1021);
   }
 
@@ -1216,6 +1332,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       for (int i = 0; i < kNumWorkers; ++i) mbar_inval(&sm.x_full[i]);
       mbar_inval(&sm.passes_issued);
       mbar_inval(&sm.tmem_ready);
+      for (int i = 0; i < 8; ++i) { mbar_inval(&sm.d_full[i]); mbar_inval(&sm.d_empty[i]); }
     }
     __syncthreads();   // also: TMEM is deallocated and every warp has left this site's shared memory
     if (p.csz > 1) cluster_sync_all();
@@ -1233,6 +1350,28 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
 OSQ_FUSED_ENTRY(fused_fq_linear_kernel_ldg, false, false, false)
 OSQ_FUSED_ENTRY(fused_fq_linear_kernel, true, false, false)
 OSQ_FUSED_ENTRY(fused_fq_linear_kernel_pair, true, true, false)
+// all sixteen workers run the epilogue (four column slices per lane quarter, one staging tile = the warp's own landing slot)
+#define OSQ_FUSED_ENTRY_E16(name, PAIR)                                                                                \
+  __global__ void __launch_bounds__(kNumThreads, 1)                                                                    \
+  name(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,                         \
+       const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,                   \
+       const __grid_constant__ CUtensorMap tmap_a, const FusedParams p) {                                              \
+    uint32_t tmem_keep = 0;                                                                                            \
+    fused_fq_linear_body<true, PAIR, false, false, false, 16>(tmap_w, tmap_y, tmap_y16, tmap_codes, tmap_a, p, tmem_keep); \
+  }
+OSQ_FUSED_ENTRY_E16(fused_fq_linear_kernel_e16, false)
+OSQ_FUSED_ENTRY_E16(fused_fq_linear_kernel_pair_e16, true)
+// drain epilogue (plain 128-bit stores of staged 256-byte rows by the idle workers)
+#define OSQ_FUSED_ENTRY_DRAIN(name, PAIR)                                                                              \
+  __global__ void __launch_bounds__(kNumThreads, 1)                                                                    \
+  name(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,                         \
+       const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,                   \
+       const __grid_constant__ CUtensorMap tmap_a, const FusedParams p) {                                              \
+    uint32_t tmem_keep = 0;                                                                                            \
+    fused_fq_linear_body<true, PAIR, false, false, true>(tmap_w, tmap_y, tmap_y16, tmap_codes, tmap_a, p, tmem_keep);  \
+  }
+OSQ_FUSED_ENTRY_DRAIN(fused_fq_linear_kernel_dr, false)
+OSQ_FUSED_ENTRY_DRAIN(fused_fq_linear_kernel_pair_dr, true)
 // epilogue with pair-shared staging tiles and 256-byte-row 3-D tensor stores (N % 32 == 0, chunks of 64 k columns)
 OSQ_FUSED_ENTRY(fused_fq_linear_kernel_ldg_s3, false, false, true)
 OSQ_FUSED_ENTRY(fused_fq_linear_kernel_s3, true, false, true)
@@ -1248,6 +1387,17 @@ OSQ_FUSED_ENTRY(fused_fq_linear_kernel_pair_s3, true, true, true)
   }
 OSQ_FUSED_ENTRY_EPI(fused_fq_linear_kernel_epi, false)
 OSQ_FUSED_ENTRY_EPI(fused_fq_linear_kernel_pair_epi, true)
+// the output stage is ALU-bound (erf, exact division): with all sixteen workers in the epilogue it runs twice as fast
+#define OSQ_FUSED_ENTRY_EPI16(name, PAIR)                                                                              \
+  __global__ void __launch_bounds__(kNumThreads, 1)                                                                    \
+  name(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,                         \
+       const __grid_constant__ CUtensorMap tmap_y16, const __grid_constant__ CUtensorMap tmap_codes,                   \
+       const __grid_constant__ CUtensorMap tmap_a, const FusedParams p) {                                              \
+    uint32_t tmem_keep = 0;                                                                                            \
+    fused_fq_linear_body<true, PAIR, false, true, false, 16>(tmap_w, tmap_y, tmap_y16, tmap_codes, tmap_a, p, tmem_keep); \
+  }
+OSQ_FUSED_ENTRY_EPI16(fused_fq_linear_kernel_epi_e16, false)
+OSQ_FUSED_ENTRY_EPI16(fused_fq_linear_kernel_pair_epi_e16, true)
 
 // Multi-site launch: one persistent grid walks a short list of INDEPENDENT sites (no site's input is another site's
 // output).  A CTA moves on to the next site as soon as its own tiles of the current one are stored, so the launch gap,
@@ -1440,7 +1590,7 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
   p.A = a->A;
   p.a_scale = a->a_scale; p.a_zp = a->a_zp; p.a_zp_is_int32 = a->a_zp_is_int32; p.g = a->lsq_grad_factor;
   p.qmin = (float)a->a_qmin; p.qmax = (float)a->a_qmax;
-  p.w_scale = a->w_scale; p.w_rowsum = a->w_rowsum; p.bias = a->bias; p.a_codes = a->a_codes;
+  p.w_scale = a->w_scale; p.w_rowsum = a->w_rowsum; p.bias = a->bias; p.a_codes = a->a_codes; p.Y = a->Y;
   p.trace = (long long*)a->debug_trace;
   p.out_act = a->out_act; p.out_scale = a->out_scale; p.out_zp = a->out_zp; p.out_zp_is_int32 = a->out_zp_is_int32;
   p.out_g = a->out_lsq_grad_factor; p.out_qmin = (float)a->out_qmin; p.out_qmax = (float)a->out_qmax; p.out_bins = a->out_bins;
@@ -1468,7 +1618,13 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_ldg_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair_s3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_e16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair_e16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_dr, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair_dr, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_epi_e16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair_epi_e16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_kernel_pair_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     OSQ_CUDA(cudaFuncSetAttribute(fused_fq_linear_multi_kernel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1654,6 +1810,22 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
     return OSQ_EINVAL;
   }
   p.store3d = (a->out_scale == nullptr && env_s3d != 0 && p.N % 32 == 0 && p.BN % 64 == 0 && p.M >= 32 && (p.alias_xo || p.out_bufs >= 1)) ? 1 : 0;
+  static int env_drain = -1;
+  if (env_drain < 0) { const char* e = getenv("OSQ_FUSED_DRAIN"); env_drain = e ? atoi(e) : 0; }
+  static int env_lsu = -1;
+  if (env_lsu < 0) { const char* e = getenv("OSQ_FUSED_LSU_MOD"); env_lsu = e ? atoi(e) : 0; }
+  p.lsu_mod = (p.trace == nullptr && env_lsu > 0) ? env_lsu : 0;
+  static int env_e16 = -1;
+  // measured: with plain Y stores the sixteen-warp epilogue changes nothing (the store path bounds the write phase: 54.1 vs 53.6 us on
+  // 768->3072), without stores it is 14 % faster (36.9 vs 42.7 us).  Default: only where the epilogue computes (output stage).
+  if (env_e16 < 0) { const char* e = getenv("OSQ_FUSED_EPI16"); env_e16 = e ? atoi(e) : 0; }
+  // drain epilogue: needs the landing slots as staging (aliased plans), whole 64-column steps, no output stage
+  p.drain = (env_drain != 0 && !p.store3d && a->out_scale == nullptr && p.x_tma && p.alias_xo && p.N % 64 == 0 && p.BN % 64 == 0 &&
+             p.trace == nullptr) ? 1 : 0;
+  // sixteen epilogue warps: needs one landing slot per worker as its staging tile (aliased plans)
+  static int env_e16o = -1;
+  if (env_e16o < 0) { const char* e = getenv("OSQ_FUSED_EPI16_OUT"); env_e16o = e ? atoi(e) : 1; }
+  p.epi16 = ((a->out_scale == nullptr ? env_e16 != 0 : env_e16o != 0) && !p.drain && !p.store3d && p.x_tma && p.alias_xo) ? 1 : 0;
   if (p.store3d) {
     if (int rc = make_map_3d_y(&map_y, a->Y, (uint64_t)p.N, (uint64_t)p.M, 32)) return rc;
     if (int rc = make_map_3d_y(&map_y16, a->Y, (uint64_t)p.N, (uint64_t)p.M, 16)) return rc;
@@ -1724,13 +1896,22 @@ static int launch_fused(const FusedPlan& pl, void* stream) {
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 2 : 1;
   const CUtensorMap &map_w = pl.map_w, &map_y = pl.map_y, &map_y16 = pl.map_y16, &map_c = pl.map_c, &map_a = pl.map_a;
-  if (p.out_scale != nullptr) {
+  if (p.out_scale != nullptr && p.epi16) {
+    if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair_epi_e16, map_w, map_y, map_y16, map_c, map_a, p));
+    else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_epi_e16, map_w, map_y, map_y16, map_c, map_a, p));
+  } else if (p.out_scale != nullptr) {
     if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair_epi, map_w, map_y, map_y16, map_c, map_a, p));
     else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_epi, map_w, map_y, map_y16, map_c, map_a, p));
   } else if (p.store3d) {
     if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair_s3, map_w, map_y, map_y16, map_c, map_a, p));
     else if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_s3, map_w, map_y, map_y16, map_c, map_a, p));
     else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_ldg_s3, map_w, map_y, map_y16, map_c, map_a, p));
+  } else if (p.epi16) {
+    if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair_e16, map_w, map_y, map_y16, map_c, map_a, p));
+    else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_e16, map_w, map_y, map_y16, map_c, map_a, p));
+  } else if (p.drain) {
+    if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair_dr, map_w, map_y, map_y16, map_c, map_a, p));
+    else OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_dr, map_w, map_y, map_y16, map_c, map_a, p));
   } else {
     if (p.csz == 2) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel_pair, map_w, map_y, map_y16, map_c, map_a, p));
     else if (p.x_tma) OSQ_CUDA(cudaLaunchKernelEx(&cfg, fused_fq_linear_kernel, map_w, map_y, map_y16, map_c, map_a, p));

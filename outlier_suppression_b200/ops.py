@@ -111,6 +111,34 @@ def fq_per_tensor(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor
     return (y, codes) if want_codes else y
 
 
+def residual_layernorm_fq(h: torch.Tensor, res: Optional[torch.Tensor], res_gamma: Optional[torch.Tensor],
+                          ln_weight: Optional[torch.Tensor], ln_bias: Optional[torch.Tensor], eps: float, scale: torch.Tensor,
+                          zero_point: torch.Tensor, qmin: int, qmax: int, lsq_grad_factor: float = 0.0, want_bins: bool = False,
+                          want_ln: bool = False):
+    """GammaResidual + LayerNorm + its output quantizer in one pass (util_layernorm.py:14-17 / :34-37, :41-52).
+    Returns y, or (y, bins, ln_out) with the optional outputs as None when not requested."""
+    _require_cuda(h, scale, zero_point)
+    if h.dtype != torch.float32 or not h.is_contiguous():
+        raise TypeError("h must be a contiguous float32 tensor")
+    H = h.shape[-1]
+    rows = h.numel() // max(H, 1)
+    for name, t, n in (("res", res, h.numel()), ("res_gamma", res_gamma, H), ("ln_weight", ln_weight, H), ("ln_bias", ln_bias, H)):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n or not t.is_cuda):
+            raise TypeError("%s must be a contiguous float32 CUDA tensor of %d elements" % (name, n))
+    if scale.dtype != torch.float32 or zero_point.dtype not in (torch.float32, torch.int32):
+        raise TypeError("scale must be float32, zero_point float32 or int32")
+    y = torch.empty_like(h)
+    bins = torch.empty_like(h, dtype=torch.uint8) if want_bins else None
+    ln = torch.empty_like(h) if want_ln else None
+    if h.numel() > 0:
+        check(_lib.load().osq_residual_layernorm_fq_f32(h.data_ptr(), _ptr(res), _ptr(res_gamma), _ptr(ln_weight), _ptr(ln_bias), float(eps),
+                                                        rows, H, scale.data_ptr(), zero_point.data_ptr(),
+                                                        int(zero_point.dtype == torch.int32), float(lsq_grad_factor), int(qmin),
+                                                        int(qmax), y.data_ptr(), _ptr(bins), _ptr(ln), _stream()),
+              "osq_residual_layernorm_fq_f32")
+    return (y, bins, ln) if (want_bins or want_ln) else y
+
+
 def fq_per_channel(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int,
                    want_codes: bool = False):
     """util_quant.py:18-26 for ch_axis = 0; x is viewed as [rows, cols]."""

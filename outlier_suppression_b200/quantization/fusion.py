@@ -23,6 +23,13 @@ warps of a 1-CTA-per-SM kernel, far from the ALU rate a full-occupancy elementwi
 
 The state togglers call this (like ``group_sibling_linears``), so an unmodified reference driver gets it for free;
 ``OSQ_DISABLE_EPILOGUE_FUSION=1`` turns it off.
+
+Second hook, same mechanism: ``fuse_layernorm_output(model)`` wraps every ``dense -> dropout -> before_LayerNorm_residual ->
+LayerNorm`` module (model/quant_bert.py:197-217 QuantizedBertSelfOutput, :283-303 QuantizedBertOutput; quant_roberta.py
+likewise).  In the quantized inference state the residual (optionally times gamma, util_layernorm.py:41-52), the LayerNorm
+(util_layernorm.py:14-15, or the split form :34-36 after gamma migration) and the LayerNorm's output quantizer (:16-17) run
+as ONE kernel (osq_residual_layernorm_fq_f32, 13 B / element instead of 12 + 8 + 9) that also writes the quantizer's uint8
+bins for the following QLinear(s).  ``OSQ_DISABLE_LN_FUSION=1`` turns it off.
 """
 from __future__ import annotations
 
@@ -121,4 +128,84 @@ def fuse_ffn_activation(model) -> int:
             continue
         mod._osq_unfused_forward = mod.forward
         mod.forward = types.MethodType(_fused_forward, mod)
+    return n
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# dense -> dropout -> GammaResidual -> LayerNorm -> quantizer  (quant_bert.py:211-217, :296-303)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _ln_fusable(mod, h, input_tensor):
+    if os.environ.get("OSQ_DISABLE_LN_FUSION") == "1" or torch.is_grad_enabled():
+        return None
+    if getattr(mod, "backend", "academic") == "tensorrt":      # an extra quantizer sits between the dense and the residual
+        return None
+    drop = getattr(mod, "dropout", None)
+    if drop is not None and getattr(drop, "training", False) and getattr(drop, "p", 0.0) > 0:
+        return None
+    lnm = mod.LayerNorm
+    inner = getattr(lnm, "layernorm", None)
+    q = getattr(lnm, "layernorm_post_act_fake_quantize", None)
+    if not isinstance(inner, torch.nn.LayerNorm) or not isinstance(q, QuantizeBase) or not getattr(lnm, "qoutput", True):
+        return None
+    if q.fake_quant_enabled != 1 or q.observer_enabled != 0 or q.ch_axis != -1:
+        return None
+    H = h.shape[-1]
+    if tuple(inner.normalized_shape) != (H,) or H % 4 != 0:
+        return None
+    if not (h.is_cuda and h.dtype == torch.float32 and h.is_contiguous() and input_tensor.shape == h.shape
+            and input_tensor.dtype == torch.float32 and input_tensor.is_contiguous()):
+        return None
+    return lnm, inner, q
+
+
+def _fused_ln_forward(self, hidden_states, input_tensor, observation_mask=None):
+    # the dense is an ordinary module call (fused fake-quant + Linear when its producer is tagged)
+    h = self.dense(hidden_states)
+    trio = _ln_fusable(self, h, input_tensor)
+    if trio is None:
+        # reference order from here on (quant_bert.py:212-217)
+        h = self.dropout(h)
+        if getattr(self, "backend", "academic") == "tensorrt":
+            h = self.output_post_act_fake_quantize(h, observation_mask, 1)
+        h = self.before_LayerNorm_residual(input_tensor, h)
+        return self.LayerNorm(h, observation_mask)
+    lnm, inner, q = trio
+    res_mod = self.before_LayerNorm_residual
+    gamma = res_mod.gamma.detach() if getattr(res_mod, "mul_gamma", False) else None
+    weight = inner.weight.detach() if inner.weight is not None else None
+    bias = inner.bias.detach() if inner.bias is not None else None
+    split_bias = getattr(lnm, "bias", None)                    # QuantizedSplitLayerNorm: non-affine LayerNorm + beta / gamma
+    if split_bias is not None:
+        if bias is not None or weight is not None:
+            h = self.before_LayerNorm_residual(input_tensor, h)
+            return self.LayerNorm(h, observation_mask)
+        bias = split_bias.detach()
+    g = (1.0 / (h.numel() * q.quant_max) ** 0.5 if q.use_grad_scaling else 1.0) if isinstance(q, LSQPlusFakeQuantize) else 0.0
+    want_bins = q._emit_bins and h.shape[-1] % 128 == 0 and q.quant_max - q.quant_min <= 255
+    r = ops.residual_layernorm_fq(h, input_tensor, gamma, weight, bias, inner.eps, q.scale.detach(), q.zero_point.detach(),
+                                  q.quant_min, q.quant_max, lsq_grad_factor=g, want_bins=want_bins)
+    stats["ln_fused"] = stats.get("ln_fused", 0) + 1
+    out = r[0] if want_bins else r
+    q._tag(out)
+    if want_bins:
+        try:
+            out._osq_bins = (r[1], out._version)
+        except Exception:  # pragma: no cover
+            pass
+    return out
+
+
+def fuse_layernorm_output(model) -> int:
+    """Wraps the forward of every ``dense -> dropout -> before_LayerNorm_residual -> LayerNorm`` module.  Idempotent; returns
+    the number of wrapped modules."""
+    n = 0
+    for mod in model.modules():
+        if not (hasattr(mod, "dense") and hasattr(mod, "before_LayerNorm_residual") and hasattr(mod, "LayerNorm")
+                and hasattr(getattr(mod, "LayerNorm"), "layernorm")):
+            continue
+        n += 1
+        if getattr(mod, "_osq_unfused_ln_forward", None) is not None:
+            continue
+        mod._osq_unfused_ln_forward = mod.forward
+        mod.forward = types.MethodType(_fused_ln_forward, mod)
     return n

@@ -34,6 +34,7 @@ def test_unmodified_quant_bert_runs_the_ptq_schedule_on_cuda(cfg_name, monkeypat
     # module-level teacher forcing needs every quantizer / QLinear call to happen: the fused output stage (which never
     # materialises the tensors in between) is checked separately below
     monkeypatch.setenv("OSQ_DISABLE_EPILOGUE_FUSION", "1")
+    monkeypatch.setenv("OSQ_DISABLE_LN_FUSION", "1")
     stats0 = dict(qm.stats)
     r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
     layers = r["layers"]
@@ -64,6 +65,7 @@ def test_fused_ffn_output_stage_inside_the_unmodified_model(cfg_name, mode, monk
     import torch
     from outlier_suppression_b200.quantization import quantized_module as qm
     monkeypatch.setenv("OSQ_DISABLE_EPILOGUE_FUSION", "1")
+    monkeypatch.setenv("OSQ_DISABLE_LN_FUSION", "1")   # the fused LayerNorm rounds differently from torch's: checked in its own test
     r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
     model = r["model"]
     batches = [{k: v.cuda() for k, v in b.items()} for b in RM.synth_batches(3, 4, 32, 100, "cpu", seed=5)]
@@ -83,3 +85,32 @@ def test_fused_ffn_output_stage_inside_the_unmodified_model(cfg_name, mode, monk
     assert qm.stats["epilogue_fused"] - before == 3 * r["layers"], qm.stats
     for a, b in zip(on, off):
         assert torch.equal(a, b), float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("cfg_name", list(CONFIGS))
+def test_fused_residual_layernorm_quantizer_inside_the_unmodified_model(cfg_name, monkeypatch):
+    """The togglers also wrap every dense -> dropout -> GammaResidual -> LayerNorm -> quantizer block (quant_bert.py:211-217,
+    :296-303) with osq_residual_layernorm_fq_f32.  Its LayerNorm is plain fp32 with another summation order than torch's kernel,
+    so activations differ by ~1e-6 relative and an occasional bin flips: the logits agree to the tolerance written below (the
+    same one the CPU-vs-GPU comparison of the reference itself uses), and the fused path must really have been taken -- after
+    gamma migration (config 2) through the split LayerNorm + gamma-scaled residual, without it through the affine LayerNorm."""
+    import torch
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    monkeypatch.setenv("OSQ_DISABLE_LN_FUSION", "1")
+    r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
+    model = r["model"]
+    batches = [{k: v.cuda() for k, v in b.items()} for b in RM.synth_batches(3, 4, 32, 100, "cpu", seed=5)]
+
+    def logits():
+        with torch.no_grad():
+            return [(lambda o: o[0] if isinstance(o, tuple) else o.logits)(model(**b)).clone() for b in batches]
+
+    off = logits()
+    monkeypatch.delenv("OSQ_DISABLE_LN_FUSION")
+    before = qm.stats.get("ln_fused", 0)
+    on = logits()
+    # two blocks per layer; the last layer's output LayerNorm has no quantizer (qoutput=False, quant_bert.py) and stays unfused
+    assert qm.stats.get("ln_fused", 0) - before == 3 * (2 * r["layers"] - 1), qm.stats
+    for a, b in zip(on, off):
+        d = float((a - b).abs().max())
+        assert d <= 2e-2 * float(b.abs().max()) + 1e-3, (d, a, b)
