@@ -324,6 +324,40 @@ int osq_fused_fq_linear(const osq_fused_linear_t* args, void* stream);
  * synthetic site stack), or sibling projections that cannot share one weight concatenation. */
 int osq_fused_fq_linear_multi(const osq_fused_linear_t* sites, int n_sites, void* stream);
 
+/* A per-tensor activation quantizer as the attention kernels consume it: device-resident parameters (no .item() sync),
+ * FixedFakeQuantize (lsq_grad_factor = 0, fake_quant.py:123-125) or LSQPlusFakeQuantize (lsq_grad_factor = 1 / sqrt(numel * qmax),
+ * float zero_point, fake_quant.py:188-195); at most 8 bits. */
+typedef struct {
+  const float* scale;      /* device [1] */
+  const void* zero_point;  /* device [1], float or int32 */
+  int zp_is_int32;
+  float lsq_grad_factor;
+  int qmin, qmax;
+} osq_quantizer_t;
+
+/* K8  attention scores with the query / key quantizers as prologue, one launch:
+ *       scores = fq_q(Q) @ fq_k(K)^T  [* out_mul]  [+ mask]
+ *     replaces model/quant_bert.py:148-150 (query_permute_post_act_fake_quantize, key_transpose_post_act_fake_quantize,
+ *     torch.matmul) and, with out_mul / mask, :169-172 (/ sqrt(d), + attention_mask).  Q and K are the [batch, tokens, heads * d]
+ *     projections viewed as [batch, heads, tokens, d] (transpose_for_scores): strides {batch, head, token} in elements, the
+ *     channel stride is 1.  Both operands are fake-quantised activations, so the product of the dequantised tensors equals
+ *     s_q s_k * sum (q_bin - Zq)(k_bin - Zk): an exact integer contraction (u8 x u8 -> s32) and one scale.  out_mul = the fp32
+ *     reciprocal ATen multiplies by for `scores / math.sqrt(d)` (1 = none); mask = additive [batch, sk] or NULL.
+ *     d in {32, 64, 128}; sk % 4 == 0; scores [batch, heads, sq, sk] fp32. */
+int osq_attn_scores_fq_f32(const float* q, const float* k, int64_t batch, int64_t heads, int64_t sq, int64_t sk, int64_t d,
+                           const int64_t* q_strides, const int64_t* k_strides, const osq_quantizer_t* qq, const osq_quantizer_t* kq,
+                           float out_mul, const float* mask, float* scores, void* stream);
+
+/* K9  attention context with the probability / value quantizers as prologue and the context quantizer as epilogue:
+ *       context = fq_p(P) @ fq_v(V)            written as [batch, sq, heads * d] (the permute + view of quant_bert.py:189-191)
+ *       oq != NULL: context <- fq_o(context), bins (optional) = its uint8 bins for the bins-in Linear behind it
+ *     replaces quant_bert.py:185-187 (attention_probs_post_act_fake_quantize, value_permute_post_act_fake_quantize, torch.matmul)
+ *     and :192-193 (context_view_post_act_fake_quantize).  P [batch, heads, sq, sk] fp32 is read once (it is 8x larger than
+ *     everything else this kernel touches); V like K8's operands. */
+int osq_attn_context_fq_f32(const float* probs, const float* v, int64_t batch, int64_t heads, int64_t sq, int64_t sk, int64_t d,
+                            const int64_t* v_strides, const osq_quantizer_t* pq, const osq_quantizer_t* vq, const osq_quantizer_t* oq,
+                            float* context, uint8_t* bins, void* stream);
+
 /* LSQ+ backward (fine stage `learn_scale`, token_wise_clipping.py:72-108; gradients of
  * util_quant.py:48-55):  dx = dy * 1[qmin <= q <= qmax];
  *   dscale += g * sum dy * (inside ? rint(x/s) - x/s : q_clamped - z);  dzp += g * sum dy * (inside ? 0 : -s)

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("OSQ_LIB_PATH") or os.path.join(_PKG, "libosq_b200.so"
 EXPORTS = [
     "osq_version", "osq_last_error", "osq_sm_count", "osq_workspace_bytes",
     "osq_fq_per_tensor_f32", "osq_fq_per_tensor_bins_f32", "osq_act_fq_per_tensor_bins_f32", "osq_fq_per_channel_f32",
-    "osq_residual_layernorm_fq_f32",
+    "osq_residual_layernorm_fq_f32", "osq_attn_scores_fq_f32", "osq_attn_context_fq_f32",
     "osq_minmax_masked_f32", "osq_minmax_flat_f32", "osq_token_minmax_f32", "osq_prune_select_f32", "osq_prune_select_unsorted_f32",
     "osq_prune_observe_f32", "osq_quantile_observe_f32", "osq_replay_average_f32", "osq_replay_average_peer_f32",
     "osq_rowwise_minmax_qparams_f32", "osq_calc_qparams_f32",
@@ -51,6 +51,12 @@ class FusedLinearArgs(C.Structure):
                 ("Y", C.c_void_p), ("N", C.c_int64), ("mma_kind", C.c_int), ("a_codes", C.c_void_p), ("debug_trace", C.c_void_p),
                 ("out_act", C.c_int), ("out_scale", C.c_void_p), ("out_zp", C.c_void_p), ("out_zp_is_int32", C.c_int),
                 ("out_lsq_grad_factor", C.c_float), ("out_qmin", C.c_int), ("out_qmax", C.c_int), ("out_bins", C.c_void_p)]
+
+
+class QuantizerArgs(C.Structure):
+    """osq_quantizer_t"""
+    _fields_ = [("scale", C.c_void_p), ("zero_point", C.c_void_p), ("zp_is_int32", C.c_int), ("lsq_grad_factor", C.c_float),
+                ("qmin", C.c_int), ("qmax", C.c_int)]
 
 
 _lock = threading.Lock()
@@ -91,6 +97,10 @@ def _declare(lib):
         "osq_pack_weight_s8": [vp, i64, i64, vp, vp, i32, i32, vp, vp, vp],
         "osq_fused_fq_linear": [C.POINTER(FusedLinearArgs), vp],
         "osq_fused_fq_linear_multi": [C.POINTER(FusedLinearArgs), i32, vp],
+        "osq_attn_scores_fq_f32": [vp, vp, i64, i64, i64, i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(QuantizerArgs),
+                                   C.POINTER(QuantizerArgs), f32, vp, vp, vp],
+        "osq_attn_context_fq_f32": [vp, vp, i64, i64, i64, i64, i64, C.POINTER(i64), C.POINTER(QuantizerArgs), C.POINTER(QuantizerArgs),
+                                    C.POINTER(QuantizerArgs), vp, vp, vp],
         "osq_lsqplus_backward_f32": [vp, vp, vp, i64, vp, vp, f32, i32, i32, vp, vp],
     }
     for name, argtypes in sig.items():

@@ -139,6 +139,60 @@ def residual_layernorm_fq(h: torch.Tensor, res: Optional[torch.Tensor], res_gamm
     return (y, bins, ln) if (want_bins or want_ln) else y
 
 
+def _quantizer_args(q: dict):
+    """dict(scale=, zp=, qmin=, qmax=, g=) -> osq_quantizer_t (the tensors must stay alive until the launch is issued)."""
+    scale, zp = q["scale"], q["zp"]
+    if scale.dtype != torch.float32 or zp.dtype not in (torch.float32, torch.int32) or not scale.is_cuda or not zp.is_cuda:
+        raise TypeError("quantizer scale must be a float32 CUDA tensor, zero_point float32 or int32")
+    a = _lib.QuantizerArgs()
+    a.scale = scale.data_ptr(); a.zero_point = zp.data_ptr(); a.zp_is_int32 = int(zp.dtype == torch.int32)
+    a.lsq_grad_factor = float(q.get("g", 0.0)); a.qmin = int(q["qmin"]); a.qmax = int(q["qmax"])
+    return a
+
+
+def _head_view(x: torch.Tensor, what: str):
+    """[B, h, S, d] view with unit channel stride -> (strides {batch, head, token})."""
+    if x.dim() != 4 or x.dtype != torch.float32 or not x.is_cuda or x.stride(3) != 1:
+        raise TypeError("%s must be a float32 CUDA [batch, heads, tokens, d] view with contiguous channels" % what)
+    import ctypes as C
+    return (C.c_int64 * 3)(x.stride(0), x.stride(1), x.stride(2))
+
+
+def attn_scores_fq(q: torch.Tensor, k: torch.Tensor, qq: dict, kq: dict, out_mul: float = 1.0, mask: Optional[torch.Tensor] = None):
+    """fq_q(q) @ fq_k(k)^T [* out_mul] [+ mask] in one launch (quant_bert.py:148-150, :169-172).  q [B, h, Sq, d], k [B, h, Sk, d]
+    (transpose_for_scores views); mask additive, broadcastable from [B, 1, 1, Sk].  Returns scores [B, h, Sq, Sk]."""
+    qs, ks = _head_view(q, "q"), _head_view(k, "k")
+    B, h, sq, d = q.shape
+    sk = k.shape[2]
+    if k.shape[0] != B or k.shape[1] != h or k.shape[3] != d:
+        raise ValueError("q / k shape mismatch")
+    if mask is not None:
+        if mask.dtype != torch.float32 or mask.numel() != B * sk or not mask.is_contiguous() or not mask.is_cuda:
+            raise TypeError("mask must be a contiguous float32 CUDA tensor of batch * sk elements")
+    out = torch.empty(B, h, sq, sk, device=q.device, dtype=torch.float32)
+    qa, ka = _quantizer_args(qq), _quantizer_args(kq)
+    check(_lib.load().osq_attn_scores_fq_f32(q.data_ptr(), k.data_ptr(), B, h, sq, sk, d, qs, ks, qa, ka, float(out_mul), _ptr(mask),
+                                             out.data_ptr(), _stream()), "osq_attn_scores_fq_f32")
+    return out
+
+
+def attn_context_fq(probs: torch.Tensor, v: torch.Tensor, pq: dict, vq: dict, oq: Optional[dict] = None, want_bins: bool = False):
+    """fq_p(probs) @ fq_v(v), written as [B, Sq, h * d] (quant_bert.py:185-191); with ``oq`` the context quantizer (:192-193) runs in
+    the epilogue and ``want_bins`` adds its uint8 bins.  probs [B, h, Sq, Sk] contiguous, v [B, h, Sk, d] view."""
+    vs = _head_view(v, "v")
+    B, h, sk, d = v.shape
+    if probs.dim() != 4 or probs.dtype != torch.float32 or not probs.is_contiguous() or probs.shape[0] != B or probs.shape[1] != h or probs.shape[3] != sk:
+        raise TypeError("probs must be a contiguous float32 [batch, heads, sq, sk] tensor matching v")
+    sq = probs.shape[2]
+    out = torch.empty(B, sq, h * d, device=v.device, dtype=torch.float32)
+    bins = torch.empty(B, sq, h * d, device=v.device, dtype=torch.uint8) if (want_bins and oq is not None) else None
+    pa, va = _quantizer_args(pq), _quantizer_args(vq)
+    oa = _quantizer_args(oq) if oq is not None else None
+    check(_lib.load().osq_attn_context_fq_f32(probs.data_ptr(), v.data_ptr(), B, h, sq, sk, d, vs, pa, va, oa, out.data_ptr(), _ptr(bins),
+                                              _stream()), "osq_attn_context_fq_f32")
+    return (out, bins) if want_bins else out
+
+
 def fq_per_channel(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int,
                    want_codes: bool = False):
     """util_quant.py:18-26 for ch_axis = 0; x is viewed as [rows, cols]."""

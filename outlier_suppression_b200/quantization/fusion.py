@@ -30,6 +30,14 @@ likewise).  In the quantized inference state the residual (optionally times gamm
 (util_layernorm.py:14-15, or the split form :34-36 after gamma migration) and the LayerNorm's output quantizer (:16-17) run
 as ONE kernel (osq_residual_layernorm_fq_f32, 13 B / element instead of 12 + 8 + 9) that also writes the quantizer's uint8
 bins for the following QLinear(s).  ``OSQ_DISABLE_LN_FUSION=1`` turns it off.
+
+Third hook: ``fuse_self_attention(model)`` wraps every self-attention module that owns the query / key / value projections
+and the five attention-side quantizers (model/quant_bert.py:100-195, quant_roberta.py likewise).  In the quantized
+inference state its forward becomes: grouped q | k | v launch -> osq_attn_scores_fq_f32 (query and key quantizers as the
+prologue of q @ k^T, 1 / sqrt(d) and the attention mask in its epilogue) -> softmax -> osq_attn_context_fq_f32 (probability and
+value quantizers as the prologue of probs @ v, the permute + view and the context quantizer + bins in its epilogue):
+four fake-quant launches, two scale / mask passes and a permute copy less per layer, and the exact integer contraction
+instead of an fp32 GEMM over dequantised values.  ``OSQ_DISABLE_ATTN_FUSION=1`` turns it off.
 """
 from __future__ import annotations
 
@@ -208,4 +216,97 @@ def fuse_layernorm_output(model) -> int:
             continue
         mod._osq_unfused_ln_forward = mod.forward
         mod.forward = types.MethodType(_fused_ln_forward, mod)
+    return n
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# self-attention: q @ k^T and probs @ v with their quantizers  (quant_bert.py:134-195)
+# ---------------------------------------------------------------------------------------------------------------------------
+_ATTN_Q = ("query_permute_post_act_fake_quantize", "key_transpose_post_act_fake_quantize", "value_permute_post_act_fake_quantize",
+           "attention_probs_post_act_fake_quantize")
+
+
+def _q_ready(q) -> bool:
+    return (isinstance(q, QuantizeBase) and q.fake_quant_enabled == 1 and q.observer_enabled == 0 and q.ch_axis == -1
+            and q.quant_max - q.quant_min <= 255)
+
+
+def _q_args(q, numel):
+    g = (1.0 / (numel * q.quant_max) ** 0.5 if q.use_grad_scaling else 1.0) if isinstance(q, LSQPlusFakeQuantize) else 0.0
+    return dict(scale=q.scale.detach(), zp=q.zero_point.detach(), qmin=q.quant_min, qmax=q.quant_max, g=g)
+
+
+def _attn_fusable(mod, hidden_states, attention_mask, head_mask, output_attentions):
+    if os.environ.get("OSQ_DISABLE_ATTN_FUSION") == "1" or torch.is_grad_enabled():
+        return False
+    if head_mask is not None or output_attentions or getattr(mod, "position_embedding_type", "absolute") != "absolute":
+        return False
+    drop = getattr(mod, "dropout", None)
+    if drop is not None and getattr(drop, "training", False) and getattr(drop, "p", 0.0) > 0:
+        return False
+    if not all(_q_ready(getattr(mod, n, None)) for n in _ATTN_Q):
+        return False
+    if getattr(mod, "qoutput", True) and not _q_ready(getattr(mod, "context_view_post_act_fake_quantize", None)):
+        return False
+    if not (hidden_states.is_cuda and hidden_states.dtype == torch.float32 and hidden_states.dim() == 3):
+        return False
+    B, S, _ = hidden_states.shape
+    if mod.attention_head_size not in (32, 64, 128) or S % 4 != 0:
+        return False
+    if attention_mask is not None and not (attention_mask.dtype == torch.float32 and attention_mask.numel() == B * S
+                                           and attention_mask.shape[-1] == S and attention_mask.shape[0] == B):
+        return False
+    return True
+
+
+def _fused_attn_forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False, observation_mask=None):
+    if not _attn_fusable(self, hidden_states, attention_mask, head_mask, output_attentions):
+        return self._osq_unfused_attn_forward(hidden_states, attention_mask, head_mask, output_attentions, observation_mask)
+    q3 = self.query(hidden_states)          # one grouped launch for the three projections (QLinearGroup)
+    k3 = self.key(hidden_states)
+    v3 = self.value(hidden_states)
+    # (a grouped launch returns the three projections as column slices of one [.., 3 * hidden] tensor: token stride 3 * hidden, which
+    #  the kernels take as is -- only the channels must be contiguous)
+    if not (q3.stride(-1) == 1 and k3.stride(-1) == 1 and v3.stride(-1) == 1):
+        return self._osq_unfused_attn_forward(hidden_states, attention_mask, head_mask, output_attentions, observation_mask)
+    qh, kh, vh = self.transpose_for_scores(q3), self.transpose_for_scores(k3), self.transpose_for_scores(v3)
+    d = self.attention_head_size
+    # `attention_scores / math.sqrt(d)` (quant_bert.py:169): ATen multiplies by the fp32 reciprocal of the scalar
+    inv = float(torch.tensor(1.0, dtype=torch.float32) / torch.tensor(d ** 0.5, dtype=torch.float32))
+    mask = attention_mask.contiguous() if attention_mask is not None else None
+    scores = ops.attn_scores_fq(qh, kh, _q_args(self.query_permute_post_act_fake_quantize, q3.numel()),
+                                _q_args(self.key_transpose_post_act_fake_quantize, k3.numel()), out_mul=inv, mask=mask)
+    probs = torch.nn.functional.softmax(scores, dim=-1)
+    del scores
+    pq = self.attention_probs_post_act_fake_quantize
+    vq = self.value_permute_post_act_fake_quantize
+    oq = self.context_view_post_act_fake_quantize if getattr(self, "qoutput", True) else None
+    stats["attn_fused"] = stats.get("attn_fused", 0) + 1
+    if oq is None:
+        return (ops.attn_context_fq(probs, vh, _q_args(pq, probs.numel()), _q_args(vq, v3.numel())),)
+    want_bins = oq._emit_bins and q3.shape[-1] % 128 == 0
+    r = ops.attn_context_fq(probs, vh, _q_args(pq, probs.numel()), _q_args(vq, v3.numel()), oq=_q_args(oq, q3.numel()), want_bins=want_bins)
+    ctx = r[0] if want_bins else r
+    oq._tag(ctx)
+    if want_bins:
+        try:
+            ctx._osq_bins = (r[1], ctx._version)
+        except Exception:  # pragma: no cover
+            pass
+    return (ctx,)
+
+
+def fuse_self_attention(model) -> int:
+    """Wraps the forward of every self-attention module with query / key / value projections and the attention-side quantizers.
+    Idempotent; returns the number of wrapped modules."""
+    n = 0
+    for mod in model.modules():
+        if not (all(hasattr(mod, a) for a in ("query", "key", "value", "transpose_for_scores", "attention_head_size")) and
+                all(hasattr(mod, a) for a in _ATTN_Q)):
+            continue
+        n += 1
+        if getattr(mod, "_osq_unfused_attn_forward", None) is not None:
+            continue
+        mod._osq_unfused_attn_forward = mod.forward
+        mod.forward = types.MethodType(_fused_attn_forward, mod)
     return n

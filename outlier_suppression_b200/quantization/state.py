@@ -18,9 +18,10 @@ def _drop_weight_caches(model):
     from .quantized_module import group_sibling_linears
     group_sibling_linears(model)
     # dense -> GELU -> quantizer blocks get the fused output stage in the quantized state (quantization/fusion.py)
-    from .fusion import fuse_ffn_activation, fuse_layernorm_output
+    from .fusion import fuse_ffn_activation, fuse_layernorm_output, fuse_self_attention
     fuse_ffn_activation(model)
     fuse_layernorm_output(model)
+    fuse_self_attention(model)
 
 
 def _apply(model, quantizer_type, except_quantizer, observer_on, fq_on, lsq_observer_off=False):

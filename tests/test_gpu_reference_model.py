@@ -35,6 +35,7 @@ def test_unmodified_quant_bert_runs_the_ptq_schedule_on_cuda(cfg_name, monkeypat
     # materialises the tensors in between) is checked separately below
     monkeypatch.setenv("OSQ_DISABLE_EPILOGUE_FUSION", "1")
     monkeypatch.setenv("OSQ_DISABLE_LN_FUSION", "1")
+    monkeypatch.setenv("OSQ_DISABLE_ATTN_FUSION", "1")
     stats0 = dict(qm.stats)
     r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
     layers = r["layers"]
@@ -66,6 +67,7 @@ def test_fused_ffn_output_stage_inside_the_unmodified_model(cfg_name, mode, monk
     from outlier_suppression_b200.quantization import quantized_module as qm
     monkeypatch.setenv("OSQ_DISABLE_EPILOGUE_FUSION", "1")
     monkeypatch.setenv("OSQ_DISABLE_LN_FUSION", "1")   # the fused LayerNorm rounds differently from torch's: checked in its own test
+    monkeypatch.setenv("OSQ_DISABLE_ATTN_FUSION", "1")  # likewise the integer-exact attention contractions
     r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
     model = r["model"]
     batches = [{k: v.cuda() for k, v in b.items()} for b in RM.synth_batches(3, 4, 32, 100, "cpu", seed=5)]
@@ -97,6 +99,7 @@ def test_fused_residual_layernorm_quantizer_inside_the_unmodified_model(cfg_name
     import torch
     from outlier_suppression_b200.quantization import quantized_module as qm
     monkeypatch.setenv("OSQ_DISABLE_LN_FUSION", "1")
+    monkeypatch.setenv("OSQ_DISABLE_ATTN_FUSION", "1")
     r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
     model = r["model"]
     batches = [{k: v.cuda() for k, v in b.items()} for b in RM.synth_batches(3, 4, 32, 100, "cpu", seed=5)]
@@ -111,6 +114,35 @@ def test_fused_residual_layernorm_quantizer_inside_the_unmodified_model(cfg_name
     on = logits()
     # two blocks per layer; the last layer's output LayerNorm has no quantizer (qoutput=False, quant_bert.py) and stays unfused
     assert qm.stats.get("ln_fused", 0) - before == 3 * (2 * r["layers"] - 1), qm.stats
+    for a, b in zip(on, off):
+        d = float((a - b).abs().max())
+        assert d <= 2e-2 * float(b.abs().max()) + 1e-3, (d, a, b)
+
+
+@pytest.mark.parametrize("cfg_name", list(CONFIGS))
+def test_fused_attention_contractions_inside_the_unmodified_model(cfg_name, monkeypatch):
+    """The togglers wrap every self-attention module (quant_bert.py:134-195): q @ k^T and probs @ v run as integer contractions
+    with their quantizers as prologues (K8 / K9).  The integer contraction is exact where the reference's fp32 GEMM over the
+    dequantised operands rounds, so scores differ by ~1e-6 relative and an occasional downstream bin flips: same logits
+    tolerance as the CPU-vs-GPU comparison of the reference itself; the fused path must really have been taken, once per layer
+    and forward."""
+    import torch
+    from outlier_suppression_b200.quantization import quantized_module as qm
+    monkeypatch.setenv("OSQ_DISABLE_LN_FUSION", "1")
+    monkeypatch.setenv("OSQ_DISABLE_ATTN_FUSION", "1")
+    r = lockstep.run("b200", "cuda", RM.quant_config(**CONFIGS[cfg_name]))
+    model = r["model"]
+    batches = [{k: v.cuda() for k, v in b.items()} for b in RM.synth_batches(3, 4, 32, 100, "cpu", seed=5)]
+
+    def logits():
+        with torch.no_grad():
+            return [(lambda o: o[0] if isinstance(o, tuple) else o.logits)(model(**b)).clone() for b in batches]
+
+    off = logits()
+    monkeypatch.delenv("OSQ_DISABLE_ATTN_FUSION")
+    before = qm.stats.get("attn_fused", 0)
+    on = logits()
+    assert qm.stats.get("attn_fused", 0) - before == 3 * r["layers"], qm.stats
     for a, b in zip(on, off):
         d = float((a - b).abs().max())
         assert d <= 2e-2 * float(b.abs().max()) + 1e-3, (d, a, b)
