@@ -56,22 +56,8 @@ struct ContextParams {
   uint8_t* bins;          // optional, same shape
 };
 
-// bins (q - qmin) of four adjacent elements, bit-exact with util_quant.py:12-14 (K1's fast path + exact redo near a tie)
-__device__ __forceinline__ uint32_t bins4(const float4 x, float s, float rinv, float z, float qmin, float qmax) {
-  float q0, q1, q2, q3;
-  bool k0, k1, k2, k3;
-  fq_elem_fast(x.x, s, rinv, z, qmin, qmax, q0, k0);
-  fq_elem_fast(x.y, s, rinv, z, qmin, qmax, q1, k1);
-  fq_elem_fast(x.z, s, rinv, z, qmin, qmax, q2, k2);
-  fq_elem_fast(x.w, s, rinv, z, qmin, qmax, q3, k3);
-  if (k0 | k1 | k2 | k3) {
-    fq_elem(x.x, s, z, qmin, qmax, q0); fq_elem(x.y, s, z, qmin, qmax, q1);
-    fq_elem(x.z, s, z, qmin, qmax, q2); fq_elem(x.w, s, z, qmin, qmax, q3);
-    // NaN inputs (outside the contract) saturate to bin 0 instead of propagating
-    q0 = (q0 != q0) ? qmin : q0; q1 = (q1 != q1) ? qmin : q1; q2 = (q2 != q2) ? qmin : q2; q3 = (q3 != q3) ? qmin : q3;
-  }
-  return (uint32_t)(int)(q0 - qmin) | ((uint32_t)(int)(q1 - qmin) << 8) | ((uint32_t)(int)(q2 - qmin) << 16) | ((uint32_t)(int)(q3 - qmin) << 24);
-}
+// Bins (q - qmin) of four adjacent elements: quant_bin4 (common.cuh) -- magic-number rounding of x * (1/s), the whole group redone
+// with the IEEE division when any element is within 1e-4 of a rounding tie, i.e. bit-exact with util_quant.py:12-14.
 
 // sum of the four bytes of w, added to acc
 __device__ __forceinline__ int bytesum(uint32_t w, int acc) { return (int)__dp4a(w, 0x01010101u, (unsigned int)acc); }
@@ -98,8 +84,9 @@ attn_scores_kernel(const ScoresParams p) {
   uint8_t* qc = sm_raw;                                  // [128][kRow]
   uint8_t* kc = qc + kAttRows * kRow;                    // [KC][kRow]
   int* qsum = reinterpret_cast<int*>(kc + (size_t)KC * kRow);  // [128]
-  int* ksum = qsum + kAttRows;                           // [KC]
-  float* stage = reinterpret_cast<float*>(ksum + KC);    // [8][16][kHalfStage]
+  int* ksum = qsum + kAttRows;                           // [KC]  per key: kconst - Zq * (sum of the key's bins)
+  float* kmask = reinterpret_cast<float*>(ksum + KC);    // [KC]  per key: additive mask (-0.0f without one: x + -0.0f == x bit for bit)
+  float* stage = kmask + KC;                             // [8][16][kHalfStage]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -107,18 +94,27 @@ attn_scores_kernel(const ScoresParams p) {
   const bool wb = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
   const QParam qq = load_qparam(p.qq.scale, p.qq.zp, p.qq.zp_is_int32, p.qq.g, p.qq.qmin, p.qq.qmax, wb);
   const QParam kq = load_qparam(p.kq.scale, p.kq.zp, p.kq.zp_is_int32, p.kq.g, p.kq.qmin, p.kq.qmax, wb);
-  const float q_rinv = __frcp_rn(qq.s), k_rinv = __frcp_rn(kq.s);
-  const int zcq = (int)(rintf(qq.z) - p.qq.qmin), zck = (int)(rintf(kq.z) - p.kq.qmin);
+  const ConvParam qcp = make_conv_param(qq.s, qq.z, p.qq.qmin, p.qq.qmax), kcp = make_conv_param(kq.s, kq.z, p.kq.qmin, p.kq.qmax);
+  const int zcq = (int)qcp.zc, zck = (int)kcp.zc;
   const float sqk = __fmul_rn(qq.s, kq.s);
   const int kconst = D * zcq * zck;
 
   // ---- Q tile: quantise on load
   const float* qbase = p.q + (size_t)b * p.qs[0] + (size_t)head * p.qs[1];
-  for (int idx = tid; idx < kAttRows * (D / 4); idx += kAttThreads) {
-    const int r = idx / (D / 4), c4 = idx % (D / 4);
-    uint32_t w = 0;
-    if (q0 + r < p.sq) w = bins4(ldg_stream(reinterpret_cast<const float4*>(qbase + (size_t)(q0 + r) * p.qs[2]) + c4), qq.s, q_rinv, qq.z, p.qq.qmin, p.qq.qmax);
-    *reinterpret_cast<uint32_t*>(qc + r * kRow + c4 * 4) = w;
+  // (four independent 128-bit loads in flight per thread: the loop is latency-bound otherwise)
+  for (int base = tid; base < kAttRows * (D / 4); base += 4 * kAttThreads) {
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * kAttThreads, r = idx / (D / 4), c4 = idx % (D / 4);
+      x[u] = (idx < kAttRows * (D / 4) && q0 + r < p.sq) ? ldg_stream(reinterpret_cast<const float4*>(qbase + (size_t)(q0 + r) * p.qs[2]) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * kAttThreads, r = idx / (D / 4), c4 = idx % (D / 4);
+      if (idx < kAttRows * (D / 4))
+        *reinterpret_cast<uint32_t*>(qc + r * kRow + c4 * 4) = (q0 + r < p.sq) ? quant_bin4(x[u], qcp) : 0u;
+    }
   }
   const float* kbase = p.k + (size_t)b * p.ks[0] + (size_t)head * p.ks[1];
   float* obase = p.out + (((size_t)b * p.heads + head) * (size_t)p.sq) * (size_t)p.sk;
@@ -128,18 +124,27 @@ attn_scores_kernel(const ScoresParams p) {
   for (int c0 = 0; c0 < p.sk; c0 += KC) {
     const int rows = min(KC, (p.sk - c0 + kAttRows - 1) / kAttRows * kAttRows);   // key rows of this chunk, whole 128-key steps
     if (c0 > 0) __syncthreads();   // every warp is through with the previous chunk's bins
-    for (int idx = tid; idx < rows * (D / 4); idx += kAttThreads) {
-      const int r = idx / (D / 4), c4 = idx % (D / 4);
-      uint32_t w = 0;
-      if (c0 + r < p.sk) w = bins4(ldg_stream(reinterpret_cast<const float4*>(kbase + (size_t)(c0 + r) * p.ks[2]) + c4), kq.s, k_rinv, kq.z, p.kq.qmin, p.kq.qmax);
-      *reinterpret_cast<uint32_t*>(kc + r * kRow + c4 * 4) = w;
+    for (int base = tid; base < rows * (D / 4); base += 8 * kAttThreads) {
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * kAttThreads, r = idx / (D / 4), c4 = idx % (D / 4);
+        x[u] = (idx < rows * (D / 4) && c0 + r < p.sk) ? ldg_stream(reinterpret_cast<const float4*>(kbase + (size_t)(c0 + r) * p.ks[2]) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * kAttThreads, r = idx / (D / 4), c4 = idx % (D / 4);
+        if (idx < rows * (D / 4))
+          *reinterpret_cast<uint32_t*>(kc + r * kRow + c4 * 4) = (c0 + r < p.sk) ? quant_bin4(x[u], kcp) : 0u;
+      }
     }
     __syncthreads();
     for (int r = tid; r < rows; r += kAttThreads) {
       int s = 0;
 #pragma unroll
       for (int c = 0; c < D / 4; ++c) s = bytesum(*reinterpret_cast<const uint32_t*>(kc + r * kRow + c * 4), s);
-      ksum[r] = s;
+      ksum[r] = kconst - zcq * s;
+      kmask[r] = (p.mask != nullptr && c0 + r < p.sk) ? __ldg(p.mask + (size_t)b * p.sk + c0 + r) : -0.0f;
     }
     if (c0 == 0) {
       if (tid < kAttRows) {
@@ -159,7 +164,7 @@ attn_scores_kernel(const ScoresParams p) {
       }
     }
     __syncthreads();
-    if (c0 == 0) { qs_lo = qsum[warp * 16 + g]; qs_hi = qsum[warp * 16 + g + 8]; }
+    if (c0 == 0) { qs_lo = -zck * qsum[warp * 16 + g]; qs_hi = -zck * qsum[warp * 16 + g + 8]; }   // per row: -Zk * (sum of the row's bins)
     if (q0 + warp * 16 >= p.sq) continue;   // this warp's rows do not exist (it still takes part in the chunk barriers)
     for (int kt = 0; kt < rows / kAttRows; ++kt) {
       const int kl = kt * kAttRows;          // first key of the step inside the chunk
@@ -182,21 +187,15 @@ attn_scores_kernel(const ScoresParams p) {
         for (int n8 = 0; n8 < 8; ++n8) {
           const int nt = half * 8 + n8;
           const int c = nt * 8 + 2 * t;        // column inside the 128-key step
-          const int ks0 = ksum[kl + c], ks1 = ksum[kl + c + 1];
-          float m0 = 0.f, m1 = 0.f;
-          if (p.mask != nullptr) {
-            if (k0 + c < p.sk) m0 = __ldg(p.mask + (size_t)b * p.sk + k0 + c);
-            if (k0 + c + 1 < p.sk) m1 = __ldg(p.mask + (size_t)b * p.sk + k0 + c + 1);
-          }
-          auto fin = [&](int v, int qs_, int ks_, float m) -> float {
-            float f = __fmul_rn((float)(v - zck * qs_ - zcq * ks_ + kconst), sqk);
-            if (p.out_mul != 1.f) f = __fmul_rn(f, p.out_mul);
-            if (p.mask != nullptr) f = __fadd_rn(f, m);
-            return f;
+          const int2 kk = *reinterpret_cast<const int2*>(ksum + kl + c);
+          const float2 mm = *reinterpret_cast<const float2*>(kmask + kl + c);
+          // all terms are integers below 2^24: the sum is exact; then the reference's roundings: * (s_q s_k), * 1/sqrt(d), + mask
+          auto fin = [&](int v, int rc, int cc, float m) -> float {
+            return __fadd_rn(__fmul_rn(__fmul_rn((float)(v + rc + cc), sqk), p.out_mul), m);
           };
           const int cs = n8 * 8 + 2 * t;       // column inside the staged half
-          *reinterpret_cast<float2*>(my_stage + g * kHalfStage + cs) = make_float2(fin(acc[nt][0], qs_lo, ks0, m0), fin(acc[nt][1], qs_lo, ks1, m1));
-          *reinterpret_cast<float2*>(my_stage + (g + 8) * kHalfStage + cs) = make_float2(fin(acc[nt][2], qs_hi, ks0, m0), fin(acc[nt][3], qs_hi, ks1, m1));
+          *reinterpret_cast<float2*>(my_stage + g * kHalfStage + cs) = make_float2(fin(acc[nt][0], qs_lo, kk.x, mm.x), fin(acc[nt][1], qs_lo, kk.y, mm.y));
+          *reinterpret_cast<float2*>(my_stage + (g + 8) * kHalfStage + cs) = make_float2(fin(acc[nt][2], qs_hi, kk.x, mm.x), fin(acc[nt][3], qs_hi, kk.y, mm.y));
         }
         __syncwarp();
         const int col = k0 + half * 64 + (lane & 15) * 4;
@@ -239,8 +238,8 @@ attn_context_kernel(const ContextParams p) {
   const bool wb = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
   const QParam pq = load_qparam(p.pq.scale, p.pq.zp, p.pq.zp_is_int32, p.pq.g, p.pq.qmin, p.pq.qmax, wb);
   const QParam vq = load_qparam(p.vq.scale, p.vq.zp, p.vq.zp_is_int32, p.vq.g, p.vq.qmin, p.vq.qmax, wb);
-  const float p_rinv = __frcp_rn(pq.s), v_rinv = __frcp_rn(vq.s);
-  const int zcp = (int)(rintf(pq.z) - p.pq.qmin), zcv = (int)(rintf(vq.z) - p.vq.qmin);
+  const ConvParam pcp = make_conv_param(pq.s, pq.z, p.pq.qmin, p.pq.qmax), vcp = make_conv_param(vq.s, vq.z, p.vq.qmin, p.vq.qmax);
+  const int zcp = (int)pcp.zc, zcv = (int)vcp.zc;
   const float spv = __fmul_rn(pq.s, vq.s);
 
   const float* pbase = p.probs + (((size_t)b * p.heads + head) * (size_t)p.sq) * (size_t)p.sk;
@@ -259,12 +258,14 @@ attn_context_kernel(const ContextParams p) {
     for (int idx = tid; idx < (keys / 4) * (D / 4); idx += kAttThreads) {
       const int key4 = idx % (keys / 4), c4 = idx / (keys / 4);
       uint32_t w[4];
+      float4 xv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int key = c0 + key4 * 4 + i;
-        w[i] = 0;
-        if (key < p.sk) w[i] = bins4(__ldg(reinterpret_cast<const float4*>(vbase + (size_t)key * p.vs[2]) + c4), vq.s, v_rinv, vq.z, p.vq.qmin, p.vq.qmax);
+        xv[i] = key < p.sk ? __ldg(reinterpret_cast<const float4*>(vbase + (size_t)key * p.vs[2]) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = (c0 + key4 * 4 + i < p.sk) ? quant_bin4(xv[i], vcp) : 0u;
       const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[2], w[3], 0x5140);
       const uint32_t t2 = __byte_perm(w[0], w[1], 0x7362), t3 = __byte_perm(w[2], w[3], 0x7362);
       uint8_t* dst = vT + (size_t)(c4 * 4) * kRowV + key4 * 4;
@@ -278,27 +279,70 @@ attn_context_kernel(const ContextParams p) {
       for (int c = 0; c < keys / 4; ++c) vcol = bytesum(*reinterpret_cast<const uint32_t*>(vT + (size_t)tid * kRowV + c * 4), vcol);
     }
     if (!warp_has_rows) continue;
-    for (int kt = 0; kt < keys / kKT; ++kt) {
-      const int kl = kt * kKT, k0 = c0 + kl;
-      // probabilities: this warp's 16 rows x 64 keys, two rows per 128-bit load instruction, all eight loads in flight
-      float4 x[8];
+    // probabilities: this warp's 16 rows x 64 keys per step, two rows per 128-bit load instruction.  The rows travel in two halves
+    // of four loads each, and the next step's half is requested as soon as the current one has been converted: loads stay in
+    // flight while the other half is converted and the fragments are multiplied (a warp alone would alternate between
+    // waiting for DRAM and converting).
+    const int n_steps = keys / kKT;
+    const int prow_l = lane >> 4, pc4 = lane & 15;
+    // one base pointer per lane (row 0 of its row pair, its 16-byte column of step 0); rows advance by 2 * sk floats, steps by 64
+    const float* lane_base = pbase + (size_t)(q0 + warp * 16 + prow_l) * (size_t)p.sk + (size_t)(c0 + pc4 * 4);
+    const uint32_t row_step = 2u * (uint32_t)p.sk;
+    uint8_t* lane_pc = pc + (warp * 16 + prow_l) * kRowP + pc4 * 4;
+    // whole tile inside the matrix (the usual case): no per-load predicates
+    const bool rows_full = q0 + warp * 16 + 16 <= p.sq;
+    auto load_half = [&](float4 (&x)[4], int kt, int half) {
+      const float* src = lane_base + kt * kKT + (uint32_t)(half * 4) * row_step;
+      if (rows_full && c0 + kt * kKT + kKT <= p.sk) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = q0 + warp * 16 + 2 * i + (lane >> 4), key = k0 + (lane & 15) * 4;
-        x[i] = (row < p.sq && key < p.sk) ? ldg_stream(reinterpret_cast<const float4*>(pbase + (size_t)row * p.sk + key)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) x[i] = ldg_stream(reinterpret_cast<const float4*>(src + (uint32_t)i * row_step));
+      } else {
+        const int key = c0 + kt * kKT + pc4 * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = q0 + warp * 16 + 2 * (half * 4 + i) + prow_l;
+          x[i] = (row < p.sq && key < p.sk) ? ldg_stream(reinterpret_cast<const float4*>(src + (uint32_t)i * row_step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    // Rows / keys outside the matrix were loaded as zeros and must contribute bin 0 (not the bin of 0.0): masked after the
+    // conversion.  The conversion itself is branch-free; groups near a rounding tie (~0.1 %) are redone exactly afterwards.
+    auto convert_half = [&](const float4 (&x)[4], int kt, int half) {
+      const int key = c0 + kt * kKT + pc4 * 4;
+      const bool key_ok = key < p.sk;
+      uint32_t w[4];
+      uint32_t risky_mask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bool risky;
+        w[i] = quant_bin4_fast(x[i], pcp, risky);
+        risky_mask |= (uint32_t)risky << i;
+      }
+      if (risky_mask != 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (risky_mask & (1u << i)) w[i] = quant_bin4_exact(x[i].x, x[i].y, x[i].z, x[i].w, pcp.s, pcp.zc, pcp.span);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = 2 * i + (lane >> 4), c4 = lane & 15;
-        const int row = q0 + warp * 16 + r, key = k0 + c4 * 4;
-        uint32_t w = 0;
-        if (row < p.sq && key < p.sk) w = bins4(x[i], pq.s, p_rinv, pq.z, p.pq.qmin, p.pq.qmax);
-        *reinterpret_cast<uint32_t*>(pc + (warp * 16 + r) * kRowP + c4 * 4) = w;
-        int s = bytesum(w, 0);
+      for (int i = 0; i < 4; ++i) {
+        const int r2 = half * 4 + i;
+        if (!(rows_full && key_ok)) { if (!(key_ok && q0 + warp * 16 + 2 * r2 + prow_l < p.sq)) w[i] = 0; }
+        *reinterpret_cast<uint32_t*>(lane_pc + (2 * r2) * kRowP) = w[i];
+        int s = bytesum(w[i], 0);
         s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 4);
         s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 1);
-        prow[i] += s;
+        prow[r2] += s;
       }
+    };
+    float4 xa[4], xb[4];
+    load_half(xa, 0, 0);
+    load_half(xb, 0, 1);
+    for (int kt = 0; kt < n_steps; ++kt) {
+      const int kl = kt * kKT;
+      convert_half(xa, kt, 0);
+      if (kt + 1 < n_steps) load_half(xa, kt + 1, 0);
+      convert_half(xb, kt, 1);
+      if (kt + 1 < n_steps) load_half(xb, kt + 1, 1);
       __syncwarp();
 #pragma unroll
       for (int ks = 0; ks < kKT / 32; ++ks) {
@@ -411,7 +455,7 @@ int osq_attn_scores_fq_f32(const float* q, const float* k, int64_t batch, int64_
   p.out_mul = out_mul; p.mask = mask; p.out = scores;
   const dim3 grid((unsigned)((sq + kAttRows - 1) / kAttRows), (unsigned)heads, (unsigned)batch);
   p.kc = (int)((sk + kAttRows - 1) / kAttRows * kAttRows < 512 ? (sk + kAttRows - 1) / kAttRows * kAttRows : 512);
-  const size_t smem = (size_t)(kAttRows + p.kc) * (size_t)(d + kPad) + (size_t)(kAttRows + p.kc) * sizeof(int) + 8 * 16 * kHalfStage * sizeof(float);
+  const size_t smem = (size_t)(kAttRows + p.kc) * (size_t)(d + kPad) + (size_t)(kAttRows + 2 * p.kc) * sizeof(int) + 8 * 16 * kHalfStage * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set[64] = {false};
   int dev = 0;

@@ -102,6 +102,75 @@ __device__ __forceinline__ float fq_elem_fast(float x, float s, float rinv, floa
 }
 
 
+constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: fp32 ulp is 1 in [2^23, 2^24)
+
+// ------------------------------------------------------------------------------------------
+// fp32 -> bin conversion.  Bit-exact with clamp(rint(x / s) + Z, qmin, qmax) (true IEEE division):
+// u = fma(x, 1/s, magic + Zc) rounds x/s (approximately) to the integer grid; the residual
+// e = fma(x, 1/s, -(u - magic - Zc)) tells how close x/s is to a rounding tie.  Only when
+// |e| > 0.4999 (probability 2e-4) can the reciprocal's <=2 ulp error change the bin, and only then
+// the exact division is evaluated.  For |x/s| >= 400 the bin saturates on both paths.
+// ------------------------------------------------------------------------------------------
+struct ConvParam {
+  float s, rinv, mz, lo, hi, zc, span;
+};
+
+
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// four bins -> one packed word.  The fast path of the four elements is straight-line code (full ILP);
+// ONE branch per float4 sends the whole group through the exact path when any element is near a tie.
+static __device__ __noinline__ uint32_t quant_bin4_exact(float x0, float x1, float x2, float x3, float s, float zc, float span) {
+  // exact path (true division), taken by ~0.1 % of the float4 groups: kept out of line so the unrolled
+  // conversion loop stays a few KB of straight-line code
+  float v0 = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(x0, s)), zc), 0.f), span);
+  float v1 = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(x1, s)), zc), 0.f), span);
+  float v2 = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(x2, s)), zc), 0.f), span);
+  float v3 = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(x3, s)), zc), 0.f), span);
+  return (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+}
+
+__device__ __forceinline__ uint32_t quant_bin4(const float4 x, const ConvParam& c) {
+  float u0 = fmaf(x.x, c.rinv, c.mz), u1 = fmaf(x.y, c.rinv, c.mz), u2 = fmaf(x.z, c.rinv, c.mz), u3 = fmaf(x.w, c.rinv, c.mz);
+  const float e0 = fmaf(x.x, c.rinv, -__fsub_rn(u0, c.mz)), e1 = fmaf(x.y, c.rinv, -__fsub_rn(u1, c.mz));
+  const float e2 = fmaf(x.z, c.rinv, -__fsub_rn(u2, c.mz)), e3 = fmaf(x.w, c.rinv, -__fsub_rn(u3, c.mz));
+  const float worst = fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fmaxf(fabsf(e2), fabsf(e3)));
+  const bool nan_in = (e0 != e0) | (e1 != e1) | (e2 != e2) | (e3 != e3);
+  if (!(worst <= 0.4999f) | nan_in) return quant_bin4_exact(x.x, x.y, x.z, x.w, c.s, c.zc, c.span);
+  u0 = fminf(fmaxf(u0, c.lo), c.hi); u1 = fminf(fmaxf(u1, c.lo), c.hi);
+  u2 = fminf(fmaxf(u2, c.lo), c.hi); u3 = fminf(fmaxf(u3, c.lo), c.hi);
+  return pack4(__float_as_uint(u0), __float_as_uint(u1), __float_as_uint(u2), __float_as_uint(u3));
+}
+
+// branch-free fast path for one float4: returns the packed bins and sets `risky` when any element is within
+// 1e-4 of a rounding tie (or huge / NaN): those groups (~0.1 %) are redone with the exact division AFTER the
+// unrolled loop, so the hot loop is straight-line code that the scheduler can interleave across all rows
+__device__ __forceinline__ uint32_t quant_bin4_fast(const float4 x, const ConvParam& c, bool& risky) {
+  float u0 = fmaf(x.x, c.rinv, c.mz), u1 = fmaf(x.y, c.rinv, c.mz), u2 = fmaf(x.z, c.rinv, c.mz), u3 = fmaf(x.w, c.rinv, c.mz);
+  const float e0 = fmaf(x.x, c.rinv, -__fsub_rn(u0, c.mz)), e1 = fmaf(x.y, c.rinv, -__fsub_rn(u1, c.mz));
+  const float e2 = fmaf(x.z, c.rinv, -__fsub_rn(u2, c.mz)), e3 = fmaf(x.w, c.rinv, -__fsub_rn(u3, c.mz));
+  const float worst = fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fmaxf(fabsf(e2), fabsf(e3)));
+  risky = !(worst <= 0.4999f);  // NaN residuals (non-finite A) are dropped by fmaxf: such inputs are outside the contract
+  u0 = fminf(fmaxf(u0, c.lo), c.hi); u1 = fminf(fmaxf(u1, c.lo), c.hi);
+  u2 = fminf(fmaxf(u2, c.lo), c.hi); u3 = fminf(fmaxf(u3, c.lo), c.hi);
+  return pack4(__float_as_uint(u0), __float_as_uint(u1), __float_as_uint(u2), __float_as_uint(u3));
+}
+
+// conversion constants of one quantizer (effective scale s, effective zero point z)
+__device__ __forceinline__ ConvParam make_conv_param(float s, float z, float qmin, float qmax) {
+  ConvParam cp;
+  cp.s = s;
+  cp.rinv = __frcp_rn(s);
+  cp.zc = rintf(z) - qmin;
+  cp.span = qmax - qmin;
+  cp.mz = kMagic + cp.zc;
+  cp.lo = kMagic;
+  cp.hi = kMagic + cp.span;
+  return cp;
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
