@@ -84,6 +84,7 @@ struct FusedParams {
   const float* bias;
   uint8_t* a_codes;  // optional [M, K]: bins side output / code cache
   float* Y;          // [M, N] output (the drain epilogue writes it with plain stores; the other variants go through tmap_y)
+  int pre_l2;        // k-blocks of this CTA's fp32 tile prefetched into L2 before the wait for the previous grid (0 = off)
   int lsu_mod;       // plain tile stores: every lsu_mod-th step of a warp is written by the LSU instead of the TMA unit (0 = never)
   int epi16;         // epilogue variant: all sixteen workers (four column slices), single staging tile per warp
   int drain;         // epilogue variant: staged tiles drained by workers 8..15 with 128-bit stores instead of TMA tensor stores
@@ -664,6 +665,19 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     // The conversion warps can keep only 8 x 512 B per warp in flight (registers), too little to cover DRAM
     // latency at this CTA's share of the HBM bandwidth.  One thread pulls the tile's [rows x 128] fp32 boxes into
     // L2 a bounded distance ahead (in the order the workers consume them), so their loads see L2 latency.
+    if constexpr (kXTma) {
+      // Programmatic dependent launch: this CTA starts as soon as its SM is free, up to several microseconds before the last CTA
+      // of the previous grid has finished.  Until then nothing may be READ INTO THE SM (A may still be written), but pulling this
+      // CTA's fp32 tile into L2 is safe at any time -- L2 is the point of coherence: a line prefetched early is simply updated
+      // by a later write -- and turns the first DRAM round trips of the read phase into L2 hits.
+      if (lane == 0 && p.pre_l2 && p.pdl && !p.codes_in && mb_lane < p.n_mblocks) {
+        const int row0 = mb_lane * p.rows_per_tile;
+        const int rows = min(p.rows_per_tile, p.M - row0);
+        const int kb_n = min(p.KB, p.pre_l2);
+        for (int kb = 0; kb < kb_n; ++kb)
+          for (int r = 0; r < rows; r += kRowsPerWorker) tma_prefetch_l2_2d(&tmap_a, kb * kStageK, row0 + r);
+      }
+    }
     if (lane == 0 && p.prefetch > 0) {
       if (p.pdl) pdl_wait_prior_grids();
       const int passes_per_block = (p.resident || p.cached) ? 1 : ncn;  // fp32 A is re-read per chunk only without a cache
@@ -1756,6 +1770,9 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
   p.store3d = (a->out_scale == nullptr && env_s3d != 0 && p.N % 32 == 0 && p.BN % 64 == 0 && p.M >= 32 && (p.alias_xo || p.out_bufs >= 1)) ? 1 : 0;
   static int env_drain = -1;
   if (env_drain < 0) { const char* e = getenv("OSQ_FUSED_DRAIN"); env_drain = e ? atoi(e) : 0; }
+  static int env_pre = -1;
+  if (env_pre < 0) { const char* e = getenv("OSQ_FUSED_PRE_L2"); env_pre = e ? atoi(e) : 0; }
+  p.pre_l2 = env_pre;
   static int env_lsu = -1;
   if (env_lsu < 0) { const char* e = getenv("OSQ_FUSED_LSU_MOD"); env_lsu = e ? atoi(e) : 0; }
   p.lsu_mod = (p.trace == nullptr && env_lsu > 0) ? env_lsu : 0;

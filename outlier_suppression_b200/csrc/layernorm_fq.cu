@@ -168,7 +168,7 @@ int osq_residual_layernorm_fq_f32(const float* h, const float* res, const float*
   p.g = lsq_grad_factor; p.qmin = (float)qmin; p.qmax = (float)qmax;
   const int wpc = kLnThreads / 32;
   const int64_t want = (rows + wpc - 1) / wpc;
-  const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+  const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);   // (one CTA per 8-row block, up to 96 per SM, measured no faster)
   cudaStream_t st = (cudaStream_t)stream;
   const int vec = (hidden % 128 == 0 && hidden / 128 <= kLnMaxVec) ? (int)(hidden / 128) : 0;
   switch (vec) {

@@ -700,6 +700,45 @@ __device__ __forceinline__ void sweep_pairs(const float* __restrict__ tmin, cons
   }
 }
 
+// The same sweep handing out whole quads (four adjacent slots of both vectors): callers that only rarely act on an element test
+// the quad first -- one warp vote per quad instead of one or two per element (cross-lane instructions are what a single SM
+// runs out of in this kernel).  `kBatch` quads per thread are requested before the first one is used.
+template <int kBatch, class F>
+__device__ __forceinline__ void sweep_quads(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n, F&& f) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float4 inv_a = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), inv_b = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (((((uintptr_t)tmin) | ((uintptr_t)tmax)) & 15) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(tmin);
+    const float4* b4 = reinterpret_cast<const float4*>(tmax);
+    const int64_t nv = n >> 2;
+    for (int64_t base = tid - lane; base < nv; base += (int64_t)kBatch * kSelThreads) {   // warp-uniform trip count
+      float4 a[kBatch], b[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int64_t i = base + lane + (int64_t)u * kSelThreads;
+        a[u] = i < nv ? __ldcg(a4 + i) : inv_a;
+        b[u] = i < nv ? __ldcg(b4 + i) : inv_b;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) f(a[u], b[u]);
+    }
+    if (tid < 32 && (n & 3)) {                                              // up to three trailing slots: warp 0
+      const int64_t i = (nv << 2) + lane;
+      f(make_float4(i < n ? __ldcg(tmin + i) : INFINITY, INFINITY, INFINITY, INFINITY),
+        make_float4(i < n ? __ldcg(tmax + i) : -INFINITY, -INFINITY, -INFINITY, -INFINITY));
+    }
+  } else {
+    for (int64_t base = tid - lane; base < n; base += kSelThreads) {
+      const int64_t i = base + lane;
+      f(make_float4(i < n ? __ldcg(tmin + i) : INFINITY, INFINITY, INFINITY, INFINITY),
+        make_float4(i < n ? __ldcg(tmax + i) : -INFINITY, -INFINITY, -INFINITY, -INFINITY));
+    }
+  }
+}
+// total order of finite floats and infinities as unsigned integers (REDUX has integer min / max only)
+__device__ __forceinline__ unsigned int f2ord(float f) { const unsigned int u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned int o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
+
 // sixteen 16-bit counters in eight 32-bit registers.  Combined across the warp with the REDUX unit (__reduce_add_sync:
 // one instruction per word) -- a shuffle tree would cost 80 SHFL per warp, side and pass, and SHFL issues at one warp
 // instruction per clock per SM: with 32 warps that alone was 13 us.
@@ -774,14 +813,29 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
       base = __shfl_sync(0xffffffffu, base, leader);
       if (pred) list[side][base + __popc(m & ((1u << lane) - 1u))] = u;
     };
-    sweep_pairs(tmin, tmax, n_slots, [&](float a, float b) {
-      const bool ok = a <= b;
-      const unsigned int ub = __float_as_uint(fabsf(b)), ua = __float_as_uint(fabsf(a));
-      const unsigned int db = ub >> 20, da = ua >> 20;
-      if (listed_mx) append(0, ok && db == bin_mx, ub);
-      if (listed_mn) append(1, ok && da == bin_mn, ua);
-      if (ok && db > bin_mx) above_mx = min(above_mx, ub);
-      if (ok && da > bin_mn) above_mn = min(above_mn, ua);
+    sweep_quads<4>(tmin, tmax, n_slots, [&](const float4 a4, const float4 b4) {
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+      unsigned int ub[4], ua[4];
+      bool in_mx[4], in_mn[4], any = false;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = av[e] <= bv[e];
+        ub[e] = __float_as_uint(fabsf(bv[e])); ua[e] = __float_as_uint(fabsf(av[e]));
+        const unsigned int db = ub[e] >> 20, da = ua[e] >> 20;
+        in_mx[e] = listed_mx && ok && db == bin_mx;
+        in_mn[e] = listed_mn && ok && da == bin_mn;
+        any |= in_mx[e] | in_mn[e];
+        if (ok && db > bin_mx) above_mx = min(above_mx, ub[e]);
+        if (ok && da > bin_mn) above_mn = min(above_mn, ua[e]);
+      }
+      // members of the two chosen bins are rare (a 2048-bin first digit): one vote per quad decides whether anybody appends
+      if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (listed_mx) append(0, in_mx[e], ub[e]);
+          if (listed_mn) append(1, in_mn[e], ua[e]);
+        }
+      }
     });
     above_mx = __reduce_min_sync(0xffffffffu, above_mx);
     above_mn = __reduce_min_sync(0xffffffffu, above_mn);
@@ -938,14 +992,19 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
   OBS_STAMP(7);
   float lower = INFINITY, upper = -INFINITY;
   if (T > 0)
-    sweep_pairs(tmin, tmax, n_slots, [&](float a, float b) {
-      if (a <= b) {
-        if (b <= thr_up) upper = fmaxf(upper, b);
-        if (a >= thr_lo) lower = fminf(lower, a);
+    sweep_quads<4>(tmin, tmax, n_slots, [&](const float4 a4, const float4 b4) {
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (av[e] <= bv[e]) {
+          if (bv[e] <= thr_up) upper = fmaxf(upper, bv[e]);
+          if (av[e] >= thr_lo) lower = fminf(lower, av[e]);
+        }
       }
     });
-  lower = warp_min(lower);
-  upper = warp_max(upper);
+  // (one REDUX per value instead of five shuffles: no NaNs here, the vectors come out of fminf / fmaxf)
+  lower = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lower)));
+  upper = ord2f(__reduce_max_sync(0xffffffffu, f2ord(upper)));
   if (lane == 0) { red[0][warp] = lower; red[1][warp] = upper; }
   __syncthreads();
   if (warp == 0) {
