@@ -422,6 +422,57 @@ def bart_large_sites(device, ops, peak, m_tokens=4096):
             "M": m_tokens, "sites": out, "us_per_layer": layer_us, "tokens_per_s_12_layers": m_tokens / (12 * layer_us * 1e-6)}
 
 
+def f3_kernels(device, ops, peak):
+    """SURVEY section 8 f3 at config 2's size (B = 32, S = 512, h = 12, d = 64, hidden 768): K7 residual + LayerNorm + quantizer (+ bins),
+    K8 scores = fq(q) @ fq(k)^T / sqrt(d) + mask, K9 context = fq(probs) @ fq(v) -> context quantizer (+ bins); per-launch device time
+    (CUDA events around graph-replayed chains), algorithmic bytes, fraction of the HBM peak."""
+    import math
+    B, S, h, d = 32, 512, 12, 64
+    H = h * d
+    g = torch.Generator(device=device).manual_seed(11)
+    rnd = lambda *shape: torch.randn(*shape, generator=g, device=device)
+
+    def timed(fn, chain):
+        fn(0); torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(chain):
+                fn(i)
+        gr.replay()
+        evs = []
+        for _ in range(5):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(); gr.replay(); b_.record(); evs.append((a_, b_))
+        torch.cuda.synchronize()
+        return statistics.median(x.elapsed_time(y) for x, y in evs) / chain * 1e3
+
+    def qd(scale, zp, numel):
+        return dict(scale=torch.tensor([scale], device=device), zp=torch.tensor([float(zp)], device=device), qmin=0, qmax=63, g=1.0 / (numel * 63) ** 0.5)
+    out = {}
+    hs, rs = [rnd(B * S, H) for _ in range(4)], [rnd(B * S, H) for _ in range(4)]     # 4 x 100 MB in: rotates past L2
+    gm, bias = torch.rand(H, generator=g, device=device) + 0.5, rnd(H) * 0.1
+    q_ln = qd(0.1, 31, B * S * H)
+    us = timed(lambda i: ops.residual_layernorm_fq(hs[i % 4], rs[i % 4], gm, None, bias, 1e-12, q_ln["scale"], q_ln["zp"], 0, 63,
+                                                   lsq_grad_factor=q_ln["g"], want_bins=True), 8)
+    by = 13 * B * S * H
+    out["K7_residual_layernorm_fq_bins"] = {"us": us, "bytes": by, "frac_of_hbm_peak": by / (us * 1e-6) / 1e9 / peak}
+    del hs, rs
+    q3, k3, v3 = rnd(B, S, H), rnd(B, S, H), rnd(B, S, H)
+    heads = lambda t: t.view(B, S, h, d).permute(0, 2, 1, 3)
+    mask = torch.zeros(B, 1, 1, S, device=device)
+    qq, kq, vq = qd(0.12, 31, q3.numel()), qd(0.12, 31, q3.numel()), qd(0.12, 31, q3.numel())
+    pq, oq = qd(1 / 63, 0, B * h * S * S), qd(0.05, 31, q3.numel())
+    inv = float(torch.tensor(1.0) / torch.tensor(math.sqrt(d), dtype=torch.float32))
+    us = timed(lambda i: ops.attn_scores_fq(heads(q3), heads(k3), qq, kq, out_mul=inv, mask=mask), 2)   # 403 MB out per launch
+    by = 8 * q3.numel() + 4 * B * h * S * S
+    out["K8_attn_scores_fq"] = {"us": us, "bytes": by, "frac_of_hbm_peak": by / (us * 1e-6) / 1e9 / peak}
+    probs = torch.softmax(ops.attn_scores_fq(heads(q3), heads(k3), qq, kq, out_mul=inv, mask=mask), -1)
+    us = timed(lambda i: ops.attn_context_fq(probs, heads(v3), pq, vq, oq=oq, want_bins=True), 2)
+    by = 4 * B * h * S * S + 4 * v3.numel() + 5 * q3.numel()
+    out["K9_attn_context_fq_bins"] = {"us": us, "bytes": by, "frac_of_hbm_peak": by / (us * 1e-6) / 1e9 / peak}
+    return {"workload": "config 2 geometry: batch 32, seq 512, 12 heads x 64, hidden 768, 6-bit LSQ+ quantizers", "kernels": out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -693,8 +744,12 @@ def main():
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "error": repr(ex)}
 
-    sweep_rec = bart_rec = None
+    sweep_rec = bart_rec = f3_rec = None
     if not args.no_sweep:
+        try:
+            f3_rec = f3_kernels(device, ops, peak) if rank == 0 else None
+        except Exception as ex:  # pragma: no cover
+            f3_rec = {"error": repr(ex)}
         try:
             bart_rec = bart_large_sites(device, ops, peak) if rank == 0 else None
             sweep_rec = observer_sweep(device, rank, world, dist, peak, peak_src)
@@ -715,7 +770,7 @@ def main():
                           "multi_site": "off" if not args.multi else "a layer's %d independent sites per persistent launch (osq_fused_fq_linear_multi)" % len(order),
                           "grouping": "none" if args.no_group else "q|k|v of a layer share one launch"},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * (LAYERS * len(order) if not args.multi else LAYERS),
-               "clocks": clocks, "observer_sweep": sweep_rec, "config4_bart_large": bart_rec}
+               "clocks": clocks, "observer_sweep": sweep_rec, "config4_bart_large": bart_rec, "f3_kernels": f3_rec}
         print(json.dumps(rec))
     if dist is not None:
         dist.destroy_process_group()

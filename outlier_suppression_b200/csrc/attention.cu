@@ -59,6 +59,14 @@ struct ContextParams {
 // Bins (q - qmin) of four adjacent elements: quant_bin4 (common.cuh) -- magic-number rounding of x * (1/s), the whole group redone
 // with the IEEE division when any element is within 1e-4 of a rounding tie, i.e. bit-exact with util_quant.py:12-14.
 
+// four 8 x 16-byte tiles of bins in one instruction: lane l supplies the address of row (l & 7) of tile (l >> 3); thread (g, t) of
+// the warp receives bytes [4t, 4t + 4) of row g of each tile -- exactly the m16n8k32 fragment words
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"((uint32_t)__cvta_generic_to_shared(row_ptr)));
+}
+
 // sum of the four bytes of w, added to acc
 __device__ __forceinline__ int bytesum(uint32_t w, int acc) { return (int)__dp4a(w, 0x01010101u, (unsigned int)acc); }
 
@@ -155,13 +163,8 @@ attn_scores_kernel(const ScoresParams p) {
       }
       // this warp's A fragments stay in registers for every key step
 #pragma unroll
-      for (int ks = 0; ks < D / 32; ++ks) {
-        const uint8_t* r0 = qc + (warp * 16 + g) * kRow + ks * 32 + t * 4;
-        a[ks][0] = *reinterpret_cast<const uint32_t*>(r0);
-        a[ks][1] = *reinterpret_cast<const uint32_t*>(r0 + 8 * kRow);
-        a[ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 16);
-        a[ks][3] = *reinterpret_cast<const uint32_t*>(r0 + 8 * kRow + 16);
-      }
+      for (int ks = 0; ks < D / 32; ++ks)   // tiles: rows 0-7 / 8-15 at k 0-15, rows 0-7 / 8-15 at k 16-31
+        ldsm_x4(a[ks][0], a[ks][1], a[ks][2], a[ks][3], qc + (warp * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * kRow + ks * 32 + (lane >> 4) * 16);
     }
     __syncthreads();
     if (c0 == 0) { qs_lo = -zck * qsum[warp * 16 + g]; qs_hi = -zck * qsum[warp * 16 + g + 8]; }   // per row: -Zk * (sum of the row's bins)
@@ -175,9 +178,11 @@ attn_scores_kernel(const ScoresParams p) {
 #pragma unroll
       for (int ks = 0; ks < D / 32; ++ks) {
 #pragma unroll
-        for (int nt = 0; nt < 16; ++nt) {
-          const uint8_t* br = kc + (kl + nt * 8 + g) * kRow + ks * 32 + t * 4;
-          mma_u8(acc[nt], a[ks][0], a[ks][1], a[ks][2], a[ks][3], *reinterpret_cast<const uint32_t*>(br), *reinterpret_cast<const uint32_t*>(br + 16));
+        for (int nt = 0; nt < 16; nt += 2) {   // tiles: keys of n-tile nt at k 0-15 / 16-31, keys of n-tile nt + 1 at k 0-15 / 16-31
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(b0, b1, b2, b3, kc + (kl + (nt + (lane >> 4)) * 8 + (lane & 7)) * kRow + ks * 32 + ((lane >> 3) & 1) * 16);
+          mma_u8(acc[nt], a[ks][0], a[ks][1], a[ks][2], a[ks][3], b0, b1);
+          mma_u8(acc[nt + 1], a[ks][0], a[ks][1], a[ks][2], a[ks][3], b2, b3);
         }
       }
       // ---- epilogue, one 64-column half at a time: exact integer zero-point corrections, one scale, optional 1/sqrt(d) and mask
@@ -346,13 +351,14 @@ attn_context_kernel(const ContextParams p) {
       __syncwarp();
 #pragma unroll
       for (int ks = 0; ks < kKT / 32; ++ks) {
-        const uint8_t* r0 = pc + (warp * 16 + g) * kRowP + ks * 32 + t * 4;
-        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(r0), a1 = *reinterpret_cast<const uint32_t*>(r0 + 8 * kRowP);
-        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(r0 + 16), a3 = *reinterpret_cast<const uint32_t*>(r0 + 8 * kRowP + 16);
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(a0, a1, a2, a3, pc + (warp * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * kRowP + ks * 32 + (lane >> 4) * 16);
 #pragma unroll
-        for (int nt = 0; nt < D / 8; ++nt) {
-          const uint8_t* br = vT + (size_t)(nt * 8 + g) * kRowV + kl + ks * 32 + t * 4;
-          mma_u8(acc[nt], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(br), *reinterpret_cast<const uint32_t*>(br + 16));
+        for (int nt = 0; nt < D / 8; nt += 2) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(b0, b1, b2, b3, vT + (size_t)((nt + (lane >> 4)) * 8 + (lane & 7)) * kRowV + kl + ks * 32 + ((lane >> 3) & 1) * 16);
+          mma_u8(acc[nt], a0, a1, a2, a3, b0, b1);
+          mma_u8(acc[nt + 1], a0, a1, a2, a3, b2, b3);
         }
       }
       __syncwarp();   // the fragments are consumed before the next step overwrites this warp's probability bins

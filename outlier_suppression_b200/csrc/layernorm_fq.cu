@@ -64,7 +64,7 @@ __device__ __forceinline__ float4 fq4(const float4 a, float s, float rinv, float
 // kVec = float4 per lane (H = 128 * kVec exactly); kVec = 0: generic H (multiple of 4), three sweeps over the row (the second and
 // third hit L1 / L2)
 template <int kVec>
-__global__ void __launch_bounds__(kLnThreads)
+__global__ void __launch_bounds__(kLnThreads, 4)   // <= 64 registers: four CTAs (32 warps) per SM hide the DRAM latency of the row loads
 residual_layernorm_fq_kernel(const LnFqParams p) {
   const QParam qp = load_qparam(p.scale, p.zp, p.zp_is_int32, p.g, p.qmin, p.qmax, blockIdx.x == 0 && threadIdx.x == 0);
   const float s = qp.s, z = qp.z, rinv = __frcp_rn(qp.s);

@@ -50,3 +50,33 @@ if which in ("all", "fq"):
     c, d = ops.fq_per_tensor(x, sc, zp, 0, 63, lsq_grad_factor=1e-3, want_bins=True, act="gelu")
     assert torch.equal(a, c) and torch.equal(b, d)
     print("k1c ok", flush=True)
+if which in ("all", "f3"):
+    # K7 / K8 / K9 (layernorm_fq.cu, attention.cu) at small ragged sizes; parity as in tests/test_gpu_layernorm_fq.py / test_gpu_attention.py
+    import math
+    sc, zp = torch.tensor([0.11], device="cuda"), torch.tensor([30.0], device="cuda")
+    for rows, H in ((37, 768), (9, 1024), (21, 200)):
+        h, r = torch.randn(rows, H, device="cuda"), torch.randn(rows, H, device="cuda")
+        gm, b = torch.rand(H, device="cuda") + 0.5, torch.randn(H, device="cuda")
+        y, bins, ln = ops.residual_layernorm_fq(h, r, gm, None, b, 1e-12, sc, zp, 0, 63, lsq_grad_factor=1e-3, want_bins=True, want_ln=True)
+        y1, b1 = ops.fq_per_tensor(ln, sc, zp, 0, 63, lsq_grad_factor=1e-3, want_bins=True)
+        assert torch.equal(y, y1) and torch.equal(bins, b1)
+        print("k7 ok", rows, H, flush=True)
+    for B, h_, Sq, Sk, d in ((1, 2, 70, 132, 64), (1, 1, 20, 600, 32), (1, 1, 130, 64, 128)):
+        H = h_ * d
+        q3, k3, v3 = torch.randn(B, Sq, H, device="cuda"), torch.randn(B, Sk, H, device="cuda"), torch.randn(B, Sk, H, device="cuda")
+        hd = lambda t, S: t.view(B, S, h_, d).permute(0, 2, 1, 3)
+        qa = dict(scale=sc, zp=zp, qmin=0, qmax=63, g=1e-3)
+        pa = dict(scale=torch.tensor([1 / 63], device="cuda"), zp=torch.tensor([0.0], device="cuda"), qmin=0, qmax=63, g=1e-3)
+        mask = torch.zeros(B, 1, 1, Sk, device="cuda")
+        s_ = ops.attn_scores_fq(hd(q3, Sq), hd(k3, Sk), qa, qa, out_mul=1 / math.sqrt(d), mask=mask)
+        fq = lambda x, q: ops.fq_per_tensor(x.contiguous(), q["scale"], q["zp"], 0, 63, lsq_grad_factor=1e-3)
+        ref = torch.matmul(fq(hd(q3, Sq), qa).double(), fq(hd(k3, Sk), qa).double().transpose(-1, -2)) / math.sqrt(d)
+        assert float((s_.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+        probs = torch.softmax(s_, -1)
+        ctx, cb = ops.attn_context_fq(probs, hd(v3, Sk), pa, qa, oq=qa, want_bins=True)
+        plain = ops.attn_context_fq(probs, hd(v3, Sk), pa, qa)
+        refc = torch.matmul(fq(probs, pa).double(), fq(hd(v3, Sk), qa).double()).permute(0, 2, 1, 3).reshape(B, Sq, H)
+        assert float((plain.double() - refc).abs().max()) <= 1e-5 * float(refc.abs().max())
+        y1, b1 = ops.fq_per_tensor(plain, sc, zp, 0, 63, lsq_grad_factor=1e-3, want_bins=True)
+        assert torch.equal(ctx, y1) and torch.equal(cb, b1)
+        print("k8 k9 ok", B, h_, Sq, Sk, d, flush=True)

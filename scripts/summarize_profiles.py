@@ -68,3 +68,29 @@ json.dump(traffic, open(os.path.join(PROF, tag + "_traffic.json"), "w"), indent=
 print(open(os.path.join(PROF, tag + "_fused_full.md")).read())
 if os.path.exists(os.path.join(OUT, "bench.json")):
     open(os.path.join(PROF, tag + "_bench.json"), "w").write(open(os.path.join(OUT, "bench.json")).read())
+
+# ---- K7 / K8 / K9 full capture (scripts/profile_f3_kernels.py)
+rep3 = os.path.join(OUT, "prof_f3.ncu-rep")
+if os.path.exists(rep3):
+    raw = subprocess.run(["ncu", "-i", rep3, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]; units = rows[1]; body = rows[2:]
+    keys3 = keys + ["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+                    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+                    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+    idx3 = {k: hdr.index(k) for k in keys3 if k in hdr}
+    ni = hdr.index("Kernel Name")
+    # the second launch of each kernel (the first is the warm-up)
+    seen, pick = {}, []
+    for r in body:
+        n = r[ni].split("(")[0]
+        seen[n] = seen.get(n, 0) + 1
+        if seen[n] == 2:
+            pick.append(r)
+    with open(os.path.join(PROF, tag + "_f3_full.md"), "w") as f:
+        f.write("# %s: `ncu --set full --clock-control none --import-source on` of K7 / K8 / K9 at config 2's size (batch 32, seq 512, 12 heads x 64)\n\n" % tag)
+        f.write("Second launch of each kernel (`scripts/profile_f3_kernels.py`).  Algorithmic bytes: K7 163.6 MB, K8 503.3 MB, K9 515.9 MB.\n\n")
+        f.write("| metric | unit | " + " | ".join(r[ni].split("(")[0].replace("void ", "").replace("osq::", "") for r in pick) + " |\n|---|---|" + "---|" * len(pick) + "\n")
+        for k, i in idx3.items():
+            f.write("| %s | %s | %s |\n" % (k, units[i], " | ".join(r[i] for r in pick)))
+    print(open(os.path.join(PROF, tag + "_f3_full.md")).read())
