@@ -927,6 +927,7 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
         }
         cle = __reduce_add_sync(0xffffffffu, cle);
         nxt = __reduce_min_sync(0xffffffffu, nxt);
+        __syncwarp();   // every lane has read s_prefix / s_krem (above) before lane 0 overwrites them
         if (lane == 0) { s_prefix[sd] = prefix; s_krem[sd] = krem; s_cntle[sd] = cle; s_next[sd] = nxt; }
       }
     } else {
