@@ -84,6 +84,7 @@ struct FusedParams {
   const float* bias;
   uint8_t* a_codes;  // optional [M, K]: bins side output / code cache
   float* Y;          // [M, N] output (the drain epilogue writes it with plain stores; the other variants go through tmap_y)
+  int x_depth;       // fp32 landing slots per worker (1, or 2 on streamed plans: k-block kb lands in slot kb & 1)
   int pre_l2;        // k-blocks of this CTA's fp32 tile prefetched into L2 before the wait for the previous grid (0 = off)
   int lsu_mod;       // plain tile stores: every lsu_mod-th step of a warp is written by the LSU instead of the TMA unit (0 = never)
   int epi16;         // epilogue variant: all sixteen workers (four column slices), single staging tile per warp
@@ -356,7 +357,7 @@ struct Smem {
   uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   uint64_t acc_full[kMaxAccStages], acc_empty[kMaxAccStages];
   uint64_t codes_ready, passes_issued, tmem_ready;
-  uint64_t x_full[kNumWorkers];  // per-worker fp32 landing slot filled (TMA complete_tx)
+  uint64_t x_full[2 * kNumWorkers];  // per-worker fp32 landing slot(s) filled (TMA complete_tx); second set: x_depth = 2
   uint64_t d_full[8], d_empty[8];  // drain epilogue: staging tile (lane quarter q, buffer b) staged by both column slices / drained by both drainers
   uint32_t tmem_base;
   volatile uint32_t converted;  // k-blocks worker 0 has converted so far (paces the L2 prefetcher)
@@ -412,8 +413,9 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
   uint8_t* a_ring = smem_raw;
   uint8_t* w_ring = a_ring + (size_t)p.a_stages * p.a_stage_bytes;
   uint8_t* x_ring = w_ring + (size_t)p.w_stages * p.w_stage_bytes;  // 16 fp32 landing slots of 4 KB (x_tma only)
-  uint8_t* o_ring = p.alias_xo ? x_ring : x_ring + (kXTma ? kNumWorkers * kXSlotBytes : 0);
-  Smem& sm = *reinterpret_cast<Smem*>(p.alias_xo ? x_ring + kNumWorkers * kXSlotBytes
+  const int x_slots = kNumWorkers * (p.x_depth > 1 ? 2 : 1);
+  uint8_t* o_ring = p.alias_xo ? x_ring : x_ring + (kXTma ? x_slots * kXSlotBytes : 0);
+  Smem& sm = *reinterpret_cast<Smem*>(p.alias_xo ? x_ring + x_slots * kXSlotBytes
                                                  : o_ring + (size_t)kEW * p.out_bufs * kOutTileBytes);
   // per-column constants; the arrays are padded to a multiple of 32 columns (the epilogue reads 32-column groups)
   const int bn_pad = (p.BN + 31) & ~31;
@@ -439,7 +441,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     for (int i = 0; i < p.w_stages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
     for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kEW * p.csz); }
     mbar_init(&sm.codes_ready, kNumWorkers);
-    for (int i = 0; i < kNumWorkers; ++i) mbar_init(&sm.x_full[i], 1);
+    for (int i = 0; i < 2 * kNumWorkers; ++i) mbar_init(&sm.x_full[i], 1);
     mbar_init(&sm.passes_issued, 1);
     mbar_init(&sm.tmem_ready, 1);
     for (int i = 0; i < 8; ++i) { mbar_init(&sm.d_full[i], 2); mbar_init(&sm.d_empty[i], 2); }
@@ -703,8 +705,14 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       const int row0 = mb_lane * p.rows_per_tile + w * kRowsPerWorker;
       if (lane == 0 && !p.codes_in && w * kRowsPerWorker < p.rows_per_tile && row0 < p.M) {
         const uint32_t bar = smem_u32(&sm.x_full[w]);
-        mbar_arrive_expect_tx_u32(bar, (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker) * (uint32_t)(kStageK * 4));
+        const uint32_t box_bytes = (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker) * (uint32_t)(kStageK * 4);
+        mbar_arrive_expect_tx_u32(bar, box_bytes);
         tma_load_2d_u32(smem_u32(x_ring + (size_t)w * kXSlotBytes), &tmap_a, bar, 0, row0);
+        if (p.x_depth > 1 && p.KB > 1) {   // second landing slot of this worker: k-block 1
+          const uint32_t bar1 = smem_u32(&sm.x_full[w + kNumWorkers]);
+          mbar_arrive_expect_tx_u32(bar1, box_bytes);
+          tma_load_2d_u32(smem_u32(x_ring + (size_t)(w + kNumWorkers) * kXSlotBytes), &tmap_a, bar1, kStageK, row0);
+        }
       }
     }
     // streamed A with a code cache: the bins must survive in L2 until the later sweeps re-load them, so everything that is
@@ -810,11 +818,14 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
     // k-block, so 16 x 4 KB stay in flight per SM no matter what the warps are doing, without going through the L1
     // (whose capacity bounds plain loads in flight once 227 KB are carved out as shared memory).  Rows past M are
     // zero-filled by the TMA unit: no ragged path.
-    uint32_t x_ph = 0;
+    // x_depth = 2 (streamed plans with room for it): two slots per worker, k-block kb lands in slot kb & 1 and is re-armed with
+    // kb + 2 -- twice the bytes in flight per SM (the read phase is bound by bytes in flight x DRAM latency, not by the conversion)
+    uint32_t x_phv[2] = {0u, 0u};
     const uint32_t leader_a_full0 = pair ? mapa_u32(smem_u32(&sm.a_full[0]), 0) : 0u;
     auto convert_pass_tma = [&](int mb, uint32_t pa0, bool first_issued) {
-      const uint32_t x_bar = smem_u32(&sm.x_full[w]);
-      uint8_t* const x_slot = x_ring + (size_t)w * kXSlotBytes;
+      const uint32_t x_bar0 = smem_u32(&sm.x_full[w]);
+      uint8_t* const x_slot0 = x_ring + (size_t)w * kXSlotBytes;
+      const int xd = p.x_depth > 1 ? 2 : 1;
       const uint32_t x_box_bytes = (uint32_t)(p.M < kRowsPerWorker ? p.M : kRowsPerWorker) * (uint32_t)(kStageK * 4);
       const int row_first = mb * p.rows_per_tile + r_base;
       const bool active = r_base < p.rows_per_tile && row_first < p.M;  // warp uniform
@@ -822,8 +833,12 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       const size_t rs = (size_t)p.K;
       uint8_t* cptr = (p.a_codes != nullptr && active) ? p.a_codes + (size_t)row_first * rs + lane * 4 : nullptr;
       if (active && lane == 0 && !first_issued) {
-        mbar_arrive_expect_tx_u32(x_bar, x_box_bytes);
-        tma_load_2d_u32(smem_u32(x_slot), &tmap_a, x_bar, 0, row_first);
+        mbar_arrive_expect_tx_u32(x_bar0, x_box_bytes);
+        tma_load_2d_u32(smem_u32(x_slot0), &tmap_a, x_bar0, 0, row_first);
+        if (xd > 1 && p.KB > 1) {
+          mbar_arrive_expect_tx_u32(x_bar0 + kNumWorkers * 8, x_box_bytes);
+          tma_load_2d_u32(smem_u32(x_slot0 + kNumWorkers * kXSlotBytes), &tmap_a, x_bar0 + kNumWorkers * 8, kStageK, row_first);
+        }
       }
       for (int kb = 0; kb < p.KB; ++kb) {
         const uint32_t pa = pa0 + kb;
@@ -831,19 +846,22 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
         if (pa >= (uint32_t)p.a_stages) mbar_wait(&sm.a_empty[a_st], c_ph ^ 1);  // first fill: ring is empty
         if (active) {
           uint8_t* st = a_ring + a_st * (uint32_t)p.a_stage_bytes + r_base * kStageK + lane_in;
-          mbar_wait_u32(x_bar, x_ph);
-          x_ph ^= 1;
+          const int xs = (xd > 1) ? (kb & 1) : 0;
+          const uint32_t x_bar = x_bar0 + (uint32_t)xs * (kNumWorkers * 8);
+          uint8_t* const x_slot = x_slot0 + (size_t)xs * (kNumWorkers * kXSlotBytes);
+          mbar_wait_u32(x_bar, x_phv[xs]);
+          x_phv[xs] ^= 1;
 #pragma unroll
           for (int i = 0; i < kRowsPerWorker; ++i)
             x[i] = *reinterpret_cast<const float4*>(x_slot + i * (kStageK * 4) + lane * 16);
-          if (kb + 1 < p.KB) {
+          if (kb + xd < p.KB) {
             // the slot's contents are in registers: order these generic-proxy reads before the async-proxy refill
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
               mbar_arrive_expect_tx_u32(x_bar, x_box_bytes);
-              if (hint_a) tma_load_2d_hint_u32(smem_u32(x_slot), &tmap_a, x_bar, (kb + 1) * kStageK, row_first, pol_once);
-              else tma_load_2d_u32(smem_u32(x_slot), &tmap_a, x_bar, (kb + 1) * kStageK, row_first);
+              if (hint_a) tma_load_2d_hint_u32(smem_u32(x_slot), &tmap_a, x_bar, (kb + xd) * kStageK, row_first, pol_once);
+              else tma_load_2d_u32(smem_u32(x_slot), &tmap_a, x_bar, (kb + xd) * kStageK, row_first);
             }
           }
           uint32_t risky_mask = 0;
@@ -1287,7 +1305,7 @@ __device__ __forceinline__ void fused_fq_linear_body(const CUtensorMap& tmap_w, 
       for (int i = 0; i < p.w_stages; ++i) { mbar_inval(&sm.w_full[i]); mbar_inval(&sm.w_empty[i]); }
       for (int i = 0; i < p.acc_stages; ++i) { mbar_inval(&sm.acc_full[i]); mbar_inval(&sm.acc_empty[i]); }
       mbar_inval(&sm.codes_ready);
-      for (int i = 0; i < kNumWorkers; ++i) mbar_inval(&sm.x_full[i]);
+      for (int i = 0; i < 2 * kNumWorkers; ++i) mbar_inval(&sm.x_full[i]);
       mbar_inval(&sm.passes_issued);
       mbar_inval(&sm.tmem_ready);
       for (int i = 0; i < 8; ++i) { mbar_inval(&sm.d_full[i]); mbar_inval(&sm.d_empty[i]); }
@@ -1612,7 +1630,7 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
   const int x_bytes = kNumWorkers * kXSlotBytes;          // 64 KB
   const int out1 = kNumEpiWarps * kOutTileBytes;          // 32 KB per buffer set
   const int total = env_kb * 1024 - (int)sizeof(Smem);
-  struct Plan { int ok, bn, resident, cached, a_stages, w_stages, out_bufs, x_tma, alias, score; };
+  struct Plan { int ok, bn, resident, cached, a_stages, w_stages, out_bufs, x_tma, alias, score, x_depth; };
   Plan best; memset(&best, 0, sizeof(best));
   static int max_ctas[64][3] = {{0}};
   int grid = 0, nsplit_max = 1;
@@ -1653,8 +1671,10 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
       // groups of CTAs instead (each group converts the same rows, which come from L2 after the first touch).
       static int env_nsplit = -1;
       if (env_nsplit < 0) { const char* e = getenv("OSQ_FUSED_NSPLIT"); env_nsplit = e ? atoi(e) : 1; }
-      split_n = env_nsplit != 0 && rpt < 64 && p.M > 64 && p.N > 256;
-      if (split_n) rpt = 64;
+      split_n = env_nsplit != 0 && rpt < 64 && p.N > 256;
+      // (decode-sized launches, M <= 64 -- BART generation runs every decoder Linear at batch x beams rows: ONE row tile holding
+      //  all rows, N spread over as many CTAs as there are chunks; without this a 24-row launch ran on two CTAs: 20-60 us)
+      if (split_n) rpt = p.M > 64 ? 64 : (p.M + 15) / 16 * 16;
       p.rows_per_tile = (int)rpt;
     }
     p.n_mblocks = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
@@ -1667,9 +1687,13 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
     nsplit_max = split_n ? G / grid : 1;
     p.a_stage_bytes = p.rows_per_tile * kStageK;
 
+    // one row tile and a column split: narrow chunks spread N over more CTAs (the launch is bound by the W stream per CTA)
+    const bool narrow = split_n && p.n_mblocks == 1 && p.N % 128 == 0 && p.N >= 512;
+    static int env_xdepth = -1;
+    if (env_xdepth < 0) { const char* e = getenv("OSQ_FUSED_XDEPTH"); env_xdepth = e ? atoi(e) : 1; }
     auto make_plan = [&](int bn, int x_tma) {
       Plan pl; memset(&pl, 0, sizeof(pl));
-      pl.bn = bn; pl.x_tma = x_tma;
+      pl.bn = bn; pl.x_tma = x_tma; pl.x_depth = 1;
       const int nc = (p.N + bn - 1) / bn;
       const int w_stage = (bn / csz * kStageK + 1023) / 1024 * 1024;
       const int budget = total - 2 * ((bn + 31) & ~31) * (int)sizeof(float);
@@ -1677,12 +1701,19 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
       pl.resident = (p.KB <= kMaxAStages && p.KB * p.a_stage_bytes + 2 * w_stage + xo_min <= budget) ? 1 : 0;
       if (csz > 1 && !x_tma) return pl;
       pl.cached = (!pl.resident && (nc > 1 || a->A == nullptr) && a->a_codes != nullptr) ? 1 : 0;
+      // a single decode-sized row tile: re-converting its few rows per chunk is cheaper than tying four chunks to one CTA
+      if (narrow && a->A != nullptr) pl.cached = 0;
       if (csz > 1 && !(pl.resident || pl.cached)) return pl;  // the pair needs resident A or the code-cache sweeps
       pl.a_stages = pl.resident ? p.KB : 4;
       // X and O can share memory only when conversion and epilogue never interleave inside a tile
       const bool can_alias = pl.resident || pl.cached || nc == 1;
       int rest = budget - pl.a_stages * p.a_stage_bytes - 2 * w_stage;
       pl.w_stages = 2;
+      // streamed fp32-in plans: a second landing slot per worker when it fits next to 4 A and 2 W stages (the read phase of
+      // K > 1024 sites is bound by bytes in flight)
+      if (x_tma && env_xdepth == 2 && pl.cached && a->A != nullptr && can_alias && rest >= 2 * x_bytes) {
+        pl.x_depth = 2; pl.alias = 1; pl.out_bufs = 2; rest -= 2 * x_bytes;
+      } else
       if (x_tma) {
         if (can_alias && rest >= x_bytes) { pl.alias = 1; pl.out_bufs = 2; rest -= x_bytes; }
         else if (rest >= x_bytes + out1) { pl.alias = 0; pl.out_bufs = 1; rest -= x_bytes + out1; }
@@ -1713,6 +1744,7 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
       for (int i = 0; i < 3; ++i) {
         int bn = bn_cands[i];
         if (env_bn > 0 && bn != env_bn) continue;
+        if (env_bn <= 0 && narrow && bn != 128) continue;
         if (p.N < bn) { if (i == 0) bn = p.N; else continue; }   // narrow layers: one chunk of N columns
         else if (p.N % bn != 0 && i != 0) continue;               // 192 / 128 only when they tile N exactly
         if (bn % (16 * csz) != 0) continue;
@@ -1729,7 +1761,7 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
   p.resident = best.resident; p.cached = best.cached;
   p.codes_in = (a->A == nullptr) ? 1 : 0;
   p.a_stages = best.a_stages; p.w_stages = best.w_stages; p.out_bufs = best.out_bufs;
-  p.x_tma = best.x_tma; p.alias_xo = best.alias;
+  p.x_tma = best.x_tma; p.alias_xo = best.alias; p.x_depth = best.x_tma ? best.x_depth : 1;
   // streamed A with a code cache: all accumulator stages are fed in one sweep over K (the later sweeps re-load the
   // bins by TMA).  Without a cache the workers re-convert per chunk and must keep one stage free for the epilogue
   // they run in between, so they stay at one chunk per sweep.
@@ -1747,7 +1779,7 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
   p.a_passes = p.resident ? 1 : (p.cps + p.cpp - 1) / p.cpp;
   const int const_bytes = 2 * ((p.BN + 31) & ~31) * (int)sizeof(float);
   const size_t smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes +
-                            (p.x_tma ? (size_t)x_bytes : 0) + (p.alias_xo ? 0 : (size_t)p.out_bufs * out1) +
+                            (p.x_tma ? (size_t)x_bytes * (size_t)p.x_depth : 0) + (p.alias_xo ? 0 : (size_t)p.out_bufs * out1) +
                             sizeof(Smem) + (size_t)const_bytes;
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.gridDim = dim3((unsigned)grid);
@@ -1825,9 +1857,9 @@ static int plan_fused(const osq_fused_linear_t* a, FusedPlan* out) {
     if (!known && n_seen < 16) {
       seen[n_seen][0] = p.M; seen[n_seen][1] = p.K; seen[n_seen][2] = p.N; ++n_seen;
       fprintf(stderr, "[osq] fused M=%d K=%d N=%d: grid=%d (n-split %d) cluster=%d rows/tile=%d tiles/cta=%d BN=%d chunks=%d mode=%s a_stages=%d(%d B) "
-                      "w_stages=%d(%d B) acc_stages=%d out_bufs=%d x_tma=%d alias=%d sweeps=%d smem=%zu\n",
+                      "w_stages=%d(%d B) acc_stages=%d out_bufs=%d x_tma=%d(x%d) alias=%d sweeps=%d smem=%zu\n",
               p.M, p.K, p.N, grid, p.nsplit, p.csz, p.rows_per_tile, p.n_iters, p.BN, p.NC, p.codes_in ? (p.resident ? "bins-in resident" : "bins-in streamed") : p.resident ? "resident" : (p.cached ? "streamed+cache" : "streamed"),
-              p.a_stages, p.a_stage_bytes, p.w_stages, p.w_stage_bytes, p.acc_stages, p.out_bufs, p.x_tma, p.alias_xo, p.a_passes, smem_bytes);
+              p.a_stages, p.a_stage_bytes, p.w_stages, p.w_stage_bytes, p.acc_stages, p.out_bufs, p.x_tma, p.x_depth, p.alias_xo, p.a_passes, smem_bytes);
     }
   }
   p.first_site = 1;

@@ -64,6 +64,16 @@ def test_fused_shapes_6bit(m, k, n):
     run_case(m, k, n, 6, 6, False, seed=m + k + n)
 
 
+@pytest.mark.parametrize("m,k,n", [(24, 1024, 1024), (24, 1024, 3072), (24, 4096, 1024), (24, 1024, 4096), (6, 768, 3072), (64, 1024, 1024),
+                                   (40, 3072, 768), (17, 256, 640)])
+def test_fused_decode_sized_launches(m, k, n):
+    """BART generation (config 4) runs every decoder Linear at batch x beams rows per step (4 x 6 = 24): one row tile, N split over
+    the CTAs in 128-column chunks; with and without the code cache for K > 1024."""
+    y = run_case(m, k, n, 6, 6, True, seed=m + k + n)
+    if k > 1024:
+        assert torch.equal(y, run_case(m, k, n, 6, 6, True, seed=m + k + n, use_code_cache=False))
+
+
 @pytest.mark.parametrize("a_bit,w_bit,lsq", [(8, 8, False), (4, 4, False), (6, 4, False), (6, 6, True), (8, 8, True)])
 def test_fused_bits_and_lsqplus(a_bit, w_bit, lsq):
     run_case(384, 768, 768, a_bit, w_bit, lsq, seed=a_bit * 10 + w_bit, gamma=True)
