@@ -37,6 +37,17 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"null pointer" in lib.osq_last_error()
     rc = lib.osq_fused_fq_linear(None, None)
     assert rc == -1
+    # round-2 entry points: argument checks come before any CUDA call
+    rc = lib.osq_residual_layernorm_fq_f32(None, None, None, None, None, 1e-5, 4, 768, None, None, 0, 0.0, 0, 63, None, None, None, None)
+    assert rc == -1 and b"null pointer" in lib.osq_last_error()
+    rc = lib.osq_residual_layernorm_fq_f32(None, None, None, None, None, 1e-5, 0, 768, None, None, 0, 0.0, 0, 63, None, None, None, None)
+    assert rc == 0                                    # empty input: nothing to do
+    rc = lib.osq_attn_scores_fq_f32(None, None, 1, 2, 8, 8, 64, None, None, None, None, 1.0, None, None, None)
+    assert rc == -1 and b"null pointer" in lib.osq_last_error()
+    rc = lib.osq_attn_scores_fq_f32(None, None, 0, 2, 8, 8, 64, None, None, None, None, 1.0, None, None, None)
+    assert rc == 0
+    rc = lib.osq_attn_context_fq_f32(None, None, 1, 2, 8, 8, 64, None, None, None, None, None, None, None)
+    assert rc == -1
 
 
 def test_no_cpu_fallback():
@@ -208,7 +219,8 @@ def test_ctypes_structures_match_the_header():
         return names
 
     for cname, cls in (("osq_tokens_t", _lib.Tokens), ("osq_stat_epilogue_t", _lib.StatEpilogue),
-                       ("osq_fused_linear_t", _lib.FusedLinearArgs), ("osq_replay_target_t", _lib.ReplayTarget)):
+                       ("osq_fused_linear_t", _lib.FusedLinearArgs), ("osq_replay_target_t", _lib.ReplayTarget),
+                       ("osq_quantizer_t", _lib.QuantizerArgs)):
         assert fields(cname) == [f[0] for f in cls._fields_], cname
 
 
@@ -280,3 +292,66 @@ def test_fused_linear_supported_mirrors_the_kernel_contract():
     assert ops.fused_linear_supported(768, 768) and ops.fused_linear_supported(32768, 16)
     for k, n in ((100, 768), (768, 100), (65536, 768), (768, 8), (768, (1 << 20) + 16)):
         assert not ops.fused_linear_supported(k, n)
+
+
+def test_model_level_hooks_are_found_by_duck_typing_and_idempotent():
+    """fusion.py attaches to the reference's blocks by their attribute names (no import of reference classes): the FFN block
+    (dense / intermediate_act_fn / its quantizer), the residual + LayerNorm block, the self-attention block.  Wrapping twice
+    changes nothing; unrelated modules are left alone."""
+    from outlier_suppression_b200.quantization import fusion
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer
+    a = QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1)
+    w = QC("FixedFakeQuantize", "MinMaxObserver", 6, True, 0)
+
+    class Res(torch.nn.Module):
+        mul_gamma = False
+        def forward(self, x, h):
+            return x + h
+
+    class LN(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.qoutput = True
+            self.layernorm = torch.nn.LayerNorm(128)
+            self.layernorm_post_act_fake_quantize = Quantizer(None, a)
+
+    class Out(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dense = Quantizer(torch.nn.Linear(128, 128), w)
+            self.dropout = torch.nn.Dropout(0.1)
+            self.before_LayerNorm_residual = Res()
+            self.LayerNorm = LN()
+        def forward(self, hidden_states, input_tensor, observation_mask=None):
+            return hidden_states
+
+    class Attn(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_attention_heads, self.attention_head_size, self.qoutput = 2, 64, True
+            for n in ("query", "key", "value"):
+                setattr(self, n, Quantizer(torch.nn.Linear(128, 128), w))
+            for n in fusion._ATTN_Q + ("context_view_post_act_fake_quantize",):
+                setattr(self, n, Quantizer(None, a))
+            self.dropout = torch.nn.Dropout(0.1)
+        def transpose_for_scores(self, x):
+            return x.view(x.shape[0], x.shape[1], 2, 64).permute(0, 2, 1, 3)
+        def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False, observation_mask=None):
+            return (hidden_states,)
+
+    net = torch.nn.Module()
+    net.a, net.o, net.plain = Attn(), Out(), torch.nn.Linear(4, 4)
+    assert fusion.fuse_layernorm_output(net) == 1 and fusion.fuse_self_attention(net) == 1 and fusion.fuse_ffn_activation(net) == 0
+    f_o, f_a = net.o.forward, net.a.forward
+    assert fusion.fuse_layernorm_output(net) == 1 and fusion.fuse_self_attention(net) == 1
+    assert net.o.forward == f_o and net.a.forward == f_a and not hasattr(net.plain, "_osq_unfused_forward")
+    # outside the quantized inference state (here: autograd on, quantizers off) the original forward runs
+    x = torch.randn(2, 8, 128)
+    assert net.a(x)[0] is x
+    assert not fusion._attn_fusable(net.a, x, None, None, False)
+    with torch.no_grad():
+        assert not fusion._attn_fusable(net.a, x, None, None, False)          # fake-quant disabled
+        for n in fusion._ATTN_Q + ("context_view_post_act_fake_quantize",):
+            getattr(net.a, n).enable_fake_quant(); getattr(net.a, n).disable_observer()
+        assert not fusion._attn_fusable(net.a, x, None, None, False)          # CPU tensor: no CPU fallback, reference forward
+        assert not fusion._attn_fusable(net.a, x, None, torch.ones(2), False)  # head_mask
