@@ -71,6 +71,19 @@ int osq_residual_layernorm_fq_f32(const float* h, const float* res, const float*
                                   const void* zero_point, int zp_is_int32, float lsq_grad_factor, int qmin, int qmax, float* y,
                                   uint8_t* bins, float* ln_out, void* stream);
 
+/* K1d the per-tensor fake-quantize WITHOUT its fp32 output: only the uint8 bins (bin - qmin) leave, 5 bytes per element instead of 9.
+ *     For an activation quantizer (fake_quant.py:107-126 / :170-209) whose output is consumed by fused QLinears alone: those read
+ *     the bins (A = NULL, a_codes = bins) and the dequantised tensor of util_quant.py:14 is never needed.  `eff` (device float[2],
+ *     optional) receives the effective (scale, zero_point) the launch used -- after LSQ+'s sanitise / grad_scale -- for
+ *     osq_dequant_bins_f32.  n % 4 == 0, x 16-byte aligned. */
+int osq_fq_per_tensor_bins_only_f32(const float* x, uint8_t* bins, int64_t n, const float* scale, const void* zero_point,
+                                    int zp_is_int32, float lsq_grad_factor, int qmin, int qmax, float* eff, void* stream);
+
+/*     the fp32 tensor K1 would have written for those bins: y = (bin + qmin - z) * s with (s, z) = eff (util_quant.py:14).
+ *     Bit-identical to K1's output whenever z is integer valued (FixedFakeQuantize always; LSQ+ except for its rare 1-ulp
+ *     zero-point drift, where the un-clamped bins are rebuilt as clamp((q - rint(z)) + z) like util_quant.py:13). */
+int osq_dequant_bins_f32(const uint8_t* bins, const float* eff, int qmin, int qmax, float* y, int64_t n, void* stream);
+
 /* K2  per-channel (ch_axis = 0) fake-quantize of a [rows, cols] matrix.
  *     replaces util_quant.py:18-26 (fake_quantize_per_channel_affine), fake_quant.py:119-122. */
 /* K1b the same per-tensor fake-quantize with the bins as a uint8 side output in the operand format of

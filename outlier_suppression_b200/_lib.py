@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("OSQ_LIB_PATH") or os.path.join(_PKG, "libosq_b200.so"
 
 EXPORTS = [
     "osq_version", "osq_last_error", "osq_sm_count", "osq_workspace_bytes",
-    "osq_fq_per_tensor_f32", "osq_fq_per_tensor_bins_f32", "osq_act_fq_per_tensor_bins_f32", "osq_fq_per_channel_f32",
+    "osq_fq_per_tensor_f32", "osq_fq_per_tensor_bins_f32", "osq_act_fq_per_tensor_bins_f32", "osq_fq_per_channel_f32", "osq_fq_per_tensor_bins_only_f32",
+    "osq_dequant_bins_f32",
     "osq_residual_layernorm_fq_f32", "osq_attn_scores_fq_f32", "osq_attn_context_fq_f32",
     "osq_minmax_masked_f32", "osq_minmax_flat_f32", "osq_token_minmax_f32", "osq_prune_select_f32", "osq_prune_select_unsorted_f32",
     "osq_prune_observe_f32", "osq_quantile_observe_f32", "osq_replay_average_f32", "osq_replay_average_peer_f32",
@@ -79,6 +80,8 @@ def _declare(lib):
         "osq_fq_per_tensor_bins_f32": [vp, vp, vp, i64, vp, vp, i32, f32, i32, i32, vp],
         "osq_act_fq_per_tensor_bins_f32": [vp, vp, vp, i64, i32, vp, vp, i32, f32, i32, i32, vp],
         "osq_fq_per_channel_f32": [vp, vp, vp, i64, i64, vp, vp, i32, i32, vp],
+        "osq_fq_per_tensor_bins_only_f32": [vp, vp, i64, vp, vp, i32, f32, i32, i32, vp, vp],
+        "osq_dequant_bins_f32": [vp, vp, i32, i32, vp, i64, vp],
         "osq_residual_layernorm_fq_f32": [vp, vp, vp, vp, vp, f32, i64, i64, vp, vp, i32, f32, i32, i32, vp, vp, vp, vp],
         "osq_minmax_masked_f32": [vp, C.POINTER(Tokens), vp, i32, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_minmax_flat_f32": [vp, i64, vp, C.POINTER(StatEpilogue), vp, vp],

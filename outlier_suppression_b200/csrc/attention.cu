@@ -413,8 +413,8 @@ attn_context_kernel(const ContextParams p) {
           y.z = fq_elem(o.z, oq.s, oq.z, p.oq.qmin, p.oq.qmax, q2_); y.w = fq_elem(o.w, oq.s, oq.z, p.oq.qmin, p.oq.qmax, q3_);
         }
         if (p.bins != nullptr)
-          *reinterpret_cast<uint32_t*>(p.bins + off) = (uint32_t)(int)(q0_ - p.oq.qmin) | ((uint32_t)(int)(q1_ - p.oq.qmin) << 8) |
-                                                       ((uint32_t)(int)(q2_ - p.oq.qmin) << 16) | ((uint32_t)(int)(q3_ - p.oq.qmin) << 24);
+          *reinterpret_cast<uint32_t*>(p.bins + off) = (uint32_t)__float2int_rn(q0_ - p.oq.qmin) | ((uint32_t)__float2int_rn(q1_ - p.oq.qmin) << 8) |
+                                                       ((uint32_t)__float2int_rn(q2_ - p.oq.qmin) << 16) | ((uint32_t)__float2int_rn(q3_ - p.oq.qmin) << 24);
         o = y;
       }
       *reinterpret_cast<float4*>(p.out + off) = o;

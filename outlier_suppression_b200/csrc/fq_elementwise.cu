@@ -14,7 +14,7 @@ constexpr int kFqUnroll = 4;  // float4s in flight per thread
 template <int kCodes>
 __device__ __forceinline__ void put_code(void* codes, int64_t i, float q, float qmin) {
   if (kCodes == 1) static_cast<int16_t*>(codes)[i] = (int16_t)rintf(q);
-  if (kCodes == 2) static_cast<uint8_t*>(codes)[i] = (uint8_t)(int)(q - qmin);
+  if (kCodes == 2) static_cast<uint8_t*>(codes)[i] = (uint8_t)__float2int_rn(q - qmin);   // (nearest: LSQ+ zero points may sit 1 ulp off an integer)
 }
 
 // GELU(x) = (x * 0.5) * (1 + erf(x / sqrt(2))) with the operation order of ATen's CUDA kernel (approximate = 'none'):
@@ -83,8 +83,8 @@ fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, void* _
         if (kCodes != 0) {
           const int64_t e = head + (i << 2);
           if (word_codes) {
-            const uint32_t w = (uint32_t)(int)(q0 - qmin) | ((uint32_t)(int)(q1 - qmin) << 8) | ((uint32_t)(int)(q2 - qmin) << 16) |
-                               ((uint32_t)(int)(q3 - qmin) << 24);
+            const uint32_t w = (uint32_t)__float2int_rn(q0 - qmin) | ((uint32_t)__float2int_rn(q1 - qmin) << 8) | ((uint32_t)__float2int_rn(q2 - qmin) << 16) |
+                               ((uint32_t)__float2int_rn(q3 - qmin) << 24);
             *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(codes) + e) = w;
           } else {
             put_code<kCodes>(codes, e, q0, qmin); put_code<kCodes>(codes, e + 1, q1, qmin);
@@ -208,6 +208,66 @@ lsqplus_backward_kernel(const float* __restrict__ x, const float* __restrict__ d
   }
 }
 
+// K1d  bins only: the per-tensor fake-quantize of K1 / K1b without its fp32 output -- 5 bytes per element instead of 9.  For a
+// quantizer whose output is consumed by fused QLinears alone (the dequantised tensor is then never read); `eff` receives the
+// effective (scale, zero point) the launch used, so that osq_dequant_bins_f32 can rebuild the fp32 tensor later.
+__global__ void __launch_bounds__(kFqThreads)
+fq_bins_only_kernel(const float4* __restrict__ x, uint32_t* __restrict__ bins, int64_t nvec, const float* __restrict__ scale,
+                    const void* __restrict__ zp, int zp_is_int32, float g, float qmin, float qmax, float* __restrict__ eff) {
+  const QParam p = load_qparam(scale, zp, zp_is_int32, g, qmin, qmax, blockIdx.x == 0 && threadIdx.x == 0);
+  const float s = p.s, z = p.z, rinv = __frcp_rn(s);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && eff != nullptr) { eff[0] = s; eff[1] = z; }
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = tid; base < nvec; base += nthreads * kFqUnroll) {
+    float4 v[kFqUnroll];
+#pragma unroll
+    for (int u = 0; u < kFqUnroll; ++u) {
+      const int64_t i = base + (int64_t)u * nthreads;
+      if (i < nvec) v[u] = ldg_stream(x + i);
+    }
+#pragma unroll
+    for (int u = 0; u < kFqUnroll; ++u) {
+      const int64_t i = base + (int64_t)u * nthreads;
+      if (i < nvec) {
+        float q0, q1, q2, q3;
+        bool k0, k1, k2, k3;
+        fq_elem_fast(v[u].x, s, rinv, z, qmin, qmax, q0, k0);
+        fq_elem_fast(v[u].y, s, rinv, z, qmin, qmax, q1, k1);
+        fq_elem_fast(v[u].z, s, rinv, z, qmin, qmax, q2, k2);
+        fq_elem_fast(v[u].w, s, rinv, z, qmin, qmax, q3, k3);
+        if (k0 | k1 | k2 | k3) {
+          fq_elem(v[u].x, s, z, qmin, qmax, q0); fq_elem(v[u].y, s, z, qmin, qmax, q1);
+          fq_elem(v[u].z, s, z, qmin, qmax, q2); fq_elem(v[u].w, s, z, qmin, qmax, q3);
+        }
+        bins[i] = (uint32_t)__float2int_rn(q0 - qmin) | ((uint32_t)__float2int_rn(q1 - qmin) << 8) | ((uint32_t)__float2int_rn(q2 - qmin) << 16) |
+                  ((uint32_t)__float2int_rn(q3 - qmin) << 24);
+      }
+    }
+  }
+}
+
+// (bins, eff) -> the fp32 tensor K1 would have written: y = (q - z) * s with q = bin + qmin.  Bit-identical to K1 whenever the
+// effective zero point is integer valued (always for FixedFakeQuantize; LSQ+'s grad_scale leaves rint(z) untouched except for
+// a rare 1-ulp drift, in which case q is rebuilt as clamp((q_int - rint(z)) + z) exactly as util_quant.py:13 forms it).
+__global__ void __launch_bounds__(kFqThreads)
+dequant_bins_kernel(const uint32_t* __restrict__ bins, float4* __restrict__ y, int64_t nvec, const float* __restrict__ eff, float qmin,
+                    float qmax) {
+  const float s = eff[0], z = eff[1], t = rintf(eff[1]);
+  const bool drift = z != t;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  auto one = [&](uint32_t b) -> float {
+    float q = __fadd_rn((float)b, qmin);
+    if (drift && q > qmin && q < qmax) q = fminf(fmaxf(__fadd_rn(__fsub_rn(q, t), z), qmin), qmax);
+    return __fmul_rn(__fsub_rn(q, z), s);
+  };
+  for (int64_t i = tid; i < nvec; i += nthreads) {
+    const uint32_t w = __ldg(bins + i);
+    __stcs(y + i, make_float4(one(w & 0xFFu), one((w >> 8) & 0xFFu), one((w >> 16) & 0xFFu), one(w >> 24)));
+  }
+}
+
 __global__ void calc_qparams_kernel(const float* __restrict__ mn, const float* __restrict__ mx, int64_t n, int qmin,
                                     int qmax, int symmetric, float* __restrict__ scale, float* __restrict__ zp_f32,
                                     int32_t* __restrict__ zp_i32) {
@@ -314,6 +374,47 @@ int osq_act_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int6
     fq_per_tensor_kernel<2, 1><<<grid, kFqThreads, 0, st>>>(x, y, bins, n, scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax);
   else
     fq_per_tensor_kernel<0, 1><<<grid, kFqThreads, 0, st>>>(x, y, nullptr, n, scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_fq_per_tensor_bins_only_f32(const float* x, uint8_t* bins, int64_t n, const float* scale, const void* zero_point,
+                                    int zp_is_int32, float lsq_grad_factor, int qmin, int qmax, float* eff, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(n >= 0, "osq_fq_per_tensor_bins_only_f32: n < 0");
+  if (n == 0) return OSQ_OK;
+  OSQ_CHECK_ARG(x && bins && scale && zero_point, "osq_fq_per_tensor_bins_only_f32: null pointer");
+  OSQ_CHECK_ARG(qmin < qmax && qmax - qmin <= 255, "osq_fq_per_tensor_bins_only_f32: uint8 bins need at most 8 bits");
+  OSQ_CHECK_ARG(!(lsq_grad_factor > 0.f && zp_is_int32), "osq_fq_per_tensor_bins_only_f32: LSQ+ needs a float zero_point");
+  OSQ_CHECK_ARG(n % 4 == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)bins) & 3) == 0,
+                "osq_fq_per_tensor_bins_only_f32: n must be a multiple of 4, x 16-byte and bins 4-byte aligned");
+  int sms = sm_count();
+  if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  const int64_t nvec = n >> 2;
+  const int64_t per_block = (int64_t)kFqThreads * kFqUnroll;
+  const int64_t want = (nvec + per_block - 1) / per_block;
+  const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+  fq_bins_only_kernel<<<grid, kFqThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint32_t*>(bins), nvec,
+                                                                   scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax, eff);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_dequant_bins_f32(const uint8_t* bins, const float* eff, int qmin, int qmax, float* y, int64_t n, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(n >= 0, "osq_dequant_bins_f32: n < 0");
+  if (n == 0) return OSQ_OK;
+  OSQ_CHECK_ARG(bins && eff && y, "osq_dequant_bins_f32: null pointer");
+  OSQ_CHECK_ARG(qmin < qmax && qmax - qmin <= 255, "osq_dequant_bins_f32: uint8 bins hold at most 8 bits");
+  OSQ_CHECK_ARG(n % 4 == 0 && (((uintptr_t)y) & 15) == 0 && (((uintptr_t)bins) & 3) == 0,
+                "osq_dequant_bins_f32: n must be a multiple of 4, y 16-byte and bins 4-byte aligned");
+  int sms = sm_count();
+  if (sms <= 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  const int64_t nvec = n >> 2;
+  const int64_t want = (nvec + kFqThreads - 1) / kFqThreads;
+  const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+  dequant_bins_kernel<<<grid, kFqThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(bins), reinterpret_cast<float4*>(y), nvec, eff,
+                                                                   (float)qmin, (float)qmax);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

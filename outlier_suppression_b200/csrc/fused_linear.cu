@@ -395,8 +395,8 @@ __device__ __forceinline__ float4 out_stage4(float4 o, const QParam& oq, float r
     r.z = fq_elem(o.z, oq.s, oq.z, qmin, qmax, q2);
     r.w = fq_elem(o.w, oq.s, oq.z, qmin, qmax, q3);
   }
-  bins = (uint32_t)(int)(q0 - qmin) | ((uint32_t)(int)(q1 - qmin) << 8) | ((uint32_t)(int)(q2 - qmin) << 16) |
-         ((uint32_t)(int)(q3 - qmin) << 24);
+  bins = (uint32_t)__float2int_rn(q0 - qmin) | ((uint32_t)__float2int_rn(q1 - qmin) << 8) | ((uint32_t)__float2int_rn(q2 - qmin) << 16) |
+         ((uint32_t)__float2int_rn(q3 - qmin) << 24);
   return r;
 }
 

@@ -57,7 +57,7 @@ __device__ __forceinline__ float4 fq4(const float4 a, float s, float rinv, float
     o.z = fq_elem(a.z, s, z, qmin, qmax, q2);
     o.w = fq_elem(a.w, s, z, qmin, qmax, q3);
   }
-  word = (uint32_t)(int)(q0 - qmin) | ((uint32_t)(int)(q1 - qmin) << 8) | ((uint32_t)(int)(q2 - qmin) << 16) | ((uint32_t)(int)(q3 - qmin) << 24);
+  word = (uint32_t)__float2int_rn(q0 - qmin) | ((uint32_t)__float2int_rn(q1 - qmin) << 8) | ((uint32_t)__float2int_rn(q2 - qmin) << 16) | ((uint32_t)__float2int_rn(q3 - qmin) << 24);
   return o;
 }
 

@@ -26,6 +26,13 @@ def _require_cuda(*tensors):
                                "there is no CPU fallback" % t.device)
 
 
+def plain(t):
+    """A deferred fake-quant tensor (quantization.fake_quant.LazyFakeQuant: uint8 bins now, fp32 values on demand) -> its fp32
+    tensor; anything else unchanged.  Every entry point that takes an activation's data pointer goes through this."""
+    m = getattr(t, "_osq_materialize", None)
+    return t if m is None else m()
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -73,6 +80,7 @@ def fq_per_tensor(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor
                   lsq_grad_factor: float = 0.0, want_codes: bool = False, want_bins: bool = False, act: Optional[str] = None):
     """util_quant.py:11-15 / :48-55 with device-resident qparams. Returns y (and int16 bins with want_codes, or
     uint8 ``bin - qmin`` in the fused Linear's operand format with want_bins)."""
+    x = plain(x)
     _require_cuda(x, scale, zero_point)
     x, y = _dense_like(x)
     if act not in (None, "none"):
@@ -117,6 +125,7 @@ def residual_layernorm_fq(h: torch.Tensor, res: Optional[torch.Tensor], res_gamm
                           want_ln: bool = False):
     """GammaResidual + LayerNorm + its output quantizer in one pass (util_layernorm.py:14-17 / :34-37, :41-52).
     Returns y, or (y, bins, ln_out) with the optional outputs as None when not requested."""
+    h, res = plain(h), plain(res)
     _require_cuda(h, scale, zero_point)
     if h.dtype != torch.float32 or not h.is_contiguous():
         raise TypeError("h must be a contiguous float32 tensor")
@@ -161,6 +170,7 @@ def _head_view(x: torch.Tensor, what: str):
 def attn_scores_fq(q: torch.Tensor, k: torch.Tensor, qq: dict, kq: dict, out_mul: float = 1.0, mask: Optional[torch.Tensor] = None):
     """fq_q(q) @ fq_k(k)^T [* out_mul] [+ mask] in one launch (quant_bert.py:148-150, :169-172).  q [B, h, Sq, d], k [B, h, Sk, d]
     (transpose_for_scores views); mask additive, broadcastable from [B, 1, 1, Sk].  Returns scores [B, h, Sq, Sk]."""
+    q, k = plain(q), plain(k)
     qs, ks = _head_view(q, "q"), _head_view(k, "k")
     B, h, sq, d = q.shape
     sk = k.shape[2]
@@ -179,6 +189,7 @@ def attn_scores_fq(q: torch.Tensor, k: torch.Tensor, qq: dict, kq: dict, out_mul
 def attn_context_fq(probs: torch.Tensor, v: torch.Tensor, pq: dict, vq: dict, oq: Optional[dict] = None, want_bins: bool = False):
     """fq_p(probs) @ fq_v(v), written as [B, Sq, h * d] (quant_bert.py:185-191); with ``oq`` the context quantizer (:192-193) runs in
     the epilogue and ``want_bins`` adds its uint8 bins.  probs [B, h, Sq, Sk] contiguous, v [B, h, Sk, d] view."""
+    probs, v = plain(probs), plain(v)
     vs = _head_view(v, "v")
     B, h, sk, d = v.shape
     if probs.dim() != 4 or probs.dtype != torch.float32 or not probs.is_contiguous() or probs.shape[0] != B or probs.shape[1] != h or probs.shape[3] != sk:
@@ -191,6 +202,35 @@ def attn_context_fq(probs: torch.Tensor, v: torch.Tensor, pq: dict, vq: dict, oq
     check(_lib.load().osq_attn_context_fq_f32(probs.data_ptr(), v.data_ptr(), B, h, sq, sk, d, vs, pa, va, oa, out.data_ptr(), _ptr(bins),
                                               _stream()), "osq_attn_context_fq_f32")
     return (out, bins) if want_bins else out
+
+
+def fq_bins_only(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int, lsq_grad_factor: float = 0.0):
+    """K1d: the uint8 bins of the per-tensor fake-quantize without its fp32 output (5 B / element).  Returns (bins, eff) with
+    eff = device float[2] holding the effective (scale, zero_point) of the launch, for ``dequant_bins``."""
+    _require_cuda(x, scale, zero_point)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.numel() % 4 != 0:
+        raise TypeError("x must be a contiguous float32 tensor with a multiple of 4 elements")
+    if scale.dtype != torch.float32 or zero_point.dtype not in (torch.float32, torch.int32):
+        raise TypeError("scale must be float32, zero_point float32 or int32")
+    bins = torch.empty_like(x, dtype=torch.uint8)
+    eff = torch.empty(2, dtype=torch.float32, device=x.device)
+    if x.numel() > 0:
+        check(_lib.load().osq_fq_per_tensor_bins_only_f32(x.data_ptr(), bins.data_ptr(), x.numel(), scale.data_ptr(), zero_point.data_ptr(),
+                                                          int(zero_point.dtype == torch.int32), float(lsq_grad_factor), int(qmin), int(qmax),
+                                                          eff.data_ptr(), _stream()), "osq_fq_per_tensor_bins_only_f32")
+    return bins, eff
+
+
+def dequant_bins(bins: torch.Tensor, eff: torch.Tensor, qmin: int, qmax: int) -> torch.Tensor:
+    """(bins, eff) of ``fq_bins_only`` -> the fp32 tensor the fake-quantize would have written (util_quant.py:14)."""
+    _require_cuda(bins, eff)
+    if bins.dtype != torch.uint8 or not bins.is_contiguous() or bins.numel() % 4 != 0:
+        raise TypeError("bins must be a contiguous uint8 tensor with a multiple of 4 elements")
+    y = torch.empty(bins.shape, dtype=torch.float32, device=bins.device)
+    if bins.numel() > 0:
+        check(_lib.load().osq_dequant_bins_f32(bins.data_ptr(), eff.data_ptr(), int(qmin), int(qmax), y.data_ptr(), bins.numel(), _stream()),
+              "osq_dequant_bins_f32")
+    return y
 
 
 def fq_per_channel(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int,
@@ -536,7 +576,7 @@ def fused_linear_supported(k: int, n: int, a: Optional[torch.Tensor] = None) -> 
     accumulators), N % 16 == 0, N <= 2^20, 16-byte aligned operands."""
     if not (128 <= k <= 32768 and k % 128 == 0 and 16 <= n <= (1 << 20) and n % 16 == 0):
         return False
-    if a is not None and a.is_contiguous() and a.data_ptr() % 16 != 0:
+    if a is not None and not getattr(a, "_osq_lazy", False) and a.is_contiguous() and a.data_ptr() % 16 != 0:
         return False
     return True
 
@@ -548,6 +588,8 @@ def fused_fq_linear(a, a_scale, a_zp, a_qmin, a_qmax, w_codes, w_scale, w_rowsum
     the fp32 tensor is not read at all (only its shape is used); the result is bit-identical.
     out_q (dict: scale, zp, qmin, qmax, g, act in {None, "gelu"}, bins: bool): fuse the NEXT activation quantizer into the
     epilogue -- the call returns (fq(act(Linear)), uint8 bins or None) instead of the Linear's output."""
+    if a_bins is None:
+        a = plain(a)
     _require_cuda(a, a_scale, a_zp, w_codes, w_scale, w_rowsum, bias)
     if a_bins is not None:
         if a_bins.dtype != torch.uint8 or a_bins.numel() != a.numel() or not a_bins.is_contiguous() or not a_bins.is_cuda:
@@ -608,7 +650,7 @@ def fused_fq_linear_multi(sites):
     arr = (FusedLinearArgs * len(sites))()
     outs, keep = [], []
     for args, st in zip(arr, sites):
-        a = st["a"]
+        a = plain(st["a"])
         _require_cuda(a, st["a_scale"], st["a_zp"], st["w_codes"], st["w_scale"], st["w_rowsum"], st.get("bias"))
         a2 = a.reshape(-1, a.shape[-1])
         if a2.dtype != torch.float32 or not a2.is_contiguous():

@@ -8,6 +8,7 @@ fused fake-quant + Linear tcgen05 kernel (fake-quant is idempotent, SURVEY.md se
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 import torch
@@ -18,6 +19,7 @@ from .observer import MinMaxObserver
 from . import util_quant as UQ
 
 _TAG = "_osq_producer"
+_lazy_stats = {"deferred": 0, "materialized": 0}   # how often a quantizer output stayed bins-only / had to be materialised
 
 
 def producer_of(t: torch.Tensor):
@@ -46,6 +48,55 @@ def _qparam_stamp(q):
     """Everything that identifies the (scale, zero_point) a quantizer used: rewritten by an observer pass or
     load_state_dict (epoch), or edited in place by an optimizer step / the LSQ+ sanitiser (tensor versions)."""
     return (q.qparam_epoch, q.scale.data_ptr(), q.scale._version, q.zero_point.data_ptr(), q.zero_point._version)
+
+
+class LazyFakeQuant(torch.Tensor):
+    """Deferred output of a per-tensor activation quantizer whose consumers are fused QLinears.
+
+    The launch that produced it wrote ONLY the uint8 bins (osq_fq_per_tensor_bins_only_f32: 5 B / element instead of 9); the bins
+    ride along as ``_osq_bins`` and a fused QLinear reads them without ever touching fp32 values.  It still IS the quantizer's
+    output -- an fp32 tensor of the input's shape: any other consumer (an add, a print, ``.cpu()``, another kernel of this package)
+    reaches ``__torch_dispatch__`` / ``ops.plain`` and gets the real values, produced on first use
+
+      * by running the ordinary fake-quant kernel on the quantizer's input, if that tensor and the quantizer's parameters are
+        untouched since (bit-identical to the eager path by construction), else
+      * from the bins and the effective (scale, zero_point) the launch recorded (osq_dequant_bins_f32: bit-identical whenever
+        the effective zero point is integer valued; within 1 ulp under LSQ+'s rare 1-ulp zero-point drift).
+
+    A quantizer whose deferred output was materialised once stops deferring (``_lazy_ok``): the second pass over the input would
+    cost more than the eager launch.  ``OSQ_DISABLE_LAZY_FQ=1`` turns the mechanism off."""
+
+    _osq_lazy = True
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
+    @staticmethod
+    def __new__(cls, bins, eff, qmin, qmax, recompute, on_materialize):
+        return torch.Tensor._make_wrapper_subclass(cls, bins.shape, strides=bins.stride(), dtype=torch.float32, device=bins.device,
+                                                   requires_grad=False)
+
+    def __init__(self, bins, eff, qmin, qmax, recompute, on_materialize):
+        self._lz = (bins, eff, int(qmin), int(qmax), recompute, on_materialize)
+        self._real = None
+
+    def _osq_materialize(self) -> torch.Tensor:
+        if self._real is None:
+            bins, eff, qmin, qmax, recompute, on_materialize = self._lz
+            y = recompute() if recompute is not None else None
+            if y is None:
+                y = ops.dequant_bins(bins, eff, qmin, qmax)
+            self._real = y
+            if on_materialize is not None:
+                on_materialize()
+        return self._real
+
+    def __repr__(self):  # pragma: no cover
+        return "LazyFakeQuant(%s)" % (repr(self._osq_materialize()),)
+
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        from torch.utils._pytree import tree_map
+        unwrap = lambda t: t._osq_materialize() if isinstance(t, LazyFakeQuant) else t
+        return func(*tree_map(unwrap, args), **tree_map(unwrap, kwargs or {}))
 
 
 class QuantizeBase(nn.Module):
@@ -140,6 +191,9 @@ class QuantizeBase(nn.Module):
         known to consume it, the bins in the fused kernel's operand format."""
         if (self._emit_bins and X.is_cuda and X.dim() >= 2 and X.shape[-1] % 128 == 0 and X.is_contiguous()
                 and self.quant_max - self.quant_min <= 255 and X.numel() > 0):
+            if (self._lazy_ok and X.dtype == torch.float32 and not getattr(X, "_osq_lazy", False) and X.data_ptr() % 16 == 0
+                    and not torch.is_grad_enabled() and os.environ.get("OSQ_DISABLE_LAZY_FQ") != "1"):
+                return self._fq_deferred(X, scale, zero_point, g)
             y, bins = ops.fq_per_tensor(X, scale, zero_point, self.quant_min, self.quant_max, lsq_grad_factor=g, want_bins=True)
             self._tag(y)
             try:
@@ -148,6 +202,32 @@ class QuantizeBase(nn.Module):
                 pass
             return y
         return self._tag(ops.fq_per_tensor(X, scale, zero_point, self.quant_min, self.quant_max, lsq_grad_factor=g))
+
+    # cleared the first time a deferred output of this quantizer had to be materialised (a non-Linear consumer exists)
+    _lazy_ok = True
+
+    def _fq_deferred(self, X, scale, zero_point, g):
+        """bins-only launch; the fp32 values exist only if somebody other than a fused QLinear asks for them (LazyFakeQuant)"""
+        bins, eff = ops.fq_bins_only(X, scale, zero_point, self.quant_min, self.quant_max, lsq_grad_factor=g)
+        me, x_ver, stamp = weakref.ref(self), X._version, _qparam_stamp(self)
+
+        def recompute():
+            q = me()
+            if q is None or X._version != x_ver or _qparam_stamp(q) != stamp:
+                return None      # input or parameters changed since: rebuild from the bins
+            return ops.fq_per_tensor(X, scale, zero_point, q.quant_min, q.quant_max, lsq_grad_factor=g)
+
+        def on_materialize():
+            q = me()
+            if q is not None:
+                q._lazy_ok = False
+            _lazy_stats["materialized"] += 1
+
+        y = LazyFakeQuant(bins, eff, self.quant_min, self.quant_max, recompute, on_materialize)
+        _lazy_stats["deferred"] += 1
+        self._tag(y)
+        y._osq_bins = (bins, y._version)
+        return y
 
     def _tag(self, y: torch.Tensor) -> torch.Tensor:
         try:
