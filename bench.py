@@ -784,7 +784,8 @@ def main():
                "d2h_bytes_per_step": runner.d2h_bytes, "steps": n_e2e, "host_issue_ms_per_step": e2e_issue_ms, "parts": parts, "pipeline_depth": args.e2e_depth, "numa_binding": numa,
                "ms_per_step": ms_e2e / n_e2e,
                "api": "hostio.HostStepRunner over quantization.Quantizer modules: 4 activation quantizers + 6 QLinear per layer, x12 "
-                      "(the same 72 sites the reference arm runs on the CPU); "
+                      "(the same 72 sites the reference arm runs on the CPU); quantizers whose output only fused QLinears consume launch "
+                      "bins-only (LazyFakeQuant: fp32 values on demand, bit-identical); "
                       "pinned H2D / D2H on side streams, double-buffered, module stack %s; CUDA-event time up to the last download" % ("eager" if args.no_graph else "replayed as a CUDA graph") + ""}
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "error": repr(ex)}
