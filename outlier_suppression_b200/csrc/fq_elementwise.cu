@@ -2,12 +2,41 @@
 //
 // HBM-bound: 8 algorithmic bytes per element (4 read + 4 written).  Grid = multiple of the SM
 // count, 128-bit streaming loads/stores, device-resident quantisation parameters (no .item()).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace osq {
 
 constexpr int kFqThreads = 256;
 constexpr int kFqUnroll = 4;  // float4s in flight per thread
+
+// Programmatic dependent launch for the activation fake-quant kernels (they sit between fused Linears on the module path):
+// launched with the programmatic-serialization attribute, each starts its CTAs while the previous kernel drains and parks them
+// at griddepcontrol.wait; it releases its own dependents at once -- a dependent that reads this kernel's output orders itself
+// with its own griddepcontrol.wait (the fused Linear does, for everything but its static weights).  Measured on the e2e module
+// stack (96 kernels per step): 3.16 ms with it, 3.12 ms without -- CTAs parked on the SMs cost more than the launch gaps they
+// save -- so it is OFF by default (OSQ_FQ_PDL=1 enables it); without the attribute the two instructions are no-ops.
+__device__ __forceinline__ void fq_pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+static cudaError_t fq_launch(void (*kernel)(KArgs...), int grid, cudaStream_t st, Args... args) {
+  static int env_pdl = -1;
+  if (env_pdl < 0) { const char* e = getenv("OSQ_FQ_PDL"); env_pdl = e ? atoi(e) : 0; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kFqThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // kCodes: 0 = no side output, 1 = int16 bins q (parity tests), 2 = uint8 bins q - qmin (the operand format of the
 // fused Linear kernel: a downstream QLinear can consume them instead of re-reading and re-quantising the fp32 tensor)
@@ -32,6 +61,7 @@ __global__ void __launch_bounds__(kFqThreads)
 fq_per_tensor_kernel(const float* __restrict__ x, float* __restrict__ y, void* __restrict__ codes,
                      int64_t n, const float* __restrict__ scale, const void* __restrict__ zp,
                      int zp_is_int32, float g, float qmin, float qmax) {
+  fq_pdl_prologue();
   const QParam p = load_qparam(scale, zp, zp_is_int32, g, qmin, qmax,
                                blockIdx.x == 0 && threadIdx.x == 0);
   const float s = p.s, z = p.z;
@@ -214,6 +244,7 @@ lsqplus_backward_kernel(const float* __restrict__ x, const float* __restrict__ d
 __global__ void __launch_bounds__(kFqThreads)
 fq_bins_only_kernel(const float4* __restrict__ x, uint32_t* __restrict__ bins, int64_t nvec, const float* __restrict__ scale,
                     const void* __restrict__ zp, int zp_is_int32, float g, float qmin, float qmax, float* __restrict__ eff) {
+  fq_pdl_prologue();
   const QParam p = load_qparam(scale, zp, zp_is_int32, g, qmin, qmax, blockIdx.x == 0 && threadIdx.x == 0);
   const float s = p.s, z = p.z, rinv = __frcp_rn(s);
   if (blockIdx.x == 0 && threadIdx.x == 0 && eff != nullptr) { eff[0] = s; eff[1] = z; }
@@ -328,11 +359,11 @@ static int launch_fq_per_tensor(const char* who, const float* x, float* y, void*
   cudaStream_t st = (cudaStream_t)stream;
   const float fmin_ = (float)qmin, fmax_ = (float)qmax;
   if (codes == nullptr)
-    fq_per_tensor_kernel<0><<<grid, kFqThreads, 0, st>>>(x, y, nullptr, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_);
+    OSQ_CUDA(fq_launch(fq_per_tensor_kernel<0>, grid, st, x, y, (void*)nullptr, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_));
   else if (code_kind == 1)
-    fq_per_tensor_kernel<1><<<grid, kFqThreads, 0, st>>>(x, y, codes, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_);
+    OSQ_CUDA(fq_launch(fq_per_tensor_kernel<1>, grid, st, x, y, codes, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_));
   else
-    fq_per_tensor_kernel<2><<<grid, kFqThreads, 0, st>>>(x, y, codes, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_);
+    OSQ_CUDA(fq_launch(fq_per_tensor_kernel<2>, grid, st, x, y, codes, n, scale, zero_point, zp_is_int32, lsq_grad_factor, fmin_, fmax_));
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }
@@ -371,9 +402,9 @@ int osq_act_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int6
   int grid = (int)(want < (int64_t)sms * 8 ? (want < 1 ? 1 : want) : (int64_t)sms * 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (bins != nullptr)
-    fq_per_tensor_kernel<2, 1><<<grid, kFqThreads, 0, st>>>(x, y, bins, n, scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax);
+    OSQ_CUDA(fq_launch(fq_per_tensor_kernel<2, 1>, grid, st, x, y, (void*)bins, n, scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax));
   else
-    fq_per_tensor_kernel<0, 1><<<grid, kFqThreads, 0, st>>>(x, y, nullptr, n, scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax);
+    OSQ_CUDA(fq_launch(fq_per_tensor_kernel<0, 1>, grid, st, x, y, (void*)nullptr, n, scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax));
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }
@@ -394,8 +425,8 @@ int osq_fq_per_tensor_bins_only_f32(const float* x, uint8_t* bins, int64_t n, co
   const int64_t per_block = (int64_t)kFqThreads * kFqUnroll;
   const int64_t want = (nvec + per_block - 1) / per_block;
   const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-  fq_bins_only_kernel<<<grid, kFqThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint32_t*>(bins), nvec,
-                                                                   scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax, eff);
+  OSQ_CUDA(fq_launch(fq_bins_only_kernel, grid, (cudaStream_t)stream, reinterpret_cast<const float4*>(x), reinterpret_cast<uint32_t*>(bins), nvec,
+                     scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax, eff));
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

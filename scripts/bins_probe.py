@@ -57,6 +57,11 @@ for K, N in ((768, 2304), (768, 768), (768, 3072), (3072, 768)):
         def fq_bins():
             j = i[0]; i[0] += 1
             ops.fq_per_tensor(acts[j % len(acts)], a_scale, a_zp, 0, 63, lsq_grad_factor=1e-4, want_bins=True)
+        def fq_only_bins():
+            j = i[0]; i[0] += 1
+            ops.fq_bins_only(acts[j % len(acts)], a_scale, a_zp, 0, 63, lsq_grad_factor=1e-4)
+        res["fq_[%d,%d]_bins_only_us" % (M, K)] = chain_time(fq_only_bins)
         res["fq_[%d,%d]_us" % (M, K)] = chain_time(fq_plain)
         res["fq_[%d,%d]_with_bins_us" % (M, K)] = chain_time(fq_bins)
 print(json.dumps(res, indent=1))
+json.dump(res, open('gpurun_out/bins_probe.json', 'w'), indent=1)
