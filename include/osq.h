@@ -75,8 +75,9 @@ int osq_residual_layernorm_fq_f32(const float* h, const float* res, const float*
  *     For an activation quantizer (fake_quant.py:107-126 / :170-209) whose output is consumed by fused QLinears alone: those read
  *     the bins (A = NULL, a_codes = bins) and the dequantised tensor of util_quant.py:14 is never needed.  `eff` (device float[2],
  *     optional) receives the effective (scale, zero_point) the launch used -- after LSQ+'s sanitise / grad_scale -- for
- *     osq_dequant_bins_f32.  n % 4 == 0, x 16-byte aligned. */
-int osq_fq_per_tensor_bins_only_f32(const float* x, uint8_t* bins, int64_t n, const float* scale, const void* zero_point,
+ *     osq_dequant_bins_f32.  act = 1 applies GELU (erf form, as K1c) in front: quant_bert.py:278-280 feeding output.dense alone.
+ *     n % 4 == 0, x 16-byte aligned. */
+int osq_fq_per_tensor_bins_only_f32(const float* x, uint8_t* bins, int64_t n, int act, const float* scale, const void* zero_point,
                                     int zp_is_int32, float lsq_grad_factor, int qmin, int qmax, float* eff, void* stream);
 
 /*     the fp32 tensor K1 would have written for those bins: y = (bin + qmin - z) * s with (s, z) = eff (util_quant.py:14).

@@ -80,7 +80,7 @@ def _declare(lib):
         "osq_fq_per_tensor_bins_f32": [vp, vp, vp, i64, vp, vp, i32, f32, i32, i32, vp],
         "osq_act_fq_per_tensor_bins_f32": [vp, vp, vp, i64, i32, vp, vp, i32, f32, i32, i32, vp],
         "osq_fq_per_channel_f32": [vp, vp, vp, i64, i64, vp, vp, i32, i32, vp],
-        "osq_fq_per_tensor_bins_only_f32": [vp, vp, i64, vp, vp, i32, f32, i32, i32, vp, vp],
+        "osq_fq_per_tensor_bins_only_f32": [vp, vp, i64, i32, vp, vp, i32, f32, i32, i32, vp, vp],
         "osq_dequant_bins_f32": [vp, vp, i32, i32, vp, i64, vp],
         "osq_residual_layernorm_fq_f32": [vp, vp, vp, vp, vp, f32, i64, i64, vp, vp, i32, f32, i32, i32, vp, vp, vp, vp],
         "osq_minmax_masked_f32": [vp, C.POINTER(Tokens), vp, i32, vp, C.POINTER(StatEpilogue), vp, vp],

@@ -241,6 +241,7 @@ lsqplus_backward_kernel(const float* __restrict__ x, const float* __restrict__ d
 // K1d  bins only: the per-tensor fake-quantize of K1 / K1b without its fp32 output -- 5 bytes per element instead of 9.  For a
 // quantizer whose output is consumed by fused QLinears alone (the dequantised tensor is then never read); `eff` receives the
 // effective (scale, zero point) the launch used, so that osq_dequant_bins_f32 can rebuild the fp32 tensor later.
+template <int kAct>
 __global__ void __launch_bounds__(kFqThreads)
 fq_bins_only_kernel(const float4* __restrict__ x, uint32_t* __restrict__ bins, int64_t nvec, const float* __restrict__ scale,
                     const void* __restrict__ zp, int zp_is_int32, float g, float qmin, float qmax, float* __restrict__ eff) {
@@ -263,13 +264,14 @@ fq_bins_only_kernel(const float4* __restrict__ x, uint32_t* __restrict__ bins, i
       if (i < nvec) {
         float q0, q1, q2, q3;
         bool k0, k1, k2, k3;
-        fq_elem_fast(v[u].x, s, rinv, z, qmin, qmax, q0, k0);
-        fq_elem_fast(v[u].y, s, rinv, z, qmin, qmax, q1, k1);
-        fq_elem_fast(v[u].z, s, rinv, z, qmin, qmax, q2, k2);
-        fq_elem_fast(v[u].w, s, rinv, z, qmin, qmax, q3, k3);
+        const float a0 = act_in<kAct>(v[u].x), a1 = act_in<kAct>(v[u].y), a2 = act_in<kAct>(v[u].z), a3 = act_in<kAct>(v[u].w);
+        fq_elem_fast(a0, s, rinv, z, qmin, qmax, q0, k0);
+        fq_elem_fast(a1, s, rinv, z, qmin, qmax, q1, k1);
+        fq_elem_fast(a2, s, rinv, z, qmin, qmax, q2, k2);
+        fq_elem_fast(a3, s, rinv, z, qmin, qmax, q3, k3);
         if (k0 | k1 | k2 | k3) {
-          fq_elem(v[u].x, s, z, qmin, qmax, q0); fq_elem(v[u].y, s, z, qmin, qmax, q1);
-          fq_elem(v[u].z, s, z, qmin, qmax, q2); fq_elem(v[u].w, s, z, qmin, qmax, q3);
+          fq_elem(a0, s, z, qmin, qmax, q0); fq_elem(a1, s, z, qmin, qmax, q1);
+          fq_elem(a2, s, z, qmin, qmax, q2); fq_elem(a3, s, z, qmin, qmax, q3);
         }
         bins[i] = (uint32_t)__float2int_rn(q0 - qmin) | ((uint32_t)__float2int_rn(q1 - qmin) << 8) | ((uint32_t)__float2int_rn(q2 - qmin) << 16) |
                   ((uint32_t)__float2int_rn(q3 - qmin) << 24);
@@ -409,12 +411,13 @@ int osq_act_fq_per_tensor_bins_f32(const float* x, float* y, uint8_t* bins, int6
   return OSQ_OK;
 }
 
-int osq_fq_per_tensor_bins_only_f32(const float* x, uint8_t* bins, int64_t n, const float* scale, const void* zero_point,
+int osq_fq_per_tensor_bins_only_f32(const float* x, uint8_t* bins, int64_t n, int act, const float* scale, const void* zero_point,
                                     int zp_is_int32, float lsq_grad_factor, int qmin, int qmax, float* eff, void* stream) {
   using namespace osq;
   OSQ_CHECK_ARG(n >= 0, "osq_fq_per_tensor_bins_only_f32: n < 0");
   if (n == 0) return OSQ_OK;
   OSQ_CHECK_ARG(x && bins && scale && zero_point, "osq_fq_per_tensor_bins_only_f32: null pointer");
+  OSQ_CHECK_ARG(act == 0 || act == 1, "osq_fq_per_tensor_bins_only_f32: act must be 0 (none) or 1 (GELU, erf form)");
   OSQ_CHECK_ARG(qmin < qmax && qmax - qmin <= 255, "osq_fq_per_tensor_bins_only_f32: uint8 bins need at most 8 bits");
   OSQ_CHECK_ARG(!(lsq_grad_factor > 0.f && zp_is_int32), "osq_fq_per_tensor_bins_only_f32: LSQ+ needs a float zero_point");
   OSQ_CHECK_ARG(n % 4 == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)bins) & 3) == 0,
@@ -425,8 +428,12 @@ int osq_fq_per_tensor_bins_only_f32(const float* x, uint8_t* bins, int64_t n, co
   const int64_t per_block = (int64_t)kFqThreads * kFqUnroll;
   const int64_t want = (nvec + per_block - 1) / per_block;
   const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-  OSQ_CUDA(fq_launch(fq_bins_only_kernel, grid, (cudaStream_t)stream, reinterpret_cast<const float4*>(x), reinterpret_cast<uint32_t*>(bins), nvec,
-                     scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax, eff));
+  if (act == 1)
+    OSQ_CUDA(fq_launch(fq_bins_only_kernel<1>, grid, (cudaStream_t)stream, reinterpret_cast<const float4*>(x), reinterpret_cast<uint32_t*>(bins), nvec,
+                       scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax, eff));
+  else
+    OSQ_CUDA(fq_launch(fq_bins_only_kernel<0>, grid, (cudaStream_t)stream, reinterpret_cast<const float4*>(x), reinterpret_cast<uint32_t*>(bins), nvec,
+                       scale, zero_point, zp_is_int32, lsq_grad_factor, (float)qmin, (float)qmax, eff));
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

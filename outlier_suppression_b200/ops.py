@@ -204,7 +204,8 @@ def attn_context_fq(probs: torch.Tensor, v: torch.Tensor, pq: dict, vq: dict, oq
     return (out, bins) if want_bins else out
 
 
-def fq_bins_only(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int, lsq_grad_factor: float = 0.0):
+def fq_bins_only(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int, lsq_grad_factor: float = 0.0,
+                 act: Optional[str] = None):
     """K1d: the uint8 bins of the per-tensor fake-quantize without its fp32 output (5 B / element).  Returns (bins, eff) with
     eff = device float[2] holding the effective (scale, zero_point) of the launch, for ``dequant_bins``."""
     _require_cuda(x, scale, zero_point)
@@ -215,7 +216,8 @@ def fq_bins_only(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor,
     bins = torch.empty_like(x, dtype=torch.uint8)
     eff = torch.empty(2, dtype=torch.float32, device=x.device)
     if x.numel() > 0:
-        check(_lib.load().osq_fq_per_tensor_bins_only_f32(x.data_ptr(), bins.data_ptr(), x.numel(), scale.data_ptr(), zero_point.data_ptr(),
+        check(_lib.load().osq_fq_per_tensor_bins_only_f32(x.data_ptr(), bins.data_ptr(), x.numel(), {None: 0, "none": 0, "gelu": 1}[act],
+                                                          scale.data_ptr(), zero_point.data_ptr(),
                                                           int(zero_point.dtype == torch.int32), float(lsq_grad_factor), int(qmin), int(qmax),
                                                           eff.data_ptr(), _stream()), "osq_fq_per_tensor_bins_only_f32")
     return bins, eff

@@ -206,16 +206,17 @@ class QuantizeBase(nn.Module):
     # cleared the first time a deferred output of this quantizer had to be materialised (a non-Linear consumer exists)
     _lazy_ok = True
 
-    def _fq_deferred(self, X, scale, zero_point, g):
-        """bins-only launch; the fp32 values exist only if somebody other than a fused QLinear asks for them (LazyFakeQuant)"""
-        bins, eff = ops.fq_bins_only(X, scale, zero_point, self.quant_min, self.quant_max, lsq_grad_factor=g)
+    def _fq_deferred(self, X, scale, zero_point, g, act=None):
+        """bins-only launch; the fp32 values exist only if somebody other than a fused QLinear asks for them (LazyFakeQuant).
+        ``act="gelu"``: the activation in front of the quantizer is part of the launch (quant_bert.py:278-280)."""
+        bins, eff = ops.fq_bins_only(X, scale, zero_point, self.quant_min, self.quant_max, lsq_grad_factor=g, act=act)
         me, x_ver, stamp = weakref.ref(self), X._version, _qparam_stamp(self)
 
         def recompute():
             q = me()
             if q is None or X._version != x_ver or _qparam_stamp(q) != stamp:
                 return None      # input or parameters changed since: rebuild from the bins
-            return ops.fq_per_tensor(X, scale, zero_point, q.quant_min, q.quant_max, lsq_grad_factor=g)
+            return ops.fq_per_tensor(X, scale, zero_point, q.quant_min, q.quant_max, lsq_grad_factor=g, act=act)
 
         def on_materialize():
             q = me()

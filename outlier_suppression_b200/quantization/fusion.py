@@ -95,6 +95,10 @@ def _fused_forward(self, hidden_states, observation_mask=None):
         n_out = y.numel()
         g_out = (1.0 / (n_out * q.quant_max) ** 0.5 if q.use_grad_scaling else 1.0) if isinstance(q, LSQPlusFakeQuantize) else 0.0
         want_bins = q._emit_bins and y.shape[-1] % 128 == 0
+        if (want_bins and q._lazy_ok and y.is_contiguous() and y.data_ptr() % 16 == 0 and os.environ.get("OSQ_DISABLE_LAZY_FQ") != "1"):
+            # the block's output normally feeds output.dense alone: bins only (5 B / element instead of 9), fp32 values on demand
+            stats["epilogue_fused"] = stats.get("epilogue_fused", 0) + 1
+            return q._fq_deferred(y, q.scale.detach(), q.zero_point.detach(), g_out, act="gelu")
         r = ops.fq_per_tensor(y, q.scale.detach(), q.zero_point.detach(), q.quant_min, q.quant_max, lsq_grad_factor=g_out,
                               want_bins=want_bins, act="gelu")
         stats["epilogue_fused"] = stats.get("epilogue_fused", 0) + 1

@@ -40,6 +40,8 @@ for act in (None, "gelu"):
                                            out_q=dict(scale=osc, zp=ozp, qmin=0, qmax=63, g=g_out, act=act, bins=False)))
 res["gelu_us"] = timeit(lambda i: torch.nn.functional.gelu(ys[i % 2]))
 res["gelu+fq_bins_one_pass_us"] = timeit(lambda i: ops.fq_per_tensor(ys[i % 2], osc, ozp, 0, 63, lsq_grad_factor=g_out, want_bins=True, act="gelu"))
+res["gelu+fq_bins_only_us"] = timeit(lambda i: ops.fq_bins_only(ys[i % 2], osc, ozp, 0, 63, lsq_grad_factor=g_out, act="gelu"))
+res["fq_bins_only_us"] = timeit(lambda i: ops.fq_bins_only(ys[i % 2], osc, ozp, 0, 63, lsq_grad_factor=g_out))
 res["fq_nobins_us"] = timeit(lambda i: ops.fq_per_tensor(ys[i % 2], osc, ozp, 0, 63, lsq_grad_factor=g_out))
 res["fq_bins_us"] = timeit(lambda i: ops.fq_per_tensor(ys[i % 2], osc, ozp, 0, 63, lsq_grad_factor=g_out, want_bins=True))
 print(json.dumps(res, indent=1))

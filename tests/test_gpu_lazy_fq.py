@@ -28,6 +28,10 @@ def test_bins_only_and_dequant_match_k1(bits, lsq):
     b2, eff = ops.fq_bins_only(x.cuda(), sc.cuda(), zp, qmin, qmax, lsq_grad_factor=gf)
     assert torch.equal(b2, bins)
     assert torch.equal(ops.dequant_bins(b2, eff, qmin, qmax), y)
+    # GELU in front (K1c), bins only
+    yg, bg = ops.fq_per_tensor(x.cuda(), sc.cuda(), zp, qmin, qmax, lsq_grad_factor=gf, want_bins=True, act="gelu")
+    b3, eff3 = ops.fq_bins_only(x.cuda(), sc.cuda(), zp, qmin, qmax, lsq_grad_factor=gf, act="gelu")
+    assert torch.equal(b3, bg) and torch.equal(ops.dequant_bins(b3, eff3, qmin, qmax), yg)
     want = O.fq_lsqplus_per_tensor(x, sc.clone(), z.clone(), qmin, qmax) if lsq else O.fq_per_tensor(x, float(sc), int(z), qmin, qmax)
     assert torch.equal(y.cpu(), want)
 
