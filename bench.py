@@ -362,18 +362,21 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
     # (cnt = 0) is part of the captured replay launch, exactly like the eager pass above.
     ms_eager_exchange, issue_mode = ms, "per-batch launches replayed as one CUDA graph; collective + replay issued eagerly"
     if graph[0] is not None and table.hdl is None and os.environ.get("OSQ_BENCH_SWEEP_FULLGRAPH", "1") == "1":
+        ctl_graph, full, err = graph[0], None, None
         try:
-            ctl_graph = graph[0]
             graph[0] = None                      # capture the eager form of the batch launches inside the pass
             full = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            if dist is not None:
-                dist.barrier()
             with torch.cuda.graph(full):
                 one_pass()
-            graph[0] = ctl_graph
-            torch.cuda.synchronize()
-
+        except Exception as ex:  # pragma: no cover  (capture of the collective unsupported: the eager exchange stands)
+            full, err = None, repr(ex)
+        graph[0] = ctl_graph
+        torch.cuda.synchronize()
+        ok = torch.tensor([1 if full is not None else 0], device=device)
+        if dist is not None:                     # every rank takes the same branch below (the timed loop contains barriers)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 1:
             def full_pass(timed=False):
                 if timed:
                     e[0].record()
@@ -399,9 +402,10 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
             q.observer.cnt = NB
             if ms_full < ms:
                 ms, issue_mode = ms_full, "the whole pass (table reset, observer launches, all-reduce, replay) replayed as ONE CUDA graph"
-        except Exception as ex:  # pragma: no cover  (capture of the collective unsupported: the eager exchange stands)
-            graph[0] = graph[0] or ctl_graph
-            issue_mode += " (full-pass capture failed: %r)" % (ex,)
+        else:
+            issue_mode += " (full-pass capture unavailable on some rank: %s)" % (err,)
+            one_pass()                           # leave the observer in the state of a completed eager pass
+            torch.cuda.synchronize()
     state = [float(q.observer.min_val), float(q.observer.max_val), float(q.scale.data), float(q.zero_point.data)]
     same_on_all_ranks = True
     if dist is not None:

@@ -252,7 +252,9 @@ attn_context_kernel(const ContextParams p) {
   int acc[D / 8][4];
 #pragma unroll
   for (int nt = 0; nt < D / 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0; }
-  int prow[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // lanes 0 and 16: running bin sums of rows 2i + lane / 16 of this warp
+  // row sums of the probability bins (zero-point correction) come out of the tensor core: one extra n-tile whose B fragment is all
+  // ones accumulates sum_k p[row][k] in every column -- no cross-lane reduction in the conversion loop
+  int acc1[4] = {0, 0, 0, 0};
   int vcol = 0;                              // threads < D: running bin sum of channel tid
   const bool warp_has_rows = q0 + warp * 16 < p.sq;
   for (int c0 = 0; c0 < p.sk; c0 += KC) {
@@ -333,10 +335,6 @@ attn_context_kernel(const ContextParams p) {
         const int r2 = half * 4 + i;
         if (!(rows_full && key_ok)) { if (!(key_ok && q0 + warp * 16 + 2 * r2 + prow_l < p.sq)) w[i] = 0; }
         *reinterpret_cast<uint32_t*>(lane_pc + (2 * r2) * kRowP) = w[i];
-        int s = bytesum(w[i], 0);
-        s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 1);
-        prow[r2] += s;
       }
     };
     float4 xa[4], xb[4];
@@ -360,20 +358,18 @@ attn_context_kernel(const ContextParams p) {
           mma_u8(acc[nt], a0, a1, a2, a3, b0, b1);
           mma_u8(acc[nt + 1], a0, a1, a2, a3, b2, b3);
         }
+        mma_u8(acc1, a0, a1, a2, a3, 0x01010101u, 0x01010101u);
       }
       __syncwarp();   // the fragments are consumed before the next step overwrites this warp's probability bins
     }
   }
   // ---- epilogue
-  if ((lane & 15) == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) psum[warp * 16 + 2 * i + (lane >> 4)] = prow[i];
-  }
   if (tid < D) vsum[tid] = vcol;
   __syncthreads();
   const int kconst = p.sk * zcp * zcv;
   float* my_stage = stage + warp * 16 * kStage;
-  const int ps_lo = psum[warp * 16 + g], ps_hi = psum[warp * 16 + g + 8];
+  const int ps_lo = acc1[0], ps_hi = acc1[2];   // rows g and g + 8 of this warp (every column of the ones tile holds the row sum)
+  (void)psum;
 #pragma unroll
   for (int nt = 0; nt < D / 8; ++nt) {
     const int c = nt * 8 + 2 * t;

@@ -146,7 +146,8 @@ def fuse_ffn_activation(model) -> int:
 # ---------------------------------------------------------------------------------------------------------------------------
 # dense -> dropout -> GammaResidual -> LayerNorm -> quantizer  (quant_bert.py:211-217, :296-303)
 # ---------------------------------------------------------------------------------------------------------------------------
-def _ln_fusable(mod, h, input_tensor):
+def _ln_fusable(mod, hidden_states, input_tensor):
+    """Decided BEFORE anything runs (from shapes and module state), so that the unfused case is the module's own forward."""
     if os.environ.get("OSQ_DISABLE_LN_FUSION") == "1" or torch.is_grad_enabled():
         return None
     if getattr(mod, "backend", "academic") == "tensorrt":      # an extra quantizer sits between the dense and the residual
@@ -161,36 +162,32 @@ def _ln_fusable(mod, h, input_tensor):
         return None
     if q.fake_quant_enabled != 1 or q.observer_enabled != 0 or q.ch_axis != -1:
         return None
-    H = h.shape[-1]
-    if tuple(inner.normalized_shape) != (H,) or H % 4 != 0:
+    H = getattr(mod.dense, "out_features", None)
+    if H is None or tuple(inner.normalized_shape) != (H,) or H % 4 != 0:
         return None
-    if not (h.is_cuda and h.dtype == torch.float32 and h.is_contiguous() and input_tensor.shape == h.shape
+    split_bias = getattr(lnm, "bias", None)                    # QuantizedSplitLayerNorm: non-affine LayerNorm + beta / gamma
+    if split_bias is not None and (inner.weight is not None or inner.bias is not None):
+        return None
+    if not (hidden_states.is_cuda and tuple(input_tensor.shape) == tuple(hidden_states.shape[:-1]) + (H,)
             and input_tensor.dtype == torch.float32 and input_tensor.is_contiguous()):
         return None
     return lnm, inner, q
 
 
 def _fused_ln_forward(self, hidden_states, input_tensor, observation_mask=None):
-    # the dense is an ordinary module call (fused fake-quant + Linear when its producer is tagged)
-    h = self.dense(hidden_states)
-    trio = _ln_fusable(self, h, input_tensor)
+    trio = _ln_fusable(self, hidden_states, input_tensor)
     if trio is None:
-        # reference order from here on (quant_bert.py:212-217)
-        h = self.dropout(h)
-        if getattr(self, "backend", "academic") == "tensorrt":
-            h = self.output_post_act_fake_quantize(h, observation_mask, 1)
-        h = self.before_LayerNorm_residual(input_tensor, h)
-        return self.LayerNorm(h, observation_mask)
+        return self._osq_unfused_ln_forward(hidden_states, input_tensor, observation_mask=observation_mask)
     lnm, inner, q = trio
+    h = self.dense(hidden_states)           # an ordinary module call (fused fake-quant + Linear when its producer is tagged)
+    if not (h.dtype == torch.float32 and h.is_contiguous()):
+        h = h.float().contiguous()
     res_mod = self.before_LayerNorm_residual
     gamma = res_mod.gamma.detach() if getattr(res_mod, "mul_gamma", False) else None
     weight = inner.weight.detach() if inner.weight is not None else None
     bias = inner.bias.detach() if inner.bias is not None else None
-    split_bias = getattr(lnm, "bias", None)                    # QuantizedSplitLayerNorm: non-affine LayerNorm + beta / gamma
+    split_bias = getattr(lnm, "bias", None)
     if split_bias is not None:
-        if bias is not None or weight is not None:
-            h = self.before_LayerNorm_residual(input_tensor, h)
-            return self.LayerNorm(h, observation_mask)
         bias = split_bias.detach()
     g = (1.0 / (h.numel() * q.quant_max) ** 0.5 if q.use_grad_scaling else 1.0) if isinstance(q, LSQPlusFakeQuantize) else 0.0
     want_bins = q._emit_bins and h.shape[-1] % 128 == 0 and q.quant_max - q.quant_min <= 255
