@@ -361,7 +361,7 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
     # graph: one host launch per pass instead of four (NCCL collectives are capturable).  The running-average restart
     # (cnt = 0) is part of the captured replay launch, exactly like the eager pass above.
     ms_eager_exchange, issue_mode = ms, "per-batch launches replayed as one CUDA graph; collective + replay issued eagerly"
-    if graph[0] is not None and table.hdl is None and os.environ.get("OSQ_BENCH_SWEEP_FULLGRAPH", "1") == "1":
+    if graph[0] is not None and os.environ.get("OSQ_BENCH_SWEEP_FULLGRAPH", "1") == "1":
         ctl_graph, full, err = graph[0], None, None
         try:
             graph[0] = None                      # capture the eager form of the batch launches inside the pass
@@ -429,10 +429,11 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
             "valid_token_fraction": valid_tokens / (OB * OS),
             "token_minmax_kernel": {"ms_per_slab": k_ms, "gbs_valid": valid_bytes / (k_ms * 1e-3) / 1e9,
                                     "frac_of_hbm_peak": valid_bytes / (k_ms * 1e-3) / 1e9 / peak},
-            "launches_per_batch": 2, "exchange": ("cross-rank barrier + peer loads over NVLink inside the replay launch (CUDA symmetric memory, no collective library)"
+            "launches_per_batch": 2, "exchange": ("inside the replay launch over NVLink peer memory: publish own slots, one remote flag store per peer, wait for every peer, peer loads (CUDA symmetric memory, no collective library, no host-side barrier)"
                                                 if table.hdl is not None else ("one NCCL all_reduce(SUM) of the slot table" if dist is not None else "none (1 GPU)")),
             "issue": "eager" if graph[0] is None else issue_mode, "ms_per_pass_eager_exchange": ms_eager_exchange,
-            "collective": "one all_reduce(SUM) of the [n_obs, 8, 2] slot table + one replay launch",
+            "collective": ("none: exchange fused into the replay launch" if table.hdl is not None else "one all_reduce(SUM) of the [n_obs, 8, 2] slot table + one replay launch"),
+            "exchange_error_flag": (int(table.err_flag) if table.hdl is not None else None),
             "state": state, "state_identical_on_all_ranks": same_on_all_ranks}
 
 

@@ -215,6 +215,17 @@ int osq_replay_average_f32(const float* table, int n_obs, int n_batches, int cnt
 int osq_replay_average_peer_f32(const float* const* peer_tables, int world, int n_obs, int n_batches, int cnt0,
                                 const osq_replay_target_t* targets, void* stream);
 
+/* Exchange AND replay as one launch over peer memory (NVLink / NVSwitch), no collective library and no host-side barrier:
+ * `regions[r]` (device array of `world` pointers) is rank r's symmetric-memory region, mapped into this process, laid out as
+ * float slots[2][n_obs * n_batches * 2] followed by uint32 flags[world].  The kernel publishes this rank's slots (batches b with
+ * b mod world == rank) from `local_table` into generation (pass & 1) of its own region, signals every peer's flags[rank] = pass
+ * with a remote release-store, waits (acquire loads of its own flags) until every rank has signalled, then runs the replay of
+ * osq_replay_average_f32 with slot (i, b) loaded from rank b mod world's region.  pass = *pass_counter + 1, written back by the
+ * kernel (graph-replayable); the two generations remove the need for a trailing barrier.  A peer that does not signal within
+ * OSQ_EXCHANGE_TIMEOUT_MS (default 5000) makes the launch store `pass` to *err_flag and return without touching the targets. */
+int osq_replay_exchange_f32(const float* local_table, float* const* regions, int rank, int world, int n_obs, int n_batches, int cnt0,
+                            const osq_replay_target_t* targets, uint32_t* pass_counter, uint32_t* err_flag, void* stream);
+
 /* per-row min/max of a [rows, cols] matrix with the running-extrema update of
  * MinMaxObserver(ch_axis=0) (observer.py:141-144) and per-row calculate_qparams.
  * state_min/state_max [rows] are updated in place (first = 1 overwrites them). */

@@ -1130,6 +1130,76 @@ replay_average_kernel(const float* __restrict__ table, const float* const* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// Exchange + replay as ONE launch over NVLink peer memory (no collective library, no host-side barrier).
+//
+// Every rank owns a symmetric-memory region, mapped by all ranks:  float slots[2][n_obs * n_batches * 2]  (two generations,
+// selected by the parity of the pass number), then  uint32 flags[world].  The launch
+//   1. publishes this rank's slots (batches b with b mod world == rank) from its private slot table into its own region,
+//      generation `pass & 1`                                                     (plain stores + __threadfence_system)
+//   2. signals every peer:  peer.flags[rank] = pass                               (one remote release-store per peer)
+//   3. waits until flags[r] >= pass for every r                                   (acquire loads of LOCAL memory)
+//   4. replays observer.py:194-202 in batch order for every observer, loading slot (i, b) from rank b mod world's region.
+// Two generations make a trailing barrier unnecessary: generation g is rewritten in pass p + 2, which a rank can only reach
+// after every peer has signalled pass p + 1, i.e. after every peer has finished reading pass p.  `pass` lives in device memory
+// (pass_counter) and is advanced by the kernel, so a CUDA graph can replay the launch.  A peer that never signals (a rank
+// died) is given `timeout_ns`, then the launch records the failure in err_flag and returns without touching the targets.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+__global__ void __launch_bounds__(256)
+replay_exchange_kernel(const float* __restrict__ local_table, float* const* __restrict__ regions, int rank, int world, int n_obs, int n_batches,
+                       int cnt0, const osq_replay_target_t* __restrict__ tgt, uint32_t* __restrict__ pass_counter, uint32_t* __restrict__ err_flag,
+                       long long timeout_ns) {
+  __shared__ int s_fail;
+  const int tid = threadIdx.x;
+  const uint32_t pass = *pass_counter + 1u;
+  const int n_f = n_obs * n_batches * 2;
+  float* mine = regions[rank] + (size_t)(pass & 1u) * n_f;
+  for (int j = tid; j < n_obs * n_batches; j += blockDim.x)
+    if ((j % n_batches) % world == rank) {
+      mine[2 * j] = local_table[2 * j];
+      mine[2 * j + 1] = local_table[2 * j + 1];
+    }
+  if (tid == 0) s_fail = 0;
+  __threadfence_system();
+  __syncthreads();
+  if (tid < world) {
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(regions[tid] + 2 * (size_t)n_f) + rank, pass);
+    const uint32_t* my_flag = reinterpret_cast<const uint32_t*>(regions[rank] + 2 * (size_t)n_f) + tid;
+    const long long t0 = obs_gtimer();
+    while ((int32_t)(ld_acquire_sys_u32(my_flag) - pass) < 0) {
+      __nanosleep(100);
+      if (obs_gtimer() - t0 > timeout_ns) { s_fail = 1; break; }
+    }
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) { *err_flag = pass; *pass_counter = pass; }
+    return;
+  }
+  for (int i = tid; i < n_obs; i += blockDim.x) {
+    osq_replay_target_t t = tgt[i];
+    osq_stat_epilogue_t e;
+    e.mode = 1;
+    e.state_min = t.state_min;
+    e.state_max = t.state_max;
+    e.scale_out = nullptr;   // qparams once, after the last batch
+    e.zp_out = nullptr;
+    e.zp_out_is_int32 = t.zp_out_is_int32;
+    e.qmin = t.qmin; e.qmax = t.qmax; e.symmetric = t.symmetric;
+    for (int b = 0; b < n_batches; ++b) {
+      e.cnt = cnt0 + b;
+      if (b == n_batches - 1) { e.scale_out = t.scale_out; e.zp_out = t.zp_out; }
+      const float* src = regions[b % world] + (size_t)(pass & 1u) * n_f;
+      const float2 v = __ldcv(reinterpret_cast<const float2*>(src + ((int64_t)i * n_batches + b) * 2));   // never a cached copy
+      stat_epilogue(e, v.x, v.y);
+    }
+  }
+  if (tid == 0) *pass_counter = pass;
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-row min/max + running extrema + per-row qparams (weights, MinMaxObserver ch_axis=0)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -1351,6 +1421,20 @@ int osq_replay_average_peer_f32(const float* const* peer_tables, int world, int 
   using namespace osq;
   OSQ_CHECK_ARG(peer_tables && targets && world >= 1 && n_obs > 0 && n_batches > 0 && cnt0 >= 0, "osq_replay_average_peer_f32: bad argument");
   replay_average_kernel<<<(n_obs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nullptr, peer_tables, world, n_obs, n_batches, cnt0, targets);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_replay_exchange_f32(const float* local_table, float* const* regions, int rank, int world, int n_obs, int n_batches, int cnt0,
+                            const osq_replay_target_t* targets, uint32_t* pass_counter, uint32_t* err_flag, void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(local_table && regions && targets && pass_counter && err_flag, "osq_replay_exchange_f32: null pointer");
+  OSQ_CHECK_ARG(world >= 1 && world <= 256 && rank >= 0 && rank < world && n_obs > 0 && n_batches > 0 && cnt0 >= 0,
+                "osq_replay_exchange_f32: bad argument");
+  static long long timeout_ns = -1;
+  if (timeout_ns < 0) { const char* e = getenv("OSQ_EXCHANGE_TIMEOUT_MS"); timeout_ns = (long long)(e ? atoi(e) : 5000) * 1000000ll; }
+  replay_exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(local_table, regions, rank, world, n_obs, n_batches, cnt0, targets, pass_counter,
+                                                            err_flag, timeout_ns);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

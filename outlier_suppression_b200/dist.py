@@ -21,9 +21,9 @@ class SlotTable:
     """[n_obs, n_batches, 2] fp32 per-batch statistics + the packed collective + the replay."""
 
     def __init__(self, n_obs: int, n_batches: int, device="cpu", peer: bool = False, group=None):
-        """peer=True (CUDA, NCCL world > 1): the table lives in CUDA symmetric memory, every rank maps every other rank's
-        table over NVLink, and the exchange is a cross-rank barrier + peer loads inside the replay kernel instead of an
-        all-reduce (falls back to the all-reduce if symmetric memory cannot be set up)."""
+        """peer=True (CUDA, NCCL world > 1): every rank owns a CUDA symmetric-memory region mapped by all ranks over NVLink, and the
+        exchange happens INSIDE the replay launch -- publish own slots, one remote flag store per peer, wait for every peer's
+        flag, peer loads -- instead of an all-reduce (falls back to the all-reduce if symmetric memory cannot be set up)."""
         self.n_obs, self.n_batches = n_obs, n_batches
         self.hdl = self.peer_ptrs = None
         self.world = 1
@@ -31,15 +31,23 @@ class SlotTable:
         if peer and dev.type == "cuda" and tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1:
             try:
                 import torch.distributed._symmetric_memory as symm
-                flat = symm.empty(n_obs * n_batches * 2, dtype=torch.float32, device=dev)
+                self.world = tdist.get_world_size(group)
+                self.rank = tdist.get_rank(group)
+                n_f = n_obs * n_batches * 2
+                # this rank's region: two generations of the slot table + one flag per rank (see osq_replay_exchange_f32)
+                flat = symm.empty(2 * n_f + self.world, dtype=torch.float32, device=dev)
                 flat.zero_()
                 self.hdl = symm.rendezvous(flat, group if group is not None else tdist.group.WORLD)
-                self.buf = flat.view(n_obs, n_batches, 2)
-                self.world = tdist.get_world_size(group)
+                self.region = flat
                 self.peer_ptrs = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+                self.pass_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+                self.err_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                self.hdl.barrier(channel=0)          # once: every region is zeroed before anybody signals into it
+                self.buf = torch.zeros(n_obs, n_batches, 2, dtype=torch.float32, device=dev)   # private: the observers write here
                 return
             except Exception as ex:  # pragma: no cover  (no P2P / fabric support: the collective path is always there)
                 self.hdl = self.peer_ptrs = None
+                self.world = 1
                 self.peer_error = repr(ex)
         self.buf = torch.zeros(n_obs, n_batches, 2, dtype=torch.float32, device=device)
 
@@ -126,7 +134,7 @@ def sharded_calibration(model, n_batches: int, group=None, table: Optional[SlotT
         table = SlotTable(len(observers), n_batches, device)
     else:
         assert table.n_obs == len(observers) and table.n_batches == n_batches and table.buf.device == torch.device(device)
-        if table.hdl is None:   # the all-reduce sums: slots of other ranks must be zero.  Peer tables are read slot by slot.
+        if table.hdl is None:   # the all-reduce sums: slots of other ranks must be zero.  The peer exchange publishes own slots only.
             table.buf.zero_()
     ctl = _Controller(table, observers, owners)
     for i, o in enumerate(observers):
@@ -140,16 +148,15 @@ def sharded_calibration(model, n_batches: int, group=None, table: Optional[SlotT
         return
     cnt0 = observers[0].cnt
     if table.hdl is not None:
-        # no collective: a cross-rank barrier on the stream (every rank's slots are written), one replay launch that loads
-        # each slot from its owner's table over NVLink, a second barrier before anybody may rewrite its table
+        # no collective and no host-side barrier: ONE launch publishes this rank's slots, signals and awaits its peers over NVLink
+        # and replays the recurrence with every slot loaded from its owner's region (osq_replay_exchange_f32)
         entries = []
         for o, q in zip(observers, owners):
             o._ensure_scalar_state(device)
             s_out, z_out = q._per_tensor_qparam_targets()
             entries.append((o.min_val, o.max_val, s_out, z_out, o.quant_min, o.quant_max, o.symmetric))
-        table.hdl.barrier(channel=0)
-        ops.replay_average_peer(table.peer_ptrs, table.world, table.n_obs, table.n_batches, cnt0, _targets(table, entries, device))
-        table.hdl.barrier(channel=1)
+        ops.replay_exchange(table.buf, table.peer_ptrs, table.rank, table.world, table.n_obs, table.n_batches, cnt0,
+                            _targets(table, entries, device), table.pass_counter, table.err_flag)
         for o, q in zip(observers, owners):
             o.cnt = cnt0 + n_batches
             q.qparam_epoch += 1

@@ -461,6 +461,18 @@ def replay_average_peer(peer_ptrs: torch.Tensor, world: int, n_obs: int, n_batch
                                                   targets.data_ptr(), _stream()), "osq_replay_average_peer_f32")
 
 
+def replay_exchange(local_table: torch.Tensor, region_ptrs: torch.Tensor, rank: int, world: int, n_obs: int, n_batches: int, cnt0: int,
+                    targets: torch.Tensor, pass_counter: torch.Tensor, err_flag: torch.Tensor) -> None:
+    """Exchange + replay in one launch over peer memory (osq_replay_exchange_f32): publish this rank's slots into its symmetric
+    region, signal every peer, wait for every peer, replay with each slot loaded from its owner's region."""
+    _require_cuda(local_table, region_ptrs, targets, pass_counter, err_flag)
+    assert region_ptrs.dtype == torch.int64 and region_ptrs.numel() == world and local_table.dtype == torch.float32
+    assert pass_counter.dtype == torch.int32 and err_flag.dtype == torch.int32
+    check(_lib.load().osq_replay_exchange_f32(local_table.data_ptr(), region_ptrs.data_ptr(), int(rank), int(world), int(n_obs), int(n_batches),
+                                              int(cnt0), targets.data_ptr(), pass_counter.data_ptr(), err_flag.data_ptr(), _stream()),
+          "osq_replay_exchange_f32")
+
+
 def rowwise_minmax_qparams(w, first, state_min, state_max, scale_out, zp_out, qmin, qmax, symmetric):
     """MinMaxObserver(ch_axis=0) + calculate_qparams on a [N, K] weight in one launch."""
     _require_cuda(w, state_min, state_max)
