@@ -305,3 +305,45 @@ def test_avg_mse_fast_per_tensor_golden(golden):
     o(T(g["p_x"]).cuda())
     assert o.one_side_dist == "pos" and float(o.min_val) == 0.0
     np.testing.assert_allclose(float(o.max_val), float(g["p_max"]), rtol=2e-3)
+
+
+def test_exchange_fused_into_the_replay_launch_two_ranks_on_one_device():
+    """osq_replay_exchange_f32 (publish own slots -> one flag store per peer -> acquire-wait -> peer loads -> replay) with two
+    "ranks" played by two streams of one GPU: each has a private slot table holding only ITS batches, a region of its own, and
+    must end with the state the plain replay produces from the complete table -- for three consecutive passes (both table
+    generations, flags that keep counting), the second and third with stale values left in the other rank's slots."""
+    from outlier_suppression_b200 import ops
+    dev = torch.device("cuda")
+    n_obs, n_batches, world = 5, 7, 2
+    n_f = n_obs * n_batches * 2
+    regions = [torch.zeros(2 * n_f + world, dtype=torch.float32, device=dev) for _ in range(world)]
+    region_ptrs = torch.tensor([r.data_ptr() for r in regions], dtype=torch.int64, device=dev)
+    pass_ctr = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
+    err = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+
+    def targets(state_min, state_max, scale, zp):
+        return ops.replay_targets([(state_min[i], state_max[i], scale[i], zp[i], 0, 63, False) for i in range(n_obs)], dev)
+
+    def fresh():
+        return (torch.full((n_obs, 1), float("inf"), device=dev), torch.full((n_obs, 1), float("-inf"), device=dev),
+                torch.zeros(n_obs, 1, device=dev), torch.zeros(n_obs, 1, device=dev))
+
+    g = torch.Generator().manual_seed(9)
+    want_state, got_state = fresh(), [fresh() for _ in range(world)]
+    cnt0 = 0
+    for p in range(3):
+        full = torch.randn(n_obs, n_batches, 2, generator=g).sort(dim=-1).values.to(dev)      # (min, max) per observer and batch
+        ops.replay_average(full, cnt0, targets(*want_state))
+        torch.cuda.synchronize()
+        for r in range(world):
+            local = torch.full_like(full, 777.0)                                               # other ranks' slots: garbage
+            local[:, r::world] = full[:, r::world]
+            with torch.cuda.stream(streams[r]):
+                ops.replay_exchange(local, region_ptrs, r, world, n_obs, n_batches, cnt0, targets(*got_state[r]), pass_ctr[r], err[r])
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert int(err[r]) == 0 and int(pass_ctr[r]) == p + 1
+            for a, b in zip(want_state, got_state[r]):
+                same(a, b)
+        cnt0 += n_batches
