@@ -412,6 +412,57 @@ def fused_fq_linear(a: torch.Tensor, a_scale: torch.Tensor, a_zp: torch.Tensor, 
 
 
 # --------------------------------------------------------------------------------------
+# model-level blocks around the quantizers: restated from model/quant_bert.py and
+# model/util_layernorm.py, pinned by tests/golden/blocks.npz (generated from the reference's unmodified modules)
+# --------------------------------------------------------------------------------------
+def act_fq(x: torch.Tensor, scale: torch.Tensor, zero_point: torch.Tensor, qmin: int, qmax: int, lsqplus: bool) -> torch.Tensor:
+    """An activation quantizer in the quantized state: LSQPlusFakeQuantize (fake_quant.py:188-195) or FixedFakeQuantize
+    (fake_quant.py:123-125); scale / zero_point are one-element tensors."""
+    if lsqplus:
+        return fq_lsqplus_per_tensor(x, scale.clone(), zero_point.clone(), qmin, qmax)
+    return fq_per_tensor(x, float(scale), int(zero_point), qmin, qmax)
+
+
+def attention_block(q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, mask: Optional[torch.Tensor], heads: int,
+                    qq, kq, pq, vq, oq, qmin: int, qmax: int, lsqplus: bool, dtype=torch.float32):
+    """model/quant_bert.py:141-193 (QuantizedBertSelfAttention.forward) after the three projections, dropout inactive:
+    q3 / k3 / v3 are the [B, S, H] outputs of query / key / value; qq .. oq = (scale, zero_point) of the query_permute,
+    key_transpose, attention_probs, value_permute and context_view quantizers (oq None: qoutput=False).
+    ``dtype``: arithmetic type of the two matmuls and the softmax (fp32 = the reference; fp64 = the exact value of the
+    contraction of the fake-quantised operands).  Returns (scores, probs, context)."""
+    B, S, H = q3.shape
+    d = H // heads
+    tfs = lambda x: x.view(B, -1, heads, d).permute(0, 2, 1, 3)                                  # :128-132
+    ql = act_fq(tfs(q3), *qq, qmin, qmax, lsqplus)                                               # :148
+    kt = act_fq(tfs(k3).transpose(-1, -2), *kq, qmin, qmax, lsqplus)                             # :150
+    scores = torch.matmul(ql.to(dtype), kt.to(dtype)) / (d ** 0.5)                               # :150, :169
+    if mask is not None:
+        scores = scores + mask.to(dtype)                                                         # :172
+    probs = torch.nn.functional.softmax(scores, dim=-1)                                          # :175
+    pf = act_fq(probs.float(), *pq, qmin, qmax, lsqplus)                                         # :185
+    vl = act_fq(tfs(v3), *vq, qmin, qmax, lsqplus)                                               # :186
+    ctx = torch.matmul(pf.to(dtype), vl.to(dtype))                                               # :187
+    ctx = ctx.permute(0, 2, 1, 3).contiguous().view(B, S, H)                                     # :189-191
+    if oq is not None:
+        ctx = act_fq(ctx.float(), *oq, qmin, qmax, lsqplus)                                      # :192-193
+    return scores, probs, ctx
+
+
+def residual_layernorm_fq(h: torch.Tensor, res: torch.Tensor, gamma: Optional[torch.Tensor], ln_weight: Optional[torch.Tensor],
+                          ln_bias: Optional[torch.Tensor], eps: float, q, qmin: int, qmax: int, lsqplus: bool, dtype=torch.float32):
+    """model/quant_bert.py:214-216 behind the dense: GammaResidual (util_layernorm.py:49-52), then QuantizedLayerNorm
+    (util_layernorm.py:14-17, affine) or QuantizedSplitLayerNorm (util_layernorm.py:34-37: non-affine LayerNorm, then
+    ``+= bias``), then the LayerNorm's output quantizer q = (scale, zero_point).  Returns (LayerNorm output, its fake-quant)."""
+    u = (res * gamma if gamma is not None else res) + h
+    u = u.to(dtype)
+    ln = torch.nn.functional.layer_norm(u, (u.shape[-1],), None if ln_weight is None else ln_weight.to(dtype),
+                                        None if ln_weight is None or ln_bias is None else ln_bias.to(dtype), eps)
+    if ln_weight is None and ln_bias is not None:
+        ln = ln + ln_bias.to(dtype)
+    return ln, act_fq(ln.float(), *q, qmin, qmax, lsqplus)
+
+
+# --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d) -- shared by tests and bench so CPU and GPU see identical bits
 # --------------------------------------------------------------------------------------
 def synth_activation(b: int, s: int, h: int, seed: int = 0, outlier_channels: int = 6, outlier_gain: float = 30.0):

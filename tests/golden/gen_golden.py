@@ -394,6 +394,61 @@ def gen_extra():
     save("extra", **out)
 
 
+def gen_blocks():
+    """Goldens for the model-level blocks of SURVEY section 8 f3, taken from the reference's UNMODIFIED quant_bert.py running its own
+    quantization package on the CPU, in the quantized state of config 2 (LSQ+ / AvgPruneMinMax 6-bit, gamma migration) and of
+    config 1 (Fixed / AvgMinMax 8-bit): every tensor that crosses the self-attention block (quant_bert.py:134-195) and the
+    dense -> residual -> LayerNorm -> quantizer block (quant_bert.py:197-217, util_layernorm.py:14-52) of layer 0."""
+    import copy
+    from oracle import ref_model as RM
+    out = {}
+    for tag, kw in (("c2", dict(a_bit=6, w_bit=6, a_quantizer="LSQPlusFakeQuantize", a_observer="AvgPruneMinMaxObserver", delay=True)),
+                    ("c1", dict(a_bit=8, w_bit=8, a_quantizer="FixedFakeQuantize", a_observer="AvgMinMaxObserver", delay=False))):
+        ns = RM.load_stack("reference")
+        qcfg = RM.quant_config(**kw)
+        fp = RM.fp_bert(layers=2, hidden=128, heads=2, inter=256)
+        model = RM.build_model(ns, copy.deepcopy(fp), qcfg, "cpu")
+        batches = RM.synth_batches(3, 4, 32, 100, "cpu", seed=21)
+        model, _ = RM.run_schedule(ns, model, qcfg, batches)
+        layer = model.bert.encoder.layer[0]
+        att, so = layer.attention.self, layer.attention.output
+        cap = {}
+
+        def grab(name, what="out"):
+            def hook(mod, args, output):
+                cap[name] = (args[0] if what == "in" else (output[0] if isinstance(output, tuple) else output)).detach().clone()
+            return hook
+        hs = [att.query.register_forward_hook(grab("q3")), att.key.register_forward_hook(grab("k3")), att.value.register_forward_hook(grab("v3")),
+              att.attention_probs_post_act_fake_quantize.register_forward_hook(grab("probs", "in")),
+              att.attention_probs_post_act_fake_quantize.register_forward_hook(grab("probs_fq")),
+              att.register_forward_hook(grab("ctx_fq")), att.register_forward_pre_hook(lambda m, a: cap.__setitem__("mask", a[1].detach().clone())),
+              so.dense.register_forward_hook(grab("so_h")), so.register_forward_pre_hook(lambda m, a: cap.__setitem__("so_res", a[1].detach().clone())),
+              so.LayerNorm.layernorm_post_act_fake_quantize.register_forward_hook(grab("so_ln", "in")),
+              so.register_forward_hook(grab("so_y"))]
+        with torch.no_grad():
+            model(**batches[1])
+        for h in hs:
+            h.remove()
+        for k, v in cap.items():
+            out["%s_%s" % (tag, k)] = v
+        for qname in ("query_permute", "key_transpose", "value_permute", "attention_probs", "context_view"):
+            q = getattr(att, qname + "_post_act_fake_quantize")
+            out["%s_%s_scale" % (tag, qname)] = q.scale.detach().reshape(-1).float().clone()
+            out["%s_%s_zp" % (tag, qname)] = q.zero_point.detach().reshape(-1).float().clone()
+        q = so.LayerNorm.layernorm_post_act_fake_quantize
+        out["%s_so_scale" % tag], out["%s_so_zp" % tag] = q.scale.detach().reshape(-1).float().clone(), q.zero_point.detach().reshape(-1).float().clone()
+        res = so.before_LayerNorm_residual
+        out["%s_so_gamma" % tag] = res.gamma.detach().clone() if getattr(res, "mul_gamma", False) else torch.zeros(0)
+        ln = so.LayerNorm
+        inner = ln.layernorm
+        out["%s_so_ln_weight" % tag] = inner.weight.detach().clone() if inner.weight is not None else torch.zeros(0)
+        out["%s_so_ln_bias" % tag] = (inner.bias.detach().clone() if inner.bias is not None else
+                                     (ln.bias.detach().clone() if getattr(ln, "bias", None) is not None else torch.zeros(0)))
+        out["%s_meta" % tag] = np.array([att.num_attention_heads, att.attention_head_size, kw["a_bit"], int(kw["a_quantizer"] == "LSQPlusFakeQuantize")])
+        out["%s_eps" % tag] = np.array([inner.eps], dtype=np.float64)
+    save("blocks", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # reduction order independent of the thread count
     gen_fq_per_tensor()
@@ -405,3 +460,4 @@ if __name__ == "__main__":
     gen_mse()
     gen_qlinear()
     gen_extra()
+    gen_blocks()

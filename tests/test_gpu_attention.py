@@ -96,3 +96,46 @@ def test_error_paths():
         ops.attn_scores_fq(q.cpu(), q.cpu(), qa, qa)
     with pytest.raises(Exception):
         ops.attn_scores_fq(q, q, dict(scale=sc, zp=zp, qmin=0, qmax=1023, g=0.0), qa)         # 10 bits
+
+
+@pytest.mark.parametrize("tag", ["c2", "c1"])
+def test_blocks_against_the_reference_goldens(tag):
+    """tests/golden/blocks.npz: layer 0 of the reference's unmodified quant_bert.py on the CPU (config 2 after gamma migration,
+    config 1).  K8 -> softmax -> K9 must land on the reference's quantized context, K7 on its quantized LayerNorm output: equal
+    except where a value sits on a rounding tie (the reference's fp32 GEMM / LayerNorm round differently from an exact
+    contraction / another summation order), and then by one quantization step."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blocks.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    heads, d, bit, lsq = (int(v) for v in g[tag + "_meta"])
+    qmin, qmax = 0, 2 ** bit - 1
+    q3, k3, v3 = t(tag + "_q3").cuda(), t(tag + "_k3").cuda(), t(tag + "_v3").cuda()
+    B, S, H = q3.shape
+    hv = lambda x: x.view(B, S, heads, d).permute(0, 2, 1, 3)
+
+    def qd(name, numel):
+        sc, z = t("%s_%s_scale" % (tag, name)), t("%s_%s_zp" % (tag, name))
+        return dict(scale=sc.cuda(), zp=(z if lsq else z.to(torch.int32)).cuda(), qmin=qmin, qmax=qmax,
+                    g=(1.0 / (numel * qmax) ** 0.5 if lsq else 0.0))
+    inv = float(torch.tensor(1.0) / torch.tensor(math.sqrt(d), dtype=torch.float32))
+    scores = ops.attn_scores_fq(hv(q3), hv(k3), qd("query_permute", q3.numel()), qd("key_transpose", k3.numel()), out_mul=inv,
+                                mask=t(tag + "_mask").cuda().contiguous())
+    probs = torch.softmax(scores, -1)
+    assert float((probs.cpu() - t(tag + "_probs")).abs().max()) <= 2e-6
+    ctx = ops.attn_context_fq(probs, hv(v3), qd("attention_probs", probs.numel()), qd("value_permute", v3.numel()),
+                              oq=qd("context_view", q3.numel()))
+    want = t(tag + "_ctx_fq")
+    diff = (ctx.cpu() - want).abs()
+    assert float(diff.max()) <= float(t("%s_context_view_scale" % tag)) * 1.001
+    assert float((diff > 0).float().mean()) <= 2e-3
+    # K7 on the block behind it
+    gam, w, b = t(tag + "_so_gamma"), t(tag + "_so_ln_weight"), t(tag + "_so_ln_bias")
+    dev = lambda x: x.cuda() if x.numel() else None
+    sc, z = t(tag + "_so_scale"), t(tag + "_so_zp")
+    y, _, ln = ops.residual_layernorm_fq(t(tag + "_so_h").cuda(), t(tag + "_so_res").cuda(), dev(gam), dev(w), dev(b), float(g[tag + "_eps"][0]),
+                                         sc.cuda(), (z if lsq else z.to(torch.int32)).cuda(), qmin, qmax,
+                                         lsq_grad_factor=(1.0 / (q3.numel() * qmax) ** 0.5 if lsq else 0.0), want_ln=True)
+    assert float((ln.cpu() - t(tag + "_so_ln")).abs().max()) <= 4e-6 * float(t(tag + "_so_ln").abs().max())
+    sdiff = (y.cpu() - t(tag + "_so_y")).abs()
+    assert float(sdiff.max()) <= float(sc) * 1.001 and float((sdiff > 0).float().mean()) <= 2e-3

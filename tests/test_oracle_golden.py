@@ -1,5 +1,6 @@
 """Pins the CPU oracle (oracle/osq_oracle.py) against vectors produced by the unmodified reference
 (tests/golden/gen_golden.py).  Bit-exact unless stated."""
+import os
 import warnings
 
 import numpy as np
@@ -165,3 +166,34 @@ def test_qlinear_chain(golden):
         y2 = (acc * (s_a * w_scale.double())[None, :] + b.double()[None, :]).reshape(y.shape)
         ref = T(g["y%d" % i]).double()
         assert torch.all((y2 - ref).abs() <= 1e-3 * ref.abs() + 1e-3 * ref.abs().max())
+
+
+def test_oracle_model_blocks_match_the_reference_modules():
+    """tests/golden/blocks.npz holds every tensor crossing layer 0's self-attention block and dense -> residual -> LayerNorm ->
+    quantizer block of the reference's unmodified quant_bert.py (config 2: LSQ+ 6-bit after gamma migration; config 1: Fixed
+    8-bit).  The oracle restatement must reproduce them: quantizer outputs exactly (same inputs, same arithmetic), matmul /
+    softmax / LayerNorm results to the last bits torch's CPU kernels may round differently across builds."""
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blocks.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    for tag in ("c2", "c1"):
+        heads, d, bit, lsq = (int(v) for v in g[tag + "_meta"])
+        qmin, qmax = O.quant_range(bit, False)
+        qp = lambda n: (t("%s_%s_scale" % (tag, n)), t("%s_%s_zp" % (tag, n)))
+        scores, probs, ctx = O.attention_block(t(tag + "_q3"), t(tag + "_k3"), t(tag + "_v3"), t(tag + "_mask"), heads, qp("query_permute"),
+                                               qp("key_transpose"), qp("attention_probs"), qp("value_permute"), qp("context_view"),
+                                               qmin, qmax, bool(lsq))
+        assert float((probs - t(tag + "_probs")).abs().max()) <= 1e-6
+        # the quantizers themselves, on the reference's own inputs: exact
+        assert torch.equal(O.act_fq(t(tag + "_probs"), *qp("attention_probs"), qmin, qmax, bool(lsq)), t(tag + "_probs_fq"))
+        assert torch.equal(O.act_fq(t(tag + "_so_ln"), t(tag + "_so_scale"), t(tag + "_so_zp"), qmin, qmax, bool(lsq)), t(tag + "_so_y"))
+        step = float(t("%s_context_view_scale" % tag))
+        diff = (ctx - t(tag + "_ctx_fq")).abs()
+        assert float(diff.max()) <= step * 1.001 and float((diff > 0).float().mean()) <= 1e-3   # a tie may flip one bin
+        gam = t(tag + "_so_gamma"); w = t(tag + "_so_ln_weight"); b = t(tag + "_so_ln_bias")
+        ln, y = O.residual_layernorm_fq(t(tag + "_so_h"), t(tag + "_so_res"), gam if gam.numel() else None, w if w.numel() else None,
+                                        b if b.numel() else None, float(g[tag + "_eps"][0]), (t(tag + "_so_scale"), t(tag + "_so_zp")),
+                                        qmin, qmax, bool(lsq))
+        assert float((ln - t(tag + "_so_ln")).abs().max()) <= 2e-6 * float(t(tag + "_so_ln").abs().max())
+        sdiff = (y - t(tag + "_so_y")).abs()
+        assert float(sdiff.max()) <= float(t(tag + "_so_scale")) * 1.001 and float((sdiff > 0).float().mean()) <= 1e-3
