@@ -184,6 +184,26 @@ int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t
                           const float* percentile_dev, float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
                           const osq_stat_epilogue_t* epi, void* workspace, void* stream);
 
+/* Token-wise clipping (solver/token_wise_clipping.py:50-66) re-calibrates every AvgPruneMinMaxObserver for every candidate ratio, with
+ * activation fake-quant switched off (set_ratio, :12-19): the per-token extrema of an (observer, batch) pair do not depend on the
+ * ratio.  osq_token_minmax_hist_f32 records them once -- tmin / tmax [B*S], n_valid and the first-digit table hist0 (uint32
+ * [2 * 2048 + 64], zeroed by the caller) -- and osq_prune_select_cached_f32 evaluates observer.py:50-70 on any number of recorded
+ * problems in ONE launch (one CTA each): cur[0..1] = (min, max) after pruning at `percentile` (or *percentile_dev), bit-identical
+ * to osq_prune_observe_f32 on the original activation.  The running average / qparams follow with osq_replay_average_f32. */
+typedef struct {
+  const float* tmin;
+  const float* tmax;
+  int64_t n_slots;         /* B * S */
+  const int32_t* n_valid;
+  const uint32_t* hist0;
+  float* cur;              /* device float[2] */
+} osq_select_problem_t;
+
+int osq_token_minmax_hist_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float* tmin, float* tmax,
+                              int32_t* n_valid, uint32_t* hist0, void* stream);
+int osq_prune_select_cached_f32(const osq_select_problem_t* problems, int n_problems, float percentile, const float* percentile_dev,
+                                void* stream);
+
 /* AvgQuantileObserver.forward (observer.py:253-282) in two launches: K3 (masked min/max -> cur_minmax), then a histogram
  * of |x| over the valid tokens in `bins` equal bins of [0, R], R = max(-min, max) (ATen CPU histc binning, fp32), the
  * reference's sequential cumulative scan (`cur_total + cnt >= threshold * numel`, compared in fp32), the clip of

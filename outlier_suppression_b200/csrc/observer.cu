@@ -13,7 +13,7 @@
 namespace osq {
 
 __device__ __forceinline__ long long obs_gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define OBS_STAMP(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) trace[(slot)] = obs_gtimer(); } while (0)
+#define OBS_STAMP(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0 && trace != nullptr) trace[(slot)] = obs_gtimer(); } while (0)
 
 constexpr int kObsThreads = 512;
 constexpr int kObsWarps = kObsThreads / 32;
@@ -761,10 +761,13 @@ struct Packed16 {
   __device__ __forceinline__ unsigned int get(int j) const { return (q[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu; }
 };
 
-__global__ void __launch_bounds__(kSelThreads, 1)
-prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
-                         const int32_t* __restrict__ n_valid, float percentile, const float* __restrict__ percentile_dev,
-                         unsigned int* __restrict__ ghist0, float* __restrict__ cur, osq_stat_epilogue_t epi) {
+// `keep_table`: the first-digit table belongs to a cache (osq_prune_select_cached_f32) and is left as it is; otherwise it is the
+// workspace table of the launch pair and is re-armed (zeroed) for the next call on this stream.  `trace`: optional stamps.
+static __device__ __forceinline__ void
+prune_select_tail_body(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
+                       const int32_t* __restrict__ n_valid, float percentile, const float* __restrict__ percentile_dev,
+                       unsigned int* __restrict__ ghist0, float* __restrict__ cur, const osq_stat_epilogue_t& epi, const bool keep_table,
+                       long long* trace) {
   extern __shared__ __align__(16) unsigned int sel_smem[];
   unsigned int* h0 = sel_smem;                                                              // [2][kSelBins0]
   unsigned int (*list)[kSelCap] = reinterpret_cast<unsigned int (*)[kSelCap]>(h0 + 2 * kSelBins0);  // [2][kSelCap]
@@ -773,7 +776,6 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
   __shared__ float red[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  long long* trace = reinterpret_cast<long long*>(ghist0 + 2 * kSelBins0);
   OBS_STAMP(2);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // token_minmax_kernel's vectors, n_valid and first-digit table are complete
   OBS_STAMP(3);
@@ -788,7 +790,7 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
   for (int i = tid; i < 2 * kSelBins0; i += kSelThreads) {
     const unsigned int c = __ldcg(ghist0 + i);
     h0[i] = c;
-    if (c) ghist0[i] = 0;
+    if (c && !keep_table) ghist0[i] = 0;
   }
   if (tid < 2) { s_nlist[tid] = 0; s_minabove[tid] = 0xFFFFFFFFu; s_cntle[tid] = 0; s_next[tid] = 0xFFFFFFFFu; }
   __syncthreads();
@@ -1018,6 +1020,29 @@ prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict
       OBS_STAMP(8);
     }
   }
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
+                         const int32_t* __restrict__ n_valid, float percentile, const float* __restrict__ percentile_dev,
+                         unsigned int* __restrict__ ghist0, float* __restrict__ cur, osq_stat_epilogue_t epi) {
+  prune_select_tail_body(tmin, tmax, n_slots, n_valid, percentile, percentile_dev, ghist0, cur, epi, false,
+                         reinterpret_cast<long long*>(ghist0 + 2 * kSelBins0));
+}
+
+// The select on CACHED per-token vectors, many problems per launch (one CTA each): token-wise clipping re-calibrates every
+// observer for every candidate ratio, but its calibration forwards run with activation fake-quant off (token_wise_clipping.py:12-19),
+// so the per-token extrema of every (observer, batch) are the same for all ratios -- only the quantile moves.  The vectors and
+// their first-digit tables are recorded once (osq_token_minmax_hist_f32); each ratio then costs one launch of this kernel plus one
+// replay launch instead of a model forward per batch.
+__global__ void __launch_bounds__(kSelThreads, 1)
+prune_select_cached_kernel(const osq_select_problem_t* __restrict__ problems, float percentile, const float* __restrict__ percentile_dev) {
+  const osq_select_problem_t pr = problems[blockIdx.x];
+  osq_stat_epilogue_t none;
+  none.mode = 0; none.cnt = 0; none.state_min = nullptr; none.state_max = nullptr; none.scale_out = nullptr; none.zp_out = nullptr;
+  none.zp_out_is_int32 = 0; none.qmin = 0; none.qmax = 1; none.symmetric = 0;
+  prune_select_tail_body(pr.tmin, pr.tmax, pr.n_slots, pr.n_valid, percentile, percentile_dev, const_cast<unsigned int*>(pr.hist0), pr.cur, none,
+                         true, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1287,6 +1312,38 @@ int osq_token_minmax_f32(const float* x, const osq_tokens_t* tok, const int64_t*
   int grid = reduction_grid(tok->B * tok->S);
   if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
   token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, nullptr);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_token_minmax_hist_f32(const float* x, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float* tmin, float* tmax,
+                              int32_t* n_valid, uint32_t* hist0, void* stream) {
+  using namespace osq;
+  if (int rc = check_tokens(tok, "osq_token_minmax_hist_f32")) return rc;
+  OSQ_CHECK_ARG(x && tmin && tmax && n_valid && hist0, "osq_token_minmax_hist_f32: null pointer");
+  OSQ_CHECK_ARG(tok->B * tok->S < kSelMaxTokens, "osq_token_minmax_hist_f32: too many tokens for the cached select");
+  int grid = reduction_grid(tok->B * tok->S);
+  if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, hist0);
+  OSQ_LAUNCH_CHECK();
+  return OSQ_OK;
+}
+
+int osq_prune_select_cached_f32(const osq_select_problem_t* problems, int n_problems, float percentile, const float* percentile_dev,
+                                void* stream) {
+  using namespace osq;
+  OSQ_CHECK_ARG(problems != nullptr && n_problems >= 0, "osq_prune_select_cached_f32: bad argument");
+  OSQ_CHECK_ARG(percentile >= 0.f && percentile <= 1.f, "osq_prune_select_cached_f32: percentile outside [0,1]");
+  if (n_problems == 0) return OSQ_OK;
+  constexpr size_t kSelSmem = (size_t)(2 * kSelBins0 + 2 * kSelCap) * 4;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OSQ_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    OSQ_CUDA(cudaFuncSetAttribute(prune_select_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmem));
+    attr_set[dev & 63] = true;
+  }
+  prune_select_cached_kernel<<<n_problems, kSelThreads, kSelSmem, (cudaStream_t)stream>>>(problems, percentile, percentile_dev);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }

@@ -408,6 +408,40 @@ def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0,
 _hist_scratch = {}
 
 
+def token_minmax_hist(x, lens, seq_pos):
+    """Per-token extrema of one activation plus the first-digit table of the select, into FRESH buffers (a cache entry of the
+    token-wise-clipping sweep, osq_token_minmax_hist_f32).  Returns (tmin, tmax, n_valid, hist0) or None when the token count is
+    beyond the cached select."""
+    x = _prep_act(x)
+    tok = token_geometry(x, seq_pos)
+    n = tok.B * tok.S
+    if n >= (1 << 21):
+        return None
+    tmin = torch.empty(n, dtype=torch.float32, device=x.device)
+    tmax = torch.empty(n, dtype=torch.float32, device=x.device)
+    n_valid = torch.zeros(1, dtype=torch.int32, device=x.device)
+    hist0 = torch.zeros(2 * 2048 + 64, dtype=torch.int32, device=x.device)
+    lens_t, n_lens = _lens_arg(lens, x.device)
+    check(_lib.load().osq_token_minmax_hist_f32(x.data_ptr(), C.byref(tok), _ptr(lens_t), n_lens, tmin.data_ptr(), tmax.data_ptr(),
+                                                n_valid.data_ptr(), hist0.data_ptr(), _stream()), "osq_token_minmax_hist_f32")
+    return tmin, tmax, n_valid, hist0
+
+
+def select_problems(entries, device) -> torch.Tensor:
+    """Device copy of an osq_select_problem_t array.  entries: ((tmin, tmax, n_valid, hist0), cur) with cur a float32[2] view."""
+    arr = (_lib.SelectProblem * len(entries))()
+    for t, ((tmin, tmax, n_valid, hist0), cur) in zip(arr, entries):
+        t.tmin, t.tmax, t.n_slots, t.n_valid, t.hist0, t.cur = tmin.data_ptr(), tmax.data_ptr(), tmin.numel(), n_valid.data_ptr(), hist0.data_ptr(), cur.data_ptr()
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+
+def prune_select_cached(problems: torch.Tensor, n_problems: int, percentile: float, percentile_dev: Optional[torch.Tensor] = None) -> None:
+    """observer.py:50-70 on ``n_problems`` recorded (observer, batch) pairs in one launch (osq_prune_select_cached_f32)."""
+    _require_cuda(problems, percentile_dev)
+    check(_lib.load().osq_prune_select_cached_f32(problems.data_ptr(), int(n_problems), float(percentile), _ptr(percentile_dev), _stream()),
+          "osq_prune_select_cached_f32")
+
+
 def observe_quantile(x, lens, seq_pos, bins, threshold, *, mode=STAT_NONE, cnt=0, state_min=None, state_max=None,
                      scale_out=None, zp_out=None, qmin=0, qmax=255, symmetric=False, out=None) -> torch.Tensor:
     """AvgQuantileObserver.forward (observer.py:253-282): masked min/max, |x| histogram, cumulative-threshold clip and

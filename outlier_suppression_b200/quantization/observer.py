@@ -180,10 +180,15 @@ class AvgPruneMinMaxObserver(ObserverBase):
         if shard is not None:  # rank-sharded pass (dist.py): record this batch's pair only
             kw = dict(out=shard[0].table.slot(shard[1], shard[0].batch))
         tokenwise = observation_mask is not None or seq_pos != -1
+        record = getattr(self, "_twc_record", None)   # twc.GraphedFindRatio: keep what this call depends on besides the ratio
         if tokenwise and "attention_probs" not in self.name:  # observer.py:62-63
+            if record is not None:
+                record.append(("prune", ops.token_minmax_hist(x, observation_mask, seq_pos)))
             ops.observe_prune_minmax(x, observation_mask, seq_pos, self.percentile, percentile_dev=self._percentile_dev, **kw)
         else:
-            ops.observe_minmax(x, observation_mask, seq_pos, **kw)
+            cur = ops.observe_minmax(x, observation_mask, seq_pos, **kw)
+            if record is not None:
+                record.append(("plain", cur if shard is None else None))
         if shard is not None:
             return True
         self.cnt += 1

@@ -14,6 +14,13 @@ count that is baked into a calibration graph (``cnt`` = position of the batch), 
 
 Results are bit-identical to the eager loop on this backend (``tests/test_gpu_twc.py``): same per-ratio losses, same best
 ratio, same final ``(scale, zero_point)`` of every quantizer.
+
+Beyond the graphs (``cache_vectors=True``, the default): ``set_ratio`` switches activation fake-quant OFF for the calibration
+forwards (token_wise_clipping.py:12-19), so those forwards compute the same activations for every ratio -- only the quantile
+the observers cut at moves.  The per-token extrema of every (observer, batch) pair (and the plain min / max of the
+observers that do not prune: ``attention_probs``, pooled inputs) are therefore recorded ONCE, and "re-calibrating at another
+ratio" becomes one launch of the cached select over all (observer, batch) problems (osq_prune_select_cached_f32) plus one replay
+launch of the running averages and qparams (osq_replay_average_f32) instead of a model forward per batch.
 """
 from __future__ import annotations
 
@@ -37,7 +44,7 @@ class GraphedFindRatio:
     """
 
     def __init__(self, model, fp_input: Sequence[Dict[str, torch.Tensor]], fp_output: Sequence[torch.Tensor],
-                 loss_fn: Optional[Callable] = None):
+                 loss_fn: Optional[Callable] = None, cache_vectors: bool = True):
         self.model = model
         self.batches = list(fp_input)
         self.targets = [t.detach() for t in fp_output]
@@ -54,6 +61,8 @@ class GraphedFindRatio:
         self._quant: List[torch.cuda.CUDAGraph] = []
         self._loss: List[torch.Tensor] = []
         self._pool = None
+        self._use_cache = bool(cache_vectors)
+        self._cache = None   # recorded per-token vectors + slot table + replay targets (cache_vectors)
 
     # ---- the reference's two state switches (token_wise_clipping.py:12-26), verbatim in effect ----
     def set_ratio(self, ratio: float) -> None:
@@ -92,12 +101,14 @@ class GraphedFindRatio:
         self._pool = torch.cuda.graph_pool_handle()
         self._cal, self._quant, self._loss = [], [], []
         self.set_ratio(ratio)
+        self._cache = self._record_vectors() if self._use_cache else None
         with torch.no_grad():
-            for b in self.batches:                     # observer.cnt advances while capturing: graph i carries cnt = i
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=self._pool):
-                    self.model(**b)
-                self._cal.append(g)
+            if self._cache is None:
+                for b in self.batches:                 # observer.cnt advances while capturing: graph i carries cnt = i
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=self._pool):
+                        self.model(**b)
+                    self._cal.append(g)
             self.enable_quantization()
             for b, t in zip(self.batches, self.targets):
                 g = torch.cuda.CUDAGraph()
@@ -109,12 +120,9 @@ class GraphedFindRatio:
 
     def evaluate(self, ratio: float) -> torch.Tensor:
         """calibrate at ``ratio`` + quantized loss, all replays; returns the summed loss as a device scalar."""
-        if not self._cal:
+        if not self._quant:
             self.capture(ratio)
-        for _, q in self.act_q:
-            q.observer.set_percentile(ratio)
-        for g in self._cal:
-            g.replay()
+        self._calibrate(ratio)
         for g in self._quant:
             g.replay()
         total = self._loss[0].clone()
@@ -134,9 +142,59 @@ class GraphedFindRatio:
         ratio = 1.0 - step * best_i
         # final calibration at the best ratio (:64-65); the quantizers are left in the calibration state like the reference's
         self.set_ratio(ratio)
-        for g in self._cal:
-            g.replay()
+        self._calibrate(ratio)
         for _, q in self.act_q:
             q.observer.cnt = len(self.batches)
             q.qparam_epoch += 1
         return ratio, losses
+
+    # ---- calibration at one ratio: replayed forwards, or (cache_vectors) the cached select + one replay launch ----
+    def _calibrate(self, ratio: float) -> None:
+        for _, q in self.act_q:
+            q.observer.set_percentile(ratio)
+        c = self._cache
+        if c is None:
+            for g in self._cal:
+                g.replay()
+            return
+        from . import ops
+        if c["n"]:
+            ops.prune_select_cached(c["problems"], c["n"], float(ratio), percentile_dev=self.act_q[0][1].observer._percentile_dev)
+        ops.replay_average(c["table"], 0, c["targets"])     # set_ratio restarted the running averages: cnt0 = 0
+
+    def _record_vectors(self):
+        """One eager calibration pass that keeps, per (observer, batch), what the observer's result depends on besides the ratio.
+        Returns None (-> replayed forwards) when an observer cannot be cached: another observer class, a call pattern other than
+        once per batch, or a token count beyond the cached select."""
+        from . import ops
+        from .quantization.observer import AvgPruneMinMaxObserver
+        obs = [q.observer for _, q in self.act_q]
+        if not all(type(o) is AvgPruneMinMaxObserver for o in obs):
+            return None
+        for o in obs:
+            o._twc_record = []
+        try:
+            self.calibrate_eager()
+        finally:
+            recs = [o._twc_record for o in obs]
+            for o in obs:
+                o._twc_record = None
+        n_b = len(self.batches)
+        if any(len(r) != n_b or any(payload is None for _, payload in r) for r in recs):
+            return None
+        dev = self.targets[0].device
+        table = torch.zeros(len(obs), n_b, 2, dtype=torch.float32, device=dev)
+        problems = []
+        for i, r in enumerate(recs):
+            for b, (kind, payload) in enumerate(r):
+                if kind == "plain":
+                    table[i, b].copy_(payload.reshape(2))
+                else:
+                    problems.append((payload, table[i, b]))
+        entries = []
+        for (_, q), o in zip(self.act_q, obs):
+            o._ensure_scalar_state(dev)
+            s_out, z_out = q._per_tensor_qparam_targets()
+            entries.append((o.min_val, o.max_val, s_out, z_out, o.quant_min, o.quant_max, o.symmetric))
+        return {"table": table, "n": len(problems), "problems": ops.select_problems(problems, dev) if problems else None,
+                "targets": ops.replay_targets(entries, dev), "keep": recs}

@@ -31,7 +31,10 @@ def _prepare(ns, qcfg, seed):
     return model, batches, fp_out
 
 
-def test_graphed_find_ratio_matches_the_reference_loop():
+@pytest.mark.parametrize("cache_vectors", [True, False])
+def test_graphed_find_ratio_matches_the_reference_loop(cache_vectors):
+    """cache_vectors=True: calibration at a ratio = the cached select over the recorded per-token vectors + one replay launch;
+    False: replayed calibration forwards.  Both must reproduce the reference's eager loop bit for bit."""
     from outlier_suppression_b200.quantization.fake_quant import QuantizeBase
     from outlier_suppression_b200.twc import GraphedFindRatio
     ns = RM.load_stack("b200")
@@ -57,8 +60,9 @@ def test_graphed_find_ratio_matches_the_reference_loop():
     model2, batches2, fp_out2 = _prepare(ns, qcfg, seed=0)
     for a, b in zip(fp_out, fp_out2):
         assert torch.equal(a, b)
-    sweep = GraphedFindRatio(model2, batches2, fp_out2)
+    sweep = GraphedFindRatio(model2, batches2, fp_out2, cache_vectors=cache_vectors)
     ratio, losses = sweep.find_ratio(iters, step)
+    assert (sweep._cache is not None) == cache_vectors and (len(sweep._cal) == 0) == cache_vectors
     assert ratio == 1.0 - step * best_i
     np.testing.assert_array_equal(np.array(losses, dtype=np.float64), np.array(ref_losses, dtype=np.float64))
     assert len(set(losses)) > 1, "the sweep must actually depend on the ratio"
