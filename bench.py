@@ -306,7 +306,14 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
     table = SlotTable(1, NB, device, peer=(dist is not None and os.environ.get("OSQ_BENCH_PEER") == "1"))
     graph = [None]
 
+    batched = os.environ.get("OSQ_BENCH_SWEEP_BATCHED", "1") == "1"
+
     def my_batches_eager(ctl):
+        if batched and len(mine) > 1:
+            # the rank's batches as ONE call (Quantizer.observe_many -> osq_prune_observe_many_f32): same slots, and batch i + 1's
+            # per-token pass runs next to batch i's one-CTA select tail instead of behind it
+            q.observe_many([slabs[i] for i in mine], lens, 1, batch_indices=mine)
+            return
         for i in mine:
             ctl.set_batch(i)
             q(slabs[i], lens, 1)
@@ -429,7 +436,7 @@ def observer_sweep(device, rank, world, dist, peak, peak_src, reps=5):
             "valid_token_fraction": valid_tokens / (OB * OS),
             "token_minmax_kernel": {"ms_per_slab": k_ms, "gbs_valid": valid_bytes / (k_ms * 1e-3) / 1e9,
                                     "frac_of_hbm_peak": valid_bytes / (k_ms * 1e-3) / 1e9 / peak},
-            "launches_per_batch": 2, "exchange": ("inside the replay launch over NVLink peer memory: publish own slots, one remote flag store per peer, wait for every peer, peer loads (CUDA symmetric memory, no collective library, no host-side barrier)"
+            "launches_per_batch": 2, "batched_call": bool(batched and len(mine) > 1), "exchange": ("inside the replay launch over NVLink peer memory: publish own slots, one remote flag store per peer, wait for every peer, peer loads (CUDA symmetric memory, no collective library, no host-side barrier)"
                                                 if table.hdl is not None else ("one NCCL all_reduce(SUM) of the slot table" if dist is not None else "none (1 GPU)")),
             "issue": "eager" if graph[0] is None else issue_mode, "ms_per_pass_eager_exchange": ms_eager_exchange,
             "collective": ("none: exchange fused into the replay launch" if table.hdl is not None else "one all_reduce(SUM) of the [n_obs, 8, 2] slot table + one replay launch"),

@@ -184,6 +184,16 @@ int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t
                           const float* percentile_dev, float* tmin, float* tmax, int32_t* n_valid, float* cur_minmax,
                           const osq_stat_epilogue_t* epi, void* workspace, void* stream);
 
+/*     The same step for `n` calibration batches of one geometry in ONE call (observer.py:214-237 called once per batch by
+ *     ptq_glue_quant.calibrate / token_wise_clipping.calibrate): results and running statistics are what n consecutive calls of
+ *     osq_prune_observe_f32 produce (epis[i] carries batch i's cnt), but batch i + 1's per-token pass is launched as a programmatic
+ *     dependent of batch i's one-CTA select tail and runs next to it instead of behind it -- only this library's own launches sit in
+ *     between, which is what makes skipping the dependency safe.  xs / curs / epis are HOST arrays of n entries; tmin2 / tmax2
+ *     ([2 * ceil4(B*S)] fp32) and n_valid2 (int32[2]) are two alternating scratch sets; the workspace holds two first-digit tables. */
+int osq_prune_observe_many_f32(const float* const* xs, int n, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float percentile,
+                               const float* percentile_dev, float* tmin2, float* tmax2, int32_t* n_valid2, float* const* curs,
+                               const osq_stat_epilogue_t* epis, void* workspace, void* stream);
+
 /* Token-wise clipping (solver/token_wise_clipping.py:50-66) re-calibrates every AvgPruneMinMaxObserver for every candidate ratio, with
  * activation fake-quant switched off (set_ratio, :12-19): the per-token extrema of an (observer, batch) pair do not depend on the
  * ratio.  osq_token_minmax_hist_f32 records them once -- tmin / tmax [B*S], n_valid and the first-digit table hist0 (uint32

@@ -19,7 +19,7 @@ EXPORTS = [
     "osq_dequant_bins_f32",
     "osq_residual_layernorm_fq_f32", "osq_attn_scores_fq_f32", "osq_attn_context_fq_f32",
     "osq_minmax_masked_f32", "osq_minmax_flat_f32", "osq_token_minmax_f32", "osq_prune_select_f32", "osq_prune_select_unsorted_f32",
-    "osq_prune_observe_f32", "osq_token_minmax_hist_f32", "osq_prune_select_cached_f32", "osq_quantile_observe_f32", "osq_replay_average_f32", "osq_replay_average_peer_f32", "osq_replay_exchange_f32",
+    "osq_prune_observe_f32", "osq_prune_observe_many_f32", "osq_token_minmax_hist_f32", "osq_prune_select_cached_f32", "osq_quantile_observe_f32", "osq_replay_average_f32", "osq_replay_average_peer_f32", "osq_replay_exchange_f32",
     "osq_rowwise_minmax_qparams_f32", "osq_calc_qparams_f32",
     "osq_mse_multi_f32", "osq_mse_brent_rows_f32", "osq_mse_brent_tensor_f32", "osq_mse_tensor_scratch_bytes",
     "osq_pack_weight_s8", "osq_fused_fq_linear", "osq_fused_fq_linear_multi", "osq_lsqplus_backward_f32",
@@ -95,6 +95,7 @@ def _declare(lib):
         "osq_prune_select_f32": [vp, vp, vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_prune_select_unsorted_f32": [vp, vp, i64, vp, f32, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_prune_observe_f32": [vp, C.POINTER(Tokens), vp, i32, f32, vp, vp, vp, vp, vp, C.POINTER(StatEpilogue), vp, vp],
+        "osq_prune_observe_many_f32": [vp, i32, C.POINTER(Tokens), vp, i32, f32, vp, vp, vp, vp, vp, C.POINTER(StatEpilogue), vp, vp],
         "osq_token_minmax_hist_f32": [vp, C.POINTER(Tokens), vp, i32, vp, vp, vp, vp, vp],
         "osq_prune_select_cached_f32": [vp, i32, f32, vp, vp],
         "osq_quantile_observe_f32": [vp, C.POINTER(Tokens), vp, i32, i32, C.c_double, vp, vp, C.POINTER(StatEpilogue), vp, vp],

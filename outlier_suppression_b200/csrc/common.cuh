@@ -37,7 +37,8 @@ constexpr int kMaxPartialBlocks = 2048;  // upper bound on the grid of any reduc
 constexpr int64_t kSelectWsOffset = (2 * kMaxPartialBlocks) * 4 + 64;  // multi-CTA radix select state (observer.cu)
 constexpr int64_t kSelectHist0Offset = kSelectWsOffset + 2 * 256 * 4 + 64;  // first-digit table of the fused prune path: 2 x 2048 u32
 constexpr int64_t kTraceOffset = kSelectHist0Offset + 2 * 2048 * 4;  // 32 x int64 globaltimer stamps of the last fused prune call (profiling aid)
-constexpr int64_t kWorkspaceBytes = kTraceOffset + 32 * 8;
+constexpr int64_t kSelectHist1Offset = kTraceOffset + 32 * 8;   // second first-digit table (+ stamps): osq_prune_observe_many_f32 alternates tables
+constexpr int64_t kWorkspaceBytes = kSelectHist1Offset + 2 * 2048 * 4 + 32 * 8;
 
 // ---------------------------------------------------------------------------------------------
 // Quantisation parameters as the kernels consume them.

@@ -183,7 +183,7 @@ minmax_flat_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ c
 __global__ void __launch_bounds__(kObsThreads)
 token_minmax_kernel(const float* __restrict__ x, osq_tokens_t tk, const int64_t* __restrict__ lens,
                     int n_lens, float* __restrict__ tmin, float* __restrict__ tmax,
-                    int32_t* __restrict__ n_valid, unsigned int* __restrict__ hist0) {
+                    int32_t* __restrict__ n_valid, unsigned int* __restrict__ hist0, int end_wait) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kObsWarps + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * kObsWarps;
@@ -240,6 +240,11 @@ token_minmax_kernel(const float* __restrict__ x, osq_tokens_t tk, const int64_t*
     }
     OBS_STAMP(1);
   }
+  // osq_prune_observe_many_f32 launches this grid as a programmatic dependent of the PREVIOUS batch's one-CTA select tail, so it runs
+  // next to that tail instead of behind it (it touches none of the tail's buffers: vectors and tables alternate).  The tails
+  // themselves must stay ordered (both update the running statistics): one thread holds this grid open until every prerequisite
+  // grid has completed.
+  if (end_wait && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -767,7 +772,7 @@ static __device__ __forceinline__ void
 prune_select_tail_body(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
                        const int32_t* __restrict__ n_valid, float percentile, const float* __restrict__ percentile_dev,
                        unsigned int* __restrict__ ghist0, float* __restrict__ cur, const osq_stat_epilogue_t& epi, const bool keep_table,
-                       long long* trace) {
+                       long long* trace, const bool release_early = false) {
   extern __shared__ __align__(16) unsigned int sel_smem[];
   unsigned int* h0 = sel_smem;                                                              // [2][kSelBins0]
   unsigned int (*list)[kSelCap] = reinterpret_cast<unsigned int (*)[kSelCap]>(h0 + 2 * kSelBins0);  // [2][kSelCap]
@@ -778,6 +783,7 @@ prune_select_tail_body(const float* __restrict__ tmin, const float* __restrict__
 
   OBS_STAMP(2);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // token_minmax_kernel's vectors, n_valid and first-digit table are complete
+  if (release_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next batch's per-token pass starts next to this CTA
   OBS_STAMP(3);
   const int T = *n_valid;
   if (percentile_dev != nullptr) percentile = fminf(fmaxf(*percentile_dev, 0.f), 1.f);   // CUDA-graph replays: the ratio is data
@@ -1025,9 +1031,9 @@ prune_select_tail_body(const float* __restrict__ tmin, const float* __restrict__
 __global__ void __launch_bounds__(kSelThreads, 1)
 prune_select_tail_kernel(const float* __restrict__ tmin, const float* __restrict__ tmax, int64_t n_slots,
                          const int32_t* __restrict__ n_valid, float percentile, const float* __restrict__ percentile_dev,
-                         unsigned int* __restrict__ ghist0, float* __restrict__ cur, osq_stat_epilogue_t epi) {
+                         unsigned int* __restrict__ ghist0, float* __restrict__ cur, osq_stat_epilogue_t epi, int release_early) {
   prune_select_tail_body(tmin, tmax, n_slots, n_valid, percentile, percentile_dev, ghist0, cur, epi, false,
-                         reinterpret_cast<long long*>(ghist0 + 2 * kSelBins0));
+                         reinterpret_cast<long long*>(ghist0 + 2 * kSelBins0), release_early != 0);
 }
 
 // The select on CACHED per-token vectors, many problems per launch (one CTA each): token-wise clipping re-calibrates every
@@ -1311,7 +1317,7 @@ int osq_token_minmax_f32(const float* x, const osq_tokens_t* tok, const int64_t*
   OSQ_CHECK_ARG(tok->B * tok->S < (int64_t)INT32_MAX, "osq_token_minmax_f32: too many tokens");
   int grid = reduction_grid(tok->B * tok->S);
   if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
-  token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, nullptr);
+  token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, nullptr, 0);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }
@@ -1324,7 +1330,7 @@ int osq_token_minmax_hist_f32(const float* x, const osq_tokens_t* tok, const int
   OSQ_CHECK_ARG(tok->B * tok->S < kSelMaxTokens, "osq_token_minmax_hist_f32: too many tokens for the cached select");
   int grid = reduction_grid(tok->B * tok->S);
   if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
-  token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, hist0);
+  token_minmax_kernel<<<grid, kObsThreads, 0, (cudaStream_t)stream>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, hist0, 0);
   OSQ_LAUNCH_CHECK();
   return OSQ_OK;
 }
@@ -1427,7 +1433,7 @@ int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t
     attr_set[dev & 63] = true;
   }
   unsigned int* hist0 = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + kSelectHist0Offset);
-  token_minmax_kernel<<<grid, kObsThreads, 0, st>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, hist0);
+  token_minmax_kernel<<<grid, kObsThreads, 0, st>>>(x, *tok, lens, n_lens, tmin, tmax, n_valid, hist0, 0);
   OSQ_LAUNCH_CHECK();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(1, 1, 1);
@@ -1440,7 +1446,63 @@ int osq_prune_observe_f32(const float* x, const osq_tokens_t* tok, const int64_t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OSQ_CUDA(cudaLaunchKernelEx(&cfg, prune_select_tail_kernel, (const float*)tmin, (const float*)tmax, n_slots,
-                              (const int32_t*)n_valid, percentile, percentile_dev, hist0, cur_minmax, *epi));
+                              (const int32_t*)n_valid, percentile, percentile_dev, hist0, cur_minmax, *epi, 0));
+  return OSQ_OK;
+}
+
+int osq_prune_observe_many_f32(const float* const* xs, int n, const osq_tokens_t* tok, const int64_t* lens, int n_lens, float percentile,
+                               const float* percentile_dev, float* tmin2, float* tmax2, int32_t* n_valid2, float* const* curs,
+                               const osq_stat_epilogue_t* epis, void* workspace, void* stream) {
+  using namespace osq;
+  if (int rc = check_tokens(tok, "osq_prune_observe_many_f32")) return rc;
+  OSQ_CHECK_ARG(xs && n >= 1 && tmin2 && tmax2 && n_valid2 && curs && epis && workspace, "osq_prune_observe_many_f32: bad argument");
+  OSQ_CHECK_ARG(percentile >= 0.f && percentile <= 1.f, "osq_prune_observe_many_f32: percentile outside [0,1]");
+  const int64_t n_slots = tok->B * tok->S;
+  OSQ_CHECK_ARG(n_slots > 0 && n_slots < kSelMaxTokens, "osq_prune_observe_many_f32: token count out of range (use osq_prune_observe_f32)");
+  for (int i = 0; i < n; ++i) OSQ_CHECK_ARG(xs[i] && curs[i], "osq_prune_observe_many_f32: null activation / output pointer");
+  // make sure the shared-memory attributes of the pair are set (first use of the device)
+  if (n == 1) return osq_prune_observe_f32(xs[0], tok, lens, n_lens, percentile, percentile_dev, tmin2, tmax2, n_valid2, curs[0], &epis[0], workspace, stream);
+  {
+    static bool warmed[64] = {false};
+    int dev = 0;
+    OSQ_CUDA(cudaGetDevice(&dev));
+    if (!warmed[dev & 63]) {   // the single-call path sets the function attributes; run it for batch 0 and continue with the rest
+      if (int rc = osq_prune_observe_f32(xs[0], tok, lens, n_lens, percentile, percentile_dev, tmin2, tmax2, n_valid2, curs[0], &epis[0], workspace, stream)) return rc;
+      warmed[dev & 63] = true;
+      return osq_prune_observe_many_f32(xs + 1, n - 1, tok, lens, n_lens, percentile, percentile_dev, tmin2, tmax2, n_valid2, curs + 1, epis + 1, workspace, stream);
+    }
+  }
+  int grid = reduction_grid(n_slots);
+  if (grid < 0) { set_error("no CUDA device"); return OSQ_ECUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  constexpr size_t kSelSmem = (size_t)(2 * kSelBins0 + 2 * kSelCap) * 4;
+  const int64_t n4 = (n_slots + 3) & ~(int64_t)3;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  for (int i = 0; i < n; ++i) {
+    const int par = i & 1;   // vectors and first-digit tables alternate: batch i + 1's per-token pass never touches what tail i reads
+    float* tmin = tmin2 + par * n4;
+    float* tmax = tmax2 + par * n4;
+    int32_t* n_valid = n_valid2 + par;
+    unsigned int* hist0 = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + (par ? kSelectHist1Offset : kSelectHist0Offset));
+    cudaLaunchConfig_t tcfg = {};
+    tcfg.gridDim = dim3((unsigned)grid, 1, 1);
+    tcfg.blockDim = dim3(kObsThreads, 1, 1);
+    tcfg.stream = st;
+    tcfg.attrs = attr;
+    tcfg.numAttrs = i > 0 ? 1 : 0;   // batch 0 is an ordinary launch: whatever produced the activations has completed
+    OSQ_CUDA(cudaLaunchKernelEx(&tcfg, token_minmax_kernel, xs[i], *tok, lens, n_lens, tmin, tmax, n_valid, hist0, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, 1);
+    cfg.blockDim = dim3(kSelThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSelSmem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OSQ_CUDA(cudaLaunchKernelEx(&cfg, prune_select_tail_kernel, (const float*)tmin, (const float*)tmax, n_slots, (const int32_t*)n_valid,
+                                percentile, percentile_dev, hist0, curs[i], epis[i], i + 1 < n ? 1 : 0));
+  }
   return OSQ_OK;
 }
 

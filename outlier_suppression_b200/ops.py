@@ -405,6 +405,39 @@ def observe_prune_minmax(x, lens, seq_pos, percentile, *, mode=STAT_NONE, cnt=0,
     return cur
 
 
+_many_scratch = {}
+
+
+def observe_prune_minmax_many(xs, lens, seq_pos, percentile, epilogues, outs=None, percentile_dev=None):
+    """``observe_prune_minmax`` for a list of calibration batches of one geometry in ONE call (osq_prune_observe_many_f32): the same
+    results as calling it once per batch, with batch i + 1's per-token pass running next to batch i's one-CTA select tail.
+    ``epilogues``: one dict per batch with the keyword arguments of ``_epilogue`` (mode, cnt, state_min, ...); ``outs``: optional
+    list of float32[2] outputs (e.g. slots of a sharded calibration table).  Returns the list of per-batch (min, max) tensors."""
+    xs = [_prep_act(x) for x in xs]
+    tok = token_geometry(xs[0], seq_pos)
+    for x in xs[1:]:
+        if x.shape != xs[0].shape or x.stride() != xs[0].stride():
+            raise ValueError("all batches of one call must share shape and strides")
+    n, n_slots = len(xs), tok.B * tok.S
+    dev = xs[0].device
+    n4 = (n_slots + 3) & ~3
+    key = (dev.index, _stream())
+    buf = _many_scratch.get(key)
+    if buf is None or buf[0].numel() < 4 * n4:
+        buf = (torch.empty(max(4 * n4, 1 << 17), dtype=torch.float32, device=dev), torch.empty(2, dtype=torch.int32, device=dev))
+        _many_scratch[key] = buf
+    tmin2, tmax2 = buf[0][:2 * n4], buf[0][2 * n4:4 * n4]
+    curs = [_cur_out(None if outs is None else outs[i], dev) for i in range(n)]
+    epis = (StatEpilogue * n)(*[_epilogue(**e) for e in epilogues])
+    xp = (C.c_void_p * n)(*[x.data_ptr() for x in xs])
+    cp = (C.c_void_p * n)(*[c.data_ptr() for c in curs])
+    lens_t, n_lens = _lens_arg(lens, dev)
+    check(_lib.load().osq_prune_observe_many_f32(xp, n, C.byref(tok), _ptr(lens_t), n_lens, float(percentile), _ptr(percentile_dev),
+                                                 tmin2.data_ptr(), tmax2.data_ptr(), buf[1].data_ptr(), cp, epis, workspace(dev).data_ptr(),
+                                                 _stream()), "osq_prune_observe_many_f32")
+    return curs
+
+
 _hist_scratch = {}
 
 

@@ -175,6 +175,38 @@ class QuantizeBase(nn.Module):
             return obs._last_fused
         return obs._observe(X, observation_mask, seq_pos, owner)
 
+    def observe_many(self, Xs, observation_mask=None, seq_pos=-1, batch_indices=None) -> None:
+        """Calibration on a LIST of batches: the state afterwards is what ``forward`` on each batch in order leaves (observer enabled;
+        the fake-quantised outputs are not produced).  AvgPruneMinMaxObserver runs the list as one batched launch sequence
+        (osq_prune_observe_many_f32); every other observer is called once per batch."""
+        if self.observer_enabled != 1:
+            return
+        many = getattr(self.observer, "_observe_many", None)
+        if many is not None and not (self.observer._forward_hooks or self.observer._forward_pre_hooks):
+            fused = many([X.detach() for X in Xs], observation_mask, seq_pos, self, batch_indices)
+            if not fused:
+                self._refresh_qparams_from_observer()
+            self.qparam_epoch += 1
+            return
+        shard = getattr(self.observer, "_shard", None)
+        for i, X in enumerate(Xs):
+            if shard is not None and batch_indices is not None:
+                shard[0].set_batch(batch_indices[i])
+            fq, self.fake_quant_enabled = self.fake_quant_enabled, 0
+            try:
+                self(X, observation_mask, seq_pos)
+            finally:
+                self.fake_quant_enabled = fq
+
+    def _refresh_qparams_from_observer(self):
+        _scale, _zero_point = self.observer.calculate_qparams(self.observer.min_val, self.observer.max_val)
+        _scale, _zero_point = _scale.to(self.scale.device), _zero_point.to(self.zero_point.device)
+        if self.scale.shape != _scale.shape:
+            self.scale.data.resize_(_scale.shape)
+            self.zero_point.data.resize_(_zero_point.shape)
+        self.scale.data.copy_(_scale)
+        self.zero_point.data.copy_(_zero_point.to(self.zero_point.dtype))
+
     # ---- where the observer kernels may write the refreshed qparams ----
     def _per_tensor_qparam_targets(self):
         return None, None

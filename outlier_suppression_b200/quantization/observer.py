@@ -195,6 +195,43 @@ class AvgPruneMinMaxObserver(ObserverBase):
         return s_out is not None
 
 
+def _observe_many_prune(self, xs, observation_mask, seq_pos, quantizer=None, batch_indices=None) -> bool:
+    """``_observe`` for a list of calibration batches of one geometry in ONE call (osq_prune_observe_many_f32): same state as calling
+    it once per batch in order, with the one-CTA select tails overlapped by the next batch's per-token pass.  ``batch_indices``:
+    the batches' positions in a rank-sharded pass (dist.sharded_calibration)."""
+    assert self.ch_axis == -1
+    xs = [x for x in xs if x.numel() > 0]
+    if not xs:
+        return False
+    tokenwise = (observation_mask is not None or seq_pos != -1) and "attention_probs" not in self.name
+    same = all(x.shape == xs[0].shape and x.stride() == xs[0].stride() for x in xs)
+    shard = getattr(self, "_shard", None)
+    if not (tokenwise and same and len(xs) > 1 and getattr(self, "_twc_record", None) is None):
+        fused = False
+        for i, x in enumerate(xs):   # anything else: one call per batch
+            if shard is not None and batch_indices is not None:
+                shard[0].set_batch(batch_indices[i])
+            fused = self._observe(x, observation_mask, seq_pos, quantizer)
+        return fused
+    self._ensure_scalar_state(xs[0].device)
+    s_out, z_out = self._fused_targets(quantizer)
+    if shard is not None:
+        idx = batch_indices if batch_indices is not None else list(range(shard[0].batch, shard[0].batch + len(xs)))
+        outs = [shard[0].table.slot(shard[1], b) for b in idx]
+        epis = [dict(mode=ops.STAT_NONE, cnt=0, state_min=None, state_max=None, scale_out=None, zp_out=None, qmin=self.quant_min,
+                     qmax=self.quant_max, symmetric=self.symmetric) for _ in xs]
+        ops.observe_prune_minmax_many(xs, observation_mask, seq_pos, self.percentile, epis, outs=outs, percentile_dev=self._percentile_dev)
+        return True
+    epis = [dict(mode=ops.STAT_AVERAGE, cnt=self.cnt + i, state_min=self.min_val, state_max=self.max_val, scale_out=s_out, zp_out=z_out,
+                 qmin=self.quant_min, qmax=self.quant_max, symmetric=self.symmetric) for i in range(len(xs))]
+    ops.observe_prune_minmax_many(xs, observation_mask, seq_pos, self.percentile, epis, percentile_dev=self._percentile_dev)
+    self.cnt += len(xs)
+    return s_out is not None
+
+
+AvgPruneMinMaxObserver._observe_many = _observe_many_prune
+
+
 class MSEFastObserver(ObserverBase):
     """Golden-section / Brent search of the clipping range that minimises the fake-quant MSE
     (observer.py:412-536).  Per-channel 1-D searches (config 3 weights) run entirely on-chip

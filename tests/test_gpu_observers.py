@@ -347,3 +347,44 @@ def test_exchange_fused_into_the_replay_launch_two_ranks_on_one_device():
             for a, b in zip(want_state, got_state[r]):
                 same(a, b)
         cnt0 += n_batches
+
+
+@pytest.mark.parametrize("n_batches", [2, 5])
+def test_observe_many_matches_one_call_per_batch(n_batches):
+    """Quantizer.observe_many -> osq_prune_observe_many_f32: the calibration batches of one geometry in ONE call (per-token passes
+    overlapped with the previous batch's select tail by programmatic dependent launch, alternating scratch sets and first-digit
+    tables).  Observer state, qparams and -- in a rank-sharded pass -- the per-batch slots must be bit-identical to one call per
+    batch, for a masked 3-D and a 4-D (query_permute-like) activation."""
+    from outlier_suppression_b200.dist import sharded_calibration
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer
+    g = torch.Generator().manual_seed(31 + n_batches)
+    lens = torch.tensor([96, 17, 60, 1]).cuda()
+    for shape, seq_pos in (((4, 96, 192), 1), ((4, 3, 96, 64), 2)):
+        xs = [(torch.randn(*shape, generator=g) * (1 + 0.5 * b)).cuda() for b in range(n_batches)]
+
+        def make():
+            net = torch.nn.Module()
+            net.a_act_fake_quant = Quantizer(None, QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1)).cuda()
+            q = net.a_act_fake_quant
+            q.observer.set_name("x"); q.observer.set_percentile(0.93); q.enable_observer()
+            return net, q
+        (_, q1), (_, q2) = make(), make()
+        for x in xs:
+            q1(x, lens, seq_pos)
+        q2.observe_many(xs, lens, seq_pos)
+        for a, b in ((q1.observer.min_val, q2.observer.min_val), (q1.observer.max_val, q2.observer.max_val),
+                     (q1.scale.detach(), q2.scale.detach()), (q1.zero_point.detach(), q2.zero_point.detach())):
+            same(a, b)
+        assert q1.observer.cnt == q2.observer.cnt == n_batches
+        # rank-sharded pass: slots written by the batched call == slots written call by call
+        (n3, q3), (n4, q4) = make(), make()
+        with sharded_calibration(n3, n_batches) as c3:
+            for i, x in enumerate(xs):
+                c3.set_batch(i); q3(x, lens, seq_pos)
+            t3 = c3.table.buf.clone()
+        with sharded_calibration(n4, n_batches) as c4:
+            q4.observe_many(xs, lens, seq_pos, batch_indices=list(range(n_batches)))
+            t4 = c4.table.buf.clone()
+        same(t3, t4)
+        same(q3.scale.detach(), q4.scale.detach()); same(q3.observer.max_val, q4.observer.max_val)
+        same(q1.scale.detach(), q3.scale.detach())
