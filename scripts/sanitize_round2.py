@@ -27,6 +27,24 @@ if which in ("all", "observers"):
         cur = ops.observe_prune_minmax(x.cuda(), lens.cuda(), 1, 0.5, percentile_dev=pd)
         assert torch.equal(cur.cpu(), torch.stack([lo, hi]))
         print("prune ok", n_tok, flush=True)
+    # batched call (per-token passes overlapped with the previous select tail) and the cached multi-problem select
+    from outlier_suppression_b200.quantization.quantized_module import Quantizer as _Q
+    from tests.test_host_logic import QC as _QC
+    lens3 = torch.tensor([90, 11, 47], device="cuda")
+    xs3 = [torch.randn(3, 90, 64, device="cuda") * (1 + b) for b in range(3)]
+    qa, qb = _Q(None, _QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1)).cuda(), _Q(None, _QC("LSQPlusFakeQuantize", "AvgPruneMinMaxObserver", 6, False, -1)).cuda()
+    for q_ in (qa, qb):
+        q_.observer.set_name("x"); q_.observer.set_percentile(0.9); q_.enable_observer()
+    for x_ in xs3:
+        qa(x_, lens3, 1)
+    qb.observe_many(xs3, lens3, 1)
+    assert torch.equal(qa.scale.detach(), qb.scale.detach()) and torch.equal(qa.observer.min_val, qb.observer.min_val)
+    vecs = [ops.token_minmax_hist(x_, lens3, 1) for x_ in xs3]
+    table = torch.zeros(3, 2, device="cuda")
+    ops.prune_select_cached(ops.select_problems([(v, table[i]) for i, v in enumerate(vecs)], "cuda"), 3, 0.9)
+    for i, x_ in enumerate(xs3):
+        assert torch.equal(table[i], ops.observe_prune_minmax(x_, lens3, 1, 0.9))
+    print("observe_many / cached select ok", flush=True)
     o = AvgQuantileObserver(bit=6).cuda()
     o(torch.randn(4, 50, 96, device="cuda"), torch.tensor([50, 3, 20, 1], device="cuda"), 1)
     torch.cuda.synchronize(); print("quantile ok", float(o.min_val), float(o.max_val), flush=True)
