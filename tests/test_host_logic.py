@@ -220,7 +220,7 @@ def test_ctypes_structures_match_the_header():
 
     for cname, cls in (("osq_tokens_t", _lib.Tokens), ("osq_stat_epilogue_t", _lib.StatEpilogue),
                        ("osq_fused_linear_t", _lib.FusedLinearArgs), ("osq_replay_target_t", _lib.ReplayTarget),
-                       ("osq_quantizer_t", _lib.QuantizerArgs)):
+                       ("osq_quantizer_t", _lib.QuantizerArgs), ("osq_select_problem_t", _lib.SelectProblem)):
         assert fields(cname) == [f[0] for f in cls._fields_], cname
 
 
