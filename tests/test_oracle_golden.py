@@ -197,3 +197,34 @@ def test_oracle_model_blocks_match_the_reference_modules():
         assert float((ln - t(tag + "_so_ln")).abs().max()) <= 2e-6 * float(t(tag + "_so_ln").abs().max())
         sdiff = (y - t(tag + "_so_y")).abs()
         assert float(sdiff.max()) <= float(t(tag + "_so_scale")) * 1.001 and float((sdiff > 0).float().mean()) <= 1e-3
+
+
+def test_integer_contraction_identity_behind_the_attention_kernels():
+    """K8 / K9 never form the dequantised operands: fq(a) @ fq(b)^T = s_a s_b (sum_k A B - Zb rowsum(A) - Za rowsum(B) + K Za Zb) with
+    A, B the uint8 bins (bin - qmin) and Za, Zb the zero points relative to qmin.  Checked here on the CPU, in exact integer
+    arithmetic, against the fp64 product of the oracle's fake-quantised tensors, on the reference-generated block inputs."""
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blocks.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    for tag in ("c2", "c1"):
+        heads, d, bit, lsq = (int(v) for v in g[tag + "_meta"])
+        qmin, qmax = O.quant_range(bit, False)
+        B, S, H = g[tag + "_q3"].shape
+        hv = lambda x: x.view(B, S, heads, d).permute(0, 2, 1, 3)
+
+        def bins_and_params(x, name):
+            sc, zp = t("%s_%s_scale" % (tag, name)), t("%s_%s_zp" % (tag, name))
+            if lsq:
+                s, z, _ = O.lsqplus_effective_qparams(sc.clone(), zp.clone(), x.numel(), qmax)
+                q = torch.clamp(O.round_ste_value(x / s) + z, qmin, qmax)
+                return torch.round(q).to(torch.int64) - qmin, float(s), int(torch.round(z)) - qmin, (q - z) * s
+            q = O.fq_bins(x, float(sc), int(zp), qmin, qmax)
+            return q.to(torch.int64) - qmin, float(sc), int(zp) - qmin, (q - int(zp)) * float(sc)
+        qa, sq, zq, q_fq = bins_and_params(hv(t(tag + "_q3")), "query_permute")
+        ka, sk, zk, k_fq = bins_and_params(hv(t(tag + "_k3")), "key_transpose")
+        acc = torch.matmul(qa, ka.transpose(-1, -2))                                  # exact: int64
+        corr = acc - zk * qa.sum(-1, keepdim=True) - zq * ka.sum(-1, keepdim=True).transpose(-1, -2) + d * zq * zk
+        got = corr.double() * (np.float64(np.float32(sq) * np.float32(sk)))           # the kernel's single fp32 scale product
+        want = torch.matmul(q_fq.double(), k_fq.double().transpose(-1, -2))
+        assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
+        assert int(corr.abs().max()) < 2 ** 24                                        # every term the kernel adds in fp32 is exact
